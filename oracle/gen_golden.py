@@ -1,0 +1,172 @@
+#!/usr/bin/env python
+"""oracle/gen_golden.py — ORACLE tooling (test infrastructure).  Generates tests/golden/*.npz by running the
+UNMODIFIED reference module `models/slim_yolo_v2.py::SlimYOLOv2_quantize_bnfuse` imported from /root/reference.
+
+Run in the build container only (the reference is not on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+Harness-side shims (no reference file is edited or copied):
+  * `pycocotools` is imported unconditionally (tools.py:2 -> data/__init__.py:3 -> data/cocodataset.py:7) and is
+    not installed: stub modules are put into sys.modules.
+  * `np.int` / `np.bool` (models/slim_yolo_v2.py:195) were removed from NumPy >= 1.24: aliased.
+  * the weight/bias quantiser functions are taken from retune_bias_quantize.py:73-97 by parsing that file and
+    exec'ing only those two function definitions (the script runs argparse at import time).
+
+What is recorded (see tests/test_oracle.py, tests/test_gpu_parity.py):
+  * the integers behind every AveragedRangeTracker output (input + 10 layers) for an UNSEEN frame after one
+    calibration call, as int8 NHWC maps (small case) or sha256 digests (416x416 case);
+  * the final (bboxes, scores, cls_inds) the reference returns;
+  * the exponent tables and a digest of the int8 weights, so tests can rebuild the identical network with
+    yolo_b200.export.random_quantnet-style code and no access to the reference.
+"""
+import ast
+import hashlib
+import importlib
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("YOLO_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def import_reference():
+    sys.dont_write_bytecode = True
+    for name in ("pycocotools", "pycocotools.coco", "pycocotools.cocoeval"):
+        m = types.ModuleType(name)
+        m.COCO = object
+        m.COCOeval = object
+        sys.modules[name] = m
+    np.int = int      # noqa: reference uses the removed alias
+    np.bool = bool    # noqa
+    sys.path.insert(0, REF)
+    mod = importlib.import_module("models.slim_yolo_v2")
+    src = open(os.path.join(REF, "retune_bias_quantize.py")).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("quantize_tensor", "quantize_tensor_b"):
+            exec(compile(ast.Module([node], []), "retune_bias_quantize.py", "exec"), ns)
+    return mod, ns["quantize_tensor"], ns["quantize_tensor_b"]
+
+
+def load_pkg():
+    sys.path.insert(0, ROOT)
+    return importlib.import_module("yolo_b200")
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def nhwc_pad(t_int: torch.Tensor) -> np.ndarray:
+    """[1,C,H,W] integer-valued float tensor -> int8 [H][W][cstride(C)]"""
+    c = t_int.shape[1]
+    cs = 4 if c <= 4 else (c + 15) // 16 * 16
+    a = t_int[0].permute(1, 2, 0).numpy()
+    assert np.all(a == np.round(a)) and np.abs(a).max() <= 128, "tracker output not an int8-range integer"
+    out = np.zeros(a.shape[:2] + (cs,), dtype=np.int8)
+    out[..., :c] = a.astype(np.int8)
+    return out
+
+
+def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, head_bias_shift=0.0):
+    refmod, quantize_tensor, quantize_tensor_b = import_reference()
+    yb = load_pkg()
+    ex = yb.export
+    anchors = ex.ANCHOR_SIZE_MASK
+
+    torch.manual_seed(seed)
+    net = refmod.SlimYOLOv2_quantize_bnfuse("cpu", input_size=[H, W], num_classes=2, trainable=False,
+                                             conf_thresh=conf_thresh, nms_thresh=nms_thresh, anchor_size=anchors)
+    net.eval()
+    # our exporter must draw the same random-init weights without the reference present
+    ws, bs = ex.random_float_convs(seed)
+    if head_bias_shift:
+        with torch.no_grad():
+            net.pred.bias[:5] += head_bias_shift
+        bs[-1] = bs[-1].clone(); bs[-1][:5] += head_bias_shift
+    convs = [net.conv1.convs[0], net.conv2.convs[0], net.conv3_1.convs[0], net.conv3_2.convs[0],
+             net.conv4_1.convs[0], net.conv4_2.convs[0], net.conv5.convs[0], net.conv6.convs[0],
+             net.conv7.convs[0], net.pred]
+    for c, w, b in zip(convs, ws, bs):
+        assert torch.equal(c.weight.detach(), w) and torch.equal(c.bias.detach(), b), "RNG replay mismatch"
+
+    # reference weight/bias quantisation, retune_bias_quantize.py:111-119 (rescale=True branch)
+    with torch.no_grad():
+        for c in convs:
+            qw, s_w = quantize_tensor(c.weight.detach().clone(), 8, False)
+            qb, s_b = quantize_tensor_b(c.bias.detach().clone(), 8, False)
+            c.weight[...] = qw / s_w
+            c.bias[...] = qb / s_b
+
+    calib = ex.synthetic_frames_f32(2, H, W, seed=1000 + seed)
+    qnet = ex.build_quantnet(ws, bs, calib, anchors=anchors)
+    sd = qnet.dequantized_state_dict()
+    for c, key in zip(convs, ex.SLIM_CONV_KEYS):
+        assert torch.equal(c.weight.detach(), sd[key + ".weight"]), key
+        assert torch.equal(c.bias.detach(), sd[key + ".bias"]), key
+
+    trackers = [getattr(net, k) for k in ex.SLIM_TRACKER_KEYS]
+    captured = []
+
+    def wrap(t):
+        orig = t.quantize_activation
+
+        def f(activation, *a, **k):
+            out = orig(activation, *a, **k)
+            s = 2 ** torch.floor(torch.log2(t.scale))
+            captured.append((out.detach() * s).clone())
+            return out
+        t.quantize_activation = f
+    for t in trackers:
+        wrap(t)
+
+    with torch.no_grad():
+        # calibration call: the reference handles batch element 0 only in its head, but trackers see the batch
+        net(calib, quantization=True)
+    sa_ref = [int(math.floor(math.log2(float(t.scale)))) for t in trackers]
+    assert sa_ref == qnet.sa, (sa_ref, qnet.sa)
+
+    frames = ex.synthetic_frames_f32(n_frames, H, W, seed=2000 + seed)
+    out = {
+        "H": H, "W": W, "seed": seed, "n_frames": n_frames, "conf_thresh": conf_thresh, "nms_thresh": nms_thresh,
+        "head_bias_shift": float(head_bias_shift),
+        "anchors": np.asarray(anchors, dtype=np.float32),
+        "sa": np.asarray(qnet.sa, np.int32), "sw": np.asarray(qnet.sw, np.int32),
+        "sb": np.asarray(qnet.sb, np.int32), "retune": np.asarray(qnet.retune, np.int32),
+        "net_sha256": qnet.sha256(), "frames_sha256": sha(frames.numpy()),
+        "torch_version": torch.__version__, "numpy_version": np.__version__,
+    }
+    for i in range(n_frames):
+        captured.clear()
+        with torch.no_grad():
+            bboxes, scores, cls_inds = net(frames[i:i + 1], quantization=True)
+        assert len(captured) == 11
+        maps = [nhwc_pad(c) for c in captured]
+        for l, m in enumerate(maps):
+            out["f%d_map%d_sha256" % (i, l)] = sha(m)
+            if store_maps or l == 10:
+                out["f%d_map%d" % (i, l)] = m
+        out["f%d_bboxes" % i] = np.asarray(bboxes, np.float32)
+        out["f%d_scores" % i] = np.asarray(scores, np.float32)
+        out["f%d_cls" % i] = np.asarray(cls_inds, np.int64)
+        print(name, "frame", i, "detections:", len(scores), "max|q| per map:", [int(np.abs(m).max()) for m in maps])
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    # small, non-square, every map stored: layer-by-layer parity
+    generate("ref_p_64x96", 64, 96, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=2, store_maps=True)
+    # sparse head variant (few detections, exercises thresholding), odd grid (80/16 = 5)
+    generate("ref_p_80x64_sparse", 80, 64, seed=1, conf_thresh=0.1, nms_thresh=0.45, n_frames=1, store_maps=True,
+             head_bias_shift=-1.4)
+    # BASELINE.json configs[1]: batch 1 at 416x416; digests of the maps + input/pred maps + detections
+    generate("ref_p_416x416", 416, 416, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=1, store_maps=False)

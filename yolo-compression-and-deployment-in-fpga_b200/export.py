@@ -1,0 +1,287 @@
+"""Checkpoint -> fixed-point network exporter (host-side logic, no GPU needed).
+
+The reference has NO exporter: `c_embedding/weight.h` is produced by an unpublished step
+(`.MISSING_LARGE_BLOBS:1`).  This module is that missing link, following the reference's own rules:
+
+* weight / bias quantisation ........ retune_bias_quantize.py:73-97 (`quantize_tensor`, `quantize_tensor_b`):
+  per-tensor ``s = 2**floor(log2(127 / max|t|))``, ``q = round(s * t)`` (torch.round = half-to-even).
+* activation scale calibration ...... models/slim_yolo_v2.py:16-38 (`AveragedRangeTracker`, first-call rule).
+* accumulator scale ``retune`` ...... models/slim_yolo_v2.py:222-227 (largest r with max|y| * 2**r < 2**15).
+* layer list ........................ models/slim_yolo_v2.py:58-87, c_embedding/yolo_forward.c:1202-1262.
+* weight.h burst order .............. c_embedding/yolo_forward.c:165-173,696-701 (inferred; header is missing).
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# (cin, cout, activ, pool) — yolo_forward.c:1202-1262 / slim_yolo_v2.py:58-87
+SLIM_YOLO_V2_LAYERS = [
+    (3, 16, 1, 1), (16, 32, 1, 1), (32, 64, 1, 0), (64, 64, 1, 1), (64, 128, 1, 0),
+    (128, 128, 1, 1), (128, 256, 1, 0), (256, 256, 1, 0), (256, 256, 1, 0), (256, 35, 0, 0),
+]
+# state_dict key prefixes of SlimYOLOv2_quantize_bnfuse in layer order (slim_yolo_v2.py:58-87)
+SLIM_CONV_KEYS = ["conv1.convs.0", "conv2.convs.0", "conv3_1.convs.0", "conv3_2.convs.0", "conv4_1.convs.0",
+                  "conv4_2.convs.0", "conv5.convs.0", "conv6.convs.0", "conv7.convs.0", "pred"]
+SLIM_TRACKER_KEYS = ["a_tracker_in", "a_tracker1", "a_tracker2", "a_tracker3_1", "a_tracker3_2", "a_tracker4_1",
+                     "a_tracker4_2", "a_tracker5", "a_tracker6", "a_tracker7", "a_tracker_pred"]
+
+# data/config.py:10-14
+ANCHOR_SIZE = [[1.19, 1.98], [2.79, 4.59], [4.53, 8.92], [8.06, 5.29], [10.32, 10.65]]
+ANCHOR_SIZE_MASK = [[0.27894, 0.49337], [0.8669, 1.37835], [1.82727, 2.8404], [3.4131, 5.05744], [5.8903, 7.6757]]
+ANCHOR_SIZE_COCO = [[0.53, 0.79], [1.71, 2.36], [2.89, 6.44], [6.33, 3.79], [9.03, 9.74]]
+
+# tables exactly as shipped in yolo_forward.c:32-35 (scale_a[0]: `65536` stored in a const char -> 0)
+SHIPPED_SCALE_W = [6, 8, 8, 9, 9, 9, 10, 10, 10, 9]
+SHIPPED_SCALE_B = [7, 6, 5, 5, 5, 6, 5, 5, 5, 10]
+SHIPPED_SCALE_A = [0, 4, 8, 8, 8, 8, 8, 8, 8, 16, 4]
+SHIPPED_RETUNE = [11, 10, 10, 11, 11, 10, 11, 11, 11, 10]
+
+
+def cstride(c: int) -> int:
+    """Channel stride of an int8 NHWC feature map (matches yolo_b200_cstride)."""
+    return 4 if c <= 4 else (c + 15) // 16 * 16
+
+
+def pow2_scale_exponent(t: torch.Tensor, bitwidth: int = 8) -> int:
+    """log2 of the reference's power-of-two scale for tensor t (retune_bias_quantize.py:79-84)."""
+    _max = t.abs().max()
+    scale = (2 ** (bitwidth - 1) - 1) / _max
+    return int(torch.floor(torch.log2(scale)).item())
+
+
+def quantize_pow2(t: torch.Tensor, bitwidth: int = 8):
+    """Returns (int tensor q, exponent e) with q = round(t * 2**e)  (retune_bias_quantize.py:73-97)."""
+    e = pow2_scale_exponent(t, bitwidth)
+    q = torch.round((2.0 ** e) * t)
+    return q, e
+
+
+@dataclass
+class QuantNet:
+    """A BN-fused fixed-point network: int8 weights/biases plus the exponent tables of yolo_forward.c:32-35."""
+    layers: List[tuple]
+    w: List[np.ndarray]            # int8 [cout][3][3][cin]  (OHWI)
+    b: List[np.ndarray]            # int8 [cout]
+    sw: List[int]
+    sb: List[int]
+    sa: List[int]                  # len(layers)+1, sa[0] = input
+    retune: List[int]
+    anchors: List[List[float]] = field(default_factory=lambda: [list(a) for a in ANCHOR_SIZE_MASK])
+    num_classes: int = 2
+    stride: int = 16
+
+    def sha256(self) -> str:
+        h = hashlib.sha256()
+        for w, b in zip(self.w, self.b):
+            h.update(np.ascontiguousarray(w).tobytes())
+            h.update(np.ascontiguousarray(b).tobytes())
+        h.update(np.asarray(self.sw + self.sb + self.sa + self.retune, dtype=np.int32).tobytes())
+        return h.hexdigest()
+
+    def dequantized_state_dict(self) -> Dict[str, torch.Tensor]:
+        """The 42-key state_dict SlimYOLOv2_quantize_bnfuse.load_state_dict expects (weights as q/2**e,
+        trackers frozen at 2**sa) — retune_bias_quantize.py:411-415 stores exactly this form."""
+        sd: Dict[str, torch.Tensor] = {}
+        for l, key in enumerate(SLIM_CONV_KEYS):
+            w = torch.from_numpy(self.w[l].astype(np.float32)).permute(0, 3, 1, 2).contiguous()
+            sd[key + ".weight"] = w / (2.0 ** self.sw[l])
+            sd[key + ".bias"] = torch.from_numpy(self.b[l].astype(np.float32)) / (2.0 ** self.sb[l])
+        for l, key in enumerate(SLIM_TRACKER_KEYS):
+            sd[key + ".scale"] = torch.tensor([2.0 ** self.sa[l]])
+            sd[key + ".first_a"] = torch.ones(1)
+        return sd
+
+
+def _float_convs_from_state_dict(sd: Dict[str, torch.Tensor]):
+    ws, bs = [], []
+    for key in SLIM_CONV_KEYS:
+        ws.append(sd[key + ".weight"].detach().float().cpu())
+        bs.append(sd[key + ".bias"].detach().float().cpu())
+    return ws, bs
+
+
+def random_float_convs(seed: int = 0, layers: Sequence[tuple] = SLIM_YOLO_V2_LAYERS):
+    """Random-init weights of the named architecture, drawn exactly as constructing the reference module
+    after torch.manual_seed(seed) would (nn.Conv2d default init, construction order of slim_yolo_v2.py:58-87)."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    ws, bs = [], []
+    for cin, cout, _, _ in layers:
+        conv = torch.nn.Conv2d(cin, cout, 3, 1, padding=1)
+        ws.append(conv.weight.detach().clone())
+        bs.append(conv.bias.detach().clone())
+    torch.random.set_rng_state(g)
+    return ws, bs
+
+
+def calibrate(ws: List[torch.Tensor], bs: List[torch.Tensor], frames: torch.Tensor,
+              layers: Sequence[tuple] = SLIM_YOLO_V2_LAYERS):
+    """One calibration call of the fake-quant forward (slim_yolo_v2.py:212-328 with quantization=True on
+    fresh trackers): every tracker takes scale = 127/max|a| on its first call (:22-27).  Also derives retune
+    per layer from the same activations (:222-227).  ws/bs are the DE-quantised (q/s) float tensors.
+    Returns (sa exponents [L+1], retune [L])."""
+    sa: List[int] = []
+    retune: List[int] = []
+    with torch.no_grad():
+        x = frames.float()
+        e = pow2_scale_exponent(x)
+        sa.append(e)
+        x = torch.round(x * 2.0 ** e) / 2.0 ** e
+        for l, (cin, cout, activ, pool) in enumerate(layers):
+            y = F.conv2d(x, ws[l], bs[l], stride=1, padding=1)
+            if activ:
+                y = F.leaky_relu(y, 0.125)
+            m = float(y.abs().max())
+            # largest r with m * 2**r < 2**15
+            r = int(math.floor(math.log2((2.0 ** 15) / m))) if m > 0 else 15
+            while m * 2.0 ** r >= 2.0 ** 15:
+                r -= 1
+            retune.append(r)
+            e = pow2_scale_exponent(y)
+            sa.append(e)
+            y = torch.round(y * 2.0 ** e) / 2.0 ** e
+            if pool:
+                y = F.max_pool2d(y, 2, 2)
+            x = y
+    return sa, retune
+
+
+def quantize_convs(ws: List[torch.Tensor], bs: List[torch.Tensor]):
+    """Reference weight/bias quantisation (retune_bias_quantize.py:111-119): returns int8 OHWI weights,
+    int8 biases, exponents, and the de-quantised float tensors the fake-quant model runs with."""
+    qw, qb, sw, sb, dw, db = [], [], [], [], [], []
+    for w, b in zip(ws, bs):
+        q, e = quantize_pow2(w)
+        qw.append(q.permute(0, 2, 3, 1).contiguous().numpy().astype(np.int8))
+        sw.append(e)
+        dw.append(q / 2.0 ** e)
+        q2, e2 = quantize_pow2(b)
+        qb.append(q2.numpy().astype(np.int8))
+        sb.append(e2)
+        db.append(q2 / 2.0 ** e2)
+    return qw, qb, sw, sb, dw, db
+
+
+def build_quantnet(ws: List[torch.Tensor], bs: List[torch.Tensor], calib_frames: torch.Tensor,
+                   layers: Sequence[tuple] = SLIM_YOLO_V2_LAYERS, anchors=None, num_classes: int = 2) -> QuantNet:
+    qw, qb, sw, sb, dw, db = quantize_convs(ws, bs)
+    sa, retune = calibrate(dw, db, calib_frames, layers)
+    return QuantNet(list(layers), qw, qb, sw, sb, sa, retune,
+                    [list(a) for a in (anchors or ANCHOR_SIZE_MASK)], num_classes)
+
+
+def synthetic_frames_f32(n: int, h: int, w: int, seed: int = 0) -> torch.Tensor:
+    """Synthetic camera frames through BaseTransform's arithmetic (data/__init__.py:30-56, test.py:79-80):
+    uint8 BGR image -> /255 -> -mean -> /std -> RGB, CHW.  No resize (image generated at the target size)."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    x = img.astype(np.float32)
+    x /= 255.
+    x -= np.array((0.406, 0.456, 0.485), dtype=np.float32)
+    x /= np.array((0.225, 0.224, 0.229), dtype=np.float32)
+    x = x[..., (2, 1, 0)]
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+def random_quantnet(seed: int = 0, calib_hw=(416, 416), calib_frames: int = 2, head_bias_shift: float = 0.0,
+                    anchors=None) -> QuantNet:
+    """Random-init slim_yolo_v2 of the named architecture, quantised and calibrated by the reference's rules
+    (SURVEY.md 8d 'Weights for all configs').  head_bias_shift is added to the 5 objectness biases of `pred`
+    BEFORE quantisation: random init otherwise puts most anchors above the threshold (dense NMS worst case);
+    a negative shift gives the sparse detections of a trained network."""
+    ws, bs = random_float_convs(seed)
+    if head_bias_shift:
+        bs[-1] = bs[-1].clone()
+        bs[-1][:5] += head_bias_shift
+    frames = synthetic_frames_f32(calib_frames, calib_hw[0], calib_hw[1], seed=1000 + seed)
+    return build_quantnet(ws, bs, frames, anchors=anchors)
+
+
+def quantnet_from_state_dict(sd: Dict[str, torch.Tensor], calib_frames: Optional[torch.Tensor] = None,
+                             anchors=None, num_classes: int = 2) -> QuantNet:
+    """q_bf state_dict (float or already-quantised `*_retune_quantize*.pth`, retune_bias_quantize.py:411-415)
+    -> QuantNet.  Activation exponents come from the checkpoint's trackers when they were calibrated
+    (first_a != 0), else from `calib_frames`."""
+    ws, bs = _float_convs_from_state_dict(sd)
+    qw, qb, sw, sb, dw, db = quantize_convs(ws, bs)
+    have_trackers = all((k + ".scale") in sd and float(sd[k + ".first_a"]) != 0 for k in SLIM_TRACKER_KEYS)
+    if calib_frames is None and not have_trackers:
+        raise ValueError("state_dict has uncalibrated activation trackers: pass calib_frames")
+    if calib_frames is None:
+        calib_frames = synthetic_frames_f32(1, 64, 64)
+    sa_c, retune = calibrate(dw, db, calib_frames)
+    if have_trackers:
+        sa = [int(math.floor(math.log2(float(sd[k + ".scale"])))) for k in SLIM_TRACKER_KEYS]
+        # retune must respect the 16-bit bound for the activations actually seen; keep the calibrated one
+    else:
+        sa = sa_c
+    return QuantNet(list(SLIM_YOLO_V2_LAYERS), qw, qb, sw, sb, sa, retune,
+                    [list(a) for a in (anchors or ANCHOR_SIZE_MASK)], num_classes)
+
+
+# ---- weight.h ---------------------------------------------------------------------------------------
+
+TM, TN = 32, 16   # accelerator tile: Tm output x Tn input channels (main.c:44, yolo_forward.c:1181)
+
+
+def pack_weight_h_order(w_ohwi: np.ndarray) -> np.ndarray:
+    """[cout][3][3][cin] -> flat int8 in the burst order load_weight reads (yolo_forward.c:165-173):
+    tap-major with tap stride cin*cout; inside a tap [cout/Tm][cin/Tn][Tm][Tn] (callers advance by Tn*Tm
+    per (out-group, in-group) pass, :697).  Layers thinner than the tile use their own size as the group.
+    The order INSIDE a Tn*Tm block is not determinable from the reference; out-major is this repo's choice."""
+    cout, _, _, cin = w_ohwi.shape
+    tm, tn = min(TM, cout), min(TN, cin)
+    gco, gci = -(-cout // tm), -(-cin // tn)
+    buf = np.zeros((3, 3, gco, gci, tm, tn), dtype=np.int8)
+    for go in range(gco):
+        for gi in range(gci):
+            blk = w_ohwi[go * tm:(go + 1) * tm, :, :, gi * tn:(gi + 1) * tn]   # [<=tm][3][3][<=tn]
+            buf[:, :, go, gi, :blk.shape[0], :blk.shape[3]] = blk.transpose(1, 2, 0, 3)
+    return buf.reshape(-1)
+
+
+def unpack_weight_h_order(flat: np.ndarray, cout: int, cin: int) -> np.ndarray:
+    tm, tn = min(TM, cout), min(TN, cin)
+    gco, gci = -(-cout // tm), -(-cin // tn)
+    buf = np.asarray(flat, dtype=np.int8).reshape(3, 3, gco, gci, tm, tn)
+    w = np.zeros((gco * tm, 3, 3, gci * tn), dtype=np.int8)
+    for go in range(gco):
+        for gi in range(gci):
+            w[go * tm:(go + 1) * tm, :, :, gi * tn:(gi + 1) * tn] = buf[:, :, go, gi].transpose(2, 0, 1, 3)
+    return w[:cout, :, :, :cin]
+
+
+def write_weight_h(net: QuantNet, path: str) -> None:
+    """Emit a weight.h with the symbols yolo_forward.c uses (w_conv0..9 / b_conv0..9, :1204-1260) plus the
+    exponent tables of :32-35 as comments."""
+    with open(path, "w") as f:
+        f.write("/* generated by yolo_b200 export.write_weight_h — layout: see pack_weight_h_order */\n")
+        f.write("/* scale_w = %s\n   scale_b = %s\n   scale_a = %s\n   retune  = %s */\n"
+                % (net.sw, net.sb, net.sa, net.retune))
+        for l, (w, b) in enumerate(zip(net.w, net.b)):
+            flat = pack_weight_h_order(w)
+            f.write("const char w_conv%d[%d] = {%s};\n" % (l, flat.size, ",".join(str(int(v)) for v in flat)))
+            f.write("const char b_conv%d[%d] = {%s};\n" % (l, b.size, ",".join(str(int(v)) for v in b)))
+
+
+def read_weight_h(path: str, layers: Sequence[tuple] = SLIM_YOLO_V2_LAYERS):
+    """Parse a weight.h written in the layout above -> (weights OHWI, biases)."""
+    import re
+    txt = open(path).read()
+    ws, bs = [], []
+    for l, (cin, cout, _, _) in enumerate(layers):
+        mw = re.search(r"w_conv%d\[\d*\]\s*=\s*\{([^}]*)\}" % l, txt)
+        mb = re.search(r"b_conv%d\[\d*\]\s*=\s*\{([^}]*)\}" % l, txt)
+        if not mw or not mb:
+            raise ValueError("weight.h lacks w_conv%d / b_conv%d" % (l, l))
+        flat = np.array([int(v) for v in mw.group(1).split(",")], dtype=np.int8)
+        ws.append(unpack_weight_h_order(flat, cout, cin))
+        bs.append(np.array([int(v) for v in mb.group(1).split(",")], dtype=np.int8)[:cout])
+    return ws, bs
