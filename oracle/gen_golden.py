@@ -75,7 +75,8 @@ def nhwc_pad(t_int: torch.Tensor) -> np.ndarray:
     return out
 
 
-def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, head_bias_shift=0.0):
+def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, head_bias_shift=0.0,
+             max_seed_tries=40):
     refmod, quantize_tensor, quantize_tensor_b = import_reference()
     yb = load_pkg()
     ex = yb.export
@@ -133,30 +134,91 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
     sa_ref = [int(math.floor(math.log2(float(t.scale)))) for t in trackers]
     assert sa_ref == qnet.sa, (sa_ref, qnet.sa)
 
-    frames = ex.synthetic_frames_f32(n_frames, H, W, seed=2000 + seed)
+    # the head's inputs to postprocess() are captured by wrapping the bound method (nothing is edited)
+    head_in = []
+    orig_post = net.postprocess
+
+    def post(all_local, all_conf):
+        head_in.append((np.array(all_local, np.float32), np.array(all_conf, np.float32)))
+        return orig_post(all_local, all_conf)
+    net.postprocess = post
+
+    def tie_robust(all_bbox, all_class, ref_scores):
+        """The reference sorts with `scores.argsort()[::-1]` (slim_yolo_v2.py:154): NumPy's default sort is not
+        stable, so with tied scores its result depends on the NumPy build/CPU.  A frame is tie-robust when both
+        deterministic tie orders reproduce what the reference returned."""
+        cls = np.argmax(all_class, axis=1)
+        sc = all_class[np.arange(len(cls)), cls]
+        k = np.where(sc >= net.conf_thresh)[0]
+        bb, ss, cc = all_bbox[k], sc[k], cls[k]
+        for kind in ("hi_first", "lo_first"):
+            km = np.zeros(len(k), int)
+            for c in range(2):
+                inds = np.where(cc == c)[0]
+                if len(inds) == 0:
+                    continue
+                s_c = ss[inds]
+                order = s_c.argsort(kind="stable")[::-1] if kind == "hi_first" else np.lexsort((np.arange(len(s_c)), -s_c))
+                x1, y1, x2, y2 = bb[inds].T
+                areas = (x2 - x1) * (y2 - y1)
+                keep = []
+                while order.size > 0:
+                    i = order[0]; keep.append(i)
+                    w_ = np.maximum(1e-28, np.minimum(x2[i], x2[order[1:]]) - np.maximum(x1[i], x1[order[1:]]))
+                    h_ = np.maximum(1e-28, np.minimum(y2[i], y2[order[1:]]) - np.maximum(y1[i], y1[order[1:]]))
+                    inter = w_ * h_
+                    ovr = inter / (areas[i] + areas[order[1:]] - inter)
+                    order = order[np.where(ovr <= net.nms_thresh)[0] + 1]
+                km[inds[keep]] = 1
+            sel = ss[np.where(km > 0)[0]]
+            if len(sel) != len(ref_scores) or not np.array_equal(sel, ref_scores):
+                return False
+        return True
+
     out = {
         "H": H, "W": W, "seed": seed, "n_frames": n_frames, "conf_thresh": conf_thresh, "nms_thresh": nms_thresh,
         "head_bias_shift": float(head_bias_shift),
         "anchors": np.asarray(anchors, dtype=np.float32),
         "sa": np.asarray(qnet.sa, np.int32), "sw": np.asarray(qnet.sw, np.int32),
         "sb": np.asarray(qnet.sb, np.int32), "retune": np.asarray(qnet.retune, np.int32),
-        "net_sha256": qnet.sha256(), "frames_sha256": sha(frames.numpy()),
+        "net_sha256": qnet.sha256(),
         "torch_version": torch.__version__, "numpy_version": np.__version__,
     }
-    for i in range(n_frames):
-        captured.clear()
+    frame_seeds = []
+    fseed = 2000 + seed
+    i = 0
+    while i < n_frames:
+        frame = ex.synthetic_frames_f32(1, H, W, seed=fseed)
+        captured.clear(); head_in.clear()
         with torch.no_grad():
-            bboxes, scores, cls_inds = net(frames[i:i + 1], quantization=True)
+            bboxes, scores, cls_inds = net(frame, quantization=True)
         assert len(captured) == 11
-        maps = [nhwc_pad(c) for c in captured]
+        robust = tie_robust(head_in[0][0], head_in[0][1], np.asarray(scores, np.float32))
+        if not robust and fseed - (2000 + seed) < max_seed_tries:
+            fseed += 1          # look for a frame whose reference result does not hinge on NumPy's tie order
+            continue
+        # trackers sit BEFORE the pools (slim_yolo_v2.py:229-231); a layer's output map is after its pool.
+        # max-pool on the captured integers is exact.
+        pooled = [captured[0]] + [torch.nn.functional.max_pool2d(c, 2, 2) if ex.SLIM_YOLO_V2_LAYERS[l][3] else c
+                                  for l, c in enumerate(captured[1:])]
+        maps = [nhwc_pad(c) for c in pooled]
         for l, m in enumerate(maps):
             out["f%d_map%d_sha256" % (i, l)] = sha(m)
             if store_maps or l == 10:
                 out["f%d_map%d" % (i, l)] = m
+        out["f%d_all_bbox" % i] = head_in[0][0]
+        out["f%d_all_class" % i] = head_in[0][1]
         out["f%d_bboxes" % i] = np.asarray(bboxes, np.float32)
         out["f%d_scores" % i] = np.asarray(scores, np.float32)
         out["f%d_cls" % i] = np.asarray(cls_inds, np.int64)
-        print(name, "frame", i, "detections:", len(scores), "max|q| per map:", [int(np.abs(m).max()) for m in maps])
+        out["f%d_tie_robust" % i] = int(robust)
+        out["f%d_frame_sha256" % i] = sha(frame.numpy())
+        frame_seeds.append(fseed)
+        print(name, "frame", i, "seed", fseed, "detections:", len(scores), "tie_robust:", robust,
+              "max|q| per map:", [int(np.abs(m).max()) for m in maps])
+        i += 1
+        fseed += 1
+    out["frame_seeds"] = np.asarray(frame_seeds, np.int64)
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
@@ -169,4 +231,5 @@ if __name__ == "__main__":
     generate("ref_p_80x64_sparse", 80, 64, seed=1, conf_thresh=0.1, nms_thresh=0.45, n_frames=1, store_maps=True,
              head_bias_shift=-1.4)
     # BASELINE.json configs[1]: batch 1 at 416x416; digests of the maps + input/pred maps + detections
-    generate("ref_p_416x416", 416, 416, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=1, store_maps=False)
+    generate("ref_p_416x416", 416, 416, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=1, store_maps=False,
+             max_seed_tries=0)
