@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the fixed-point slim_yolo_v2 forward pass on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of synthetic frames: 256 frames of 416x416 int8 NHWC4 per GPU
+(BASELINE.json configs[2]); random-init weights of the named architecture quantised and calibrated by the
+reference's rules (yolo_b200.export.random_quantnet); contract F (the FPGA shift programme), round-half-even.
+Frames are independent, so ranks shard the batch with no data-path collective; only the detection lists are
+gathered at the end of every step ("scaling": "weak").
+
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same through the C-ABI host entry point with pinned HOST buffers (H2D of the frames and D2H of
+the detections inside the timed region); `roofline` describes the dominant kernel; `cpu_baseline` is the CPU
+oracle timed on this box's host cores on a bounded sample (rank 0, N=1 only).
+
+--impl reference times the reference's own CPU implementation of the path: the C restatement under oracle/
+(the C driver itself cannot run without the FPGA RTL) with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+H = W = 416
+BATCH = 256
+METRIC = "frames/sec slim_yolo_v2 fixed-point"
+CONF, NMS = 0.1, 0.5     # test.py:22-24 defaults
+
+
+def layer_work(qnet, h, w):
+    """Algorithmic MACs and activation bytes per frame per layer: in H*W*Cin + out H'*W'*Cout."""
+    rows = []
+    for (cin, cout, activ, pool) in qnet.layers:
+        oh, ow = (h // 2, w // 2) if pool else (h, w)
+        rows.append({"macs": h * w * 9 * cin * cout, "bytes": h * w * (4 if cin <= 4 else cin) + oh * ow * cout})
+        h, w = oh, ow
+    return rows
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_fps(qnet, seconds_budget, threads=None):
+    """Oracle (CPU restatement of the reference path: backbone + head) on a bounded sample of the workload."""
+    import oracle_lib as ol
+    cores = os.cpu_count() or 1
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+        cores = threads
+    rng = np.random.default_rng(123)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        x8 = rng.integers(-100, 100, (1, H, W, 4), dtype=np.int8)
+        x8[..., 3] = 0
+        outs, _ = ol.backbone(qnet, x8, contract=0)
+        ol.head_python(outs[-1][0], 5, 2, qnet.sa[10], qnet.anchors, 16, H, W, CONF, NMS)
+        done += 1
+        el = time.perf_counter() - t0
+        if el >= seconds_budget or done >= 64:
+            break
+    return done / el, cores, done
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on this box's host cores."""
+    if rank != 0:
+        return
+    import yolo_b200  # noqa: F401
+    from yolo_b200 import export as ex
+    qnet = ex.random_quantnet(seed=0, calib_hw=(H, W), calib_frames=2)
+    import oracle_lib as ol
+    ol.build()
+    rng = np.random.default_rng(123)
+    frames_per_step = 2
+    xs = rng.integers(-100, 100, (frames_per_step, H, W, 4), dtype=np.int8)
+    xs[..., 3] = 0
+
+    def step():
+        outs, _ = ol.backbone(qnet, xs, contract=0)
+        for i in range(frames_per_step):
+            ol.head_python(outs[-1][i], 5, 2, qnet.sa[10], qnet.anchors, 16, H, W, CONF, NMS)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = args.steps * frames_per_step / dt
+    cores = os.cpu_count() or 1
+    sample = "%d frames/step of the 416x416 int8 workload, OpenMP over rows, %d host threads" % (frames_per_step, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+        "config": {"workload": "slim_yolo_v2 fixed-point forward, 416x416 int8 NHWC4 frames (bounded sample of the batch-256 job)",
+                   "frames_per_step": frames_per_step, "contract": "F/RNE"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import yolo_b200  # noqa: F401
+    from yolo_b200 import export as ex
+    from yolo_b200 import lib, runner
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    qnet = ex.random_quantnet(seed=0, calib_hw=(H, W), calib_frames=2)
+    MAXDET = 4096
+    ctx = lib.Context(local)
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F, round_mode=lib.ROUND_RNE, conf_thresh=CONF, nms_thresh=NMS, max_det=MAXDET)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # synthetic frames: quantised camera frames through BaseTransform's arithmetic, 2 alternating batches
+    # (each batch is 177 MB > the 126 MB L2, so every step streams its input from HBM)
+    n_sets = 2
+    host_sets = []
+    for s in range(n_sets):
+        rng = np.random.default_rng(100 * rank + s)
+        img = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8).astype(np.float32)
+        img /= 255.
+        img -= np.array((0.406, 0.456, 0.485), dtype=np.float32)
+        img /= np.array((0.225, 0.224, 0.229), dtype=np.float32)
+        q = np.clip(np.rint(img[..., ::-1] * (2.0 ** qnet.sa[0])), -128, 127).astype(np.int8)
+        x = torch.zeros((B, H, W, 4), dtype=torch.int8).pin_memory()
+        x[..., :3] = torch.from_numpy(q)
+        host_sets.append(x)
+        del img, q
+    dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
+    d_dets = torch.zeros((B, MAXDET, 8), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(i):
+        ctx.forward_int8_dev(dev_sets[i % n_sets], B, H, W, d_dets, d_counts)
+        if world > 1:
+            runner.gather_detections(d_dets, d_counts, B * world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = world * B * args.steps / (ms / 1e3)
+    mean_dets = float(d_counts.float().mean().item())
+
+    # ---- per-layer device times (CUDA events on the context stream between layers) -> dominant kernel
+    ctx.enable_timing(True)
+    per = np.zeros(len(qnet.layers) + 1)
+    reps = 5
+    for i in range(reps):
+        ctx.forward_int8_dev(dev_sets[i % n_sets], B, H, W, d_dets, d_counts)
+        per += np.array(ctx.layer_times_ms())
+    per /= reps
+    ctx.enable_timing(False)
+    pk = peaks()
+    work = layer_work(qnet, H, W)
+    int8_peak_tops = 2.0 * pk["bf16_tflops_sustained"]            # no measured INT8 figure: 2 x measured bf16
+    names = ["conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2", "conv5", "conv6", "conv7", "pred", "head"]
+    top = int(np.argmax(per[:len(work)]))
+    t_top = per[top] / 1e3
+    ops = 2.0 * work[top]["macs"] * B
+    byts = work[top]["bytes"] * B
+    tensor_bound = ops / (int8_peak_tops * 1e12) > byts / (pk["hbm_gbs"] * 1e9)
+    if tensor_bound:
+        roof = {"bound": "tensor", "achieved": ops / t_top / 1e12, "peak": int8_peak_tops, "unit": "TFLOP/s",
+                "note": "int8 ops (2*MAC) counted as FLOPs; peak = 2 x sustained bf16 of MEASURED_PEAKS.json (%s)" % pk["source"]}
+    else:
+        roof = {"bound": "hbm", "achieved": byts / t_top / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "note": "peak from MEASURED_PEAKS.json (%s)" % pk["source"]}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = names[top]
+    roof["kernel_ms"] = per[top]
+    roof["layer_ms"] = {n: round(float(v), 4) for n, v in zip(names, per)}
+    t_roof = sum(max(2.0 * r["macs"] / (int8_peak_tops * 1e12), r["bytes"] / (pk["hbm_gbs"] * 1e9)) for r in work)
+    roof["network_t_roof_us_per_frame"] = t_roof * 1e6
+    roof["network_frac_of_roofline"] = t_roof / (ms / 1e3 / (B * args.steps))
+
+    # ---- e2e: the C-ABI host entry point, pinned host frames in, detections out
+    h_dets = torch.zeros((B, MAXDET, 8), dtype=torch.int32).pin_memory()
+    h_counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    L = ctx.L
+
+    def e2e_step(i):
+        rc = L.yolo_b200_forward_int8(ctx._h, host_sets[i % n_sets].data_ptr(), B, H, W, h_dets.data_ptr(), h_counts.data_ptr())
+        if rc:
+            raise RuntimeError(L.yolo_b200_last_error())
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * B * e2e_steps / e2e_s
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, cores, nfr = cpu_oracle_fps(qnet, args.cpu_seconds)
+            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "%d frames of the same 416x416 int8 workload (backbone + head), OpenMP over rows" % nfr}
+        except Exception as e:  # the oracle is test infrastructure; its absence must not kill the GPU number
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "oracle unavailable: %s" % e}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "slim_yolo_v2 fixed-point batched inference, batch %d x 416x416 int8 NHWC4 frames per GPU" % B,
+                       "frames_per_gpu_per_step": B, "global_frames_per_step": B * world, "contract": "F/RNE",
+                       "weights": "random-init, reference quantisation + calibration rules (export.random_quantnet seed 0)",
+                       "head": "conf %.2f nms %.2f, mean %.0f detections/frame" % (CONF, NMS, mean_dets),
+                       "l2": "each step streams a 177 MB batch (2 alternating sets) > 126 MB L2",
+                       "parallelism": "frames sharded over %d GPU(s), detections all-gathered" % world},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(host_sets[0].numel()),
+                    "d2h_bytes_per_step": int(h_dets.numel() * 4 + h_counts.numel() * 4), "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

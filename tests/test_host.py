@@ -1,0 +1,130 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol include/yolo_b200.h declares
+(no compute without a GPU), parameter tables, the exporter, and the multi-GPU sharding plumbing over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import yolo_b200  # noqa: F401
+from yolo_b200 import export as ex
+from yolo_b200 import lib, runner
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from yolo_b200 import build
+    build.build()
+    return lib.load_library()
+
+
+def test_library_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "yolo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(yolo_b200_\w+|yolo_forward)\s*\(", hdr))
+    names -= {"yolo_b200_ctx", "yolo_b200_params", "yolo_b200_det", "yolo_b200_layer"}
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(L, n), "libyolo_b200.so does not export %s" % n
+    assert names == set(lib.EXPORTS)
+
+
+def test_default_params_are_the_shipped_tables(L):
+    p = lib.Params()
+    assert L.yolo_b200_default_params(C.byref(p)) == 0
+    assert p.num_layers == 10
+    assert [(p.layers[l].cin, p.layers[l].cout, p.layers[l].activ, p.layers[l].pool) for l in range(10)] == ex.SLIM_YOLO_V2_LAYERS
+    assert list(p.scale_w)[:10] == ex.SHIPPED_SCALE_W and list(p.scale_b)[:10] == ex.SHIPPED_SCALE_B
+    assert list(p.scale_a)[:11] == ex.SHIPPED_SCALE_A and list(p.retune)[:10] == ex.SHIPPED_RETUNE
+    assert [[round(p.anchors[a][0], 4), round(p.anchors[a][1], 4)] for a in range(5)] == ex.ANCHOR_SIZE_COCO
+    assert (p.num_anchors, p.num_classes, p.stride) == (5, 2, 16)
+    assert abs(p.conf_thresh - 0.01) < 1e-9 and p.nms_thresh == 0.5
+
+
+def test_cstride(L):
+    assert [L.yolo_b200_cstride(c) for c in (3, 4, 16, 35, 256, 425)] == [4, 4, 16, 48, 256, 432]
+    assert [ex.cstride(c) for c in (3, 4, 16, 35, 256, 425)] == [4, 4, 16, 48, 256, 432]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_no_cpu_fallback(L):
+    h = C.c_void_p()
+    rc = L.yolo_b200_create(C.byref(h), 0)
+    assert rc < 0 and b"no CPU fallback" in L.yolo_b200_last_error()
+    with pytest.raises(lib.YoloB200Error):
+        lib.Context(0)
+    # null-argument error behaviour needs no device
+    assert L.yolo_b200_default_params(None) < 0
+    assert L.yolo_b200_set_stream(None, None) < 0
+
+
+def test_quantise_rule_is_idempotent_on_checkpoints():
+    """A `*_retune_quantize*.pth`-style state_dict (weights stored as q/s, retune_bias_quantize.py:411-415)
+    re-exports to the same integers."""
+    qnet = ex.random_quantnet(seed=3, calib_hw=(64, 64), calib_frames=1)
+    sd = qnet.dequantized_state_dict()
+    q2 = ex.quantnet_from_state_dict(sd, anchors=qnet.anchors)
+    for a, b in zip(qnet.w + qnet.b, q2.w + q2.b):
+        np.testing.assert_array_equal(a, b)
+    assert (qnet.sw, qnet.sb, qnet.sa) == (q2.sw, q2.sb, q2.sa)
+    assert len(sd) == 42
+
+
+def test_weight_h_order_roundtrip_and_tap_stride():
+    rng = np.random.default_rng(0)
+    for cin, cout in ((3, 16), (16, 32), (32, 64), (256, 35)):
+        w = rng.integers(-128, 128, (cout, 3, 3, cin), dtype=np.int8)
+        flat = ex.pack_weight_h_order(w)
+        np.testing.assert_array_equal(ex.unpack_weight_h_order(flat, cout, cin), w)
+        # load_weight reads tap t at offset t * (padded cin*cout) (yolo_forward.c:169)
+        assert flat.size % 9 == 0
+        tm, tn = min(32, cout), min(16, cin)
+        t4 = flat.reshape(9, -1)[4].reshape(-(-cout // tm), -(-cin // tn), tm, tn)
+        assert t4[0, 0, 1, 2] == w[1, 1, 1, 2]
+
+
+def test_shard_range_partitions_all_frames():
+    for n in (0, 1, 7, 256, 2048):
+        for world in (1, 2, 3, 8):
+            spans = [runner.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+def test_gather_detections_gloo_world2(tmp_path):
+    """world_size-2 gloo run of the only cross-rank step: gathering ragged per-rank detection lists in frame order."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import yolo_b200
+from yolo_b200 import runner
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 5
+lo, hi = runner.shard_range(n, rank, world)
+dets = torch.zeros((hi - lo, 4, 8), dtype=torch.int32)
+counts = torch.zeros((hi - lo,), dtype=torch.int32)
+for i, f in enumerate(range(lo, hi)):
+    dets[i] = f + 1
+    counts[i] = f %% 4
+ad, ac = runner.gather_detections(dets, counts, n)
+assert ad.shape == (n, 4, 8) and ac.tolist() == [f %% 4 for f in range(n)]
+assert all(int(ad[f, 0, 0]) == f + 1 for f in range(n))
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+''' % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

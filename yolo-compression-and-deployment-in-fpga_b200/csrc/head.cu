@@ -1,0 +1,268 @@
+// head.cu — YOLOv2 detection head on the device: decode + score + threshold, then per-frame greedy NMS.
+//
+// Replaces get_boxes/conf_sort/NMS (c_embedding/yolo_forward.c:1052-1147) and
+// decode_boxes/postprocess/nms (models/slim_yolo_v2.py:111-210,330-358).
+//
+// Floating-point expressions are written with explicit round-to-nearest intrinsics so the compiler cannot contract
+// them into FMAs: the reference evaluates each product/sum separately in fp32 (NumPy / torch CPU), and NMS decisions
+// compare against the threshold bit-for-bit.
+#include "kernels.h"
+#include <math.h>
+
+namespace yb {
+
+__device__ __forceinline__ float sigmoid_py(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// sigmoid() as written in the C driver: 1/(exp(x)+1) = sigma(-x) (yolo_forward.c:965-968), double math
+__device__ __forceinline__ float sigmoid_c(float x) { return (float)(1 / (exp((double)x) + 1)); }
+
+// One thread per (frame, cell, anchor).  Channel order of a cell (slim_yolo_v2.py:337-341, yolo_forward.c:1273):
+// A conf | A*C class scores (anchor-major) | A*4 box terms (anchor-major).
+__global__ void __launch_bounds__(256) head_decode_kernel(HeadArgs a)
+{
+    const int N = a.gh * a.gw * a.A;
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= a.n * N) return;
+    int f = gid / N, idx = gid % N;
+    int cell = idx / a.A, an = idx % a.A;
+    int row = cell / a.gw, col = cell % a.gw;
+    const int8_t *p = a.pred + ((size_t)f * a.gh * a.gw + cell) * a.cs;
+    const int8_t *pc = p + a.A + an * a.C;
+    const int8_t *pb = p + a.A * (1 + a.C) + an * 4;
+    float score; int best; float4 box;
+    if (a.head_mode == YOLO_B200_HEAD_PYTHON) {
+        const float inv = ldexpf(1.0f, -a.sa_pred);
+        float obj = sigmoid_py(p[an] * inv);
+        float m = -INFINITY;
+        for (int c = 0; c < a.C; ++c) m = fmaxf(m, pc[c] * inv);
+        float sum = 0.f;
+        for (int c = 0; c < a.C; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(pc[c] * inv, m)));
+        best = 0; score = -1.f;
+        for (int c = 0; c < a.C; ++c) {
+            float s = __fmul_rn(__fdiv_rn(expf(__fsub_rn(pc[c] * inv, m)), sum), obj);
+            if (s > score) { score = s; best = c; }
+        }
+        float st = (float)a.stride;
+        float cx = __fmul_rn(__fadd_rn(sigmoid_py(pb[0] * inv), (float)col), st);
+        float cy = __fmul_rn(__fadd_rn(sigmoid_py(pb[1] * inv), (float)row), st);
+        float bw = __fmul_rn(__fmul_rn(expf(pb[2] * inv), a.anchors[an][0]), st);
+        float bh = __fmul_rn(__fmul_rn(expf(pb[3] * inv), a.anchors[an][1]), st);
+        float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
+        float iw = (float)a.in_w, ih = (float)a.in_h;
+        box.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(cx, hw), iw), 0.f), 1.f);
+        box.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(cy, hh), ih), 0.f), 1.f);
+        box.z = fminf(fmaxf(__fdiv_rn(__fadd_rn(cx, hw), iw), 0.f), 1.f);
+        box.w = fminf(fmaxf(__fdiv_rn(__fadd_rn(cy, hh), ih), 0.f), 1.f);
+    } else {
+        // C head on its well-defined subset (see include/yolo_b200.h, YOLO_B200_HEAD_C)
+        const double sc = exp2((double)a.sa_pred);
+        float conf = sigmoid_c((float)(p[an] / sc));
+        float c0 = (float)exp((double)(float)(pc[0] / sc));
+        float c1 = (float)exp((double)(float)(pc[1] / sc));
+        float sum = __fadd_rn(__fadd_rn(0.f, c0), c1);
+        c0 = __fdiv_rn(c0, sum); c1 = __fdiv_rn(c1, sum);
+        best = c0 >= c1 ? 0 : 1;
+        score = __fmul_rn(conf, best ? c1 : c0);
+        float tx = (float)(pb[0] / sc), ty = (float)(pb[1] / sc), tw = (float)(pb[2] / sc), th = (float)(pb[3] / sc);
+        float st = (float)a.stride;
+        float xc = __fmul_rn(__fadd_rn(sigmoid_c(tx), (float)col), st);
+        float yc = __fmul_rn(__fadd_rn(sigmoid_c(ty), (float)row), st);
+        float bw = (float)((double)a.anchors[an][0] * exp((double)tw) * (double)a.stride);
+        float bh = (float)((double)a.anchors[an][0] * exp((double)th) * (double)a.stride);   // anchor WIDTH, :1044
+        float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
+        box.x = (float)(int)__fsub_rn(xc, hw); box.z = (float)(int)__fadd_rn(xc, hw);
+        box.y = (float)(int)__fsub_rn(yc, hh); box.w = (float)(int)__fadd_rn(yc, hh);
+    }
+    a.scores[gid] = score; a.cls[gid] = best; a.boxes[gid] = box;
+}
+
+cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
+{
+    int total = a.n * a.gh * a.gw * a.A;
+    if (total == 0) return cudaSuccess;
+    head_decode_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- NMS ------------------------------------------------------------------------------------------
+
+constexpr int NMS_THREADS = 512;
+
+struct NmsSmem {
+    unsigned long long key[HEAD_MAX_CAND];   // (score bits << 32) | tie-break, sorted descending
+    float4 box[HEAD_MAX_CAND];
+    unsigned char cls[HEAD_MAX_CAND];
+    unsigned char dead[HEAD_MAX_CAND];
+    unsigned keepmap[HEAD_MAX_CAND / 32];     // by anchor index (python mode output order)
+    int warp_sums[NMS_THREADS / 32];
+    int count;
+};
+
+// block-wide exclusive scan of a 0/1 flag; returns this thread's offset, *total = sum over the block
+__device__ __forceinline__ int block_scan_flag(bool flag, int *warp_sums, int *total)
+{
+    unsigned b = __ballot_sync(0xffffffffu, flag);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int off = __popc(b & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[wid] = __popc(b);
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < NMS_THREADS / 32; ++w) { int s = warp_sums[w]; if (w < wid) base += s; tot += s; }
+    __syncthreads();
+    *total = tot;
+    return base + off;
+}
+
+// python: overlap as in slim_yolo_v2.py:159-169, suppress when NOT (ovr <= thresh)
+__device__ __forceinline__ bool suppress_py(float4 a, float4 b, float thresh)
+{
+    float areaa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    float areab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    float w = fmaxf(1e-28f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    float h = fmaxf(1e-28f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    float inter = __fmul_rn(w, h);
+    float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(areaa, areab), inter));
+    return !(ovr <= thresh);
+}
+
+// C: integer boxes, overlap()/box_intersection()/box_union() of yolo_forward.c:1000-1036, suppress iou >= thresh
+__device__ __forceinline__ bool suppress_c(float4 a, float4 b, float thresh)
+{
+    int ax1 = (int)a.x, ay1 = (int)a.y, ax2 = (int)a.z, ay2 = (int)a.w;
+    int bx1 = (int)b.x, by1 = (int)b.y, bx2 = (int)b.z, by2 = (int)b.w;
+    int ow = (ax2 - ax1 + bx2 - bx1) - (max(ax2, bx2) - min(ax1, bx1));
+    int oh = (ay2 - ay1 + by2 - by1) - (max(ay2, by2) - min(ay1, by1));
+    int inter = (ow <= 0 || oh <= 0) ? 0 : ow * oh;
+    int uni = (ax2 - ax1) * (ay2 - ay1) + (bx2 - bx1) * (by2 - by1) - inter;
+    float iou = __fdiv_rn((float)inter, (float)uni);
+    return iou >= thresh;
+}
+
+__global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
+    const int f = blockIdx.x;
+    const int N = a.gh * a.gw * a.A;
+    const float *scores = a.scores + (size_t)f * N;
+    const int *cls = a.cls + (size_t)f * N;
+    const float4 *boxes = a.boxes + (size_t)f * N;
+    const bool py = a.head_mode == YOLO_B200_HEAD_PYTHON;
+    const int tid = threadIdx.x;
+
+    // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077)
+    int m = 0;
+    for (int base = 0; base < N; base += NMS_THREADS) {
+        int i = base + tid;
+        float sc = i < N ? scores[i] : -1.f;
+        bool cand = i < N && (py ? sc >= a.conf_thresh : sc > a.conf_thresh);
+        int tot;
+        int off = block_scan_flag(cand, s.warp_sums, &tot);
+        if (cand) {
+            // ties: python -> higher anchor index first (reversed stable ascending argsort);
+            //       C      -> lower index first
+            unsigned tb = py ? (unsigned)i : (0xffffffffu - (unsigned)i);
+            s.key[m + off] = ((unsigned long long)__float_as_uint(sc) << 32) | tb;
+        }
+        m += tot;
+    }
+    for (int i = tid; i < HEAD_MAX_CAND / 32; i += NMS_THREADS) s.keepmap[i] = 0;
+    int P = 1;
+    while (P < m) P <<= 1;
+    for (int i = m + tid; i < P; i += NMS_THREADS) s.key[i] = 0ull;
+    __syncthreads();
+
+    // 2. bitonic sort, descending
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += NMS_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long x = s.key[i], y = s.key[ixj];
+                    bool desc = (i & k) == 0;
+                    if (desc ? x < y : x > y) { s.key[i] = y; s.key[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+
+    // 3. gather boxes / classes in sorted order
+    for (int i = tid; i < m; i += NMS_THREADS) {
+        unsigned tb = (unsigned)(s.key[i] & 0xffffffffu);
+        int idx = py ? (int)tb : (int)(0xffffffffu - tb);
+        s.box[i] = boxes[idx];
+        s.cls[i] = (unsigned char)cls[idx];
+        s.dead[i] = 0;
+    }
+    __syncthreads();
+
+    // 4. greedy suppression in score order (python: within a class; C: class-agnostic)
+    for (int i = 0; i < m; ++i) {
+        if (s.dead[i]) continue;                      // uniform: written before the last barrier
+        float4 bi = s.box[i];
+        unsigned char ci = s.cls[i];
+        for (int j = i + 1 + tid; j < m; j += NMS_THREADS) {
+            if (s.dead[j]) continue;
+            if (py) { if (s.cls[j] == ci && suppress_py(bi, s.box[j], a.nms_thresh)) s.dead[j] = 1; }
+            else    { if (suppress_c(bi, s.box[j], a.nms_thresh)) s.dead[j] = 1; }
+        }
+        __syncthreads();
+    }
+
+    // 5. output
+    yolo_b200_det *dets = a.dets + (size_t)f * a.max_det;
+    if (py) {
+        // ascending anchor order (np.where(keep > 0), slim_yolo_v2.py:205)
+        for (int i = tid; i < m; i += NMS_THREADS)
+            if (!s.dead[i]) { unsigned idx = (unsigned)(s.key[i] & 0xffffffffu); atomicOr(&s.keepmap[idx >> 5], 1u << (idx & 31)); }
+        __syncthreads();
+        int cnt = 0;
+        for (int base = 0; base < N; base += NMS_THREADS) {
+            int i = base + tid;
+            bool k = i < N && ((s.keepmap[i >> 5] >> (i & 31)) & 1u);
+            int tot;
+            int off = block_scan_flag(k, s.warp_sums, &tot);
+            if (k && cnt + off < a.max_det) {
+                float4 b = boxes[i];
+                yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w; d.score = scores[i]; d.cls = cls[i];
+                d.anchor_index = i; d.pad_ = 0;
+                dets[cnt + off] = d;
+            }
+            cnt += tot;
+        }
+        if (tid == 0) a.counts[f] = cnt;
+    } else {
+        // descending score order (conf_sort, yolo_forward.c:1114-1126)
+        int cnt = 0;
+        for (int base = 0; base < m; base += NMS_THREADS) {
+            int i = base + tid;
+            bool k = i < m && !s.dead[i];
+            int tot;
+            int off = block_scan_flag(k, s.warp_sums, &tot);
+            if (k && cnt + off < a.max_det) {
+                unsigned tb = (unsigned)(s.key[i] & 0xffffffffu);
+                int idx = (int)(0xffffffffu - tb);
+                float4 b = s.box[i];
+                yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w;
+                d.score = __uint_as_float((unsigned)(s.key[i] >> 32)); d.cls = s.cls[i]; d.anchor_index = idx; d.pad_ = 0;
+                dets[cnt + off] = d;
+            }
+            cnt += tot;
+        }
+        if (tid == 0) a.counts[f] = cnt;
+    }
+}
+
+cudaError_t head_init(void)
+{
+    return cudaFuncSetAttribute(head_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+}
+
+cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
+{
+    if (a.n == 0) return cudaSuccess;
+    if (a.gh * a.gw * a.A > HEAD_MAX_CAND) return cudaErrorInvalidValue;
+    head_nms_kernel<<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace yb

@@ -1,0 +1,49 @@
+// kernels.h — internal launch interface between the host library (yolo_b200.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+#include "../../include/yolo_b200.h"
+
+namespace yb {
+
+struct ConvArgs {
+    const int8_t *in;      // [n][H][W][cs_in]
+    int n, H, W, cs_in;
+    const int8_t *wgt;     // [cout_pad][9][cs_in]  (cout_pad: multiple of 32, zero padded)
+    const int *bias_sh;    // [cout_pad] pre-shifted bias (see LayerQ)
+    int cout, cs_out;
+    LayerQ q;
+    int8_t *out;           // [n][H'][W'][cs_out]
+    unsigned *ovf;         // contract-P saturation counter
+};
+
+// conv_direct.cu
+cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
+
+// quantize.cu
+cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st);
+cudaError_t quantize_f32(const float *nchw, int n, int h, int w, int sa, int8_t *nhwc4, unsigned *ovf, cudaStream_t st);
+
+// head.cu
+struct HeadArgs {
+    const int8_t *pred;    // [n][gh][gw][cs]
+    int n, gh, gw, cs;
+    int A, C;              // anchors per cell, classes
+    int sa_pred;           // exponent of the prediction map
+    float anchors[YOLO_B200_MAX_ANCHORS][2];
+    int stride, in_h, in_w;
+    float conf_thresh, nms_thresh;
+    int head_mode;
+    int max_det;
+    // scratch [n][N]: best-class score, class, box
+    float *scores; int *cls; float4 *boxes;
+    yolo_b200_det *dets;   // [n][max_det]
+    int32_t *counts;       // [n]
+};
+constexpr int HEAD_MAX_CAND = 4096;   // candidates per frame the NMS kernel can hold in shared memory
+cudaError_t head_decode(const HeadArgs &a, cudaStream_t st);
+cudaError_t head_nms(const HeadArgs &a, cudaStream_t st);
+cudaError_t head_init(void);          // one-time function attributes (dynamic shared memory)
+
+}  // namespace yb

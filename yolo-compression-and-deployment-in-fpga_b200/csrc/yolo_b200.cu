@@ -1,0 +1,541 @@
+// yolo_b200.cu — host side of the C-ABI declared in include/yolo_b200.h.
+//
+// Owns device memory, repacks weights once at load, derives each layer's epilogue programme from the exponent
+// tables (set_quantize_scale, c_embedding/yolo_forward.c:233-257) and sequences the kernels on one CUDA stream.
+// There is no CPU fallback: every entry point that computes needs a CUDA device.
+#include "kernels.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+using namespace yb;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(-5, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+enum { E_ARG = -1, E_STATE = -2, E_UNSUPPORTED = -3, E_NOMEM = -4, E_CUDA = -5 };
+
+struct LayerDev {
+    int cin, cout, cs_in, cs_out, cout_pad;
+    LayerQ q;
+    int8_t *w = nullptr;       // [cout_pad][9][cs_in]
+    int *bias_sh = nullptr;    // [cout_pad]
+    int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
+    size_t out_cap = 0;
+    int oh = 0, ow = 0;
+};
+
+struct yolo_b200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    bool loaded = false;
+    yolo_b200_params prm;
+    std::vector<LayerDev> layers;
+    int *lut_dev = nullptr;              // 4096 packed (R,G,B,0) words
+    int8_t lut_host[4096 * 4];
+    unsigned *ovf_dev = nullptr;
+    int8_t *in_q = nullptr; size_t in_q_cap = 0;        // quantised NHWC4 input
+    void *stage_in = nullptr; size_t stage_in_cap = 0;  // device staging of host inputs
+    float *h_scores = nullptr; int *h_cls = nullptr; float4 *h_boxes = nullptr; size_t head_cap = 0;
+    yolo_b200_det *d_dets = nullptr; int32_t *d_counts = nullptr; size_t dets_cap = 0, counts_cap = 0;
+    int last_n = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    int ev_used = 0;
+};
+
+static std::mutex g_default_mu;
+static yolo_b200_ctx *g_default_ctx = nullptr;
+
+#pragma GCC visibility push(default)     // only the C-ABI is exported from the shared library
+extern "C" {
+
+int yolo_b200_abi_version(void) { return 1; }
+const char *yolo_b200_last_error(void) { return g_err; }
+int yolo_b200_cstride(int c) { return c <= 4 ? 4 : (c + 15) / 16 * 16; }
+
+int yolo_b200_default_params(yolo_b200_params *p)
+{
+    if (!p) return fail(E_ARG, "null params");
+    memset(p, 0, sizeof *p);
+    // layer list: yolo_forward.c:1202-1262 / slim_yolo_v2.py:58-87
+    static const int L[10][4] = { {3, 16, 1, 1}, {16, 32, 1, 1}, {32, 64, 1, 0}, {64, 64, 1, 1}, {64, 128, 1, 0},
+                                  {128, 128, 1, 1}, {128, 256, 1, 0}, {256, 256, 1, 0}, {256, 256, 1, 0}, {256, 35, 0, 0} };
+    // tables: yolo_forward.c:32-35 (scale_a[0]: the literal 65536 does not fit `const char` and is stored as 0)
+    static const int sw[10] = { 6, 8, 8, 9, 9, 9, 10, 10, 10, 9 };
+    static const int sb[10] = { 7, 6, 5, 5, 5, 6, 5, 5, 5, 10 };
+    static const int sa[11] = { 0, 4, 8, 8, 8, 8, 8, 8, 8, 16, 4 };
+    static const int rt[10] = { 11, 10, 10, 11, 11, 10, 11, 11, 11, 10 };
+    static const float anc[5][2] = { {0.53f, 0.79f}, {1.71f, 2.36f}, {2.89f, 6.44f}, {6.33f, 3.79f}, {9.03f, 9.74f} };
+    p->num_layers = 10;
+    for (int l = 0; l < 10; ++l) {
+        p->layers[l].cin = L[l][0]; p->layers[l].cout = L[l][1]; p->layers[l].activ = L[l][2]; p->layers[l].pool = L[l][3];
+        p->scale_w[l] = sw[l]; p->scale_b[l] = sb[l]; p->retune[l] = rt[l];
+    }
+    for (int l = 0; l < 11; ++l) p->scale_a[l] = sa[l];
+    p->contract = YOLO_B200_CONTRACT_F; p->round_mode = YOLO_B200_ROUND_RNE; p->head_mode = YOLO_B200_HEAD_PYTHON;
+    p->num_anchors = 5; p->num_classes = 2; p->stride = 16;
+    for (int a = 0; a < 5; ++a) { p->anchors[a][0] = anc[a][0]; p->anchors[a][1] = anc[a][1]; }
+    p->conf_thresh = 0.01f; p->nms_thresh = 0.5f; p->max_det = 1024;
+    return 0;
+}
+
+int yolo_b200_create(yolo_b200_ctx **out, int device)
+{
+    if (!out) return fail(E_ARG, "null out");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(E_CUDA, "no CUDA device (%s): this library has no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(E_ARG, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(E_UNSUPPORTED, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    yolo_b200_ctx *c = new yolo_b200_ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaMalloc(&c->ovf_dev, sizeof(unsigned)));
+    CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));
+    CU(cudaMalloc(&c->lut_dev, 4096 * sizeof(int)));
+    CU(head_init());
+    *out = c;
+    return 0;
+}
+
+static void free_layers(yolo_b200_ctx *c)
+{
+    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.bias_sh); cudaFree(l.out); }
+    c->layers.clear();
+}
+
+void yolo_b200_destroy(yolo_b200_ctx *c)
+{
+    if (!c) return;
+    {
+        std::lock_guard<std::mutex> g(g_default_mu);
+        if (g_default_ctx == c) g_default_ctx = nullptr;
+    }
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_layers(c);
+    cudaFree(c->lut_dev); cudaFree(c->ovf_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
+    cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
+    for (auto e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int yolo_b200_set_stream(yolo_b200_ctx *c, void *s)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+// pixel_norm_quantize (yolo_forward.c:57-85) evaluated once per 12-bit code: mask without shifting, /255.,
+// -mean, /std in the reference's float/double mix, * 2^sa, truncation toward zero.
+static void build_rgb444_lut(int sa, int8_t *lut)
+{
+    const int mask[3] = { 0x000f, 0x00f0, 0x0f00 };
+    const double mean[3] = { 0.485, 0.456, 0.406 }, sd[3] = { 0.229, 0.224, 0.225 };
+    const double s = pow(2.0, (double)sa);
+    for (int code = 0; code < 4096; ++code) {
+        for (int ch = 0; ch < 3; ++ch) {
+            float v = (float)(code & mask[ch]);
+            v = (float)((double)v / 255.);
+            v = (float)((double)v - mean[ch]);
+            v = (float)((double)v / sd[ch]);
+            double r = (double)v * s;
+            int t = (int)r;                       // toward zero
+            lut[code * 4 + ch] = (int8_t)t;       // same low byte as the reference's (char) conversion in range
+        }
+        lut[code * 4 + 3] = 0;
+    }
+}
+
+static int host_shr_round(int x, int n, int mode)
+{
+    if (n <= 0) return x;
+    int fl = x >> n, rem = x - (fl << n), half = 1 << (n - 1);
+    if (mode == YOLO_B200_ROUND_FLOOR) return fl;
+    if (mode == YOLO_B200_ROUND_HALF_UP) return fl + (rem >= half);
+    if (rem != half) return fl + (rem > half);
+    return fl + (fl & 1);
+}
+
+int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t *const *biases,
+                   const yolo_b200_params *p, int layout)
+{
+    if (!c || !weights || !biases || !p) return fail(E_ARG, "null argument");
+    if (p->num_layers < 1 || p->num_layers > YOLO_B200_MAX_LAYERS) return fail(E_ARG, "num_layers %d", p->num_layers);
+    if (layout < 0 || layout > 2) return fail(E_ARG, "weight layout %d", layout);
+    if (p->num_anchors < 1 || p->num_anchors > YOLO_B200_MAX_ANCHORS) return fail(E_ARG, "num_anchors %d", p->num_anchors);
+    if (p->num_classes < 1 || p->num_classes > 64) return fail(E_ARG, "num_classes %d", p->num_classes);
+    if (p->head_mode == YOLO_B200_HEAD_C && p->num_classes != 2) return fail(E_ARG, "the C head is 2-class (yolo_forward.c:976)");
+    if (p->max_det < 1) return fail(E_ARG, "max_det %d", p->max_det);
+    const yolo_b200_layer &last = p->layers[p->num_layers - 1];
+    if (last.cout != p->num_anchors * (5 + p->num_classes))
+        return fail(E_ARG, "last layer has %d channels, head needs %d", last.cout, p->num_anchors * (5 + p->num_classes));
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    free_layers(c);
+    c->loaded = false;
+    c->prm = *p;
+    for (int l = 0; l < p->num_layers; ++l) {
+        const yolo_b200_layer &L = p->layers[l];
+        if (L.cin < 1 || L.cout < 1 || L.cin > 4096 || L.cout > 4096) return fail(E_ARG, "layer %d channels %d->%d", l, L.cin, L.cout);
+        if (l > 0 && L.cin != p->layers[l - 1].cout) return fail(E_ARG, "layer %d cin %d != previous cout %d", l, L.cin, p->layers[l - 1].cout);
+        if (l == 0 && L.cin > 4) return fail(E_UNSUPPORTED, "network input must have <= 4 channels (NHWC4)");
+        if (!weights[l] || !biases[l]) return fail(E_ARG, "layer %d: null weights/biases", l);
+        LayerDev d;
+        d.cin = L.cin; d.cout = L.cout;
+        d.cs_in = yolo_b200_cstride(L.cin); d.cs_out = yolo_b200_cstride(L.cout);
+        d.cout_pad = (d.cs_out + 31) / 32 * 32;
+        LayerQ &q = d.q;
+        memset(&q, 0, sizeof q);
+        q.contract = p->contract; q.round_mode = p->round_mode; q.activ = L.activ; q.pool = L.pool;
+        const int sa_i = p->scale_a[l], sw = p->scale_w[l], sb = p->scale_b[l], rt = p->retune[l], sa_o = p->scale_a[l + 1];
+        std::vector<int> bsh(d.cout_pad, 0);
+        if (p->contract == YOLO_B200_CONTRACT_F) {
+            // set_quantize_scale, yolo_forward.c:235-254
+            int iofs = sa_i + sw - rt, bofs = sb - rt, oofs = rt - sa_o, bdir = 0;
+            q.idir = iofs < 0; q.iofs = abs(iofs);
+            bdir = bofs < 0; bofs = abs(bofs);
+            q.odir = oofs < 0; q.oofs = abs(oofs);
+            if (q.iofs > 24 || bofs > 20 || q.oofs > 24) return fail(E_UNSUPPORTED, "layer %d: shift out of range (iofs %d bofs %d oofs %d)", l, q.iofs, bofs, q.oofs);
+            for (int o = 0; o < L.cout; ++o)
+                bsh[o] = bdir ? (int)biases[l][o] * (1 << bofs) : host_shr_round(biases[l][o], bofs, p->round_mode);
+        } else if (p->contract == YOLO_B200_CONTRACT_P) {
+            int ea = sa_i + sw, E = ea > sb ? ea : sb;
+            q.la = E - ea; q.sh = E - sa_o;
+            if (q.la > 4 || E - sb > 22 || q.sh > 24 || q.sh < -8) return fail(E_UNSUPPORTED, "layer %d: exponents out of range (la %d lb %d sh %d)", l, q.la, E - sb, q.sh);
+            for (int o = 0; o < L.cout; ++o) bsh[o] = (int)biases[l][o] * (1 << (E - sb));
+        } else return fail(E_ARG, "contract %d", p->contract);
+
+        // repack to [cout_pad][tap][cs_in], zero padded
+        std::vector<int8_t> wp((size_t)d.cout_pad * 9 * d.cs_in, 0);
+        const int8_t *w = weights[l];
+        const int tm = L.cout < 32 ? L.cout : 32, tn = L.cin < 16 ? L.cin : 16;       // weight.h groups
+        const int gco = (L.cout + tm - 1) / tm, gci = (L.cin + tn - 1) / tn;
+        for (int o = 0; o < L.cout; ++o)
+            for (int t = 0; t < 9; ++t)
+                for (int i = 0; i < L.cin; ++i) {
+                    size_t src;
+                    if (layout == YOLO_B200_WLAYOUT_OIHW) src = ((size_t)o * L.cin + i) * 9 + t;
+                    else if (layout == YOLO_B200_WLAYOUT_OHWI) src = ((size_t)o * 9 + t) * L.cin + i;
+                    else src = ((((size_t)t * gco + o / tm) * gci + i / tn) * tm + o % tm) * tn + i % tn;
+                    wp[((size_t)o * 9 + t) * d.cs_in + i] = w[src];
+                }
+        CU(cudaMalloc(&d.w, wp.size()));
+        CU(cudaMemcpy(d.w, wp.data(), wp.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&d.bias_sh, bsh.size() * sizeof(int)));
+        CU(cudaMemcpy(d.bias_sh, bsh.data(), bsh.size() * sizeof(int), cudaMemcpyHostToDevice));
+        c->layers.push_back(d);
+    }
+    build_rgb444_lut(p->scale_a[0], c->lut_host);
+    CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
+    c->loaded = true;
+    return 0;
+}
+
+int yolo_b200_set_thresholds(yolo_b200_ctx *c, float conf, float nms)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    c->prm.conf_thresh = conf; c->prm.nms_thresh = nms;
+    return 0;
+}
+
+int yolo_b200_rgb444_lut(yolo_b200_ctx *c, int8_t *lut)
+{
+    if (!c || !lut) return fail(E_ARG, "null argument");
+    if (!c->loaded) return fail(E_STATE, "no network loaded");
+    memcpy(lut, c->lut_host, sizeof c->lut_host);
+    return 0;
+}
+
+static int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return fail(E_NOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+    *cap = need;
+    return 0;
+}
+
+static int check_ready(yolo_b200_ctx *c, int n, int h, int w)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (!c->loaded) return fail(E_STATE, "no network loaded (call yolo_b200_load)");
+    if (n < 0 || h < 1 || w < 1) return fail(E_ARG, "bad shape n=%d h=%d w=%d", n, h, w);
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static void tick(yolo_b200_ctx *c)
+{
+    if (!c->timing) return;
+    if (c->ev_used == (int)c->ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev.push_back(e); }
+    cudaEventRecord(c->ev[c->ev_used++], c->stream);
+}
+
+int yolo_b200_quantize_rgb444(yolo_b200_ctx *c, const uint16_t *d_frames, int n, int h, int w, int8_t *d_nhwc4)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (n == 0) return 0;
+    CU(quantize_rgb444(d_frames, (size_t)n * h * w, c->lut_dev, d_nhwc4, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int yolo_b200_quantize_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, int8_t *d_nhwc4)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (n == 0) return 0;
+    if (((size_t)h * w) % 4) return fail(E_UNSUPPORTED, "h*w must be a multiple of 4");
+    CU(quantize_f32(d_nchw, n, h, w, c->prm.scale_a[0], d_nhwc4, c->ovf_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out)
+{
+    LayerDev &L = c->layers[l];
+    ConvArgs a;
+    a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
+    a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
+    CU(conv3x3_direct(a, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int yolo_b200_conv_layer(yolo_b200_ctx *c, int layer, const int8_t *d_in, int n, int h, int w, int8_t *d_out)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (layer < 0 || layer >= (int)c->layers.size()) return fail(E_ARG, "layer %d out of range", layer);
+    if (!d_in || !d_out) return fail(E_ARG, "null buffer");
+    if (n == 0) return 0;
+    if (c->layers[layer].q.pool && (h < 2 || w < 2)) return fail(E_ARG, "layer %d pools: needs h,w >= 2", layer);
+    return run_layer(c, layer, d_in, n, h, w, d_out);
+}
+
+int yolo_b200_backbone(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_nhwc4 && n > 0) return fail(E_ARG, "null input");
+    const int8_t *cur = d_nhwc4;
+    c->ev_used = 0;
+    tick(c);
+    for (size_t l = 0; l < c->layers.size(); ++l) {
+        LayerDev &L = c->layers[l];
+        if (L.q.pool && (h < 2 || w < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, h, w);
+        int oh = L.q.pool ? h / 2 : h, ow = L.q.pool ? w / 2 : w;
+        size_t bytes = (size_t)(n > 0 ? n : 1) * oh * ow * L.cs_out;
+        rc = ensure((void **)&L.out, &L.out_cap, bytes); if (rc) return rc;
+        L.oh = oh; L.ow = ow;
+        if (n > 0) { rc = run_layer(c, (int)l, cur, n, h, w, L.out); if (rc) return rc; }
+        tick(c);
+        cur = L.out; h = oh; w = ow;
+    }
+    c->last_n = n;
+    if (d_pred) *d_pred = cur;
+    if (gh) *gh = h;
+    if (gw) *gw = w;
+    return 0;
+}
+
+int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, size_t bytes)
+{
+    if (!c || !host_out) return fail(E_ARG, "null argument");
+    if (layer < 0 || layer >= (int)c->layers.size()) return fail(E_ARG, "layer %d out of range", layer);
+    LayerDev &L = c->layers[layer];
+    size_t have = (size_t)c->last_n * L.oh * L.ow * L.cs_out;
+    if (bytes != have) return fail(E_ARG, "layer %d output is %zu bytes, caller passed %zu", layer, have, bytes);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(host_out, L.out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int yolo_b200_detect(yolo_b200_ctx *c, const int8_t *d_pred, int n, int gh, int gw, int in_h, int in_w,
+                     yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    int rc = check_ready(c, n, gh, gw); if (rc) return rc;
+    if (n == 0) return 0;
+    if (!d_pred || !d_dets || !d_counts) return fail(E_ARG, "null buffer");
+    const yolo_b200_params &p = c->prm;
+    size_t N = (size_t)gh * gw * p.num_anchors;
+    if (N > (size_t)HEAD_MAX_CAND) return fail(E_UNSUPPORTED, "grid %dx%d x %d anchors exceeds %d candidates per frame", gh, gw, p.num_anchors, HEAD_MAX_CAND);
+    if (c->head_cap < (size_t)n * N) {
+        cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes);
+        c->h_scores = nullptr; c->h_cls = nullptr; c->h_boxes = nullptr; c->head_cap = 0;
+        CU(cudaMalloc(&c->h_scores, (size_t)n * N * sizeof(float)));
+        CU(cudaMalloc(&c->h_cls, (size_t)n * N * sizeof(int)));
+        CU(cudaMalloc(&c->h_boxes, (size_t)n * N * sizeof(float4)));
+        c->head_cap = (size_t)n * N;
+    }
+    HeadArgs a;
+    a.pred = d_pred; a.n = n; a.gh = gh; a.gw = gw; a.cs = yolo_b200_cstride(p.num_anchors * (5 + p.num_classes));
+    a.A = p.num_anchors; a.C = p.num_classes; a.sa_pred = p.scale_a[p.num_layers];
+    for (int i = 0; i < YOLO_B200_MAX_ANCHORS; ++i) { a.anchors[i][0] = p.anchors[i][0]; a.anchors[i][1] = p.anchors[i][1]; }
+    a.stride = p.stride; a.in_h = in_h; a.in_w = in_w; a.conf_thresh = p.conf_thresh; a.nms_thresh = p.nms_thresh;
+    a.head_mode = p.head_mode; a.max_det = p.max_det;
+    a.scores = c->h_scores; a.cls = c->h_cls; a.boxes = c->h_boxes; a.dets = d_dets; a.counts = d_counts;
+    CU(head_decode(a, c->stream));
+    CU(head_nms(a, c->stream));
+    c->launches += 2;
+    tick(c);
+    return 0;
+}
+
+int yolo_b200_forward_int8_dev(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    const int8_t *pred; int gh, gw;
+    int rc = yolo_b200_backbone(c, d_nhwc4, n, h, w, &pred, &gh, &gw); if (rc) return rc;
+    return yolo_b200_detect(c, pred, n, gh, gw, h, w, d_dets, d_counts);
+}
+
+int yolo_b200_forward_rgb444_dev(yolo_b200_ctx *c, const uint16_t *d_frames, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
+    rc = yolo_b200_quantize_rgb444(c, d_frames, n, h, w, c->in_q); if (rc) return rc;
+    return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
+}
+
+int yolo_b200_forward_f32_dev(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
+    rc = yolo_b200_quantize_f32(c, d_nchw, n, h, w, c->in_q); if (rc) return rc;
+    return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
+}
+
+int yolo_b200_sync(yolo_b200_ctx *c)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// host-buffer variants: H2D of the frames, forward, D2H of detections + counts, all on the context stream
+static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
+                        yolo_b200_det *dets, int32_t *counts)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (n == 0) return 0;
+    if (!host_in || !dets || !counts) return fail(E_ARG, "null buffer");
+    rc = ensure(&c->stage_in, &c->stage_in_cap, in_bytes); if (rc) return rc;
+    size_t det_bytes = (size_t)n * c->prm.max_det * sizeof(yolo_b200_det);
+    rc = ensure((void **)&c->d_dets, &c->dets_cap, det_bytes); if (rc) return rc;
+    rc = ensure((void **)&c->d_counts, &c->counts_cap, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->stage_in, host_in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (kind == 0) rc = yolo_b200_forward_rgb444_dev(c, (const uint16_t *)c->stage_in, n, h, w, c->d_dets, c->d_counts);
+    else if (kind == 1) rc = yolo_b200_forward_int8_dev(c, (const int8_t *)c->stage_in, n, h, w, c->d_dets, c->d_counts);
+    else rc = yolo_b200_forward_f32_dev(c, (const float *)c->stage_in, n, h, w, c->d_dets, c->d_counts);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(counts, c->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(dets, c->d_dets, det_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int yolo_b200_forward_rgb444(yolo_b200_ctx *c, const uint16_t *frames, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{ return forward_host(c, frames, (size_t)n * h * w * 2, 0, n, h, w, dets, counts); }
+int yolo_b200_forward_int8(yolo_b200_ctx *c, const int8_t *nhwc4, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{ return forward_host(c, nhwc4, (size_t)n * h * w * 4, 1, n, h, w, dets, counts); }
+int yolo_b200_forward_f32(yolo_b200_ctx *c, const float *nchw, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{ return forward_host(c, nchw, (size_t)n * h * w * 12, 2, n, h, w, dets, counts); }
+
+int yolo_b200_overflow_count(yolo_b200_ctx *c, int64_t *count)
+{
+    if (!c || !count) return fail(E_ARG, "null argument");
+    unsigned v = 0;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(&v, c->ovf_dev, sizeof v, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemsetAsync(c->ovf_dev, 0, sizeof v, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *count = v;
+    return 0;
+}
+
+int64_t yolo_b200_launch_count(yolo_b200_ctx *c) { return c ? c->launches : 0; }
+
+int yolo_b200_enable_timing(yolo_b200_ctx *c, int enable)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    c->timing = enable != 0; c->ev_used = 0;
+    return 0;
+}
+
+int yolo_b200_layer_times_ms(yolo_b200_ctx *c, float *ms, int capacity)
+{
+    if (!c || !ms) return fail(E_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int n = c->ev_used - 1;
+    if (n < 0) n = 0;
+    for (int i = 0; i < n && i < capacity; ++i) CU(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    return n;
+}
+
+// ---- host-side tail of the reference ---------------------------------------------------------------
+
+int yolo_b200_draw_rectangles(uint16_t *frame, int h, int w, const yolo_b200_det *dets, int count, int normalised)
+{
+    if (!frame || (!dets && count > 0) || h < 1 || w < 1) return fail(E_ARG, "bad argument");
+    for (int i = 0; i < count; ++i) {
+        const yolo_b200_det &d = dets[i];
+        int x1 = (int)(normalised ? d.x1 * w : d.x1), x2 = (int)(normalised ? d.x2 * w : d.x2);
+        int y1 = (int)(normalised ? d.y1 * h : d.y1), y2 = (int)(normalised ? d.y2 * h : d.y2);
+        x1 = x1 < 0 ? 0 : (x1 >= w ? w - 1 : x1); x2 = x2 < 0 ? 0 : (x2 >= w ? w - 1 : x2);
+        y1 = y1 < 0 ? 0 : (y1 >= h ? h - 1 : y1); y2 = y2 < 0 ? 0 : (y2 >= h ? h - 1 : y2);
+        uint16_t px = d.cls == 0 ? 0x000f : 0x00f0;          // red / green, yolo_forward.c:1152-1153,1165-1166
+        for (int x = x1; x <= x2; ++x) { frame[(size_t)y1 * w + x] = px; frame[(size_t)y2 * w + x] = px; }
+        for (int y = y1; y <= y2; ++y) { frame[(size_t)y * w + x1] = px; frame[(size_t)y * w + x2] = px; }
+    }
+    return 0;
+}
+
+int yolo_b200_set_default_context(yolo_b200_ctx *c)
+{
+    std::lock_guard<std::mutex> g(g_default_mu);
+    g_default_ctx = c;
+    return 0;
+}
+
+void yolo_forward(const char TRow, const char TCol, const char Tr, const char Tc, const char Tm, const char Tn,
+                  short int *camera, int *vga)
+{
+    (void)Tm; (void)Tn;
+    yolo_b200_ctx *c;
+    { std::lock_guard<std::mutex> g(g_default_mu); c = g_default_ctx; }
+    if (!c) { fail(E_STATE, "yolo_forward: no default context (yolo_b200_set_default_context)"); fprintf(stderr, "%s\n", g_err); return; }
+    if (TRow != Tr + 2 || TCol != Tc + 2) { fail(E_ARG, "yolo_forward: TRow/TCol must be Tr+2/Tc+2"); fprintf(stderr, "%s\n", g_err); return; }
+    if (!camera || !vga) { fail(E_ARG, "yolo_forward: null frame buffer"); fprintf(stderr, "%s\n", g_err); return; }
+    const int W = 320, H = 240;                               // yolo_forward.c:1194-1197
+    std::vector<yolo_b200_det> dets(c->prm.max_det);
+    int32_t count = 0;
+    if (yolo_b200_forward_rgb444(c, (const uint16_t *)camera, 1, H, W, dets.data(), &count)) { fprintf(stderr, "%s\n", g_err); return; }
+    if (count > c->prm.max_det) count = c->prm.max_det;
+    yolo_b200_draw_rectangles((uint16_t *)camera, H, W, dets.data(), count, c->prm.head_mode == YOLO_B200_HEAD_PYTHON);
+    memcpy(vga, camera, (size_t)76800 * 2);                   // yolo_forward.c:1281
+}
+
+}  // extern "C"
+#pragma GCC visibility pop
