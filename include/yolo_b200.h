@@ -119,7 +119,8 @@ int yolo_b200_default_params(yolo_b200_params *p);
 int yolo_b200_create(yolo_b200_ctx **out, int device);
 void yolo_b200_destroy(yolo_b200_ctx *ctx);
 
-/* Use an existing CUDA stream (cudaStream_t cast to void*); NULL = the context's own stream. */
+/* Use an existing CUDA stream (cudaStream_t cast to void*); NULL = the context's own (non-blocking) stream.
+ * To run on the legacy default stream pass cudaStreamLegacy ((void*)0x1), not NULL. */
 int yolo_b200_set_stream(yolo_b200_ctx *ctx, void *cuda_stream);
 
 /* Replaces the `#include "weight.h"` data symbols w_conv0..9 / b_conv0..9 and the tables of
@@ -127,6 +128,11 @@ int yolo_b200_set_stream(yolo_b200_ctx *ctx, void *cuda_stream);
  * layouts the kernels consume and copied to the device. */
 int yolo_b200_load(yolo_b200_ctx *ctx, const int8_t *const *weights, const int8_t *const *biases,
                    const yolo_b200_params *params, int weight_layout);
+
+/* Which convolution kernels run: 0 = auto (tcgen05 implicit GEMM wherever the layer has a tensor-core shape, the
+ * integer dot-product kernel for the 3-channel first layer), 1 = integer dot-product kernels everywhere,
+ * 2 = tcgen05 only (error for layers without a tensor-core shape).  Both are CUDA; results are identical. */
+int yolo_b200_set_conv_backend(yolo_b200_ctx *ctx, int backend);
 
 /* Change thresholds / head mode after load (test.py --conf_thresh / --nms_thresh). */
 int yolo_b200_set_thresholds(yolo_b200_ctx *ctx, float conf_thresh, float nms_thresh);

@@ -11,6 +11,8 @@ struct ConvArgs {
     const int8_t *in;      // [n][H][W][cs_in]
     int n, H, W, cs_in;
     const int8_t *wgt;     // [cout_pad][9][cs_in]  (cout_pad: multiple of 32, zero padded)
+    const int8_t *wgt_k160; // cs_in == 16 only: [cout_pad][10][16], 10th tap all zero (two taps per K=32 MMA)
+    int w_rows;            // cout_pad
     const int *bias_sh;    // [cout_pad] pre-shifted bias (see LayerQ)
     int cout, cs_out;
     LayerQ q;
@@ -20,6 +22,10 @@ struct ConvArgs {
 
 // conv_direct.cu
 cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
+
+// conv_umma.cu (tcgen05 / TMEM / TMA implicit GEMM)
+bool conv3x3_umma_supported(const ConvArgs &a);
+cudaError_t conv3x3_umma(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // quantize.cu
 cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st);

@@ -28,6 +28,7 @@ struct LayerDev {
     int cin, cout, cs_in, cs_out, cout_pad;
     LayerQ q;
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
+    int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
     size_t out_cap = 0;
@@ -49,6 +50,8 @@ struct yolo_b200_ctx {
     yolo_b200_det *d_dets = nullptr; int32_t *d_counts = nullptr; size_t dets_cap = 0, counts_cap = 0;
     int last_n = 0;
     int64_t launches = 0;
+    int sm_count = 148;
+    int conv_backend = 0;                // 0 auto (tensor cores where the shape allows), 1 dp4a direct, 2 tcgen05 only
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     int ev_used = 0;
@@ -104,6 +107,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
     CU(cudaSetDevice(device));
     yolo_b200_ctx *c = new yolo_b200_ctx();
     c->device = device;
+    c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->ovf_dev, sizeof(unsigned)));
@@ -116,7 +120,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.bias_sh); cudaFree(l.out); }
+    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.bias_sh); cudaFree(l.out); }
     c->layers.clear();
 }
 
@@ -240,6 +244,12 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
                 }
         CU(cudaMalloc(&d.w, wp.size()));
         CU(cudaMemcpy(d.w, wp.data(), wp.size(), cudaMemcpyHostToDevice));
+        if (d.cs_in == 16) {
+            std::vector<int8_t> wk((size_t)d.cout_pad * 160, 0);
+            for (int o = 0; o < d.cout_pad; ++o) memcpy(&wk[(size_t)o * 160], &wp[(size_t)o * 144], 144);
+            CU(cudaMalloc(&d.w_k160, wk.size()));
+            CU(cudaMemcpy(d.w_k160, wk.data(), wk.size(), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&d.bias_sh, bsh.size() * sizeof(int)));
         CU(cudaMemcpy(d.bias_sh, bsh.data(), bsh.size() * sizeof(int), cudaMemcpyHostToDevice));
         c->layers.push_back(d);
@@ -247,6 +257,14 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
     build_rgb444_lut(p->scale_a[0], c->lut_host);
     CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
     c->loaded = true;
+    return 0;
+}
+
+int yolo_b200_set_conv_backend(yolo_b200_ctx *c, int backend)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (backend < 0 || backend > 2) return fail(E_ARG, "backend %d", backend);
+    c->conv_backend = backend;
     return 0;
 }
 
@@ -318,7 +336,12 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     ConvArgs a;
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    CU(conv3x3_direct(a, c->stream));
+    a.wgt_k160 = L.w_k160; a.w_rows = L.cout_pad;
+    const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
+    const bool umma_ok = aligned && conv3x3_umma_supported(a);
+    if (c->conv_backend == 2 && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
+    if (umma_ok && c->conv_backend != 1) CU(conv3x3_umma(a, c->stream, c->sm_count));
+    else CU(conv3x3_direct(a, c->stream));
     c->launches++;
     return 0;
 }

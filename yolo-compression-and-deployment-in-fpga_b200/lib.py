@@ -24,6 +24,7 @@ HEAD_PYTHON, HEAD_C = 0, 1
 EXPORTS = [
     "yolo_b200_abi_version", "yolo_b200_last_error", "yolo_b200_cstride", "yolo_b200_default_params",
     "yolo_b200_create", "yolo_b200_destroy", "yolo_b200_set_stream", "yolo_b200_load", "yolo_b200_set_thresholds",
+    "yolo_b200_set_conv_backend",
     "yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32",
     "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev", "yolo_b200_sync",
     "yolo_b200_quantize_rgb444", "yolo_b200_quantize_f32", "yolo_b200_rgb444_lut", "yolo_b200_conv_layer",
@@ -84,6 +85,7 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_set_stream.argtypes = [vp, vp]
     L.yolo_b200_load.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Params), i32]
     L.yolo_b200_set_thresholds.argtypes = [vp, C.c_float, C.c_float]
+    L.yolo_b200_set_conv_backend.argtypes = [vp, i32]
     for name in ("yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32",
                  "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, vp, vp]
@@ -181,11 +183,17 @@ class Context:
         return p
 
     def set_stream(self, stream_ptr: int):
-        self._check(self.L.yolo_b200_set_stream(self._h, stream_ptr))
+        """stream_ptr: a cudaStream_t.  torch reports its default stream as 0, which the C-ABI reads as "use the
+        context's own stream"; the legacy default stream is therefore passed as cudaStreamLegacy (0x1)."""
+        self._check(self.L.yolo_b200_set_stream(self._h, stream_ptr or 1))
 
     def set_thresholds(self, conf, nms):
         self._check(self.L.yolo_b200_set_thresholds(self._h, conf, nms))
         self.params.conf_thresh = conf; self.params.nms_thresh = nms
+
+    def set_conv_backend(self, backend: int):
+        """0 auto, 1 integer dot-product kernels only, 2 tcgen05 only."""
+        self._check(self.L.yolo_b200_set_conv_backend(self._h, backend))
 
     def set_default(self):
         self._check(self.L.yolo_b200_set_default_context(self._h))
