@@ -355,3 +355,45 @@ def test_legacy_yolo_forward_symbol(ctx):
     changed = cam != orig
     assert n == 0 or changed.any()
     assert set(np.unique(cam[changed])) <= {0x000f, 0x00f0}
+
+
+# ---- the two convolution back ends (tcgen05 implicit GEMM vs integer dot product) ---------------------------
+
+def test_tensor_core_and_dot_product_kernels_agree_at_full_size(ctx):
+    """416x416, batch 3: every layer's map from the tcgen05 path equals the dp4a path bit for bit."""
+    qnet = ex.random_quantnet(seed=0, calib_hw=(416, 416), calib_frames=1)
+    rng = np.random.default_rng(11)
+    x8 = rng.integers(-100, 100, (3, 416, 416, 4), dtype=np.int8)
+    x8[..., 3] = 0
+    for contract in (lib.CONTRACT_F, lib.CONTRACT_P):
+        ctx.load_quantnet(qnet, contract=contract)
+        ctx.set_conv_backend(1)
+        ref, _ = run_backbone(ctx, x8)
+        ctx.set_conv_backend(0)
+        got, _ = run_backbone(ctx, x8)
+        for l, (a, b) in enumerate(zip(got, ref)):
+            np.testing.assert_array_equal(a, b, err_msg="layer %d" % l)
+    ctx.set_conv_backend(0)
+
+
+@pytest.mark.parametrize("layer", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_tensor_core_layer_against_oracle(ctx, layer):
+    """Each tensor-core layer alone, tcgen05 back end forced, against the CPU oracle (odd sizes, several images)."""
+    g, qnet, frames = gu.load("ref_p_64x96")
+    cin, cout, activ, pool = qnet.layers[layer]
+    rng = np.random.default_rng(layer)
+    n, h, w = 3, 14, 18
+    x = np.zeros((n, h, w, ex.cstride(cin)), dtype=np.int8)
+    x[..., :cin] = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F)
+    ctx.set_conv_backend(2)
+    try:
+        oh, ow = (h // 2, w // 2) if pool else (h, w)
+        d_out = torch.full((n, oh, ow, ex.cstride(cout)), 77, dtype=torch.int8, device="cuda")
+        ctx.conv_layer(layer, dev(x), n, h, w, d_out)
+        ctx.sync()
+    finally:
+        ctx.set_conv_backend(0)
+    ref, _ = ol.conv_layer(x, qnet.w[layer], qnet.b[layer], cin, cout, qnet.sa[layer], qnet.sw[layer], qnet.sb[layer],
+                           qnet.retune[layer], qnet.sa[layer + 1], activ, pool, 0)
+    np.testing.assert_array_equal(d_out.cpu().numpy(), ref)
