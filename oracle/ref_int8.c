@@ -96,18 +96,17 @@ static int64_t requant_F(int64_t acc, int b, const elem_params *p)
     return clampi(o, -128, 127);
 }
 
-/* Contract P: y = acc*2^-(sa_i+sw) + b*2^-sb; leaky; o = RNE(y*2^sa_o); reference never clamps
- * (slim_yolo_v2.py:35); the int8 store saturates and *ovf counts how often. */
-static int64_t requant_P(int64_t acc, int b, const elem_params *p, int64_t *ovf)
+/* Contract P: y = acc*2^-(sa_i+sw) + b*2^-sb; leaky; o = RNE(y*2^sa_o).  The reference never clamps
+ * (slim_yolo_v2.py:35): the value is returned unclamped; the int8 STORE saturates (after the pool, as the
+ * reference pools its unclamped values, :229-231) and the caller counts how many stored elements that hit. */
+static int64_t requant_P(int64_t acc, int b, const elem_params *p)
 {
     int ea = p->sa_i + p->sw, eb = p->sb;
     int E = ea > eb ? ea : eb;
     int64_t num = acc * ((int64_t)1 << (E - ea)) + (int64_t)b * ((int64_t)1 << (E - eb));
     int s = E - p->sa_o;
     if (p->activ && num < 0) s += 3;
-    int64_t o = s >= 0 ? shr_round(num, s, ROUND_RNE) : num * ((int64_t)1 << (-s));
-    if (o < -128 || o > 127) { if (ovf) (*ovf)++; o = clampi(o, -128, 127); }
-    return o;
+    return s >= 0 ? shr_round(num, s, ROUND_RNE) : num * ((int64_t)1 << (-s));
 }
 
 /* ---- one layer ---------------------------------------------------------------------------- */
@@ -115,8 +114,10 @@ static int64_t requant_P(int64_t acc, int b, const elem_params *p, int64_t *ovf)
 /* in : [n][h][w][cs_in]   int8, first cin channels used
  * wgt: [cout][3][3][cin]  int8 (OHWI)
  * out: [n][h'][w'][cs_out] int8, channels >= cout written as 0
- * The 2x2/2 max-pool is applied to the int8 result, as the reference does (quantise, then pool,
- * slim_yolo_v2.py:229-231).  Odd trailing rows/columns are dropped (nn.MaxPool2d(2,2) floor mode). */
+ * The 2x2/2 max-pool is applied to the requantised values, as the reference does (quantise, then pool,
+ * slim_yolo_v2.py:229-231); contract P values are pooled unclamped (the reference never clamps) and saturate only
+ * when stored.  Odd trailing rows/columns are dropped (nn.MaxPool2d(2,2) floor mode).
+ * *overflow counts STORED elements that had to be saturated (contract P). */
 ORACLE_API int oracle_conv_layer(const int8_t *in, int n, int h, int w, int cs_in, int cin,
                                  const int8_t *wgt, const int8_t *bias, int cout, int cs_out,
                                  int sa_i, int sw, int sb, int retune, int sa_o,
@@ -125,14 +126,13 @@ ORACLE_API int oracle_conv_layer(const int8_t *in, int n, int h, int w, int cs_i
 {
     elem_params p = { sa_i, sw, sb, retune, sa_o, activ, contract, round_mode };
     int oh = pool ? h / 2 : h, ow = pool ? w / 2 : w;
-    int8_t *full = (int8_t *)malloc((size_t)h * w * cout);
+    int32_t *full = (int32_t *)malloc(sizeof(int32_t) * (size_t)h * w * cout);
     if (!full) return -1;
     for (int img = 0; img < n; ++img) {
         const int8_t *x = in + (size_t)img * h * w * cs_in;
         /* rows are independent; OpenMP only spreads them over host threads (bench cpu_baseline) */
         #pragma omp parallel for schedule(static)
         for (int y = 0; y < h; ++y) {
-            int64_t ovf_local = 0;
             for (int xx = 0; xx < w; ++xx)
                 for (int co = 0; co < cout; ++co) {
                     int32_t acc = 0;                 /* |acc| <= 9*cin*128*128 < 2^31 for cin <= 14000 */
@@ -147,14 +147,9 @@ ORACLE_API int oracle_conv_layer(const int8_t *in, int n, int h, int w, int cs_i
                             for (int ci = 0; ci < cin; ++ci) acc += (int32_t)a[ci] * (int32_t)k[ci];
                         }
                     }
-                    int64_t o = contract == CONTRACT_P ? requant_P(acc, bias[co], &p, &ovf_local)
-                                                       : requant_F(acc, bias[co], &p);
-                    full[((size_t)y * w + xx) * cout + co] = (int8_t)o;
+                    int64_t o = contract == CONTRACT_P ? requant_P(acc, bias[co], &p) : requant_F(acc, bias[co], &p);
+                    full[((size_t)y * w + xx) * cout + co] = (int32_t)clampi(o, INT32_MIN / 2, INT32_MAX / 2);
                 }
-            if (ovf_local && overflow) {
-                #pragma omp atomic
-                *overflow += ovf_local;
-            }
         }
         int8_t *o8 = out + (size_t)img * oh * ow * cs_out;
         for (int y = 0; y < oh; ++y)
@@ -162,13 +157,17 @@ ORACLE_API int oracle_conv_layer(const int8_t *in, int n, int h, int w, int cs_i
                 int8_t *dst = o8 + ((size_t)y * ow + xx) * cs_out;
                 for (int co = 0; co < cs_out; ++co) {
                     if (co >= cout) { dst[co] = 0; continue; }
-                    if (!pool) { dst[co] = full[((size_t)y * w + xx) * cout + co]; continue; }
-                    int m = -128;
-                    for (int dy = 0; dy < 2; ++dy)
-                        for (int dx = 0; dx < 2; ++dx) {
-                            int v = full[((size_t)(2 * y + dy) * w + (2 * xx + dx)) * cout + co];
-                            if (v > m) m = v;
-                        }
+                    int64_t m;
+                    if (!pool) m = full[((size_t)y * w + xx) * cout + co];
+                    else {
+                        m = INT32_MIN;
+                        for (int dy = 0; dy < 2; ++dy)
+                            for (int dx = 0; dx < 2; ++dx) {
+                                int v = full[((size_t)(2 * y + dy) * w + (2 * xx + dx)) * cout + co];
+                                if (v > m) m = v;
+                            }
+                    }
+                    if (m < -128 || m > 127) { if (overflow) (*overflow)++; m = clampi(m, -128, 127); }
                     dst[co] = (int8_t)m;
                 }
             }
@@ -204,7 +203,7 @@ ORACLE_API int oracle_requant(int64_t acc, int b, int sa_i, int sw, int sb, int 
                               int activ, int contract, int round_mode)
 {
     elem_params p = { sa_i, sw, sb, retune, sa_o, activ, contract, round_mode };
-    return (int)(contract == CONTRACT_P ? requant_P(acc, b, &p, NULL) : requant_F(acc, b, &p));
+    return (int)clampi(contract == CONTRACT_P ? requant_P(acc, b, &p) : requant_F(acc, b, &p), -128, 127);
 }
 
 /* The shift programme set_quantize_scale() hands to set_offset() (yolo_forward.c:233-257):

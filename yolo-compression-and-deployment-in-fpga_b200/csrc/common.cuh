@@ -57,8 +57,10 @@ __device__ __forceinline__ int shl_sat(int x, int n)
 }
 
 // Exact integer requantisation of one accumulator (all contracts / rounding modes).
-// *ovf is incremented when contract P had to saturate (the reference never clamps, slim_yolo_v2.py:35).
-__device__ __forceinline__ int requant(int acc, int bias_sh, const LayerQ &q, unsigned &ovf)
+// Contract F returns the final value (already saturated to int8 by the contract).  Contract P returns the rounded value
+// UNCLAMPED: the reference never clamps (slim_yolo_v2.py:35); store8() saturates what is finally stored and counts it.
+// Both are monotone non-decreasing in acc, so a 2x2 max-pool may be taken before or after.
+__device__ __forceinline__ int requant(int acc, int bias_sh, const LayerQ &q)
 {
     if (q.contract == CONTRACT_F) {
         int t = (q.idir ? shl_sat(acc, q.iofs) : shr_round_rt(acc, q.iofs, q.round_mode)) + bias_sh;
@@ -69,11 +71,17 @@ __device__ __forceinline__ int requant(int acc, int bias_sh, const LayerQ &q, un
     } else {
         int num = shl_sat(acc, q.la) + bias_sh;
         int s = q.sh + ((q.activ && num < 0) ? 3 : 0);
-        int o = s > 0 ? shr_round_rt(num, s, ROUND_RNE) : shl_sat(num, -s);
-        int c = clampi(o, -128, 127);
-        ovf += (c != o);
-        return c;
+        return s > 0 ? shr_round_rt(num, s, ROUND_RNE) : shl_sat(num, -s);
     }
+}
+
+// Saturate a value that is about to be STORED; ovf counts stored elements that had to be clamped (contract P only;
+// contract F values are already in range).
+__device__ __forceinline__ int store8(int o, unsigned &ovf)
+{
+    int c = clampi(o, -128, 127);
+    ovf += (c != o);
+    return c;
 }
 
 __device__ __forceinline__ int dp4a_s8(int a, int b, int c)

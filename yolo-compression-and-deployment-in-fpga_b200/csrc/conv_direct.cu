@@ -95,7 +95,7 @@ conv3x3_direct_kernel(const int8_t *__restrict__ in, int n_img, int H, int W, in
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[p][c] = (co0 + c < cout) ? requant(acc[p][c], bsh[c], q, ovf) : 0;
+        for (int c = 0; c < 8; ++c) o[p][c] = (co0 + c < cout) ? requant(acc[p][c], bsh[c], q) : 0;
 
     if (co0 < cs_out) {
         if (q.pool) {
@@ -105,7 +105,7 @@ conv3x3_direct_kernel(const int8_t *__restrict__ in, int n_img, int H, int W, in
                 unsigned lo = 0, hi = 0;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    int m = max(max(o[0][c], o[1][c]), max(o[2][c], o[3][c]));
+                    int m = store8(max(max(o[0][c], o[1][c]), max(o[2][c], o[3][c])), ovf);
                     if (c < 4) lo |= (unsigned)(m & 0xff) << (8 * c); else hi |= (unsigned)(m & 0xff) << (8 * (c - 4));
                 }
                 int8_t *dst = out + (((size_t)img * OH + oy) * OW + ox) * cs_out + co0;
@@ -119,7 +119,8 @@ conv3x3_direct_kernel(const int8_t *__restrict__ in, int n_img, int H, int W, in
                     unsigned lo = 0, hi = 0;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        if (c < 4) lo |= (unsigned)(o[p][c] & 0xff) << (8 * c); else hi |= (unsigned)(o[p][c] & 0xff) << (8 * (c - 4));
+                        int v = store8(o[p][c], ovf);
+                        if (c < 4) lo |= (unsigned)(v & 0xff) << (8 * c); else hi |= (unsigned)(v & 0xff) << (8 * (c - 4));
                     }
                     int8_t *dst = out + (((size_t)img * H + oy) * W + ox) * cs_out + co0;
                     *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);

@@ -266,7 +266,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             int c = c0 + 4 * j + b;
-                            int o = c < p.cout ? requant(v[4 * j + b], s_bias[c], p.q, ovf) : 0;
+                            int o = c < p.cout ? requant(v[4 * j + b], s_bias[c], p.q) : 0;
+                            if (valid) o = store8(o, ovf);
                             word |= (unsigned)(o & 0xff) << (8 * b);
                         }
                         w[j] = word;
@@ -313,7 +314,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         int mv[4] = { m.x, m.y, m.z, m.w };
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
-                            int o = (c + b) < p.cout ? requant(mv[b], s_bias[c + b], p.q, ovf) : 0;
+                            int o = (c + b) < p.cout ? store8(requant(mv[b], s_bias[c + b], p.q), ovf) : 0;
                             word |= (unsigned)(o & 0xff) << (8 * b);
                         }
                         *reinterpret_cast<unsigned *>(p.out + (((size_t)n * OH + oy) * OW + ox) * p.cs_out + c) = word;
@@ -368,7 +369,6 @@ static void pick_tile(int n, int H, int W, bool pool, int *TN, int *TH, int *TW)
         for (int th = step; th * tw <= 128 && th <= ((H + step - 1) / step) * step; th += step) {
             int maxn = 128 / (tw * th);
             for (int tn = 1; tn <= maxn && tn <= (n > 0 ? n : 1); ++tn) {
-                if (tn > 1 && (th < H || tw < W)) continue;      // only stack images when one tile covers a whole map
                 long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((n + tn - 1) / tn);
                 double eff = (double)n * H * W / (double)(tiles * 128);
                 eff += 1e-6 * tw;                                  // prefer long contiguous rows
@@ -384,7 +384,7 @@ bool conv3x3_umma_supported(const ConvArgs &a)
     if (a.cs_in > 128 && a.cs_in % 128) return false;
     if (a.cs_in != 16 && a.cs_in != 32 && a.cs_in != 64 && a.cs_in % 128) return false;
     if (a.cs_out < 16 || a.cs_out > 256 || a.cs_out % 16) return false;
-    if (a.q.pool && (a.H < 2 || a.W < 2)) return false;
+    if (a.q.pool && (a.H < 2 || a.W < 2 || a.cs_out % 32)) return false;
     return true;
 }
 
