@@ -131,7 +131,9 @@ int yolo_b200_load(yolo_b200_ctx *ctx, const int8_t *const *weights, const int8_
 
 /* Which convolution kernels run: 0 = auto (tcgen05 implicit GEMM wherever the layer has a tensor-core shape, the
  * integer dot-product kernel for the 3-channel first layer), 1 = integer dot-product kernels everywhere,
- * 2 = tcgen05 only (error for layers without a tensor-core shape).  Both are CUDA; results are identical. */
+ * 2 = tcgen05 only (error for layers without a tensor-core shape), 3 = as 2 but with the integer epilogue forced
+ * (the fp32 exact-rounding epilogue is the default where the exponents allow it).  All are CUDA; results are
+ * identical. */
 int yolo_b200_set_conv_backend(yolo_b200_ctx *ctx, int backend);
 
 /* Change thresholds / head mode after load (test.py --conf_thresh / --nms_thresh). */
@@ -180,6 +182,12 @@ int yolo_b200_rgb444_lut(yolo_b200_ctx *ctx, int8_t *lut_host);
  * d_in is [n][h][w][cstride(cin)] (layer 0: [n][h][w][4]); d_out is [n][h'][w'][cstride(cout)]. */
 int yolo_b200_conv_layer(yolo_b200_ctx *ctx, int layer, const int8_t *d_in, int n, int h, int w,
                          int8_t *d_out);
+
+/* Test hook: apply layer l's epilogue arithmetic (bias add, shifts, saturation, leaky-ReLU; no pool) to `count`
+ * caller-supplied int32 accumulators; element i uses the bias of channel i % cout.  Returns which implementation
+ * ran: 0 = integer, 1 = exact-fp32 contract F, 2 = exact-fp32 contract P (or < 0 on error). */
+int yolo_b200_debug_requant(yolo_b200_ctx *ctx, int layer, const int32_t *d_acc, size_t count, int8_t *d_out,
+                            int force_generic);
 
 /* All layers; returns the device pointer of the last layer's output (owned by the context,
  * valid until the next call) and its grid size. */

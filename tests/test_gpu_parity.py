@@ -397,3 +397,56 @@ def test_tensor_core_layer_against_oracle(ctx, layer):
     ref, _ = ol.conv_layer(x, qnet.w[layer], qnet.b[layer], cin, cout, qnet.sa[layer], qnet.sw[layer], qnet.sb[layer],
                            qnet.retune[layer], qnet.sa[layer + 1], activ, pool, 0)
     np.testing.assert_array_equal(d_out.cpu().numpy(), ref)
+
+
+# ---- the epilogue arithmetic alone: exact-fp32 fast paths and the integer path vs the oracle -----------------
+
+def _edge_accumulators(rng, n=200000):
+    """Accumulators that stress rounding ties, both saturation points and the fp32 exactness boundary."""
+    parts = [rng.integers(-2 ** 25, 2 ** 25, n // 4), rng.integers(-2 ** 17, 2 ** 17, n // 4), rng.integers(-4096, 4096, n // 4)]
+    edges = []
+    for e in range(0, 26):
+        for d in (-3, -2, -1, 0, 1, 2, 3):
+            edges += [2 ** e + d, -(2 ** e) + d, 3 * 2 ** e // 2 + d, -(3 * 2 ** e // 2) + d]
+    parts.append(np.array(edges * 8, dtype=np.int64))
+    a = np.concatenate(parts).astype(np.int64)
+    return np.clip(a, -(2 ** 25), 2 ** 25).astype(np.int32)
+
+
+@pytest.mark.parametrize("contract", [lib.CONTRACT_F, lib.CONTRACT_P])
+@pytest.mark.parametrize("tables", ["calibrated", "shipped", "random0", "random1", "random2", "random3"])
+def test_epilogue_arithmetic_against_oracle(ctx, contract, tables):
+    g, qnet, frames = gu.load("ref_p_64x96")
+    import copy
+    import zlib
+    q = copy.deepcopy(qnet)
+    rng = np.random.default_rng(zlib.crc32(('%d-%s' % (contract, tables)).encode()))
+    if tables == "shipped":
+        q.sa, q.sw, q.sb, q.retune = list(ex.SHIPPED_SCALE_A), list(ex.SHIPPED_SCALE_W), list(ex.SHIPPED_SCALE_B), list(ex.SHIPPED_RETUNE)
+    elif tables.startswith("random"):
+        q.sa, q.sw, q.sb, q.retune = random_tables(rng, q)
+    try:
+        ctx.load_quantnet(q, contract=contract)
+    except lib.YoloB200Error:
+        pytest.skip("table outside the supported exponent range")
+    acc = _edge_accumulators(rng)
+    d_acc = dev(acc)
+    L = ol.lib()
+    fast_seen = 0
+    for layer in range(len(q.layers)):
+        cin, cout, activ, pool = q.layers[layer]
+        ref = np.array([L.oracle_requant(int(a), int(q.b[layer][i % cout]), q.sa[layer], q.sw[layer], q.sb[layer], q.retune[layer],
+                                         q.sa[layer + 1], activ, contract, 0) for i, a in enumerate(acc[:20000])], dtype=np.int8)
+        for force in (False, True):
+            d_out = torch.zeros(acc.shape, dtype=torch.int8, device="cuda")
+            epi = ctx.debug_requant(layer, d_acc, acc.size, d_out, force_generic=force)
+            ctx.sync()
+            out = d_out.cpu().numpy()
+            fast_seen += epi > 0
+            np.testing.assert_array_equal(out[:20000], ref, err_msg="layer %d epi %d" % (layer, epi))
+            if not force:
+                fast = out
+            else:
+                np.testing.assert_array_equal(fast, out, err_msg="fp32 and integer epilogues differ, layer %d" % layer)
+    if tables in ("calibrated",):
+        assert fast_seen >= 9, "the exact-fp32 epilogue should apply to calibrated tables"

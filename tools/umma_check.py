@@ -19,38 +19,46 @@ def main():
     layers = [int(a) for a in sys.argv[1:]] or list(range(1, 10))
     qnet = ex.random_quantnet(seed=0, calib_hw=(64, 96), calib_frames=1)
     ctx = lib.Context(0)
-    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F)
     rng = np.random.default_rng(0)
     shapes = {1: [(2, 16, 32), (3, 26, 30)], 2: [(2, 8, 16), (2, 13, 13)], 3: [(2, 8, 16), (3, 14, 18)], 4: [(2, 8, 16), (3, 13, 13)],
               5: [(2, 8, 16), (3, 26, 26)], 6: [(2, 8, 16), (5, 13, 13)], 7: [(2, 8, 16), (5, 13, 13)], 8: [(1, 8, 16), (4, 15, 20)],
               9: [(2, 8, 16), (3, 13, 13)]}
     bad = 0
-    for l in layers:
-        cin, cout, activ, pool = qnet.layers[l]
-        for (n, h, w) in shapes[l]:
-            x = np.zeros((n, h, w, ex.cstride(cin)), np.int8)
-            x[..., :cin] = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
-            dx = torch.from_numpy(x).cuda()
-            oh, ow = (h // 2, w // 2) if pool else (h, w)
-            outs = []
-            for backend in (1, 2):
-                ctx.set_conv_backend(backend)
-                o = torch.full((n, oh, ow, ex.cstride(cout)), 99, dtype=torch.int8, device="cuda")
-                t0 = time.time()
-                ctx.conv_layer(l, dx, n, h, w, o)
-                ctx.sync()
-                outs.append(o.cpu().numpy())
-            a, b = outs
-            diff = a != b
-            print("layer %d cin %3d cout %3d pool %d shape %s: mismatches %d / %d" % (l, cin, cout, pool, (n, h, w), diff.sum(), diff.size), flush=True)
-            if diff.any():
-                bad += 1
-                idx = np.argwhere(diff)
-                print("   first:", idx[:6].tolist(), "direct", a[diff][:6].tolist(), "umma", b[diff][:6].tolist())
-                print("   mismatching channels histogram (mod 16):", np.bincount(idx[:, 3] % 16, minlength=16).tolist())
-                print("   mismatching x histogram:", np.bincount(idx[:, 2], minlength=ow).tolist())
-                print("   mismatching y histogram:", np.bincount(idx[:, 1], minlength=oh).tolist())
-                print("   mismatching n histogram:", np.bincount(idx[:, 0], minlength=n).tolist())
+    import copy
+    shipped = copy.deepcopy(qnet)
+    shipped.sa, shipped.sw, shipped.sb, shipped.retune = list(ex.SHIPPED_SCALE_A), list(ex.SHIPPED_SCALE_W), list(ex.SHIPPED_SCALE_B), list(ex.SHIPPED_RETUNE)
+    configs = [("F/RNE calibrated", qnet, lib.CONTRACT_F, lib.ROUND_RNE), ("P calibrated", qnet, lib.CONTRACT_P, 0),
+               ("F/RNE shipped", shipped, lib.CONTRACT_F, lib.ROUND_RNE), ("F/FLOOR calibrated", qnet, lib.CONTRACT_F, lib.ROUND_FLOOR),
+               ("P shipped", shipped, lib.CONTRACT_P, 0)]
+    for (cname, net, contract, mode) in configs:
+      ctx.load_quantnet(net, contract=contract, round_mode=mode)
+      print("==", cname, flush=True)
+      for l in layers:
+          cin, cout, activ, pool = qnet.layers[l]
+          for (n, h, w) in shapes[l]:
+              x = np.zeros((n, h, w, ex.cstride(cin)), np.int8)
+              x[..., :cin] = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
+              dx = torch.from_numpy(x).cuda()
+              oh, ow = (h // 2, w // 2) if pool else (h, w)
+              outs = []
+              for backend in (1, 2, 3):
+                  ctx.set_conv_backend(backend)
+                  o = torch.full((n, oh, ow, ex.cstride(cout)), 99, dtype=torch.int8, device="cuda")
+                  t0 = time.time()
+                  ctx.conv_layer(l, dx, n, h, w, o)
+                  ctx.sync()
+                  outs.append(o.cpu().numpy())
+              a, b = outs
+              diff = a != b
+              print("layer %d cin %3d cout %3d pool %d shape %s: mismatches %d / %d" % (l, cin, cout, pool, (n, h, w), diff.sum(), diff.size), flush=True)
+              if diff.any():
+                  bad += 1
+                  idx = np.argwhere(diff)
+                  print("   first:", idx[:6].tolist(), "direct", a[diff][:6].tolist(), "umma", b[diff][:6].tolist())
+                  print("   mismatching channels histogram (mod 16):", np.bincount(idx[:, 3] % 16, minlength=16).tolist())
+                  print("   mismatching x histogram:", np.bincount(idx[:, 2], minlength=ow).tolist())
+                  print("   mismatching y histogram:", np.bincount(idx[:, 1], minlength=oh).tolist())
+                  print("   mismatching n histogram:", np.bincount(idx[:, 0], minlength=n).tolist())
     print("UMMA CHECK:", "FAILED (%d cases)" % bad if bad else "ok")
     ctx.close()
     return 1 if bad else 0

@@ -84,6 +84,54 @@ __device__ __forceinline__ int store8(int o, unsigned &ovf)
     return c;
 }
 
+// ---- fast exact requantisation in fp32 ---------------------------------------------------------------------
+// The value MAGIC + k (|k| < 2^22, k integer) is an fp32 number whose unit in the last place is 1, so a fused
+// multiply-add that lands in [2^23, 2^24) rounds its exact real result to the nearest integer, ties to even: that IS
+// the RNE shift of the contracts.  Every step below is monotone in acc, so values outside the exact range can only
+// end at a saturation bound, where they belong.  The host enables these paths only when the exponents keep every
+// NON-saturating value exactly representable (see epi_mode_for in conv_umma.cu); otherwise the integer requant() runs.
+enum { EPI_GENERIC = 0, EPI_F_RNE = 1, EPI_P = 2 };
+#define YB_MAGIC 12582912.0f            /* 1.5 * 2^23 = 0x4B400000: low byte 0, so (bits & 0xff) is the int8 result */
+
+struct EpiConst {
+    float s_in;       // F: 2^(-iofs) or 2^(+iofs) ; P: 2^(-sh)
+    float s_in2;      // P: 2^(-(sh+3)) (leaky branch)
+    float leak_add;   // F: MAGIC * 7/8
+    float s_out;      // F: 2^(-oofs) or 2^(+oofs)
+    float out_add;    // F: MAGIC * (1 - s_out)
+    int la;           // P: left shift of acc
+};
+
+// Contract F, round-half-even.  fb = MAGIC + sh(bias).  Returns MAGIC + o as float bits.
+template <bool ACT>
+__device__ __forceinline__ unsigned requant_f_rne(int acc, float fb, const EpiConst &k)
+{
+    float v = __fmaf_rn(__int2float_rn(acc), k.s_in, fb);                 // MAGIC + rne(sh(acc)) + sh(b)
+    v = fminf(fmaxf(v, YB_MAGIC - 32768.f), YB_MAGIC + 32767.f);          // 16-bit accumulator
+    if (ACT) v = fmaxf(v, __fmaf_rn(v, 0.125f, k.leak_add));              // leaky(t) = max(t, rne(t/8))
+    v = __fmaf_rn(v, k.s_out, k.out_add);                                 // MAGIC + rne(sh(t, oofs))
+    v = fminf(fmaxf(v, YB_MAGIC - 128.f), YB_MAGIC + 127.f);
+    return __float_as_uint(v);
+}
+
+// Contract P.  bp = bias << (E - sb).  Returns MAGIC + clamp(o) as float bits; counts clamped values in ovf.
+template <bool ACT>
+__device__ __forceinline__ unsigned requant_p(int acc, int bp, const EpiConst &k, unsigned &ovf, bool count)
+{
+    float nf = __int2float_rn((acc << k.la) + bp);
+    float r = __fmaf_rn(nf, k.s_in, YB_MAGIC);
+    if (ACT) r = fmaxf(r, __fmaf_rn(nf, k.s_in2, YB_MAGIC));             // negatives: one RNE shift by sh+3
+    float c = fminf(fmaxf(r, YB_MAGIC - 128.f), YB_MAGIC + 127.f);
+    ovf += (count && c != r);
+    return __float_as_uint(c);
+}
+
+// low bytes of four words -> one word
+__device__ __forceinline__ unsigned pack_bytes(unsigned a, unsigned b, unsigned c, unsigned d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
 __device__ __forceinline__ int dp4a_s8(int a, int b, int c)
 {
     int d;

@@ -103,7 +103,7 @@ struct UmmaParams {
     int tiles_x, tiles_y, tiles_n, num_tiles;
     int N;                       // GEMM N = cstride(cout)
     int cout, cs_out;
-    int kblocks;                 // TMA box pairs per tile: 9 * cs_in / CB  (CB = 16: the 9 taps)
+    int kblocks;                 // TMA box pairs per tile: 9 * cs_in / CB  (CB = 16: the 9 taps + 1 zero tap)
     int G;                       // kblocks per pipeline stage
     int stages;
     uint32_t a_box_bytes;        // TN*TH*TW*CB
@@ -111,15 +111,125 @@ struct UmmaParams {
     uint32_t tmem_cols, tmem_buf_stride;
     uint32_t off_stage, off_bias, off_bar;       // dynamic smem offsets (from the 1024-aligned base)
     LayerQ q;
+    EpiConst k;
     const int *bias_sh;
     int8_t *out;
     unsigned *ovf;
 };
 
-constexpr int UMMA_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int UMMA_THREADS = 64 + EPI_THREADS;
 
-template <int CB>
+// Requantise 4 accumulators of channels c..c+3 and pack them into one word.  `bias` points at the per-channel
+// words in shared memory (fp32 MAGIC+bias for EPI_F_RNE, int otherwise).
+template <int EPI, bool ACT>
+__device__ __forceinline__ unsigned requant4(const int *acc, const int *bias, int c, const UmmaParams &p, unsigned &ovf, bool count)
+{
+    const int4 b = *reinterpret_cast<const int4 *>(bias + c);
+    if (EPI == EPI_F_RNE) {
+        return pack_bytes(requant_f_rne<ACT>(acc[0], __int_as_float(b.x), p.k), requant_f_rne<ACT>(acc[1], __int_as_float(b.y), p.k),
+                          requant_f_rne<ACT>(acc[2], __int_as_float(b.z), p.k), requant_f_rne<ACT>(acc[3], __int_as_float(b.w), p.k));
+    } else if (EPI == EPI_P) {
+        return pack_bytes(requant_p<ACT>(acc[0], b.x, p.k, ovf, count), requant_p<ACT>(acc[1], b.y, p.k, ovf, count),
+                          requant_p<ACT>(acc[2], b.z, p.k, ovf, count), requant_p<ACT>(acc[3], b.w, p.k, ovf, count));
+    } else {
+        const int bb[4] = { b.x, b.y, b.z, b.w };
+        unsigned word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int o = requant(acc[j], bb[j], p.q);
+            unsigned dummy = 0;
+            o = store8(o, count ? ovf : dummy);
+            word |= (unsigned)(o & 0xff) << (8 * j);
+        }
+        return word;
+    }
+}
+
+// 16 accumulators (channels c0..c0+15) -> 16 output bytes
+template <int EPI, bool ACT>
+__device__ __forceinline__ uint4 requant16(const int (&v)[16], const int *bias, int c0, const UmmaParams &p, unsigned &ovf, bool count)
+{
+    uint4 w;
+    w.x = requant4<EPI, ACT>(&v[0], bias, c0, p, ovf, count);
+    w.y = requant4<EPI, ACT>(&v[4], bias, c0 + 4, p, ovf, count);
+    w.z = requant4<EPI, ACT>(&v[8], bias, c0 + 8, p, ovf, count);
+    w.w = requant4<EPI, ACT>(&v[12], bias, c0 + 12, p, ovf, count);
+    return w;
+}
+
+template <int EPI, bool ACT>
+__device__ __forceinline__ void epilogue_tile(const UmmaParams &p, uint32_t taddr, int cbeg, int cend, int row, int et,
+                                              int x0, int y0, int n0, const int *s_bias, int *s_stage, uint32_t bar_tempty,
+                                              unsigned &ovf)
+{
+    const int tile_px = p.TN * p.TH * p.TW;
+    if (!p.q.pool) {
+        const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
+        const int x = x0 + wl, y = y0 + hl, n = n0 + nl;
+        const bool valid = row < tile_px && x < p.W && y < p.H && n < p.n_img;
+        int8_t *dst = p.out + (((size_t)n * p.H + y) * p.W + x) * p.cs_out;
+        // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is requantised
+        int va[16], vb[16];
+        if (cbeg < cend) tmem_ld16(taddr + cbeg, va);
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            tmem_ld_wait();
+            if (c0 + 16 < cend) tmem_ld16(taddr + c0 + 16, vb);
+            uint4 w = requant16<EPI, ACT>(va, s_bias, c0, p, ovf, valid);
+            if (valid) *reinterpret_cast<uint4 *>(dst + c0) = w;
+            if (c0 + 16 < cend) {
+                tmem_ld_wait();
+                if (c0 + 32 < cend) tmem_ld16(taddr + c0 + 32, va);
+                w = requant16<EPI, ACT>(vb, s_bias, c0 + 16, p, ovf, valid);
+                if (valid) *reinterpret_cast<uint4 *>(dst + c0 + 16) = w;
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty);
+    } else {
+        // raw accumulators -> smem (16-byte chunks XOR-swizzled by row to spread banks), 2x2 max, then requantise the
+        // maxima only: requantisation is monotone, so max-then-requantise == requantise-then-max.
+        const int chunks = p.N / 4;                        // 16-byte chunks per row (multiple of 8)
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            int v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int ch = (c0 / 4 + j) ^ (row & 7);
+                *reinterpret_cast<int4 *>(s_stage + (size_t)row * p.N + 4 * ch) = make_int4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty);                           // TMEM buffer is free; the rest works from smem
+        named_bar_sync(1, EPI_THREADS);
+        const int PW = p.TW / 2, PH = p.TH / 2;
+        const int pooled_px = p.TN * PH * PW;
+        const int OH = p.H / 2, OW = p.W / 2;
+        for (int item = et; item < pooled_px * chunks; item += EPI_THREADS) {
+            const int cg = item % chunks, pp = item / chunks;
+            const int pw = pp % PW, ph = (pp / PW) % PH, nl = pp / (PW * PH);
+            const int r00 = (nl * p.TH + 2 * ph) * p.TW + 2 * pw;
+            int4 m = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r00 + (k >> 1) * p.TW + (k & 1);
+                const int4 t = *reinterpret_cast<const int4 *>(s_stage + (size_t)r * p.N + 4 * (cg ^ (r & 7)));
+                m.x = max(m.x, t.x); m.y = max(m.y, t.y); m.z = max(m.z, t.z); m.w = max(m.w, t.w);
+            }
+            const int ox = x0 / 2 + pw, oy = y0 / 2 + ph, n = n0 + nl;
+            if (ox < OW && oy < OH && n < p.n_img) {
+                const int mv[4] = { m.x, m.y, m.z, m.w };
+                *reinterpret_cast<unsigned *>(p.out + (((size_t)n * OH + oy) * OW + ox) * p.cs_out + 4 * cg) =
+                    requant4<EPI, ACT>(mv, s_bias, 4 * cg, p, ovf, true);
+            }
+        }
+        named_bar_sync(1, EPI_THREADS);                    // staging buffer is reused by the next tile
+    }
+}
+
+template <int CB, int EPI>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const UmmaParams p)
 {
@@ -153,7 +263,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias_sh[i];
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+        const int b = p.bias_sh[i];
+        s_bias[i] = EPI == EPI_F_RNE ? __float_as_int(YB_MAGIC + (float)b) : b;      // |b| < 2^21: exact
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -211,7 +324,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (CB == 16) {
                         // 16-byte channel vectors: one MMA (K = 32) covers two taps; the two 16-byte K halves are
                         // separate core-matrix columns LBO apart (the next tap's box).  Tap 9 does not exist: its B
-                        // rows are zero (host packs a 10th all-zero tap) and its A box re-reads tap 8's.
+                        // rows are zero (the host packs a 10th all-zero tap); its A box is whatever TMA fetched there.
                         for (int kb = kb0; kb < kb1; kb += 2) {
                             uint64_t ad = make_desc(sa + (uint32_t)(kb - kb0) * A_BOX, A_BOX, SBO, LAYOUT);
                             uint64_t bd = make_desc(sb + (uint32_t)(kb - kb0) * B_BOX, B_BOX, SBO, LAYOUT);
@@ -235,11 +348,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
+        // ===================== epilogue warps (2..9) =====================
+        const int ew = warp - 2;
         const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
         const int row = q4 * 32 + lane;                            // tile row = TMEM lane
-        const int et = threadIdx.x - 64;                           // 0..127 within the epilogue group
-        const int tile_px = p.TN * p.TH * p.TW;
+        const int et = threadIdx.x - 64;                           // 0..255 within the epilogue group
+        const int cmid = ((p.N / 16 + 1) / 2) * 16;                // column split between the two warps of a quarter
+        const int cbeg = ew < 4 ? 0 : cmid, cend = ew < 4 ? cmid : p.N;
         unsigned ovf = 0;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
@@ -250,78 +365,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(bar_tfull(buf), bph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * p.tmem_buf_stride + ((uint32_t)(q4 * 32) << 16);
-            if (!p.q.pool) {
-                const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
-                const int x = x0 + wl, y = y0 + hl, n = n0 + nl;
-                const bool valid = row < tile_px && x < p.W && y < p.H && n < p.n_img;
-                int8_t *dst = p.out + (((size_t)n * p.H + y) * p.W + x) * p.cs_out;
-                for (int c0 = 0; c0 < p.N; c0 += 16) {
-                    int v[16];
-                    tmem_ld16(taddr + c0, v);
-                    tmem_ld_wait();
-                    unsigned w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        unsigned word = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            int c = c0 + 4 * j + b;
-                            int o = c < p.cout ? requant(v[4 * j + b], s_bias[c], p.q) : 0;
-                            if (valid) o = store8(o, ovf);
-                            word |= (unsigned)(o & 0xff) << (8 * b);
-                        }
-                        w[j] = word;
-                    }
-                    if (valid) *reinterpret_cast<uint4 *>(dst + c0) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                tc_fence_before();
-                mbar_arrive(bar_tempty(buf));
-            } else {
-                // raw accumulators -> smem (16-byte chunks XOR-swizzled by row to spread banks), pool, then requantise
-                // the maxima only: requantisation is monotone, so max-then-requantise == requantise-then-max.
-                const int chunks = p.N / 4;                        // 16-byte chunks per row
-                for (int c0 = 0; c0 < p.N; c0 += 16) {
-                    int v[16];
-                    tmem_ld16(taddr + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        int ch = (c0 / 4 + j) ^ (row & 7);
-                        *reinterpret_cast<int4 *>(s_stage + (size_t)row * p.N + 4 * ch) = make_int4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(bar_tempty(buf));                      // TMEM buffer is free; the rest works from smem
-                named_bar_sync(1, EPI_THREADS);
-                const int PW = p.TW / 2, PH = p.TH / 2;
-                const int pooled_px = p.TN * PH * PW;
-                const int OH = p.H / 2, OW = p.W / 2;
-                for (int item = et; item < pooled_px * chunks; item += EPI_THREADS) {
-                    const int cg = item % chunks, pp = item / chunks;
-                    const int pw = pp % PW, ph = (pp / PW) % PH, nl = pp / (PW * PH);
-                    const int r00 = (nl * p.TH + 2 * ph) * p.TW + 2 * pw;
-                    int4 m = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int r = r00 + (k >> 1) * p.TW + (k & 1);
-                        const int4 t = *reinterpret_cast<const int4 *>(s_stage + (size_t)r * p.N + 4 * (cg ^ (r & 7)));
-                        m.x = max(m.x, t.x); m.y = max(m.y, t.y); m.z = max(m.z, t.z); m.w = max(m.w, t.w);
-                    }
-                    const int ox = x0 / 2 + pw, oy = y0 / 2 + ph, n = n0 + nl;
-                    if (ox < OW && oy < OH && n < p.n_img) {
-                        const int c = 4 * cg;
-                        unsigned word = 0;
-                        int mv[4] = { m.x, m.y, m.z, m.w };
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            int o = (c + b) < p.cout ? store8(requant(mv[b], s_bias[c + b], p.q), ovf) : 0;
-                            word |= (unsigned)(o & 0xff) << (8 * b);
-                        }
-                        *reinterpret_cast<unsigned *>(p.out + (((size_t)n * OH + oy) * OW + ox) * p.cs_out + c) = word;
-                    }
-                }
-                named_bar_sync(1, EPI_THREADS);                    // staging buffer is reused by the next tile
-            }
+            if (p.q.activ) epilogue_tile<EPI, true>(p, taddr, cbeg, cend, row, et, x0, y0, n0, s_bias, s_stage, bar_tempty(buf), ovf);
+            else epilogue_tile<EPI, false>(p, taddr, cbeg, cend, row, et, x0, y0, n0, s_bias, s_stage, bar_tempty(buf), ovf);
         }
         if (p.q.contract == CONTRACT_P) {
             ovf = __reduce_add_sync(0xffffffffu, ovf);
@@ -388,8 +433,34 @@ bool conv3x3_umma_supported(const ConvArgs &a)
     return true;
 }
 
-template <int CB>
-static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count)
+// Which epilogue may run: the fp32 paths need every non-saturating intermediate to be exactly representable.
+static int epi_mode_for(const ConvArgs &a, EpiConst *k)
+{
+    memset(k, 0, sizeof *k);
+    const LayerQ &q = a.q;
+    if (a.force_generic_epilogue) return EPI_GENERIC;
+    if (q.contract == CONTRACT_F && q.round_mode == ROUND_RNE) {
+        const long long bmax = a.bias_abs_max;
+        const bool in_ok = q.idir ? q.iofs <= 20 : (q.iofs <= 20 && ((32769LL + bmax) << q.iofs) <= (1LL << 24));
+        if (!in_ok || bmax >= (1 << 21) || q.oofs > 20) return EPI_GENERIC;
+        k->s_in = ldexpf(1.0f, q.idir ? q.iofs : -q.iofs);
+        k->leak_add = YB_MAGIC * 0.875f;
+        k->s_out = ldexpf(1.0f, q.odir ? q.oofs : -q.oofs);
+        k->out_add = (float)((double)YB_MAGIC * (1.0 - (double)k->s_out));
+        return EPI_F_RNE;
+    }
+    if (q.contract == CONTRACT_P) {
+        if (q.sh > 13 || q.sh < -8 || q.la > 4 || a.bias_abs_max >= (1 << 28)) return EPI_GENERIC;
+        k->s_in = ldexpf(1.0f, -q.sh);
+        k->s_in2 = ldexpf(1.0f, -(q.sh + 3));
+        k->la = q.la;
+        return EPI_P;
+    }
+    return EPI_GENERIC;
+}
+
+template <int CB, int EPI>
+static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count, const EpiConst &kc)
 {
     cudaError_t e = get_encode();
     if (e != cudaSuccess) return e;
@@ -420,7 +491,7 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count)
     const uint32_t smem_bytes = p.off_bar + 256u + 1024u;
     uint32_t nb = 32; while (nb < (uint32_t)p.N) nb <<= 1;
     p.tmem_buf_stride = nb; p.tmem_cols = 2 * nb;
-    p.q = a.q; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
+    p.q = a.q; p.k = kc; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
 
     CUtensorMap map_a, map_b;
     {
@@ -447,22 +518,69 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        e = cudaFuncSetAttribute(conv3x3_umma_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(conv3x3_umma_kernel<CB, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
     int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-    conv3x3_umma_kernel<CB><<<grid, UMMA_THREADS, smem_bytes, st>>>(map_a, map_b, p);
+    conv3x3_umma_kernel<CB, EPI><<<grid, UMMA_THREADS, smem_bytes, st>>>(map_a, map_b, p);
     return cudaGetLastError();
+}
+
+// ---- debug / property-test hook: the epilogue arithmetic alone on caller-supplied accumulators -------------------
+template <int EPI>
+__global__ void requant_probe_kernel(const int *__restrict__ acc, size_t count, int cout, const int *__restrict__ bias_sh,
+                                     UmmaParams p, int8_t *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int c = (int)(i % (size_t)cout);
+    const int b = bias_sh[c];
+    unsigned ovf = 0, bits;
+    if (EPI == EPI_F_RNE) {
+        const float fb = YB_MAGIC + (float)b;
+        bits = p.q.activ ? requant_f_rne<true>(acc[i], fb, p.k) : requant_f_rne<false>(acc[i], fb, p.k);
+    } else if (EPI == EPI_P) {
+        bits = p.q.activ ? requant_p<true>(acc[i], b, p.k, ovf, true) : requant_p<false>(acc[i], b, p.k, ovf, true);
+    } else {
+        bits = (unsigned)store8(requant(acc[i], b, p.q), ovf);
+    }
+    out[i] = (int8_t)(bits & 0xff);
+}
+
+cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_t *out, int *epi_used, cudaStream_t st)
+{
+    UmmaParams p;
+    memset(&p, 0, sizeof p);
+    p.q = a.q;
+    const int epi = epi_mode_for(a, &p.k);
+    if (epi_used) *epi_used = epi;
+    if (count == 0) return cudaSuccess;
+    const int blocks = (int)((count + 255) / 256);
+    if (epi == EPI_F_RNE) requant_probe_kernel<EPI_F_RNE><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
+    else if (epi == EPI_P) requant_probe_kernel<EPI_P><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
+    else requant_probe_kernel<EPI_GENERIC><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
+    return cudaGetLastError();
+}
+
+template <int CB>
+static cudaError_t launch_epi(const ConvArgs &a, cudaStream_t st, int sm_count)
+{
+    EpiConst kc;
+    switch (epi_mode_for(a, &kc)) {
+    case EPI_F_RNE: return launch_umma<CB, EPI_F_RNE>(a, st, sm_count, kc);
+    case EPI_P:     return launch_umma<CB, EPI_P>(a, st, sm_count, kc);
+    default:        return launch_umma<CB, EPI_GENERIC>(a, st, sm_count, kc);
+    }
 }
 
 cudaError_t conv3x3_umma(const ConvArgs &a, cudaStream_t st, int sm_count)
 {
     if (a.n == 0) return cudaSuccess;
-    if (a.cs_in == 16) return launch_umma<16>(a, st, sm_count);
-    if (a.cs_in == 32) return launch_umma<32>(a, st, sm_count);
-    if (a.cs_in == 64) return launch_umma<64>(a, st, sm_count);
-    return launch_umma<128>(a, st, sm_count);
+    if (a.cs_in == 16) return launch_epi<16>(a, st, sm_count);
+    if (a.cs_in == 32) return launch_epi<32>(a, st, sm_count);
+    if (a.cs_in == 64) return launch_epi<64>(a, st, sm_count);
+    return launch_epi<128>(a, st, sm_count);
 }
 
 }  // namespace yb

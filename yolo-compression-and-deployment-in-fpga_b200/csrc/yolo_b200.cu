@@ -26,6 +26,7 @@ enum { E_ARG = -1, E_STATE = -2, E_UNSUPPORTED = -3, E_NOMEM = -4, E_CUDA = -5 }
 
 struct LayerDev {
     int cin, cout, cs_in, cs_out, cout_pad;
+    int bias_abs_max = 0;
     LayerQ q;
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
@@ -228,6 +229,7 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
             for (int o = 0; o < L.cout; ++o) bsh[o] = (int)biases[l][o] * (1 << (E - sb));
         } else return fail(E_ARG, "contract %d", p->contract);
 
+        for (int o = 0; o < L.cout; ++o) d.bias_abs_max = abs(bsh[o]) > d.bias_abs_max ? abs(bsh[o]) : d.bias_abs_max;
         // repack to [cout_pad][tap][cs_in], zero padded
         std::vector<int8_t> wp((size_t)d.cout_pad * 9 * d.cs_in, 0);
         const int8_t *w = weights[l];
@@ -254,6 +256,7 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
         CU(cudaMemcpy(d.bias_sh, bsh.data(), bsh.size() * sizeof(int), cudaMemcpyHostToDevice));
         c->layers.push_back(d);
     }
+    CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));      // the saturation counter belongs to the loaded network
     build_rgb444_lut(p->scale_a[0], c->lut_host);
     CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
     c->loaded = true;
@@ -263,7 +266,7 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
 int yolo_b200_set_conv_backend(yolo_b200_ctx *c, int backend)
 {
     if (!c) return fail(E_ARG, "null ctx");
-    if (backend < 0 || backend > 2) return fail(E_ARG, "backend %d", backend);
+    if (backend < 0 || backend > 3) return fail(E_ARG, "backend %d", backend);
     c->conv_backend = backend;
     return 0;
 }
@@ -336,14 +339,31 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     ConvArgs a;
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.w_rows = L.cout_pad;
+    a.wgt_k160 = L.w_k160; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.force_generic_epilogue = c->conv_backend == 3;
     const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
     const bool umma_ok = aligned && conv3x3_umma_supported(a);
-    if (c->conv_backend == 2 && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
+    if (c->conv_backend >= 2 && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
     if (umma_ok && c->conv_backend != 1) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else CU(conv3x3_direct(a, c->stream));
     c->launches++;
     return 0;
+}
+
+int yolo_b200_debug_requant(yolo_b200_ctx *c, int layer, const int32_t *d_acc, size_t count, int8_t *d_out, int force_generic)
+{
+    int rc = check_ready(c, 0, 1, 1); if (rc) return rc;
+    if (layer < 0 || layer >= (int)c->layers.size()) return fail(E_ARG, "layer %d out of range", layer);
+    if ((!d_acc || !d_out) && count) return fail(E_ARG, "null buffer");
+    LayerDev &L = c->layers[layer];
+    ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.bias_sh = L.bias_sh; a.bias_abs_max = L.bias_abs_max;
+    a.force_generic_epilogue = force_generic;
+    int epi = 0;
+    CU(requant_probe(a, d_acc, count, d_out, &epi, c->stream));
+    c->launches++;
+    return epi;
 }
 
 int yolo_b200_conv_layer(yolo_b200_ctx *c, int layer, const int8_t *d_in, int n, int h, int w, int8_t *d_out)
