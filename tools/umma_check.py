@@ -48,7 +48,10 @@ def main():
                   ctx.conv_layer(l, dx, n, h, w, o)
                   ctx.sync()
                   outs.append(o.cpu().numpy())
-              a, b = outs
+              a, b, c3 = outs
+              if (a != c3).any():
+                  bad += 1
+                  print("   integer-epilogue tcgen05 path differs from dp4a: %d" % (a != c3).sum())
               diff = a != b
               print("layer %d cin %3d cout %3d pool %d shape %s: mismatches %d / %d" % (l, cin, cout, pool, (n, h, w), diff.sum(), diff.size), flush=True)
               if diff.any():

@@ -102,11 +102,14 @@ struct EpiConst {
     int la;           // P: left shift of acc
 };
 
-// Contract F, round-half-even.  fb = MAGIC + sh(bias).  Returns MAGIC + o as float bits.
+// Contract F, round-half-even.  fb = (float)sh(bias).  Returns MAGIC + o as float bits.
+// The bias is added AFTER the rounding FMA: round-half-even is not invariant under adding an odd integer, so folding
+// an odd sh(bias) into the FMA's addend would flip the direction of exact ties.
 template <bool ACT>
 __device__ __forceinline__ unsigned requant_f_rne(int acc, float fb, const EpiConst &k)
 {
-    float v = __fmaf_rn(__int2float_rn(acc), k.s_in, fb);                 // MAGIC + rne(sh(acc)) + sh(b)
+    float v = __fmaf_rn(__int2float_rn(acc), k.s_in, YB_MAGIC);           // MAGIC + rne(sh(acc, iofs))   (MAGIC is even)
+    v = __fadd_rn(v, fb);                                                 // + sh(b, bofs): exact integer add
     v = fminf(fmaxf(v, YB_MAGIC - 32768.f), YB_MAGIC + 32767.f);          // 16-bit accumulator
     if (ACT) v = fmaxf(v, __fmaf_rn(v, 0.125f, k.leak_add));              // leaky(t) = max(t, rne(t/8))
     v = __fmaf_rn(v, k.s_out, k.out_add);                                 // MAGIC + rne(sh(t, oofs))

@@ -122,7 +122,7 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int UMMA_THREADS = 64 + EPI_THREADS;
 
 // Requantise 4 accumulators of channels c..c+3 and pack them into one word.  `bias` points at the per-channel
-// words in shared memory (fp32 MAGIC+bias for EPI_F_RNE, int otherwise).
+// words in shared memory (fp32 bias for EPI_F_RNE, int otherwise).
 template <int EPI, bool ACT>
 __device__ __forceinline__ unsigned requant4(const int *acc, const int *bias, int c, const UmmaParams &p, unsigned &ovf, bool count)
 {
@@ -265,7 +265,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
         const int b = p.bias_sh[i];
-        s_bias[i] = EPI == EPI_F_RNE ? __float_as_int(YB_MAGIC + (float)b) : b;      // |b| < 2^21: exact
+        s_bias[i] = EPI == EPI_F_RNE ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
     }
     tc_fence_before();
     __syncthreads();
@@ -538,7 +538,7 @@ __global__ void requant_probe_kernel(const int *__restrict__ acc, size_t count, 
     const int b = bias_sh[c];
     unsigned ovf = 0, bits;
     if (EPI == EPI_F_RNE) {
-        const float fb = YB_MAGIC + (float)b;
+        const float fb = (float)b;
         bits = p.q.activ ? requant_f_rne<true>(acc[i], fb, p.k) : requant_f_rne<false>(acc[i], fb, p.k);
     } else if (EPI == EPI_P) {
         bits = p.q.activ ? requant_p<true>(acc[i], b, p.k, ovf, true) : requant_p<false>(acc[i], b, p.k, ovf, true);
