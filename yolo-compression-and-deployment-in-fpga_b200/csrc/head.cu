@@ -84,17 +84,36 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 }
 
 // ---- NMS ------------------------------------------------------------------------------------------
+//
+// One CTA per frame.  Candidates over the threshold are compacted, sorted once by (class, score desc, tie-break)
+// with a shared-memory bitonic sort, and then greedy suppression runs in score order in chunks of 256 sorted
+// candidates:
+//   1. every candidate of the chunk is tested, in parallel, against the ALIVE candidates of all earlier chunks
+//      (their fate is final) — no barrier inside this phase;
+//   2. every candidate computes the bit-row of the later candidates of the same chunk it would suppress;
+//   3. one warp resolves the chunk in order from those bit-rows (only rows that are non-empty are visited).
+// The pair count is the same as the sequential algorithm's worst case, but it is spread over the whole CTA with
+// three barriers per chunk instead of one per candidate.  The result is identical to greedy NMS.
 
-constexpr int NMS_THREADS = 512;
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_CHUNK = 256;
 
 struct NmsSmem {
-    unsigned long long key[HEAD_MAX_CAND];   // (score bits << 32) | tie-break, sorted descending
+    union {
+        unsigned long long key[HEAD_MAX_CAND];                     // sort phase
+        struct {                                                   // suppression phase (keys no longer needed)
+            unsigned short idx[HEAD_MAX_CAND];                     // anchor index of sorted position
+            unsigned mask[NMS_CHUNK][NMS_CHUNK / 32];              // intra-chunk suppression rows
+        } s2;
+    } u;
     float4 box[HEAD_MAX_CAND];
+    float score[HEAD_MAX_CAND];
     unsigned char cls[HEAD_MAX_CAND];
     unsigned char dead[HEAD_MAX_CAND];
-    unsigned keepmap[HEAD_MAX_CAND / 32];     // by anchor index (python mode output order)
+    unsigned keepmap[HEAD_MAX_CAND / 32];                          // by anchor index (python mode output order)
+    unsigned chunk_dead[NMS_CHUNK / 32];
+    unsigned row_nonempty[NMS_CHUNK / 32];
     int warp_sums[NMS_THREADS / 32];
-    int count;
 };
 
 // block-wide exclusive scan of a 0/1 flag; returns this thread's offset, *total = sum over the block
@@ -117,10 +136,15 @@ __device__ __forceinline__ bool suppress_py(float4 a, float4 b, float thresh)
 {
     float areaa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     float areab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-    float w = fmaxf(1e-28f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-    float h = fmaxf(1e-28f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    float asum = __fadd_rn(areaa, areab);
+    // disjoint boxes: the reference clamps w,h to 1e-28, so inter <= 1e-28 and ovr is ~0 (or negative) unless both
+    // areas are zero (then it can be 0/0 = NaN, which the reference drops): only that case needs the full formula
+    if ((w <= 0.f || h <= 0.f) && asum > 1e-20f && thresh > 1e-6f) return false;
+    w = fmaxf(1e-28f, w); h = fmaxf(1e-28f, h);
     float inter = __fmul_rn(w, h);
-    float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(areaa, areab), inter));
+    float ovr = __fdiv_rn(inter, __fsub_rn(asum, inter));
     return !(ovr <= thresh);
 }
 
@@ -137,6 +161,14 @@ __device__ __forceinline__ bool suppress_c(float4 a, float4 b, float thresh)
     return iou >= thresh;
 }
 
+template <bool PY>
+__device__ __forceinline__ bool suppresses(float4 a, unsigned char ca, float4 b, unsigned char cb, float thresh)
+{
+    if (PY) return ca == cb && suppress_py(a, b, thresh);
+    return suppress_c(a, b, thresh);
+}
+
+template <bool PY>
 __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -146,74 +178,127 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
     const float *scores = a.scores + (size_t)f * N;
     const int *cls = a.cls + (size_t)f * N;
     const float4 *boxes = a.boxes + (size_t)f * N;
-    const bool py = a.head_mode == YOLO_B200_HEAD_PYTHON;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077)
+    // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
+    //    key = class | score bits | tie-break: python sorts per class, ties -> higher anchor index first (reversed stable
+    //    ascending argsort); C is class-agnostic, ties -> lower index first.
     int m = 0;
     for (int base = 0; base < N; base += NMS_THREADS) {
         int i = base + tid;
         float sc = i < N ? scores[i] : -1.f;
-        bool cand = i < N && (py ? sc >= a.conf_thresh : sc > a.conf_thresh);
+        bool cand = i < N && (PY ? sc >= a.conf_thresh : sc > a.conf_thresh);
         int tot;
         int off = block_scan_flag(cand, s.warp_sums, &tot);
         if (cand) {
-            // ties: python -> higher anchor index first (reversed stable ascending argsort);
-            //       C      -> lower index first
-            unsigned tb = py ? (unsigned)i : (0xffffffffu - (unsigned)i);
-            s.key[m + off] = ((unsigned long long)__float_as_uint(sc) << 32) | tb;
+            unsigned long long cf = PY ? (unsigned long long)(63 - cls[i]) : 0ull;
+            unsigned tb = PY ? (unsigned)i : (unsigned)(HEAD_MAX_CAND - 1 - i);
+            s.u.key[m + off] = (cf << 44) | ((unsigned long long)__float_as_uint(sc) << 12) | tb;
         }
         m += tot;
     }
     for (int i = tid; i < HEAD_MAX_CAND / 32; i += NMS_THREADS) s.keepmap[i] = 0;
     int P = 1;
     while (P < m) P <<= 1;
-    for (int i = m + tid; i < P; i += NMS_THREADS) s.key[i] = 0ull;
+    for (int i = m + tid; i < P; i += NMS_THREADS) s.u.key[i] = 0ull;
     __syncthreads();
 
     // 2. bitonic sort, descending
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < P; i += NMS_THREADS) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long x = s.key[i], y = s.key[ixj];
-                    bool desc = (i & k) == 0;
-                    if (desc ? x < y : x > y) { s.key[i] = y; s.key[ixj] = x; }
-                }
+            for (int t = tid; t < P / 2; t += NMS_THREADS) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // index with bit j clear
+                int ixj = i | j;
+                unsigned long long x = s.u.key[i], y = s.u.key[ixj];
+                bool desc = (i & k) == 0;
+                if (desc ? x < y : x > y) { s.u.key[i] = y; s.u.key[ixj] = x; }
             }
             __syncthreads();
         }
 
-    // 3. gather boxes / classes in sorted order
-    for (int i = tid; i < m; i += NMS_THREADS) {
-        unsigned tb = (unsigned)(s.key[i] & 0xffffffffu);
-        int idx = py ? (int)tb : (int)(0xffffffffu - tb);
-        s.box[i] = boxes[idx];
-        s.cls[i] = (unsigned char)cls[idx];
-        s.dead[i] = 0;
+    // 3. sorted order -> anchor index, box, class, score (keys are dead after this; their storage is reused)
+    constexpr int PER = HEAD_MAX_CAND / NMS_THREADS;
+    unsigned short my_idx[PER];
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        int i = tid + r * NMS_THREADS;
+        unsigned tb = i < m ? (unsigned)(s.u.key[i] & 0xfffu) : 0u;
+        my_idx[r] = (unsigned short)(PY ? tb : (HEAD_MAX_CAND - 1 - tb));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PER; ++r) {
+        int i = tid + r * NMS_THREADS;
+        if (i < m) {
+            int idx = my_idx[r];
+            s.u.s2.idx[i] = (unsigned short)idx;
+            s.box[i] = boxes[idx];
+            s.score[i] = scores[idx];
+            s.cls[i] = (unsigned char)cls[idx];
+            s.dead[i] = 0;
+        }
     }
     __syncthreads();
 
-    // 4. greedy suppression in score order (python: within a class; C: class-agnostic)
-    for (int i = 0; i < m; ++i) {
-        if (s.dead[i]) continue;                      // uniform: written before the last barrier
-        float4 bi = s.box[i];
-        unsigned char ci = s.cls[i];
-        for (int j = i + 1 + tid; j < m; j += NMS_THREADS) {
-            if (s.dead[j]) continue;
-            if (py) { if (s.cls[j] == ci && suppress_py(bi, s.box[j], a.nms_thresh)) s.dead[j] = 1; }
-            else    { if (suppress_c(bi, s.box[j], a.nms_thresh)) s.dead[j] = 1; }
+    // 4. greedy suppression, chunk by chunk
+    for (int cs = 0; cs < m; cs += NMS_CHUNK) {
+        const int j = cs + tid;
+        const bool have = j < m;
+        const float4 bj = have ? s.box[j] : make_float4(0, 0, 0, 0);
+        const unsigned char cj = have ? s.cls[j] : 0;
+        // 4a. against alive candidates of earlier chunks
+        bool dead = false;
+        if (have) {
+            for (int i = 0; i < cs; ++i) {
+                if (s.dead[i]) continue;
+                if (suppresses<PY>(s.box[i], s.cls[i], bj, cj, a.nms_thresh)) { dead = true; break; }
+            }
         }
+        unsigned db = __ballot_sync(0xffffffffu, dead);
+        if (lane == 0) s.chunk_dead[wid] = db;
+        // 4b. bit-row of later candidates of this chunk that j would suppress
+        unsigned row[NMS_CHUNK / 32];
+        unsigned any = 0;
+#pragma unroll
+        for (int w = 0; w < NMS_CHUNK / 32; ++w) row[w] = 0;
+        if (have && !dead) {
+            const int jend = min(m - cs, NMS_CHUNK);
+            for (int t = tid + 1; t < jend; ++t)
+                if (suppresses<PY>(bj, cj, s.box[cs + t], s.cls[cs + t], a.nms_thresh)) { row[t >> 5] |= 1u << (t & 31); any = 1; }
+        }
+#pragma unroll
+        for (int w = 0; w < NMS_CHUNK / 32; ++w) s.u.s2.mask[tid][w] = row[w];
+        unsigned nb = __ballot_sync(0xffffffffu, any != 0);
+        if (lane == 0) s.row_nonempty[wid] = nb;
+        __syncthreads();
+        // 4c. one warp resolves the chunk in order; lane w owns dead word w
+        if (wid == 0) {
+            unsigned dw = lane < NMS_CHUNK / 32 ? s.chunk_dead[lane] : 0u;
+            for (int w = 0; w < NMS_CHUNK / 32; ++w) {
+                unsigned pending = s.row_nonempty[w];
+                while (pending) {
+                    int b = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    unsigned cur = __shfl_sync(0xffffffffu, dw, w);          // dead word of row (w*32+b) as of now
+                    if (!((cur >> b) & 1u)) {
+                        unsigned mrow = lane < NMS_CHUNK / 32 ? s.u.s2.mask[w * 32 + b][lane] : 0u;
+                        dw |= mrow;
+                    }
+                }
+            }
+            if (lane < NMS_CHUNK / 32) s.chunk_dead[lane] = dw;
+        }
+        __syncthreads();
+        if (have) s.dead[j] = (s.chunk_dead[tid >> 5] >> (tid & 31)) & 1u;
         __syncthreads();
     }
 
     // 5. output
     yolo_b200_det *dets = a.dets + (size_t)f * a.max_det;
-    if (py) {
+    if (PY) {
         // ascending anchor order (np.where(keep > 0), slim_yolo_v2.py:205)
         for (int i = tid; i < m; i += NMS_THREADS)
-            if (!s.dead[i]) { unsigned idx = (unsigned)(s.key[i] & 0xffffffffu); atomicOr(&s.keepmap[idx >> 5], 1u << (idx & 31)); }
+            if (!s.dead[i]) { unsigned idx = s.u.s2.idx[i]; atomicOr(&s.keepmap[idx >> 5], 1u << (idx & 31)); }
         __syncthreads();
         int cnt = 0;
         for (int base = 0; base < N; base += NMS_THREADS) {
@@ -239,11 +324,9 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
             int tot;
             int off = block_scan_flag(k, s.warp_sums, &tot);
             if (k && cnt + off < a.max_det) {
-                unsigned tb = (unsigned)(s.key[i] & 0xffffffffu);
-                int idx = (int)(0xffffffffu - tb);
                 float4 b = s.box[i];
                 yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w;
-                d.score = __uint_as_float((unsigned)(s.key[i] >> 32)); d.cls = s.cls[i]; d.anchor_index = idx; d.pad_ = 0;
+                d.score = s.score[i]; d.cls = s.cls[i]; d.anchor_index = s.u.s2.idx[i]; d.pad_ = 0;
                 dets[cnt + off] = d;
             }
             cnt += tot;
@@ -254,14 +337,17 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
 
 cudaError_t head_init(void)
 {
-    return cudaFuncSetAttribute(head_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    cudaError_t e = cudaFuncSetAttribute(head_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(head_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
 }
 
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
-    if (a.gh * a.gw * a.A > HEAD_MAX_CAND) return cudaErrorInvalidValue;
-    head_nms_kernel<<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
+    if (a.gh * a.gw * a.A > HEAD_MAX_CAND || a.C > 64) return cudaErrorInvalidValue;
+    if (a.head_mode == YOLO_B200_HEAD_PYTHON) head_nms_kernel<true><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
+    else head_nms_kernel<false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
     return cudaGetLastError();
 }
 
