@@ -85,31 +85,36 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 
 // ---- NMS ------------------------------------------------------------------------------------------
 //
-// One CTA per frame.  Candidates over the threshold are compacted, sorted once by (class, score desc, tie-break)
-// with a shared-memory bitonic sort, and then greedy suppression runs in score order in chunks of 256 sorted
-// candidates:
-//   1. every candidate of the chunk is tested, in parallel, against the ALIVE candidates of all earlier chunks
-//      (their fate is final) — no barrier inside this phase;
-//   2. every candidate computes the bit-row of the later candidates of the same chunk it would suppress;
-//   3. one warp resolves the chunk in order from those bit-rows (only rows that are non-empty are visited).
-// The pair count is the same as the sequential algorithm's worst case, but it is spread over the whole CTA with
-// three barriers per chunk instead of one per candidate.  The result is identical to greedy NMS.
+// One CTA of 1024 threads per frame.  Candidates over the threshold are compacted and sorted once by
+// (class, score desc, tie-break) with a shared-memory bitonic sort.  Greedy suppression then runs per class segment
+// (python head; the C head is class-agnostic = one segment) in chunks of 256 sorted candidates, against a COMPACTED
+// list of the candidates kept so far (which is also the output list):
+//   a. every candidate of the chunk is tested against the kept list; 4 threads share one candidate, each taking every
+//      4th kept box (all lanes of a warp read the same kept box: a shared-memory broadcast);
+//   b. the survivors record, as bit-rows, which later candidates of the same chunk they would suppress;
+//   c. one warp resolves the chunk in score order from the (rarely non-empty) bit-rows;
+//   d. the chunk's survivors are appended to the kept list (in place: kept count <= processed count).
+// The decisions are those of sequential greedy NMS: a candidate is dropped iff a KEPT higher-ranked candidate of its
+// segment overlaps it beyond the threshold.  Most pairs are rejected without a division: disjoint boxes, boxes whose
+// area ratio already bounds the IoU below the threshold, and quotients clearly away from the threshold; only
+// borderline pairs evaluate the reference's exact fp32 expression.
 
-constexpr int NMS_THREADS = 256;
+constexpr int NMS_THREADS = 1024;
 constexpr int NMS_CHUNK = 256;
+constexpr int NMS_SLICES = NMS_THREADS / NMS_CHUNK;
+constexpr int NMS_MAX_CLASSES = 64;
 
 struct NmsSmem {
     union {
         unsigned long long key[HEAD_MAX_CAND];                     // sort phase
         struct {                                                   // suppression phase (keys no longer needed)
-            unsigned short idx[HEAD_MAX_CAND];                     // anchor index of sorted position
+            unsigned short idx[HEAD_MAX_CAND];                     // anchor index of sorted position / kept entry
             unsigned mask[NMS_CHUNK][NMS_CHUNK / 32];              // intra-chunk suppression rows
         } s2;
     } u;
-    float4 box[HEAD_MAX_CAND];
-    float score[HEAD_MAX_CAND];
+    float4 box[HEAD_MAX_CAND];                                     // sorted candidates; kept list compacted in place
+    float area[HEAD_MAX_CAND];
     unsigned char cls[HEAD_MAX_CAND];
-    unsigned char dead[HEAD_MAX_CAND];
     unsigned keepmap[HEAD_MAX_CAND / 32];                          // by anchor index (python mode output order)
     unsigned chunk_dead[NMS_CHUNK / 32];
     unsigned row_nonempty[NMS_CHUNK / 32];
@@ -124,27 +129,39 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *warp_sums, int *t
     int off = __popc(b & ((1u << lane) - 1));
     if (lane == 0) warp_sums[wid] = __popc(b);
     __syncthreads();
-    int base = 0, tot = 0;
-    for (int w = 0; w < NMS_THREADS / 32; ++w) { int s = warp_sums[w]; if (w < wid) base += s; tot += s; }
+    int v = lane < NMS_THREADS / 32 ? warp_sums[lane] : 0;       // NMS_THREADS/32 == 32 warps: one per lane
+    int tot = __reduce_add_sync(0xffffffffu, v);
+    int base = __reduce_add_sync(0xffffffffu, lane < wid ? v : 0);
     __syncthreads();
     *total = tot;
     return base + off;
 }
 
-// python: overlap as in slim_yolo_v2.py:159-169, suppress when NOT (ovr <= thresh)
-__device__ __forceinline__ bool suppress_py(float4 a, float4 b, float thresh)
+__device__ __forceinline__ float area_py(float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
+
+// python: overlap as in slim_yolo_v2.py:159-169, suppress when NOT (ovr <= thresh).
+// thr_lo = thresh*(1-1e-5) when the shortcuts are usable (thresh > 1e-6), else a negative number (shortcuts off).
+__device__ __forceinline__ bool suppress_py(float4 a, float areaa, float4 b, float areab, float thresh, float thr_lo)
 {
-    float areaa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-    float areab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
     float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
     float asum = __fadd_rn(areaa, areab);
-    // disjoint boxes: the reference clamps w,h to 1e-28, so inter <= 1e-28 and ovr is ~0 (or negative) unless both
-    // areas are zero (then it can be 0/0 = NaN, which the reference drops): only that case needs the full formula
-    if ((w <= 0.f || h <= 0.f) && asum > 1e-20f && thresh > 1e-6f) return false;
+    if (thr_lo > 0.f) {
+        // disjoint boxes: the reference clamps w,h to 1e-28, so inter <= 1e-28 and ovr is ~0 (or negative) unless both
+        // areas are ~zero (then it can be 0/0 = NaN, which the reference drops): only that case needs the full formula
+        if ((w <= 0.f || h <= 0.f) && asum > 1e-20f) return false;
+        // inter <= min(area) and union >= max(area) (fp32 rounding is monotone): IoU <= min/max
+        if (fminf(areaa, areab) < __fmul_rn(thr_lo, fmaxf(areaa, areab))) return false;
+    }
     w = fmaxf(1e-28f, w); h = fmaxf(1e-28f, h);
     float inter = __fmul_rn(w, h);
-    float ovr = __fdiv_rn(inter, __fsub_rn(asum, inter));
+    float den = __fsub_rn(asum, inter);
+    if (thr_lo > 0.f && den > 1e-20f) {
+        float p = __fmul_rn(thresh, den);
+        if (inter < __fmul_rn(p, 0.99999f)) return false;          // quotient clearly below the threshold
+        if (inter > __fmul_rn(p, 1.00001f)) return true;           // clearly above
+    }
+    float ovr = __fdiv_rn(inter, den);
     return !(ovr <= thresh);
 }
 
@@ -155,6 +172,7 @@ __device__ __forceinline__ bool suppress_c(float4 a, float4 b, float thresh)
     int bx1 = (int)b.x, by1 = (int)b.y, bx2 = (int)b.z, by2 = (int)b.w;
     int ow = (ax2 - ax1 + bx2 - bx1) - (max(ax2, bx2) - min(ax1, bx1));
     int oh = (ay2 - ay1 + by2 - by1) - (max(ay2, by2) - min(ay1, by1));
+    if ((ow <= 0 || oh <= 0) && thresh > 0.f) return false;       // iou = 0/uni = 0 (or NaN): never >= a positive threshold
     int inter = (ow <= 0 || oh <= 0) ? 0 : ow * oh;
     int uni = (ax2 - ax1) * (ay2 - ay1) + (bx2 - bx1) * (by2 - by1) - inter;
     float iou = __fdiv_rn((float)inter, (float)uni);
@@ -162,14 +180,14 @@ __device__ __forceinline__ bool suppress_c(float4 a, float4 b, float thresh)
 }
 
 template <bool PY>
-__device__ __forceinline__ bool suppresses(float4 a, unsigned char ca, float4 b, unsigned char cb, float thresh)
+__device__ __forceinline__ bool suppresses(float4 a, float areaa, float4 b, float areab, float thresh, float thr_lo)
 {
-    if (PY) return ca == cb && suppress_py(a, b, thresh);
+    if (PY) return suppress_py(a, areaa, b, areab, thresh, thr_lo);
     return suppress_c(a, b, thresh);
 }
 
 template <bool PY>
-__global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
+__global__ void __launch_bounds__(NMS_THREADS, 1) head_nms_kernel(HeadArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
@@ -179,6 +197,8 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
     const int *cls = a.cls + (size_t)f * N;
     const float4 *boxes = a.boxes + (size_t)f * N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float thresh = a.nms_thresh;
+    const float thr_lo = thresh > 1e-6f ? thresh * 0.99999f : -1.f;
 
     // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
     //    key = class | score bits | tie-break: python sorts per class, ties -> higher anchor index first (reversed stable
@@ -191,7 +211,7 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
         int tot;
         int off = block_scan_flag(cand, s.warp_sums, &tot);
         if (cand) {
-            unsigned long long cf = PY ? (unsigned long long)(63 - cls[i]) : 0ull;
+            unsigned long long cf = PY ? (unsigned long long)(NMS_MAX_CLASSES - 1 - cls[i]) : 0ull;
             unsigned tb = PY ? (unsigned)i : (unsigned)(HEAD_MAX_CAND - 1 - i);
             s.u.key[m + off] = (cf << 44) | ((unsigned long long)__float_as_uint(sc) << 12) | tb;
         }
@@ -216,7 +236,7 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
             __syncthreads();
         }
 
-    // 3. sorted order -> anchor index, box, class, score (keys are dead after this; their storage is reused)
+    // 3. sorted order -> anchor index, box, area, class (keys are dead after this; their storage is reused)
     constexpr int PER = HEAD_MAX_CAND / NMS_THREADS;
     unsigned short my_idx[PER];
 #pragma unroll
@@ -231,74 +251,109 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
         int i = tid + r * NMS_THREADS;
         if (i < m) {
             int idx = my_idx[r];
+            float4 b = boxes[idx];
             s.u.s2.idx[i] = (unsigned short)idx;
-            s.box[i] = boxes[idx];
-            s.score[i] = scores[idx];
+            s.box[i] = b;
+            s.area[i] = area_py(b);
             s.cls[i] = (unsigned char)cls[idx];
-            s.dead[i] = 0;
         }
     }
     __syncthreads();
+    // 4. greedy suppression, segment by segment, chunk by chunk
+    const int cj_local = tid & (NMS_CHUNK - 1);      // candidate within the chunk
+    const int slice = tid / NMS_CHUNK;               // warp-uniform
+    int out_count = 0;                               // C head: kept so far (= output position)
+    const int nseg = PY ? a.C : 1;
+    for (int sg = 0; sg < nseg; ++sg) {
+        // python head: the sort put the classes in ascending order; segment of class sg = [first cls >= sg, first cls > sg)
+        // (binary searches on the sorted class array; every thread computes the same bounds)
+        int seg_b = 0, seg_e = m;
+        if (PY) {
+            int lo = 0, hi = m;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (s.cls[mid] < sg) lo = mid + 1; else hi = mid; }
+            seg_b = lo; hi = m;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (s.cls[mid] <= sg) lo = mid + 1; else hi = mid; }
+            seg_e = lo;
+        }
+        if (seg_b == seg_e) continue;
 
-    // 4. greedy suppression, chunk by chunk
-    for (int cs = 0; cs < m; cs += NMS_CHUNK) {
-        const int j = cs + tid;
-        const bool have = j < m;
-        const float4 bj = have ? s.box[j] : make_float4(0, 0, 0, 0);
-        const unsigned char cj = have ? s.cls[j] : 0;
-        // 4a. against alive candidates of earlier chunks
-        bool dead = false;
-        if (have) {
-            for (int i = 0; i < cs; ++i) {
-                if (s.dead[i]) continue;
-                if (suppresses<PY>(s.box[i], s.cls[i], bj, cj, a.nms_thresh)) { dead = true; break; }
-            }
-        }
-        unsigned db = __ballot_sync(0xffffffffu, dead);
-        if (lane == 0) s.chunk_dead[wid] = db;
-        // 4b. bit-row of later candidates of this chunk that j would suppress
-        unsigned row[NMS_CHUNK / 32];
-        unsigned any = 0;
-#pragma unroll
-        for (int w = 0; w < NMS_CHUNK / 32; ++w) row[w] = 0;
-        if (have && !dead) {
-            const int jend = min(m - cs, NMS_CHUNK);
-            for (int t = tid + 1; t < jend; ++t)
-                if (suppresses<PY>(bj, cj, s.box[cs + t], s.cls[cs + t], a.nms_thresh)) { row[t >> 5] |= 1u << (t & 31); any = 1; }
-        }
-#pragma unroll
-        for (int w = 0; w < NMS_CHUNK / 32; ++w) s.u.s2.mask[tid][w] = row[w];
-        unsigned nb = __ballot_sync(0xffffffffu, any != 0);
-        if (lane == 0) s.row_nonempty[wid] = nb;
-        __syncthreads();
-        // 4c. one warp resolves the chunk in order; lane w owns dead word w
-        if (wid == 0) {
-            unsigned dw = lane < NMS_CHUNK / 32 ? s.chunk_dead[lane] : 0u;
-            for (int w = 0; w < NMS_CHUNK / 32; ++w) {
-                unsigned pending = s.row_nonempty[w];
-                while (pending) {
-                    int b = __ffs(pending) - 1;
-                    pending &= pending - 1;
-                    unsigned cur = __shfl_sync(0xffffffffu, dw, w);          // dead word of row (w*32+b) as of now
-                    if (!((cur >> b) & 1u)) {
-                        unsigned mrow = lane < NMS_CHUNK / 32 ? s.u.s2.mask[w * 32 + b][lane] : 0u;
-                        dw |= mrow;
-                    }
+        int K = 0;                                   // kept in this segment: entries [seg_b, seg_b + K)
+        for (int cs = seg_b; cs < seg_e; cs += NMS_CHUNK) {
+            const int chn = min(NMS_CHUNK, seg_e - cs);
+            const int j = cs + cj_local;
+            const bool have = cj_local < chn;
+            const float4 bj = have ? s.box[j] : make_float4(0, 0, 0, 0);
+            const float aj = have ? s.area[j] : 0.f;
+            if (tid < NMS_CHUNK / 32) { s.chunk_dead[tid] = 0; s.row_nonempty[tid] = 0; }
+            for (int i = tid; i < NMS_CHUNK * (NMS_CHUNK / 32); i += NMS_THREADS) (&s.u.s2.mask[0][0])[i] = 0;
+            __syncthreads();
+            // 4a. against the kept list of this segment
+            bool dead = false;
+            if (have) {
+                for (int i = seg_b + slice; i < seg_b + K; i += NMS_SLICES) {
+                    const float ai = s.area[i];
+                    // area-ratio bound first (IoU <= min/max): rejects most pairs before the box is even loaded
+                    if (PY && thr_lo > 0.f && fminf(ai, aj) < __fmul_rn(thr_lo, fmaxf(ai, aj))) continue;
+                    if (suppresses<PY>(s.box[i], ai, bj, aj, thresh, thr_lo)) { dead = true; break; }
                 }
             }
-            if (lane < NMS_CHUNK / 32) s.chunk_dead[lane] = dw;
+            unsigned db = __ballot_sync(0xffffffffu, dead);
+            if (lane == 0 && db) atomicOr(&s.chunk_dead[cj_local >> 5], db);
+            __syncthreads();
+            // 4b. bit-rows: which later candidates of this chunk would j suppress (skipped when j is already dead)
+            const bool jdead = (s.chunk_dead[cj_local >> 5] >> (cj_local & 31)) & 1u;
+            if (have && !jdead) {
+                bool any = false;
+                for (int t = cj_local + 1 + slice; t < chn; t += NMS_SLICES) {
+                    const float at = s.area[cs + t];
+                    if (PY && thr_lo > 0.f && fminf(at, aj) < __fmul_rn(thr_lo, fmaxf(at, aj))) continue;
+                    if (suppresses<PY>(bj, aj, s.box[cs + t], at, thresh, thr_lo)) {
+                        atomicOr(&s.u.s2.mask[cj_local][t >> 5], 1u << (t & 31));
+                        any = true;
+                    }
+                }
+                if (any) atomicOr(&s.row_nonempty[cj_local >> 5], 1u << (cj_local & 31));
+            }
+            __syncthreads();
+            // 4c. one warp resolves the chunk in order; lane w owns dead word w
+            if (wid == 0) {
+                unsigned dw = lane < NMS_CHUNK / 32 ? s.chunk_dead[lane] : 0u;
+                for (int w = 0; w < NMS_CHUNK / 32; ++w) {
+                    unsigned pending = s.row_nonempty[w];
+                    while (pending) {
+                        int b = __ffs(pending) - 1;
+                        pending &= pending - 1;
+                        unsigned cur = __shfl_sync(0xffffffffu, dw, w);          // dead word of row (w*32+b) as of now
+                        if (!((cur >> b) & 1u)) {
+                            unsigned mrow = lane < NMS_CHUNK / 32 ? s.u.s2.mask[w * 32 + b][lane] : 0u;
+                            dw |= mrow;
+                        }
+                    }
+                }
+                if (lane < NMS_CHUNK / 32) s.chunk_dead[lane] = dw;
+            }
+            __syncthreads();
+            // 4d. append the survivors to the kept list (registers first: the list grows into this chunk's storage)
+            const bool alive = tid < NMS_CHUNK && have && !((s.chunk_dead[cj_local >> 5] >> (cj_local & 31)) & 1u);
+            const unsigned short my = have ? s.u.s2.idx[j] : 0;
+            const unsigned char mc = have ? s.cls[j] : 0;
+            int tot;
+            int off = block_scan_flag(alive, s.warp_sums, &tot);     // contains the barriers that order reads before writes
+            if (alive) {
+                const int d = seg_b + K + off;
+                s.box[d] = bj; s.area[d] = aj; s.u.s2.idx[d] = my; s.cls[d] = mc;
+                if (PY) atomicOr(&s.keepmap[my >> 5], 1u << (my & 31));
+            }
+            K += tot;
+            __syncthreads();
         }
-        __syncthreads();
-        if (have) s.dead[j] = (s.chunk_dead[tid >> 5] >> (tid & 31)) & 1u;
-        __syncthreads();
+        out_count = K;
     }
 
     // 5. output
     yolo_b200_det *dets = a.dets + (size_t)f * a.max_det;
     if (PY) {
         // ascending anchor order (np.where(keep > 0), slim_yolo_v2.py:205)
-        for (int i = tid; i < m; i += NMS_THREADS)
-            if (!s.dead[i]) { unsigned idx = s.u.s2.idx[i]; atomicOr(&s.keepmap[idx >> 5], 1u << (idx & 31)); }
         __syncthreads();
         int cnt = 0;
         for (int base = 0; base < N; base += NMS_THREADS) {
@@ -316,22 +371,15 @@ __global__ void __launch_bounds__(NMS_THREADS) head_nms_kernel(HeadArgs a)
         }
         if (tid == 0) a.counts[f] = cnt;
     } else {
-        // descending score order (conf_sort, yolo_forward.c:1114-1126)
-        int cnt = 0;
-        for (int base = 0; base < m; base += NMS_THREADS) {
-            int i = base + tid;
-            bool k = i < m && !s.dead[i];
-            int tot;
-            int off = block_scan_flag(k, s.warp_sums, &tot);
-            if (k && cnt + off < a.max_det) {
-                float4 b = s.box[i];
-                yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w;
-                d.score = s.score[i]; d.cls = s.cls[i]; d.anchor_index = s.u.s2.idx[i]; d.pad_ = 0;
-                dets[cnt + off] = d;
-            }
-            cnt += tot;
+        // descending score order (conf_sort, yolo_forward.c:1114-1126): the kept list itself
+        for (int i = tid; i < out_count && i < a.max_det; i += NMS_THREADS) {
+            float4 b = s.box[i];
+            int idx = s.u.s2.idx[i];
+            yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w;
+            d.score = scores[idx]; d.cls = s.cls[i]; d.anchor_index = idx; d.pad_ = 0;
+            dets[i] = d;
         }
-        if (tid == 0) a.counts[f] = cnt;
+        if (tid == 0) a.counts[f] = out_count;
     }
 }
 
@@ -345,7 +393,7 @@ cudaError_t head_init(void)
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
-    if (a.gh * a.gw * a.A > HEAD_MAX_CAND || a.C > 64) return cudaErrorInvalidValue;
+    if (a.gh * a.gw * a.A > HEAD_MAX_CAND || a.C > NMS_MAX_CLASSES) return cudaErrorInvalidValue;
     if (a.head_mode == YOLO_B200_HEAD_PYTHON) head_nms_kernel<true><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
     else head_nms_kernel<false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
     return cudaGetLastError();
