@@ -376,27 +376,48 @@ def test_tensor_core_and_dot_product_kernels_agree_at_full_size(ctx):
     ctx.set_conv_backend(0)
 
 
+WS_LAYERS = (1, 2, 3, 4, 5, 9)     # layers whose packed weights fit in shared memory (conv_ws.cu)
+
+
+@pytest.mark.parametrize("backend", [2, 4, 5])
 @pytest.mark.parametrize("layer", [1, 2, 3, 4, 5, 6, 7, 8, 9])
-def test_tensor_core_layer_against_oracle(ctx, layer):
-    """Each tensor-core layer alone, tcgen05 back end forced, against the CPU oracle (odd sizes, several images)."""
+def test_tensor_core_layer_against_oracle(ctx, layer, backend):
+    """Each tensor-core layer alone, one tcgen05 kernel forced (2 = streaming, 4/5 = weight-stationary with the fp32 /
+    integer epilogue), against the CPU oracle (odd sizes, several images)."""
+    if backend >= 4 and layer not in WS_LAYERS:
+        pytest.skip("weights do not fit the weight-stationary kernel")
     g, qnet, frames = gu.load("ref_p_64x96")
     cin, cout, activ, pool = qnet.layers[layer]
     rng = np.random.default_rng(layer)
-    n, h, w = 3, 14, 18
-    x = np.zeros((n, h, w, ex.cstride(cin)), dtype=np.int8)
-    x[..., :cin] = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
+    for (n, h, w) in ((3, 14, 18), (5, 13, 13), (2, 40, 21)):
+        x = np.zeros((n, h, w, ex.cstride(cin)), dtype=np.int8)
+        x[..., :cin] = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
+        for contract in (lib.CONTRACT_F, lib.CONTRACT_P):
+            ctx.load_quantnet(qnet, contract=contract)
+            ctx.set_conv_backend(backend)
+            try:
+                oh, ow = (h // 2, w // 2) if pool else (h, w)
+                d_out = torch.full((n, oh, ow, ex.cstride(cout)), 77, dtype=torch.int8, device="cuda")
+                ctx.conv_layer(layer, dev(x), n, h, w, d_out)
+                ctx.sync()
+            finally:
+                ctx.set_conv_backend(0)
+            ref, _ = ol.conv_layer(x, qnet.w[layer], qnet.b[layer], cin, cout, qnet.sa[layer], qnet.sw[layer], qnet.sb[layer],
+                                   qnet.retune[layer], qnet.sa[layer + 1], activ, pool, contract)
+            np.testing.assert_array_equal(d_out.cpu().numpy(), ref, err_msg="shape %s contract %d" % ((n, h, w), contract))
+
+
+def test_weight_stationary_kernel_rejects_layers_that_do_not_fit(ctx):
+    g, qnet, frames = gu.load("ref_p_64x96")
     ctx.load_quantnet(qnet, contract=lib.CONTRACT_F)
-    ctx.set_conv_backend(2)
+    ctx.set_conv_backend(4)
     try:
-        oh, ow = (h // 2, w // 2) if pool else (h, w)
-        d_out = torch.full((n, oh, ow, ex.cstride(cout)), 77, dtype=torch.int8, device="cuda")
-        ctx.conv_layer(layer, dev(x), n, h, w, d_out)
-        ctx.sync()
+        x = torch.zeros((1, 8, 8, 256), dtype=torch.int8, device="cuda")
+        o = torch.zeros((1, 8, 8, 256), dtype=torch.int8, device="cuda")
+        with pytest.raises(lib.YoloB200Error):
+            ctx.conv_layer(7, x, 1, 8, 8, o)       # conv6: 256 x 2304 bytes of weights
     finally:
         ctx.set_conv_backend(0)
-    ref, _ = ol.conv_layer(x, qnet.w[layer], qnet.b[layer], cin, cout, qnet.sa[layer], qnet.sw[layer], qnet.sb[layer],
-                           qnet.retune[layer], qnet.sa[layer + 1], activ, pool, 0)
-    np.testing.assert_array_equal(d_out.cpu().numpy(), ref)
 
 
 # ---- the epilogue arithmetic alone: exact-fp32 fast paths and the integer path vs the oracle -----------------

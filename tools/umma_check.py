@@ -41,17 +41,31 @@ def main():
               dx = torch.from_numpy(x).cuda()
               oh, ow = (h // 2, w // 2) if pool else (h, w)
               outs = []
-              for backend in (1, 2, 3):
+              for backend in (1, 2, 3, 4, 5):
                   ctx.set_conv_backend(backend)
                   o = torch.full((n, oh, ow, ex.cstride(cout)), 99, dtype=torch.int8, device="cuda")
                   t0 = time.time()
-                  ctx.conv_layer(l, dx, n, h, w, o)
+                  try:
+                      ctx.conv_layer(l, dx, n, h, w, o)
+                  except lib.YoloB200Error as e:
+                      if backend >= 4:          # weights do not fit the weight-stationary kernel: nothing to compare
+                          outs.append(outs[0])
+                          continue
+                      raise
                   ctx.sync()
                   outs.append(o.cpu().numpy())
-              a, b, c3 = outs
+              a, b, c3, w4, w5 = outs
               if (a != c3).any():
                   bad += 1
                   print("   integer-epilogue tcgen05 path differs from dp4a: %d" % (a != c3).sum())
+              for nm, wv in (("ws", w4), ("ws/int-epilogue", w5)):
+                  dws = a != wv
+                  if dws.any():
+                      bad += 1
+                      idx = np.argwhere(dws)
+                      print("   %s kernel differs from dp4a: %d / %d  first %s direct %s ws %s" % (nm, dws.sum(), dws.size, idx[:4].tolist(), a[dws][:6].tolist(), wv[dws][:6].tolist()))
+                      print("      ch%%16:", np.bincount(idx[:, 3] % 16, minlength=16).tolist(), " x:", np.bincount(idx[:, 2], minlength=ow).tolist())
+                      print("      y:", np.bincount(idx[:, 1], minlength=oh).tolist(), " n:", np.bincount(idx[:, 0], minlength=n).tolist())
               diff = a != b
               print("layer %d cin %3d cout %3d pool %d shape %s: mismatches %d / %d" % (l, cin, cout, pool, (n, h, w), diff.sum(), diff.size), flush=True)
               if diff.any():

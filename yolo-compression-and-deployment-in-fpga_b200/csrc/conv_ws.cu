@@ -1,0 +1,463 @@
+// conv_ws.cu — weight-stationary 3x3/stride-1/pad-1 int8 NHWC convolution on the 5th-generation tensor cores.
+//
+// Replaces second_conv/conv_normal/conv_last (c_embedding/yolo_forward.c:420,575,772) for every layer whose packed
+// weights fit in shared memory (slim_yolo_v2: conv2 .. conv4_2 and pred).  Where the C driver re-sends the 3x3 weights
+// and a haloed 18x22 input tile to the FPGA for every 16x20 output tile (load_weight/psram_to_inpBuf,
+// yolo_forward.c:125-173), this kernel keeps the WHOLE layer's weights resident in shared memory for the life of a
+// persistent CTA and fetches each input pixel from L2/HBM once per tile:
+//
+//   * B (weights): the host packs them once at load into the UMMA no-swizzle K-major core-matrix image
+//     [N/8][K/16][8 rows][16 B]; one 1-D bulk copy brings it in at kernel start.
+//   * A (activations): the haloed input tile is written ONCE per tile as 16-byte channel planes
+//     [Cin/16][halo pixel][16 B] by cp.async (zero-filled outside the image = the convolution's zero padding).  In this
+//     layout the 8 rows of a core matrix are 8 x-adjacent pixels and moving the window by one pixel moves the start
+//     address by 16 bytes, so each of the 9 taps is just a different descriptor start address into the same tile: no
+//     im2col copy and no re-fetch per tap (the tap-per-TMA-box kernel in conv_umma.cu is bound by the TMA request rate).
+//   * images are stacked vertically into one tall canvas separated by `gut` zero rows, so 16-row tiles waste no rows on
+//     small maps; a gutter row serves as the bottom padding of one image and the top padding of the next.
+//   * pooled layers (PHASE): the tile is 16 x 32 pre-pool pixels held as four accumulators, one per position (dy,dx) of
+//     the 2x2 window (the planes are split by x parity so that each accumulator's rows are contiguous again), so TMEM
+//     lane i of the four accumulators holds the four members of pooled pixel i and the max-pool happens in registers.
+//     Requantisation is monotone, so max-then-requantise == requantise-then-max (slim_yolo_v2.py:229-231).
+//
+// Warp roles (544 threads): warp 0 = TMEM allocator + MMA issuer (one lane), warps 1-8 = cp.async producers (one halo
+// row per warp at a time), warps 9-16 = epilogue (two warps per TMEM lane quarter, each half of the columns).
+// Everything about a tile's MMAs except the stage and the accumulator buffer is tile-invariant, so the shared-memory
+// descriptors are built once per CTA into a table; the issuing lane only loads and fires them.
+#include "kernels.h"
+#include "ptx.cuh"
+#include "epilogue.cuh"
+#include <climits>
+
+namespace yb {
+
+constexpr int WS_PROD_WARPS = 8;
+constexpr int WS_PROD_THREADS = WS_PROD_WARPS * 32;
+constexpr int WS_EPI_WARPS = 8;
+constexpr int WS_EPI_THREADS = WS_EPI_WARPS * 32;
+constexpr int WS_THREADS = 32 + WS_PROD_THREADS + WS_EPI_THREADS;
+constexpr int WS_MAX_STAGES = 4;
+
+struct WsParams {
+    const int8_t *in;
+    int n_img, H, W, cs_in;
+    int period;                  // H + gut: canvas rows per image
+    unsigned period_magic;       // ceil(2^32 / period)
+    int canvas_rows;             // n_img * period
+    int tiles_x, num_tiles;
+    int N;                       // GEMM N = cs_out
+    int cs_out;
+    int nplanes;                 // cs_in / 16 (power of two)
+    int nplanes_log2;
+    int kc;                      // 16-byte K chunks per output channel in the weight image
+    uint32_t plane_stride;       // bytes between 16-byte channel planes of a stage (x2 parities when PHASE)
+    uint32_t stage_bytes;
+    int stages;
+    uint32_t w_bytes;
+    uint32_t off_stage, off_bias, off_bar, off_tab;
+    int nmma;                    // MMAs per accumulator per tile
+    uint32_t tmem_cols, tmem_buf_stride;
+    int OH, OW;                  // output map (pooled when q.pool)
+    LayerQ q;
+    EpiConst k;
+    const uint8_t *wimg;
+    const int *bias_sh;
+    int8_t *out;
+    unsigned *ovf;
+};
+
+// tile geometry
+//   !PHASE: 8 x 16 pixels; halo 10 x 18, plane = [18][10] pixels, tap (kh,kw) -> +(kh*10+kw) pixels, row group stride 10
+//    PHASE: 16 x 32 pre-pool pixels; halo 18 x 34, planes split by x parity: [par][34][9], accumulator (dy,dx) and tap
+//           (kh,kw) -> parity (dx+kw)&1, +((dy+kh)*9 + ((dx+kw)>>1)) pixels, row group stride 2*9
+template <bool PHASE> struct WsGeom {
+    static constexpr int TW = PHASE ? 16 : 8, TH = PHASE ? 32 : 16;
+    static constexpr int HW = TW + 2, HH = TH + 2;
+    static constexpr int PITCH = PHASE ? 9 : 10;
+    static constexpr int PIX = HW * HH;                       // halo pixels per 16-byte channel chunk
+    static constexpr int NACC = PHASE ? 4 : 1;
+    static constexpr uint32_t SBO = PHASE ? 2u * 9u * 16u : 10u * 16u;
+};
+
+template <bool PHASE, int EPI, bool ACT>
+__device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t taddr, int cbeg, int cend, int lane, int q4,
+                                                 int tx0, int ty0, const int *s_bias, uint32_t bar_tempty, unsigned &ovf)
+{
+    const int r = q4 * 32 + lane;
+    const int g = r >> 3, xl = r & 7;
+    if (PHASE) {
+        // row r = pooled pixel (ty0/2 + g, tx0/2 + xl); its four members are lane r of the four accumulators
+        const int cy = ty0 + 2 * g;                            // canvas row of the window's top row (even)
+        const int n = (int)__umulhi((unsigned)cy, p.period_magic);
+        const int y = cy - n * p.period;
+        const int oy = y >> 1, ox = (tx0 >> 1) + xl;
+        const bool valid = cy < p.canvas_rows && oy < p.OH && ox < p.OW;
+        int8_t *dst = p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.cs_out;
+        const uint32_t accs = (uint32_t)p.N;                   // column stride between the four accumulators
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+            int v0[16], v1[16], v2[16], v3[16];
+            tmem_ld16(taddr + c0, v0);
+            tmem_ld16(taddr + accs + c0, v1);
+            tmem_ld16(taddr + 2 * accs + c0, v2);
+            tmem_ld16(taddr + 3 * accs + c0, v3);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v0[j] = max(max(v0[j], v1[j]), max(v2[j], v3[j]));
+            const uint4 w = requant16<EPI, ACT>(v0, s_bias, c0, p, ovf, valid);
+            if (valid) *reinterpret_cast<uint4 *>(dst + c0) = w;
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty);
+    } else {
+        const int cy = ty0 + g, x = tx0 + xl;
+        const int n = (int)__umulhi((unsigned)cy, p.period_magic);
+        const int y = cy - n * p.period;
+        const bool inside = cy < p.canvas_rows && y < p.H && x < p.W;
+        if (!p.q.pool) {
+            int8_t *dst = p.out + (((size_t)n * p.H + y) * p.W + x) * p.cs_out;
+            // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is requantised
+            int va[16], vb[16];
+            if (cbeg < cend) tmem_ld16(taddr + cbeg, va);
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                tmem_ld_wait();
+                if (c0 + 16 < cend) tmem_ld16(taddr + c0 + 16, vb);
+                uint4 w = requant16<EPI, ACT>(va, s_bias, c0, p, ovf, inside);
+                if (inside) *reinterpret_cast<uint4 *>(dst + c0) = w;
+                if (c0 + 16 < cend) {
+                    tmem_ld_wait();
+                    if (c0 + 32 < cend) tmem_ld16(taddr + c0 + 32, va);
+                    w = requant16<EPI, ACT>(vb, s_bias, c0 + 16, p, ovf, inside);
+                    if (inside) *reinterpret_cast<uint4 *>(dst + c0 + 16) = w;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty);
+        } else {
+            // pooled layer on the un-phased tile (weights + phased tile do not fit): the 2x2 window of a pixel is lanes
+            // {l, l^1, l^8, l^9} of this warp.  Max the raw accumulators with two shuffles, then every lane requantises
+            // and stores its own quarter (4 channels) of each 16-channel chunk.
+            const int oy = y >> 1, ox = x >> 1;
+            const bool valid = inside && oy < p.OH && ox < p.OW;       // all four lanes of a window agree
+            const int role = (xl & 1) | ((g & 1) << 1);
+            int8_t *dst = p.out + (((size_t)n * p.OH + oy) * p.OW + ox) * p.cs_out + 4 * role;
+            for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                int v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                    v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+                }
+                int mine[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    mine[j] = role == 0 ? v[j] : role == 1 ? v[4 + j] : role == 2 ? v[8 + j] : v[12 + j];
+                const unsigned w = requant4<EPI, ACT>(mine, s_bias, c0 + 4 * role, p, ovf, valid);
+                if (valid) *reinterpret_cast<unsigned *>(dst + c0) = w;
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty);
+        }
+    }
+}
+
+template <bool PHASE, int EPI>
+__global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParams p)
+{
+    using G = WsGeom<PHASE>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t wsm = base;                                           // resident weight image
+    const uint32_t stage0 = base + p.off_stage;
+    int *s_bias = reinterpret_cast<int *>(base_ptr + p.off_bias);
+    const uint32_t bar0 = base + p.off_bar;
+    // barrier layout: full[MAX], empty[MAX], tmem_full[2], tmem_empty[2], weights, then the TMEM address slot
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (WS_MAX_STAGES + s); };
+    auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * WS_MAX_STAGES + b); };
+    auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * WS_MAX_STAGES + 2 + b); };
+    const uint32_t bar_w = bar0 + 8u * (2 * WS_MAX_STAGES + 4);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * WS_MAX_STAGES + 5);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * WS_MAX_STAGES + 5));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(bar_full(s), WS_PROD_THREADS); mbar_init(bar_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), WS_EPI_THREADS); }
+        mbar_init(bar_w, 1);
+        fence_barrier_init();
+        // the whole layer's weights, once
+        mbar_expect_tx(bar_w, p.w_bytes);
+        for (uint32_t o = 0; o < p.w_bytes; o += 32768u) {
+            const uint32_t n = p.w_bytes - o < 32768u ? p.w_bytes - o : 32768u;
+            bulk_load_1d(wsm + o, p.wimg + o, n, bar_w);
+        }
+    }
+    if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+        const int b = p.bias_sh[i];
+        s_bias[i] = EPI == EPI_F_RNE ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
+    }
+    // descriptor tables: tab_b[acc][m] (weights), tab_a[stage][acc][m] (A operand: stage base + channel plane + tap offset)
+    const int per_stage = G::NACC * p.nmma;
+    uint64_t *tab_b = reinterpret_cast<uint64_t *>(base_ptr + p.off_tab);
+    uint64_t *tab_a = tab_b + per_stage;
+    {
+        const uint32_t b_sbo = (uint32_t)p.kc * 128u;
+        for (int i = threadIdx.x; i < (p.stages + 1) * per_stage; i += blockDim.x) {
+            const int st = i / per_stage - 1, r = i % per_stage;      // st == -1: the B table
+            const int acc = r / p.nmma, m = r - acc * p.nmma;
+            const int dy = acc >> 1, dx = acc & 1;
+            // byte offset of tap (kh,kw) for this accumulator inside a channel plane
+            auto tap_off = [&](int tap) -> uint32_t {
+                const int kh = tap / 3, kw = tap - 3 * kh;
+                if (PHASE) return (uint32_t)(((dx + kw) & 1) * (int)(p.plane_stride >> 1) + ((dy + kh) * G::PITCH + ((dx + kw) >> 1)) * 16);
+                return (uint32_t)((kh * G::PITCH + kw) * 16);
+            };
+            const uint32_t sa = stage0 + (uint32_t)(st < 0 ? 0 : st) * p.stage_bytes;
+            uint64_t ad, bd;
+            if (p.nplanes == 1) {
+                // 16 input channels: one MMA (K = 32) spans two taps; its two 16-byte K halves are the same plane at two
+                // tap offsets (LBO = their distance).  Tap 9 has zero weights; its A half reads tap 8 + 16 B.
+                uint32_t o0 = tap_off(2 * m);
+                uint32_t o1 = m < 4 ? tap_off(2 * m + 1) : o0 + 16u;
+                uint32_t bchunk = (uint32_t)(2 * m);
+                // descriptors hold unsigned strides: when the second tap sits at the lower address (parity-split tile),
+                // start from it and use the copy of the weights whose K halves are swapped (chunks 10..19)
+                if (o1 < o0) { const uint32_t t = o0; o0 = o1; o1 = t; bchunk += 10u; }
+                ad = make_desc(sa + o0, o1 - o0, G::SBO, 0);
+                bd = make_desc(wsm + bchunk * 128u, 128u, b_sbo, 0);
+            } else {
+                const int half = p.nplanes >> 1;
+                const int tap = m / half, c2 = m - tap * half;
+                ad = make_desc(sa + (uint32_t)(2 * c2) * p.plane_stride + tap_off(tap), p.plane_stride, G::SBO, 0);
+                bd = make_desc(wsm + (uint32_t)(tap * p.nplanes + 2 * c2) * 128u, 128u, b_sbo, 0);
+            }
+            if (st < 0) tab_b[r] = bd; else tab_a[(size_t)st * per_stage + r] = ad;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+            mbar_wait(bar_w, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(bar_tempty(buf), bph ^ 1u);             // epilogue has drained this accumulator buffer
+                mbar_wait(bar_full(s), ph);                       // the haloed tile is in shared memory
+                tc_fence_after();
+                const uint64_t *ta = tab_a + (size_t)s * per_stage;
+                const uint64_t *tb = tab_b;
+                uint32_t d = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
+#pragma unroll 1
+                for (int acc = 0; acc < G::NACC; ++acc, d += (uint32_t)p.N, ta += p.nmma, tb += p.nmma) {
+                    umma_i8(d, ta[0], tb[0], idesc, 0u);
+#pragma unroll 4
+                    for (int m = 1; m < p.nmma; ++m) umma_i8(d, ta[m], tb[m], idesc, 1u);
+                }
+                umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
+                umma_commit(bar_tfull(buf));                       // accumulators complete
+            }
+        }
+    } else if (warp <= WS_PROD_WARPS) {
+        // ===================== cp.async producers =====================
+        // One halo row per warp at a time.  Along a row the 16-byte pieces are contiguous in global memory in the order
+        // (pixel, channel chunk), so piece qr of the row lives at row_src + 16*qr; only the shared-memory side scatters
+        // (channel chunk -> plane, and pixel parity -> half-plane when PHASE).
+        const int pw = warp - 1;
+        const int row_pieces = G::HW << p.nplanes_log2;
+        const int lag = p.stages >= 3 ? p.stages - 2 : 1;          // tiles in flight per thread before their arrival is signalled
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+            const int tx0 = tx * G::TW, ty0 = ty * G::TH;
+            mbar_wait(bar_empty(s), ph ^ 1u);
+            const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
+#pragma unroll 2
+            for (int hy = pw; hy < G::HH; hy += WS_PROD_WARPS) {
+                const int cy = ty0 - 1 + hy;
+                const int n = (int)__umulhi((unsigned)max(cy, 0), p.period_magic);
+                const int y = cy - n * p.period;
+                const bool rowok = cy >= 0 && cy < p.canvas_rows && y < p.H;
+                const int8_t *row_src = p.in + (((long long)n * p.H + y) * p.W + (tx0 - 1)) * (long long)p.cs_in;
+                const uint32_t row_dst = sa + (uint32_t)(hy * G::PITCH) * 16u;
+                for (int qr = lane; qr < row_pieces; qr += 32) {
+                    const int hx = qr >> p.nplanes_log2, c = qr & (p.nplanes - 1);
+                    const bool ok = rowok && (unsigned)(tx0 - 1 + hx) < (unsigned)p.W;
+                    uint32_t dst = row_dst + (uint32_t)c * p.plane_stride;
+                    if (PHASE) dst += (uint32_t)(hx & 1) * (p.plane_stride >> 1) + (uint32_t)(hx >> 1) * 16u;
+                    else dst += (uint32_t)hx * 16u;
+                    cp_async16(dst, ok ? row_src + 16 * qr : p.in, ok ? 16u : 0u);
+                }
+            }
+            cp_async_commit();
+            if (it >= lag) {
+                if (lag == 1) cp_async_wait<1>(); else cp_async_wait<2>();
+                fence_proxy_async();
+                mbar_arrive(bar_full((it - lag) % p.stages));
+            }
+        }
+        // drain: the last `lag` tiles
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int j = max(it - lag, 0); j < it; ++j) mbar_arrive(bar_full(j % p.stages));
+    } else {
+        // ===================== epilogue warps =====================
+        const int ew = warp - (1 + WS_PROD_WARPS);
+        const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int cmid = ((p.N / 16 + 1) / 2) * 16;                // column split between the two warps of a quarter
+        const int cbeg = ew < 4 ? 0 : cmid, cend = ew < 4 ? cmid : p.N;
+        unsigned ovf = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+            const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+            const int tx0 = tx * G::TW, ty0 = ty * G::TH;
+            mbar_wait(bar_tfull(buf), bph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)buf * p.tmem_buf_stride + ((uint32_t)(q4 * 32) << 16);
+            if (p.q.activ) ws_epilogue_tile<PHASE, EPI, true>(p, taddr, cbeg, cend, lane, q4, tx0, ty0, s_bias, bar_tempty(buf), ovf);
+            else ws_epilogue_tile<PHASE, EPI, false>(p, taddr, cbeg, cend, lane, q4, tx0, ty0, s_bias, bar_tempty(buf), ovf);
+        }
+        if (p.q.contract == CONTRACT_P) {
+            ovf = __reduce_add_sync(0xffffffffu, ovf);
+            if (lane == 0 && ovf) atomicAdd(p.ovf, ovf);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// Shared-memory plan; returns false when the layer does not fit this kernel.
+static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p)
+{
+    const int nplanes = a.cs_in / 16;
+    const int pix = phase ? WsGeom<true>::PIX : WsGeom<false>::PIX;
+    const int nacc = phase ? 4 : 1;
+    // pad the plane stride so that the 8 lanes of a cp.async wavefront hit 8 different 16-byte bank groups
+    int want = nplanes >= 8 ? 1 : 8 / nplanes;                           // plane stride in 16-B units, mod 8
+    uint32_t plane_px;
+    if (phase) {
+        // two parity half-planes per channel chunk; each half is [34][9] pixels (+2 pixels of slack for the zero tap);
+        // the stride must stay even so that a half-plane starts on a 16-byte boundary
+        if (want & 1) want = 2;
+        plane_px = 2u * (uint32_t)(WsGeom<true>::HH * WsGeom<true>::PITCH + 2);
+        while ((int)(plane_px % 8) != want % 8) plane_px += 2;
+    } else {
+        plane_px = (uint32_t)pix + 2;
+        while ((int)(plane_px % 8) != want % 8) ++plane_px;
+    }
+    p->plane_stride = plane_px * 16u;
+    p->nplanes = nplanes; p->nplanes_log2 = ilog2(nplanes);
+    p->kc = nplanes == 1 ? 20 : 9 * nplanes;                             // must match the image packed in yolo_b200_load
+    p->N = a.cs_out; p->cs_out = a.cs_out;
+    p->w_bytes = (uint32_t)p->N * (uint32_t)p->kc * 16u;
+    p->stage_bytes = ((uint32_t)nplanes * p->plane_stride + 127u) & ~127u;
+    uint32_t nb = 32; while (nb < (uint32_t)(nacc * p->N)) nb <<= 1;
+    if (2 * nb > 512) return false;
+    p->tmem_buf_stride = nb; p->tmem_cols = 2 * nb;
+    p->nmma = nplanes == 1 ? 5 : 9 * (nplanes / 2);
+    const uint32_t tab_bytes = (uint32_t)(WS_MAX_STAGES + 1) * (uint32_t)(nacc * p->nmma) * 8u;
+    const uint32_t fixed = ((p->w_bytes + 127u) & ~127u) + (uint32_t)p->N * 4u + 256u + tab_bytes + 128u /*alignment slack*/;
+    const uint32_t budget = 227u * 1024u;
+    if (fixed + 2 * p->stage_bytes > budget) return false;
+    int stages = (int)((budget - fixed) / p->stage_bytes);
+    if (stages > WS_MAX_STAGES) stages = WS_MAX_STAGES;
+    p->stages = stages;
+    p->off_stage = (p->w_bytes + 127u) & ~127u;
+    p->off_bias = p->off_stage + (uint32_t)stages * p->stage_bytes;
+    p->off_bar = (p->off_bias + (uint32_t)p->N * 4u + 15u) & ~15u;
+    p->off_tab = p->off_bar + 256u;
+    return true;
+}
+
+static bool ws_shape_ok(const ConvArgs &a)
+{
+    if (!a.wimg) return false;
+    const int np = a.cs_in / 16;
+    if (a.cs_in < 16 || a.cs_in % 16 || (np & (np - 1)) || np > 16) return false;
+    if (a.cs_out < 16 || a.cs_out > 256 || a.cs_out % 16) return false;
+    if (a.q.pool && (a.H < 2 || a.W < 2)) return false;
+    if ((long long)a.n * (a.H + 2) * (a.H + 2) >= (1ll << 32)) return false;   // exactness range of the multiply-high division by H + gut
+    return true;
+}
+
+bool conv3x3_ws_supported(const ConvArgs &a)
+{
+    if (!ws_shape_ok(a)) return false;
+    WsParams p;
+    return ws_plan(a, false, &p) || (a.q.pool && ws_plan(a, true, &p));
+}
+
+template <bool PHASE, int EPI>
+static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
+{
+    using G = WsGeom<PHASE>;
+    const int gut = a.q.pool ? ((a.H & 1) ? 1 : 2) : 1;                  // pooled: image origins stay on even canvas rows
+    p.in = a.in; p.n_img = a.n; p.H = a.H; p.W = a.W; p.cs_in = a.cs_in;
+    p.period = a.H + gut;
+    p.period_magic = (unsigned)(((1ull << 32) + (unsigned)p.period - 1) / (unsigned)p.period);
+    p.canvas_rows = a.n * p.period;
+    p.tiles_x = (a.W + G::TW - 1) / G::TW;
+    p.num_tiles = p.tiles_x * ((p.canvas_rows + G::TH - 1) / G::TH);
+    p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
+    p.q = a.q; p.wimg = a.wimg; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
+    const uint32_t smem_bytes = p.off_tab + (uint32_t)(p.stages + 1) * (uint32_t)(G::NACC * p.nmma) * 8u + 128u;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    conv3x3_ws_kernel<PHASE, EPI><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <bool PHASE>
+static cudaError_t launch_ws_epi(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
+{
+    switch (epi_mode_for(a, &p.k)) {
+    case EPI_F_RNE: return launch_ws<PHASE, EPI_F_RNE>(a, p, st, sm_count);
+    case EPI_P:     return launch_ws<PHASE, EPI_P>(a, p, st, sm_count);
+    default:        return launch_ws<PHASE, EPI_GENERIC>(a, p, st, sm_count);
+    }
+}
+
+cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count)
+{
+    if (a.n == 0) return cudaSuccess;
+    if (!ws_shape_ok(a)) return cudaErrorInvalidValue;
+    WsParams p;
+    memset(&p, 0, sizeof p);
+    if (a.q.pool && ws_plan(a, true, &p)) return launch_ws_epi<true>(a, p, st, sm_count);
+    memset(&p, 0, sizeof p);
+    if (ws_plan(a, false, &p)) return launch_ws_epi<false>(a, p, st, sm_count);
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace yb

@@ -12,6 +12,7 @@ struct ConvArgs {
     int n, H, W, cs_in;
     const int8_t *wgt;     // [cout_pad][9][cs_in]  (cout_pad: multiple of 32, zero padded)
     const int8_t *wgt_k160; // cs_in == 16 only: [cout_pad][10][16], 10th tap all zero (two taps per K=32 MMA)
+    const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
     int w_rows;            // cout_pad
     int bias_abs_max;      // max |bias_sh[c]| (decides whether the exact fp32 epilogue applies)
     int force_generic_epilogue;   // tests: run the integer epilogue even where the fp32 one applies
@@ -29,6 +30,10 @@ cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
 bool conv3x3_umma_supported(const ConvArgs &a);
 cudaError_t conv3x3_umma(const ConvArgs &a, cudaStream_t st, int sm_count);
 cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_t *out, int *epi_used, cudaStream_t st);
+
+// conv_ws.cu (weight-stationary tcgen05 kernel: weights resident in shared memory, haloed tile fetched once)
+bool conv3x3_ws_supported(const ConvArgs &a);
+cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // quantize.cu
 cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st);

@@ -30,6 +30,7 @@ struct LayerDev {
     LayerQ q;
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
+    uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
     size_t out_cap = 0;
@@ -121,7 +122,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.bias_sh); cudaFree(l.out); }
+    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.bias_sh); cudaFree(l.out); }
     c->layers.clear();
 }
 
@@ -252,6 +253,24 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
             CU(cudaMalloc(&d.w_k160, wk.size()));
             CU(cudaMemcpy(d.w_k160, wk.data(), wk.size(), cudaMemcpyHostToDevice));
         }
+        if (d.cs_in >= 16) {
+            // conv_ws.cu: B operand as UMMA no-swizzle K-major core matrices, [n/8][kchunk][n%8][16 B].  K chunk order is
+            // tap-major (chunk = tap * cs_in/16 + c).  16-channel layers pair two taps per K = 32 MMA and carry a zero
+            // 10th tap; chunks 10..19 repeat the pairs with their halves swapped (for tap pairs whose second half lies
+            // at the lower shared-memory address in the parity-split tile).
+            const int np = d.cs_in / 16, kc = np == 1 ? 20 : 9 * np;
+            std::vector<uint8_t> img((size_t)d.cs_out * kc * 16, 0);
+            for (int o = 0; o < d.cs_out; ++o)
+                for (int k = 0; k < kc; ++k) {
+                    int tap, c;
+                    if (np == 1) { int kk = k < 10 ? k : ((k - 10) ^ 1); tap = kk; c = 0; }
+                    else { tap = k / np; c = k % np; }
+                    if (tap >= 9) continue;
+                    memcpy(&img[(((size_t)(o / 8) * kc + k) * 8 + (o % 8)) * 16], &wp[((size_t)o * 9 + tap) * d.cs_in + 16 * c], 16);
+                }
+            CU(cudaMalloc(&d.wimg, img.size()));
+            CU(cudaMemcpy(d.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&d.bias_sh, bsh.size() * sizeof(int)));
         CU(cudaMemcpy(d.bias_sh, bsh.data(), bsh.size() * sizeof(int), cudaMemcpyHostToDevice));
         c->layers.push_back(d);
@@ -266,7 +285,7 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
 int yolo_b200_set_conv_backend(yolo_b200_ctx *c, int backend)
 {
     if (!c) return fail(E_ARG, "null ctx");
-    if (backend < 0 || backend > 3) return fail(E_ARG, "backend %d", backend);
+    if (backend < 0 || backend > 5) return fail(E_ARG, "backend %d", backend);
     c->conv_backend = backend;
     return 0;
 }
@@ -339,12 +358,18 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     ConvArgs a;
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
-    a.force_generic_epilogue = c->conv_backend == 3;
+    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
     const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
     const bool umma_ok = aligned && conv3x3_umma_supported(a);
-    if (c->conv_backend >= 2 && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
-    if (umma_ok && c->conv_backend != 1) CU(conv3x3_umma(a, c->stream, c->sm_count));
+    const bool ws_ok = aligned && conv3x3_ws_supported(a);
+    const int be = c->conv_backend;
+    if ((be == 2 || be == 3) && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
+    if ((be == 4 || be == 5) && !ws_ok) return fail(E_UNSUPPORTED, "layer %d does not fit the weight-stationary kernel (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
+    if (be == 1) CU(conv3x3_direct(a, c->stream));
+    else if (be == 2 || be == 3) CU(conv3x3_umma(a, c->stream, c->sm_count));
+    else if (be == 4 || be == 5 || ws_ok) CU(conv3x3_ws(a, c->stream, c->sm_count));
+    else if (umma_ok) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else CU(conv3x3_direct(a, c->stream));
     c->launches++;
     return 0;
