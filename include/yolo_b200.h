@@ -186,7 +186,8 @@ int yolo_b200_conv_layer(yolo_b200_ctx *ctx, int layer, const int8_t *d_in, int 
 
 /* Test hook: apply layer l's epilogue arithmetic (bias add, shifts, saturation, leaky-ReLU; no pool) to `count`
  * caller-supplied int32 accumulators; element i uses the bias of channel i % cout.  Returns which implementation
- * ran: 0 = integer, 1 = exact-fp32 contract F, 2 = exact-fp32 contract P (or < 0 on error). */
+ * ran: 0 = integer, 1 = exact-fp32 contract F, 2 = exact-fp32 contract P, 3 = as 1 without the (provably redundant)
+ * upper 16-bit clamp (or < 0 on error). */
 int yolo_b200_debug_requant(yolo_b200_ctx *ctx, int layer, const int32_t *d_acc, size_t count, int8_t *d_out,
                             int force_generic);
 

@@ -90,7 +90,7 @@ __device__ __forceinline__ int store8(int o, unsigned &ovf)
 // the RNE shift of the contracts.  Every step below is monotone in acc, so values outside the exact range can only
 // end at a saturation bound, where they belong.  The host enables these paths only when the exponents keep every
 // NON-saturating value exactly representable (see epi_mode_for in conv_umma.cu); otherwise the integer requant() runs.
-enum { EPI_GENERIC = 0, EPI_F_RNE = 1, EPI_P = 2 };
+enum { EPI_GENERIC = 0, EPI_F_RNE = 1, EPI_P = 2, EPI_F_RNE_NOHI = 3 };
 #define YB_MAGIC 12582912.0f            /* 1.5 * 2^23 = 0x4B400000: low byte 0, so (bits & 0xff) is the int8 result */
 
 struct EpiConst {

@@ -159,7 +159,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
         const int b = p.bias_sh[i];
-        s_bias[i] = EPI == EPI_F_RNE ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
+        s_bias[i] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
     }
     tc_fence_before();
     __syncthreads();
@@ -396,24 +396,27 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
 }
 
 // ---- debug / property-test hook: the epilogue arithmetic alone on caller-supplied accumulators -------------------
+// Runs the SAME requant4v the convolution epilogues run, four consecutive elements per thread.
 template <int EPI>
 __global__ void requant_probe_kernel(const int *__restrict__ acc, size_t count, int cout, const int *__restrict__ bias_sh,
                                      UmmaParams p, int8_t *__restrict__ out)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const int c = (int)(i % (size_t)cout);
-    const int b = bias_sh[c];
-    unsigned ovf = 0, bits;
-    if (EPI == EPI_F_RNE) {
-        const float fb = (float)b;
-        bits = p.q.activ ? requant_f_rne<true>(acc[i], fb, p.k) : requant_f_rne<false>(acc[i], fb, p.k);
-    } else if (EPI == EPI_P) {
-        bits = p.q.activ ? requant_p<true>(acc[i], b, p.k, ovf, true) : requant_p<false>(acc[i], b, p.k, ovf, true);
-    } else {
-        bits = (unsigned)store8(requant(acc[i], b, p.q), ovf);
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= count) return;
+    int a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const size_t i = i0 + j < count ? i0 + j : count - 1;
+        a[j] = acc[i];
+        const int bb = bias_sh[(int)(i % (size_t)cout)];
+        b[j] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)bb) : bb;
     }
-    out[i] = (int8_t)(bits & 0xff);
+    unsigned ovf = 0;
+    const unsigned w = p.q.activ ? requant4v<EPI, true>(a, make_int4(b[0], b[1], b[2], b[3]), p, ovf, true)
+                                 : requant4v<EPI, false>(a, make_int4(b[0], b[1], b[2], b[3]), p, ovf, true);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (i0 + j < count) out[i0 + j] = (int8_t)((w >> (8 * j)) & 0xff);
 }
 
 cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_t *out, int *epi_used, cudaStream_t st)
@@ -424,8 +427,9 @@ cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_
     const int epi = epi_mode_for(a, &p.k);
     if (epi_used) *epi_used = epi;
     if (count == 0) return cudaSuccess;
-    const int blocks = (int)((count + 255) / 256);
+    const int blocks = (int)((count + 1023) / 1024);
     if (epi == EPI_F_RNE) requant_probe_kernel<EPI_F_RNE><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
+    else if (epi == EPI_F_RNE_NOHI) requant_probe_kernel<EPI_F_RNE_NOHI><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
     else if (epi == EPI_P) requant_probe_kernel<EPI_P><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
     else requant_probe_kernel<EPI_GENERIC><<<blocks, 256, 0, st>>>(acc, count, a.cout, a.bias_sh, p, out);
     return cudaGetLastError();
@@ -437,6 +441,7 @@ static cudaError_t launch_epi(const ConvArgs &a, cudaStream_t st, int sm_count)
     EpiConst kc;
     switch (epi_mode_for(a, &kc)) {
     case EPI_F_RNE: return launch_umma<CB, EPI_F_RNE>(a, st, sm_count, kc);
+    case EPI_F_RNE_NOHI: return launch_umma<CB, EPI_F_RNE_NOHI>(a, st, sm_count, kc);
     case EPI_P:     return launch_umma<CB, EPI_P>(a, st, sm_count, kc);
     default:        return launch_umma<CB, EPI_GENERIC>(a, st, sm_count, kc);
     }

@@ -45,6 +45,7 @@ struct WsParams {
     unsigned period_magic;       // ceil(2^32 / period)
     int canvas_rows;             // n_img * period
     int tiles_x, num_tiles;
+    int step_x, step_y;          // gridDim.x % tiles_x, gridDim.x / tiles_x: tile coordinates advance without divisions
     int N;                       // GEMM N = cs_out
     int cs_out;
     int nplanes;                 // cs_in / 16 (power of two)
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
         const int b = p.bias_sh[i];
-        s_bias[i] = EPI == EPI_F_RNE ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
+        s_bias[i] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
     }
     // descriptor tables: tab_b[acc][m] (weights), tab_a[stage][acc][m] (A operand: stage base + channel plane + tap offset)
     const int per_stage = G::NACC * p.nmma;
@@ -249,12 +250,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         if (lane == 0) {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
             mbar_wait(bar_w, 0);
-            int it = 0;
+            int it = 0, s = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 mbar_wait(bar_tempty(buf), bph ^ 1u);             // epilogue has drained this accumulator buffer
                 mbar_wait(bar_full(s), ph);                       // the haloed tile is in shared memory
                 tc_fence_after();
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
                 }
                 umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
                 umma_commit(bar_tfull(buf));                       // accumulators complete
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp <= WS_PROD_WARPS) {
@@ -279,11 +280,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const int pw = warp - 1;
         const int row_pieces = G::HW << p.nplanes_log2;
         const int lag = p.stages >= 3 ? p.stages - 2 : 1;          // tiles in flight per thread before their arrival is signalled
-        int it = 0;
+        int it = 0, s = 0, s_arrive = 0;
+        uint32_t ph = 0;
+        int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
             const int tx0 = tx * G::TW, ty0 = ty * G::TH;
             mbar_wait(bar_empty(s), ph ^ 1u);
             const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
@@ -308,13 +308,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             if (it >= lag) {
                 if (lag == 1) cp_async_wait<1>(); else cp_async_wait<2>();
                 fence_proxy_async();
-                mbar_arrive(bar_full((it - lag) % p.stages));
+                mbar_arrive(bar_full(s_arrive));
+                if (++s_arrive == p.stages) s_arrive = 0;
             }
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+            tx += p.step_x; ty += p.step_y;
+            if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
         }
         // drain: the last `lag` tiles
         cp_async_wait<0>();
         fence_proxy_async();
-        for (int j = max(it - lag, 0); j < it; ++j) mbar_arrive(bar_full(j % p.stages));
+        for (int j = max(it - lag, 0); j < it; ++j) {
+            mbar_arrive(bar_full(s_arrive));
+            if (++s_arrive == p.stages) s_arrive = 0;
+        }
     } else {
         // ===================== epilogue warps =====================
         const int ew = warp - (1 + WS_PROD_WARPS);
@@ -323,11 +330,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const int cbeg = ew < 4 ? 0 : cmid, cend = ew < 4 ? cmid : p.N;
         unsigned ovf = 0;
         int it = 0;
+        int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-            const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
             const int tx0 = tx * G::TW, ty0 = ty * G::TH;
+            tx += p.step_x; ty += p.step_y;
+            if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
             mbar_wait(bar_tfull(buf), bph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * p.tmem_buf_stride + ((uint32_t)(q4 * 32) << 16);
@@ -434,6 +443,7 @@ static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, in
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    p.step_x = grid % p.tiles_x; p.step_y = grid / p.tiles_x;
     conv3x3_ws_kernel<PHASE, EPI><<<grid, WS_THREADS, smem_bytes, st>>>(p);
     return cudaGetLastError();
 }
@@ -443,6 +453,7 @@ static cudaError_t launch_ws_epi(const ConvArgs &a, WsParams &p, cudaStream_t st
 {
     switch (epi_mode_for(a, &p.k)) {
     case EPI_F_RNE: return launch_ws<PHASE, EPI_F_RNE>(a, p, st, sm_count);
+    case EPI_F_RNE_NOHI: return launch_ws<PHASE, EPI_F_RNE_NOHI>(a, p, st, sm_count);
     case EPI_P:     return launch_ws<PHASE, EPI_P>(a, p, st, sm_count);
     default:        return launch_ws<PHASE, EPI_GENERIC>(a, p, st, sm_count);
     }

@@ -7,18 +7,94 @@
 
 namespace yb {
 
-// Requantise 4 accumulators of channels c..c+3 and pack them into one word.  `bias` points at the per-channel
-// words in shared memory (fp32 bias for EPI_F_RNE, int otherwise).
-template <int EPI, bool ACT, class P>
-__device__ __forceinline__ unsigned requant4(const int *acc, const int *bias, int c, const P &p, unsigned &ovf, bool count)
+// ---- packed fp32 (Blackwell f32x2 pipe) and saturating pack helpers ------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
 {
-    const int4 b = *reinterpret_cast<const int4 *>(bias + c);
-    if (EPI == EPI_F_RNE) {
-        return pack_bytes(requant_f_rne<ACT>(acc[0], __int_as_float(b.x), p.k), requant_f_rne<ACT>(acc[1], __int_as_float(b.y), p.k),
-                          requant_f_rne<ACT>(acc[2], __int_as_float(b.z), p.k), requant_f_rne<ACT>(acc[3], __int_as_float(b.w), p.k));
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// d = sat8(a) | sat8(b) << 8 | c << 16   (cvt.pack.sat: two s32 -> two saturated bytes, merged above the low half of c)
+__device__ __forceinline__ unsigned pack_sat_s8(int a, int b, unsigned c)
+{
+    unsigned d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(a), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c)
+{
+    unsigned d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(a), "r"(c));
+    return d;
+}
+#define YB_MAGIC_BITS 0x4B400000
+
+// Contract F, round-half-even, two channels at a time.  fb = (float)sh(bias).  Returns o as an integer that is
+// exact inside [-128,127] and on the correct side outside it (the pack saturates).  See requant_f_rne in common.cuh for
+// the arithmetic; HI16 = false drops the upper 16-bit clamp when the host proved it cannot change the result.
+// The LOWER 16-bit clamp always runs: it keeps every float positive, which the integer view of the result needs.
+template <bool ACT, bool HI16>
+__device__ __forceinline__ int2 requant_f_rne_x2(int a0, int a1, float2 fb, const EpiConst &k)
+{
+    const float2 magic = make_float2(YB_MAGIC, YB_MAGIC);
+    float2 v = ffma2(make_float2(__int2float_rn(a0), __int2float_rn(a1)), make_float2(k.s_in, k.s_in), magic);
+    v = fadd2(v, fb);
+    v.x = fmaxf(v.x, YB_MAGIC - 32768.f); v.y = fmaxf(v.y, YB_MAGIC - 32768.f);
+    if (HI16) { v.x = fminf(v.x, YB_MAGIC + 32767.f); v.y = fminf(v.y, YB_MAGIC + 32767.f); }
+    if (ACT) {
+        const float2 l = ffma2(v, make_float2(0.125f, 0.125f), make_float2(k.leak_add, k.leak_add));
+        v.x = fmaxf(v.x, l.x); v.y = fmaxf(v.y, l.y);
+    }
+    v = ffma2(v, make_float2(k.s_out, k.s_out), make_float2(k.out_add, k.out_add));
+    return make_int2(__float_as_int(v.x) - YB_MAGIC_BITS, __float_as_int(v.y) - YB_MAGIC_BITS);
+}
+
+// Contract P, two channels.  bp = bias << (E - sb).  Returns o + 128 (exact inside [0,255], on the correct side outside).
+template <bool ACT>
+__device__ __forceinline__ int2 requant_p_x2(int a0, int a1, int bp0, int bp1, const EpiConst &k)
+{
+    const float2 magic = make_float2(YB_MAGIC, YB_MAGIC);
+    const float2 nf = make_float2(__int2float_rn((a0 << k.la) + bp0), __int2float_rn((a1 << k.la) + bp1));
+    float2 r = ffma2(nf, make_float2(k.s_in, k.s_in), magic);
+    if (ACT) {                                                             // negatives: one RNE shift by sh+3
+        const float2 r2 = ffma2(nf, make_float2(k.s_in2, k.s_in2), magic);
+        r.x = fmaxf(r.x, r2.x); r.y = fmaxf(r.y, r2.y);
+    }
+    r.x = fmaxf(r.x, YB_MAGIC - 129.f); r.y = fmaxf(r.y, YB_MAGIC - 129.f);      // keeps the float positive; -129 still reads as saturated
+    return make_int2(__float_as_int(r.x) - (YB_MAGIC_BITS - 128), __float_as_int(r.y) - (YB_MAGIC_BITS - 128));
+}
+
+// Requantise 4 accumulators with per-channel words b (fp32 bias bits for the F fast paths, int otherwise) and pack them
+// into one word.  EPI_F_RNE_NOHI is EPI_F_RNE without the upper 16-bit clamp.
+template <int EPI, bool ACT, class P>
+__device__ __forceinline__ unsigned requant4v(const int *acc, int4 b, const P &p, unsigned &ovf, bool count)
+{
+    if (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) {
+        constexpr bool HI = EPI == EPI_F_RNE;
+        const int2 lo = requant_f_rne_x2<ACT, HI>(acc[0], acc[1], make_float2(__int_as_float(b.x), __int_as_float(b.y)), p.k);
+        const int2 hi = requant_f_rne_x2<ACT, HI>(acc[2], acc[3], make_float2(__int_as_float(b.z), __int_as_float(b.w)), p.k);
+        return pack_sat_s8(lo.x, lo.y, pack_sat_s8(hi.x, hi.y, 0u));
     } else if (EPI == EPI_P) {
-        return pack_bytes(requant_p<ACT>(acc[0], b.x, p.k, ovf, count), requant_p<ACT>(acc[1], b.y, p.k, ovf, count),
-                          requant_p<ACT>(acc[2], b.z, p.k, ovf, count), requant_p<ACT>(acc[3], b.w, p.k, ovf, count));
+        const int2 lo = requant_p_x2<ACT>(acc[0], acc[1], b.x, b.y, p.k);
+        const int2 hi = requant_p_x2<ACT>(acc[2], acc[3], b.z, b.w, p.k);
+        if (count && (unsigned)(lo.x | lo.y | hi.x | hi.y) > 255u)          // some value left [0,255] (negatives set the high bits)
+            ovf += ((unsigned)lo.x > 255u) + ((unsigned)lo.y > 255u) + ((unsigned)hi.x > 255u) + ((unsigned)hi.y > 255u);
+        return pack_sat_u8(lo.x, lo.y, pack_sat_u8(hi.x, hi.y, 0u)) ^ 0x80808080u;
     } else {
         const int bb[4] = { b.x, b.y, b.z, b.w };
         unsigned word = 0;
@@ -33,6 +109,13 @@ __device__ __forceinline__ unsigned requant4(const int *acc, const int *bias, in
     }
 }
 
+// `bias` points at the per-channel words in shared memory; c is a multiple of 4.
+template <int EPI, bool ACT, class P>
+__device__ __forceinline__ unsigned requant4(const int *acc, const int *bias, int c, const P &p, unsigned &ovf, bool count)
+{
+    return requant4v<EPI, ACT, P>(acc, *reinterpret_cast<const int4 *>(bias + c), p, ovf, count);
+}
+
 // 16 accumulators (channels c0..c0+15) -> 16 output bytes
 template <int EPI, bool ACT, class P>
 __device__ __forceinline__ uint4 requant16(const int (&v)[16], const int *bias, int c0, const P &p, unsigned &ovf, bool count)
@@ -45,6 +128,21 @@ __device__ __forceinline__ uint4 requant16(const int (&v)[16], const int *bias, 
     return w;
 }
 
+// host: exact contract-F arithmetic on one value of t (after the 16-bit clamp), used to prove clamps redundant
+static inline long long host_shr_rne(long long x, int n)
+{
+    if (n <= 0) return x;
+    long long fl = x >> n, rem = x - (fl << n), half = 1ll << (n - 1);
+    if (rem != half) return fl + (rem > half);
+    return fl + (fl & 1);
+}
+static inline long long host_f_tail(long long t, const LayerQ &q)
+{
+    if (q.activ && t < 0) t = host_shr_rne(t, 3);
+    long long o = q.odir ? t * (1ll << q.oofs) : host_shr_rne(t, q.oofs);
+    return o < -128 ? -128 : o > 127 ? 127 : o;
+}
+
 // Which epilogue may run: the fp32 paths need every non-saturating intermediate to be exactly representable.
 static inline int epi_mode_for(const ConvArgs &a, EpiConst *k)
 {
@@ -54,12 +152,13 @@ static inline int epi_mode_for(const ConvArgs &a, EpiConst *k)
     if (q.contract == CONTRACT_F && q.round_mode == ROUND_RNE) {
         const long long bmax = a.bias_abs_max;
         const bool in_ok = q.idir ? q.iofs <= 20 : (q.iofs <= 20 && ((32769LL + bmax) << q.iofs) <= (1LL << 24));
-        if (!in_ok || bmax >= (1 << 21) || q.oofs > 20) return EPI_GENERIC;
+        if (!in_ok || bmax >= (1 << 21) || q.oofs > 20 || (q.odir && q.oofs > 8)) return EPI_GENERIC;
         k->s_in = ldexpf(1.0f, q.idir ? q.iofs : -q.iofs);
         k->leak_add = YB_MAGIC * 0.875f;
         k->s_out = ldexpf(1.0f, q.odir ? q.oofs : -q.oofs);
         k->out_add = (float)((double)YB_MAGIC * (1.0 - (double)k->s_out));
-        return EPI_F_RNE;
+        // the upper 16-bit clamp is redundant when t = 32767 already saturates the output: the tail is monotone
+        return host_f_tail(32767, q) == 127 ? EPI_F_RNE_NOHI : EPI_F_RNE;
     }
     if (q.contract == CONTRACT_P) {
         if (q.sh > 13 || q.sh < -8 || q.la > 4 || a.bias_abs_max >= (1 << 28)) return EPI_GENERIC;
