@@ -197,7 +197,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp converged, one elected lane issues (keeps the descriptor arithmetic in uniform registers)
+        {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
             int it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
@@ -215,30 +216,35 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int kb0 = st * p.G, kb1 = min(kb0 + p.G, p.kblocks);
                     const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
                     const uint32_t sb = sa + (uint32_t)p.G * A_BOX;
-                    if (CB == 16) {
-                        // 16-byte channel vectors: one MMA (K = 32) covers two taps; the two 16-byte K halves are
-                        // separate core-matrix columns LBO apart (the next tap's box).  Tap 9 does not exist: its B
-                        // rows are zero (the host packs a 10th all-zero tap); its A box is whatever TMA fetched there.
-                        for (int kb = kb0; kb < kb1; kb += 2) {
-                            uint64_t ad = make_desc(sa + (uint32_t)(kb - kb0) * A_BOX, A_BOX, SBO, LAYOUT);
-                            uint64_t bd = make_desc(sb + (uint32_t)(kb - kb0) * B_BOX, B_BOX, SBO, LAYOUT);
-                            umma_i8(d, ad, bd, idesc, accum);
-                            accum = 1;
-                        }
-                    } else {
-                        for (int kb = kb0; kb < kb1; ++kb) {
-#pragma unroll
-                            for (int ks = 0; ks < CB / 32; ++ks) {
-                                uint64_t ad = make_desc(sa + (uint32_t)(kb - kb0) * A_BOX + 32u * ks, 16, SBO, LAYOUT);
-                                uint64_t bd = make_desc(sb + (uint32_t)(kb - kb0) * B_BOX + 32u * ks, 16, SBO, LAYOUT);
+                    if (elect_one()) {
+                        if (CB == 16) {
+                            // 16-byte channel vectors: one MMA (K = 32) covers two taps; the two 16-byte K halves are
+                            // separate core-matrix columns LBO apart (the next tap's box).  Tap 9 does not exist: its B
+                            // rows are zero (the host packs a 10th all-zero tap); its A box is whatever TMA fetched there.
+                            for (int kb = kb0; kb < kb1; kb += 2) {
+                                uint64_t ad = make_desc(sa + (uint32_t)(kb - kb0) * A_BOX, A_BOX, SBO, LAYOUT);
+                                uint64_t bd = make_desc(sb + (uint32_t)(kb - kb0) * B_BOX, B_BOX, SBO, LAYOUT);
                                 umma_i8(d, ad, bd, idesc, accum);
                                 accum = 1;
                             }
+                        } else {
+                            uint64_t ad = make_desc(sa, 16, SBO, LAYOUT);
+                            uint64_t bd = make_desc(sb, 16, SBO, LAYOUT);
+                            for (int kb = kb0; kb < kb1; ++kb) {
+#pragma unroll
+                                for (int ks = 0; ks < CB / 32; ++ks) {
+                                    umma_i8(d, ad + 2u * ks, bd + 2u * ks, idesc, accum);     // +32 bytes of K
+                                    accum = 1;
+                                }
+                                ad += A_BOX >> 4; bd += B_BOX >> 4;
+                            }
                         }
+                        umma_commit(bar_empty(s));                 // smem slot free once these MMAs have read it
+                        if (st == stages_per_tile - 1) umma_commit(bar_tfull(buf));   // accumulator complete
                     }
-                    umma_commit(bar_empty(s));                     // smem slot free once these MMAs have read it
+                    __syncwarp();
+                    accum = 1;
                 }
-                umma_commit(bar_tfull(buf));                       // accumulator complete
             }
         }
     } else {

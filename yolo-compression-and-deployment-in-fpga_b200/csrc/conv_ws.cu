@@ -22,8 +22,8 @@
 //
 // Warp roles (544 threads): warp 0 = TMEM allocator + MMA issuer (one lane), warps 1-8 = cp.async producers (one halo
 // row per warp at a time), warps 9-16 = epilogue (two warps per TMEM lane quarter, each half of the columns).
-// Everything about a tile's MMAs except the stage and the accumulator buffer is tile-invariant, so the shared-memory
-// descriptors are built once per CTA into a table; the issuing lane only loads and fires them.
+// The MMA warp stays converged and elects one lane per tile to issue (elect.sync): with `if (lane == 0)` the issue interval
+// is ~80-120 cycles per MMA, with an elected lane ~42 (tools/micro/umma_issue.cu), which is what the thin layers need.
 #include "kernels.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -55,8 +55,7 @@ struct WsParams {
     uint32_t stage_bytes;
     int stages;
     uint32_t w_bytes;
-    uint32_t off_stage, off_bias, off_bar, off_tab;
-    int nmma;                    // MMAs per accumulator per tile
+    uint32_t off_stage, off_bias, off_bar;
     uint32_t tmem_cols, tmem_buf_stride;
     int OH, OW;                  // output map (pooled when q.pool)
     LayerQ q;
@@ -202,44 +201,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const int b = p.bias_sh[i];
         s_bias[i] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
     }
-    // descriptor tables: tab_b[acc][m] (weights), tab_a[stage][acc][m] (A operand: stage base + channel plane + tap offset)
-    const int per_stage = G::NACC * p.nmma;
-    uint64_t *tab_b = reinterpret_cast<uint64_t *>(base_ptr + p.off_tab);
-    uint64_t *tab_a = tab_b + per_stage;
-    {
-        const uint32_t b_sbo = (uint32_t)p.kc * 128u;
-        for (int i = threadIdx.x; i < (p.stages + 1) * per_stage; i += blockDim.x) {
-            const int st = i / per_stage - 1, r = i % per_stage;      // st == -1: the B table
-            const int acc = r / p.nmma, m = r - acc * p.nmma;
-            const int dy = acc >> 1, dx = acc & 1;
-            // byte offset of tap (kh,kw) for this accumulator inside a channel plane
-            auto tap_off = [&](int tap) -> uint32_t {
-                const int kh = tap / 3, kw = tap - 3 * kh;
-                if (PHASE) return (uint32_t)(((dx + kw) & 1) * (int)(p.plane_stride >> 1) + ((dy + kh) * G::PITCH + ((dx + kw) >> 1)) * 16);
-                return (uint32_t)((kh * G::PITCH + kw) * 16);
-            };
-            const uint32_t sa = stage0 + (uint32_t)(st < 0 ? 0 : st) * p.stage_bytes;
-            uint64_t ad, bd;
-            if (p.nplanes == 1) {
-                // 16 input channels: one MMA (K = 32) spans two taps; its two 16-byte K halves are the same plane at two
-                // tap offsets (LBO = their distance).  Tap 9 has zero weights; its A half reads tap 8 + 16 B.
-                uint32_t o0 = tap_off(2 * m);
-                uint32_t o1 = m < 4 ? tap_off(2 * m + 1) : o0 + 16u;
-                uint32_t bchunk = (uint32_t)(2 * m);
-                // descriptors hold unsigned strides: when the second tap sits at the lower address (parity-split tile),
-                // start from it and use the copy of the weights whose K halves are swapped (chunks 10..19)
-                if (o1 < o0) { const uint32_t t = o0; o0 = o1; o1 = t; bchunk += 10u; }
-                ad = make_desc(sa + o0, o1 - o0, G::SBO, 0);
-                bd = make_desc(wsm + bchunk * 128u, 128u, b_sbo, 0);
-            } else {
-                const int half = p.nplanes >> 1;
-                const int tap = m / half, c2 = m - tap * half;
-                ad = make_desc(sa + (uint32_t)(2 * c2) * p.plane_stride + tap_off(tap), p.plane_stride, G::SBO, 0);
-                bd = make_desc(wsm + (uint32_t)(tap * p.nplanes + 2 * c2) * 128u, 128u, b_sbo, 0);
-            }
-            if (st < 0) tab_b[r] = bd; else tab_a[(size_t)st * per_stage + r] = ad;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -247,30 +208,68 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-            mbar_wait(bar_w, 0);
-            int it = 0, s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(bar_tempty(buf), bph ^ 1u);             // epilogue has drained this accumulator buffer
-                mbar_wait(bar_full(s), ph);                       // the haloed tile is in shared memory
-                tc_fence_after();
-                const uint64_t *ta = tab_a + (size_t)s * per_stage;
-                const uint64_t *tb = tab_b;
-                uint32_t d = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
-#pragma unroll 1
-                for (int acc = 0; acc < G::NACC; ++acc, d += (uint32_t)p.N, ta += p.nmma, tb += p.nmma) {
-                    umma_i8(d, ta[0], tb[0], idesc, 0u);
-#pragma unroll 4
-                    for (int m = 1; m < p.nmma; ++m) umma_i8(d, ta[m], tb[m], idesc, 1u);
+        // The whole warp runs the loop (converged, so the descriptor arithmetic stays in uniform registers); one elected
+        // lane issues.  Descriptor start addresses are in 16-byte units (low 14 bits of the descriptor), so moving to
+        // another tap / channel-plane pair / weight chunk is an integer add on the 64-bit descriptor.
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t b_sbo = (uint32_t)p.kc * 128u;
+        const uint32_t half16 = p.plane_stride >> 5;              // PHASE: x-parity half-plane, in 16-byte units
+        const uint32_t cstep16 = p.plane_stride >> 3;             // two channel planes = one K = 32 step
+        const int khalf = p.nplanes >> 1;
+        // tap (kh,kw) of accumulator (dy,dx): offset inside a channel plane in 16-byte units
+        auto tap16 = [&](int dy, int dx, int tap) -> uint32_t {
+            const int kh = tap / 3, kw = tap - 3 * kh;
+            if (PHASE) return (uint32_t)(((dx + kw) & 1) ? half16 : 0u) + (uint32_t)((dy + kh) * G::PITCH + ((dx + kw) >> 1));
+            return (uint32_t)(kh * G::PITCH + kw);
+        };
+        mbar_wait(bar_w, 0);
+        int it = 0, s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(bar_tempty(buf), bph ^ 1u);                 // epilogue has drained this accumulator buffer
+            mbar_wait(bar_full(s), ph);                           // the haloed tile is in shared memory
+            tc_fence_after();
+            const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
+            if (elect_one()) {
+#pragma unroll
+                for (int acc = 0; acc < G::NACC; ++acc) {
+                    const int dy = acc >> 1, dx = acc & 1;
+                    const uint32_t d = tmem_base + (uint32_t)buf * p.tmem_buf_stride + (uint32_t)acc * (uint32_t)p.N;
+                    if (p.nplanes == 1) {
+                        // 16 input channels: one MMA (K = 32) spans two taps; its two 16-byte K halves are the same plane
+                        // at two tap offsets (LBO = their distance).  Tap 9 has zero weights; its A half reads tap 8 + 16 B.
+#pragma unroll
+                        for (int m = 0; m < 5; ++m) {
+                            uint32_t o0 = tap16(dy, dx, 2 * m);
+                            uint32_t o1 = m < 4 ? tap16(dy, dx, 2 * m + 1) : o0 + 1u;
+                            uint32_t bchunk = (uint32_t)(2 * m);
+                            // descriptors hold unsigned strides: when the second tap sits at the lower address (parity-split
+                            // tile), start from it and use the copy of the weights whose K halves are swapped (chunks 10..19)
+                            if (o1 < o0) { const uint32_t t = o0; o0 = o1; o1 = t; bchunk += 10u; }
+                            const uint64_t ad = make_desc(sa + o0 * 16u, (o1 - o0) * 16u, G::SBO, 0);
+                            const uint64_t bd = make_desc(wsm + bchunk * 128u, 128u, b_sbo, 0);
+                            umma_i8(d, ad, bd, idesc, m > 0 ? 1u : 0u);
+                        }
+                    } else {
+                        const uint64_t ad0 = make_desc(sa, p.plane_stride, G::SBO, 0);
+                        uint64_t bd = make_desc(wsm, 128u, b_sbo, 0);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            uint64_t ad = ad0 + tap16(dy, dx, tap);
+                            for (int c2 = 0; c2 < khalf; ++c2) {
+                                umma_i8(d, ad, bd, idesc, (tap | c2) ? 1u : 0u);
+                                ad += cstep16; bd += 16u;           // next pair of channel planes; next 256 B of weights
+                            }
+                        }
+                    }
                 }
                 umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
                 umma_commit(bar_tfull(buf));                       // accumulators complete
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp <= WS_PROD_WARPS) {
         // ===================== cp.async producers =====================
@@ -387,9 +386,7 @@ static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p)
     uint32_t nb = 32; while (nb < (uint32_t)(nacc * p->N)) nb <<= 1;
     if (2 * nb > 512) return false;
     p->tmem_buf_stride = nb; p->tmem_cols = 2 * nb;
-    p->nmma = nplanes == 1 ? 5 : 9 * (nplanes / 2);
-    const uint32_t tab_bytes = (uint32_t)(WS_MAX_STAGES + 1) * (uint32_t)(nacc * p->nmma) * 8u;
-    const uint32_t fixed = ((p->w_bytes + 127u) & ~127u) + (uint32_t)p->N * 4u + 256u + tab_bytes + 128u /*alignment slack*/;
+    const uint32_t fixed = ((p->w_bytes + 127u) & ~127u) + (uint32_t)p->N * 4u + 256u + 128u /*alignment slack*/;
     const uint32_t budget = 227u * 1024u;
     if (fixed + 2 * p->stage_bytes > budget) return false;
     int stages = (int)((budget - fixed) / p->stage_bytes);
@@ -398,7 +395,6 @@ static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p)
     p->off_stage = (p->w_bytes + 127u) & ~127u;
     p->off_bias = p->off_stage + (uint32_t)stages * p->stage_bytes;
     p->off_bar = (p->off_bias + (uint32_t)p->N * 4u + 15u) & ~15u;
-    p->off_tab = p->off_bar + 256u;
     return true;
 }
 
@@ -433,7 +429,7 @@ static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, in
     p.num_tiles = p.tiles_x * ((p.canvas_rows + G::TH - 1) / G::TH);
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
     p.q = a.q; p.wimg = a.wimg; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
-    const uint32_t smem_bytes = p.off_tab + (uint32_t)(p.stages + 1) * (uint32_t)(G::NACC * p.nmma) * 8u + 128u;
+    const uint32_t smem_bytes = p.off_bar + 256u + 128u;
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -77,6 +77,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 }
 
 
+// One lane of a fully converged warp (elect.sync): the compiler then keeps descriptor arithmetic in uniform registers,
+// which roughly halves the tcgen05.mma issue interval compared with `if (lane == 0)` (tools/micro/umma_issue.cu).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- 1-D bulk copy global -> shared (async proxy, completes on an mbarrier) ----
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
