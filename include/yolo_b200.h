@@ -130,8 +130,8 @@ int yolo_b200_load(yolo_b200_ctx *ctx, const int8_t *const *weights, const int8_
                    const yolo_b200_params *params, int weight_layout);
 
 /* Which convolution kernels run: 0 = auto (the weight-stationary tcgen05 kernel wherever the layer's packed weights fit
- * in shared memory, the streaming tcgen05 implicit GEMM for the other tensor-core shapes, the integer dot-product
- * kernel for the 3-channel first layer), 1 = integer dot-product kernels everywhere, 2 = streaming tcgen05 kernel only
+ * in shared memory, the streaming tcgen05 implicit GEMM for the other tensor-core shapes, the warp-level integer-MMA
+ * kernel for the 3-channel first layer), 1 = integer dot-product (dp4a) kernels everywhere, 2 = streaming tcgen05 kernel only
  * (error for layers without a tensor-core shape), 3 = as 2 with the integer epilogue forced (the fp32 exact-rounding
  * epilogue is the default where the exponents allow it), 4 = weight-stationary tcgen05 kernel only, 5 = as 4 with the
  * integer epilogue forced.  All are CUDA; results are identical. */

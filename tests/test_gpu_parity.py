@@ -407,6 +407,37 @@ def test_tensor_core_layer_against_oracle(ctx, layer, backend):
             np.testing.assert_array_equal(d_out.cpu().numpy(), ref, err_msg="shape %s contract %d" % ((n, h, w), contract))
 
 
+@pytest.mark.parametrize("pool", [1, 0])
+def test_first_layer_kernel_against_oracle(ctx, pool):
+    """conv1 on the warp-level integer-MMA kernel (NHWC4 input), pooled and un-pooled, odd sizes, both contracts."""
+    import copy
+    g, qnet0, frames = gu.load("ref_p_64x96")
+    qnet = copy.deepcopy(qnet0)
+    cin, cout, activ, _ = qnet.layers[0]
+    qnet.layers[0] = (cin, cout, activ, pool)
+    rng = np.random.default_rng(7 + pool)
+    for (n, h, w) in ((2, 33, 47), (3, 16, 32), (1, 50, 70)):
+        x = np.zeros((n, h, w, 4), dtype=np.int8)
+        x[..., :3] = rng.integers(-128, 128, (n, h, w, 3), dtype=np.int8)
+        for contract in (lib.CONTRACT_F, lib.CONTRACT_P):
+            ctx.load_quantnet(qnet, contract=contract)
+            oh, ow = (h // 2, w // 2) if pool else (h, w)
+            outs = []
+            for backend in (0, 1):
+                ctx.set_conv_backend(backend)
+                try:
+                    d_out = torch.full((n, oh, ow, 16), 77, dtype=torch.int8, device="cuda")
+                    ctx.conv_layer(0, dev(x), n, h, w, d_out)
+                    ctx.sync()
+                finally:
+                    ctx.set_conv_backend(0)
+                outs.append(d_out.cpu().numpy())
+            ref, _ = ol.conv_layer(x, qnet.w[0], qnet.b[0], cin, cout, qnet.sa[0], qnet.sw[0], qnet.sb[0],
+                                   qnet.retune[0], qnet.sa[1], activ, pool, contract)
+            np.testing.assert_array_equal(outs[0], ref, err_msg="mma kernel, shape %s contract %d" % ((n, h, w), contract))
+            np.testing.assert_array_equal(outs[1], ref, err_msg="dp4a kernel, shape %s contract %d" % ((n, h, w), contract))
+
+
 def test_weight_stationary_kernel_rejects_layers_that_do_not_fit(ctx):
     g, qnet, frames = gu.load("ref_p_64x96")
     ctx.load_quantnet(qnet, contract=lib.CONTRACT_F)

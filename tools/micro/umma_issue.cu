@@ -5,12 +5,6 @@
 #include "ptx.cuh"
 using namespace yb;
 
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ void umma_i8_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
 {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
@@ -18,7 +12,7 @@ __device__ __forceinline__ void umma_i8_acc(uint32_t tmem_d, uint64_t adesc, uin
 }
 
 template <int V>
-__global__ void __launch_bounds__(128, 1) bench(int N, int nmma, long long *out, int reps, uint32_t step_a, uint32_t step_b)
+__global__ void __launch_bounds__(128, 1) bench(int N, int nmma, long long *out, int reps, uint32_t step_a, uint32_t step_b, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_layout, uint32_t a_off)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -30,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nmma, long long *out,
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tm = slot;
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t ad0 = make_desc(base, 2960, 160, 0), bd0 = make_desc(base + 96 * 1024, 128, 2304, 0);
+    const uint64_t ad0 = make_desc(base + a_off, a_lbo, a_sbo, a_layout), bd0 = make_desc(base + 96 * 1024, 128, 2304, 0);
     if (warp == 0) {
         uint32_t phase = 0;
         long long best = 1ll << 60;
@@ -73,12 +67,12 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int nmma, long long *out,
     if (warp == 0) tmem_dealloc(tm, 512);
 }
 
-template <int V> void run(const char *name, long long *d)
+template <int V> void run(const char *name, long long *d, uint32_t a_lbo = 2960, uint32_t a_sbo = 160, uint32_t a_layout = 0, uint32_t a_off = 0, uint32_t step_a = 1)
 {
     cudaFuncSetAttribute(bench<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    for (int N : {16, 32, 64, 128, 256})
-        for (int nmma : {8, 64}) {
-            bench<V><<<1, 128, 200 * 1024>>>(N, nmma, d, 20, 1, 16);
+    for (int N : {32, 64, 128, 256})
+        for (int nmma : {64}) {
+            bench<V><<<1, 128, 200 * 1024>>>(N, nmma, d, 20, step_a, 16, a_lbo, a_sbo, a_layout, a_off);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); return; }
             long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
@@ -89,9 +83,15 @@ template <int V> void run(const char *name, long long *d)
 int main()
 {
     long long *d; cudaMalloc(&d, 8);
-    run<0>("lane0 rolled   ", d);
-    run<1>("lane0 unroll8  ", d);
-    run<2>("warp elect/iter", d);
-    run<3>("warp elect once", d);
+    run<2>("noswz sbo160 lbo2960 step1 ", d, 2960, 160, 0, 0, 1);
+    run<2>("noswz sbo160 lbo2960 step0 ", d, 2960, 160, 0, 0, 0);
+    run<2>("noswz sbo128 lbo2048 step0 ", d, 2048, 128, 0, 0, 0);
+    run<2>("noswz sbo128 lbo2048 +16B  ", d, 2048, 128, 0, 16, 0);
+    run<2>("noswz sbo288 lbo9920 step1 ", d, 9920, 288, 0, 0, 1);
+    run<2>("noswz sbo256 lbo9920 step1 ", d, 9920, 256, 0, 0, 1);
+    run<2>("noswz sbo256 lbo9936 +16   ", d, 9936, 256, 0, 16, 0);
+    run<2>("noswz sbo144 lbo2320       ", d, 2320, 144, 0, 0, 1);
+    run<2>("swz128 canonical step0     ", d, 16, 1024, 2, 0, 0);
+    run<2>("swz128 canonical step2     ", d, 16, 1024, 2, 0, 2);
     return 0;
 }

@@ -162,6 +162,69 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
     }
 }
 
+// All MMAs of one tile, fully unrolled (KHALF = channel-plane pairs per tap = cs_in / 32; 0 = the 16-channel case).
+// Descriptor words: lo = start>>4 | LBO>>4 << 16, hi = SBO>>4 | version | layout.  Everything except the stage base
+// (sa16), the parity half-plane (half16) and the plane-pair step (cstep16) is a compile-time constant.
+template <bool PHASE, int KHALF>
+__device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t sa16, uint32_t plane16, uint32_t half16, uint32_t cstep16,
+                                              uint32_t b16, uint32_t bhi, uint32_t idesc)
+{
+    using G = WsGeom<PHASE>;
+    const uint32_t ahi = (G::SBO >> 4) | (1u << 14);
+    const uint32_t blo0 = b16 | (8u << 16);                         // LBO = 128 B between the two K halves of the weights
+#pragma unroll
+    for (int acc = 0; acc < G::NACC; ++acc) {
+        const int dy = acc >> 1, dx = acc & 1;
+        const uint32_t d = d0 + (uint32_t)acc * N;
+        if (KHALF == 0) {
+            // 16 input channels: one MMA (K = 32) spans two taps; its two 16-byte K halves are the same plane at two tap
+            // offsets (LBO = their distance).  Tap 9 has zero weights; its A half reads tap 8 + 16 B.
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                const int t0 = 2 * m, t1 = 2 * m + 1;
+                const int kh0 = t0 / 3, kw0 = t0 % 3, kh1 = t1 / 3, kw1 = t1 % 3;
+                uint32_t o0, o1;
+                bool swapped = false;
+                if (PHASE) {
+                    const int p0 = (dx + kw0) & 1, p1 = (dx + kw1) & 1;
+                    const uint32_t c0 = (uint32_t)((dy + kh0) * G::PITCH + ((dx + kw0) >> 1));
+                    const uint32_t c1 = (uint32_t)((dy + kh1) * G::PITCH + ((dx + kw1) >> 1));
+                    o0 = (p0 ? half16 : 0u) + c0;
+                    o1 = m < 4 ? (p1 ? half16 : 0u) + c1 : o0 + 1u;
+                    // descriptors hold unsigned strides: when the second tap sits at the lower address (it is in the even
+                    // half-plane and the first in the odd one), start from it and use the copy of the weights whose K
+                    // halves are swapped (chunks 10..19)
+                    swapped = m < 4 && p0 == 1 && p1 == 0;
+                } else {
+                    o0 = (uint32_t)(kh0 * G::PITCH + kw0);
+                    o1 = m < 4 ? (uint32_t)(kh1 * G::PITCH + kw1) : o0 + 1u;
+                }
+                const uint32_t lo = swapped ? o1 : o0, hi = swapped ? o0 : o1;
+                const uint32_t alo = (sa16 + lo) | ((hi - lo) << 16);
+                const uint32_t blo = blo0 + (uint32_t)((swapped ? 10 : 0) + 2 * m) * 8u;      // 128 B per K chunk
+                if (m == 0) umma_i8_lohi<false>(d, alo, ahi, blo, bhi, idesc);
+                else umma_i8_lohi<true>(d, alo, ahi, blo, bhi, idesc);
+            }
+        } else {
+            const uint32_t a_lbo = plane16 << 16;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int kh = tap / 3, kw = tap % 3;
+                uint32_t abase;
+                if (PHASE) abase = sa16 + (((dx + kw) & 1) ? half16 : 0u) + (uint32_t)((dy + kh) * G::PITCH + ((dx + kw) >> 1));
+                else abase = sa16 + (uint32_t)(kh * G::PITCH + kw);
+#pragma unroll
+                for (int c2 = 0; c2 < KHALF; ++c2) {
+                    const uint32_t alo = (abase + (uint32_t)c2 * cstep16) | a_lbo;
+                    const uint32_t blo = blo0 + (uint32_t)(tap * KHALF + c2) * 16u;            // 256 B of weights per K = 32
+                    if (tap == 0 && c2 == 0) umma_i8_lohi<false>(d, alo, ahi, blo, bhi, idesc);
+                    else umma_i8_lohi<true>(d, alo, ahi, blo, bhi, idesc);
+                }
+            }
+        }
+    }
+}
+
 template <bool PHASE, int EPI>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParams p)
 {
@@ -212,16 +275,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         // lane issues.  Descriptor start addresses are in 16-byte units (low 14 bits of the descriptor), so moving to
         // another tap / channel-plane pair / weight chunk is an integer add on the 64-bit descriptor.
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t b_sbo = (uint32_t)p.kc * 128u;
+        const uint32_t bhi = ((uint32_t)p.kc * 8u) | (1u << 14);   // SBO = kc * 128 B between 8-channel groups of the weights
+        const uint32_t b16 = wsm >> 4;
+        const uint32_t plane16 = p.plane_stride >> 4;             // LBO of A: the next 16-byte channel plane
         const uint32_t half16 = p.plane_stride >> 5;              // PHASE: x-parity half-plane, in 16-byte units
         const uint32_t cstep16 = p.plane_stride >> 3;             // two channel planes = one K = 32 step
         const int khalf = p.nplanes >> 1;
-        // tap (kh,kw) of accumulator (dy,dx): offset inside a channel plane in 16-byte units
-        auto tap16 = [&](int dy, int dx, int tap) -> uint32_t {
-            const int kh = tap / 3, kw = tap - 3 * kh;
-            if (PHASE) return (uint32_t)(((dx + kw) & 1) ? half16 : 0u) + (uint32_t)((dy + kh) * G::PITCH + ((dx + kw) >> 1));
-            return (uint32_t)(kh * G::PITCH + kw);
-        };
         mbar_wait(bar_w, 0);
         int it = 0, s = 0;
         uint32_t ph = 0;
@@ -233,37 +292,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             tc_fence_after();
             const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
             if (elect_one()) {
-#pragma unroll
-                for (int acc = 0; acc < G::NACC; ++acc) {
-                    const int dy = acc >> 1, dx = acc & 1;
-                    const uint32_t d = tmem_base + (uint32_t)buf * p.tmem_buf_stride + (uint32_t)acc * (uint32_t)p.N;
-                    if (p.nplanes == 1) {
-                        // 16 input channels: one MMA (K = 32) spans two taps; its two 16-byte K halves are the same plane
-                        // at two tap offsets (LBO = their distance).  Tap 9 has zero weights; its A half reads tap 8 + 16 B.
-#pragma unroll
-                        for (int m = 0; m < 5; ++m) {
-                            uint32_t o0 = tap16(dy, dx, 2 * m);
-                            uint32_t o1 = m < 4 ? tap16(dy, dx, 2 * m + 1) : o0 + 1u;
-                            uint32_t bchunk = (uint32_t)(2 * m);
-                            // descriptors hold unsigned strides: when the second tap sits at the lower address (parity-split
-                            // tile), start from it and use the copy of the weights whose K halves are swapped (chunks 10..19)
-                            if (o1 < o0) { const uint32_t t = o0; o0 = o1; o1 = t; bchunk += 10u; }
-                            const uint64_t ad = make_desc(sa + o0 * 16u, (o1 - o0) * 16u, G::SBO, 0);
-                            const uint64_t bd = make_desc(wsm + bchunk * 128u, 128u, b_sbo, 0);
-                            umma_i8(d, ad, bd, idesc, m > 0 ? 1u : 0u);
-                        }
-                    } else {
-                        const uint64_t ad0 = make_desc(sa, p.plane_stride, G::SBO, 0);
-                        uint64_t bd = make_desc(wsm, 128u, b_sbo, 0);
-#pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            uint64_t ad = ad0 + tap16(dy, dx, tap);
-                            for (int c2 = 0; c2 < khalf; ++c2) {
-                                umma_i8(d, ad, bd, idesc, (tap | c2) ? 1u : 0u);
-                                ad += cstep16; bd += 16u;           // next pair of channel planes; next 256 B of weights
-                            }
-                        }
-                    }
+                const uint32_t d0 = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
+                const uint32_t sa16 = sa >> 4;
+                switch (khalf) {
+                case 0: ws_issue_tile<PHASE, 0>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
+                case 1: ws_issue_tile<PHASE, 1>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
+                case 2: ws_issue_tile<PHASE, 2>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
+                case 4: ws_issue_tile<PHASE, 4>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
+                default: ws_issue_tile<PHASE, 8>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
                 }
                 umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
                 umma_commit(bar_tfull(buf));                       // accumulators complete

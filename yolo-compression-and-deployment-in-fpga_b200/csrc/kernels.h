@@ -26,6 +26,10 @@ struct ConvArgs {
 // conv_direct.cu
 cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
 
+// conv_first.cu (first layer: NHWC4 input, <= 16 output channels, warp-level integer MMAs)
+bool conv3x3_first_supported(const ConvArgs &a);
+cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st);
+
 // conv_umma.cu (tcgen05 / TMEM / TMA implicit GEMM)
 bool conv3x3_umma_supported(const ConvArgs &a);
 cudaError_t conv3x3_umma(const ConvArgs &a, cudaStream_t st, int sm_count);

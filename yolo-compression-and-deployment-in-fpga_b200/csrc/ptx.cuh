@@ -55,6 +55,15 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same with the descriptors given as 32-bit halves (low word = start>>4 | LBO>>4 << 16: moving the operand is one 32-bit
+// add) and the accumulate flag as a compile-time constant, so that nothing but the adds sits between two MMAs.
+template <bool ACCUM>
+__device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc)
+{
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n}"
+                 ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACCUM ? 1 : 0) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])

@@ -366,7 +366,9 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     const int be = c->conv_backend;
     if ((be == 2 || be == 3) && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
     if ((be == 4 || be == 5) && !ws_ok) return fail(E_UNSUPPORTED, "layer %d does not fit the weight-stationary kernel (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
+    const bool first_ok = (((uintptr_t)d_in | (uintptr_t)d_out) & 3) == 0 && conv3x3_first_supported(a);
     if (be == 1) CU(conv3x3_direct(a, c->stream));
+    else if (be == 0 && first_ok) CU(conv3x3_first(a, c->stream));
     else if (be == 2 || be == 3) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else if (be == 4 || be == 5 || ws_ok) CU(conv3x3_ws(a, c->stream, c->sm_count));
     else if (umma_ok) CU(conv3x3_umma(a, c->stream, c->sm_count));
