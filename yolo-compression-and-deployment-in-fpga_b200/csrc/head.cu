@@ -85,13 +85,14 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 
 // ---- NMS ------------------------------------------------------------------------------------------
 //
-// One CTA of 1024 threads per frame.  Candidates over the threshold are compacted and sorted once by
+// One CTA of 512 threads per frame, two CTAs per SM (so that one frame's serial phases overlap the other's pair loops).  Candidates over the threshold are compacted and sorted once by
 // (class, score desc, tie-break) with a shared-memory bitonic sort.  Greedy suppression then runs per class segment
 // (python head; the C head is class-agnostic = one segment) in chunks of 256 sorted candidates, against a COMPACTED
 // list of the candidates kept so far (which is also the output list):
-//   a. every candidate of the chunk is tested against the kept list; 4 threads share one candidate, each taking every
-//      4th kept box (all lanes of a warp read the same kept box: a shared-memory broadcast);
-//   b. the survivors record, as bit-rows, which later candidates of the same chunk they would suppress;
+//   a. every candidate of the chunk is tested against the kept list; 2 threads share one candidate, each taking half of
+//      the list, four kept boxes at a time (all lanes of a warp read the same kept boxes: shared-memory broadcasts);
+//      a two-sided area bound (IoU <= min/max of the areas) rejects ~99 % of the pairs with two compares each;
+//   b. every candidate records, as bit-rows, which later candidates of the same chunk it would suppress;
 //   c. one warp resolves the chunk in score order from the (rarely non-empty) bit-rows;
 //   d. the chunk's survivors are appended to the kept list (in place: kept count <= processed count).
 // The decisions are those of sequential greedy NMS: a candidate is dropped iff a KEPT higher-ranked candidate of its
@@ -99,7 +100,7 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 // area ratio already bounds the IoU below the threshold, and quotients clearly away from the threshold; only
 // borderline pairs evaluate the reference's exact fp32 expression.
 
-constexpr int NMS_THREADS = 1024;
+constexpr int NMS_THREADS = 512;
 constexpr int NMS_CHUNK = 256;
 constexpr int NMS_SLICES = NMS_THREADS / NMS_CHUNK;
 constexpr int NMS_MAX_CLASSES = 64;
@@ -110,10 +111,10 @@ struct NmsSmem {
         struct {                                                   // suppression phase (keys no longer needed)
             unsigned short idx[HEAD_MAX_CAND];                     // anchor index of sorted position / kept entry
             unsigned mask[NMS_CHUNK][NMS_CHUNK / 32];              // intra-chunk suppression rows
+            float area[HEAD_MAX_CAND];                             // box areas (same order as box[])
         } s2;
     } u;
     float4 box[HEAD_MAX_CAND];                                     // sorted candidates; kept list compacted in place
-    float area[HEAD_MAX_CAND];
     unsigned char cls[HEAD_MAX_CAND];
     unsigned keepmap[HEAD_MAX_CAND / 32];                          // by anchor index (python mode output order)
     unsigned chunk_dead[NMS_CHUNK / 32];
@@ -129,7 +130,7 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *warp_sums, int *t
     int off = __popc(b & ((1u << lane) - 1));
     if (lane == 0) warp_sums[wid] = __popc(b);
     __syncthreads();
-    int v = lane < NMS_THREADS / 32 ? warp_sums[lane] : 0;       // NMS_THREADS/32 == 32 warps: one per lane
+    int v = lane < NMS_THREADS / 32 ? warp_sums[lane] : 0;       // NMS_THREADS/32 <= 32 warps: one per lane
     int tot = __reduce_add_sync(0xffffffffu, v);
     int base = __reduce_add_sync(0xffffffffu, lane < wid ? v : 0);
     __syncthreads();
@@ -187,7 +188,7 @@ __device__ __forceinline__ bool suppresses(float4 a, float areaa, float4 b, floa
 }
 
 template <bool PY>
-__global__ void __launch_bounds__(NMS_THREADS, 1) head_nms_kernel(HeadArgs a)
+__global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) head_nms_kernel(HeadArgs a)
             float4 b = boxes[idx];
             s.u.s2.idx[i] = (unsigned short)idx;
             s.box[i] = b;
-            s.area[i] = area_py(b);
+            s.u.s2.area[i] = area_py(b);
             s.cls[i] = (unsigned char)cls[idx];
         }
     }
@@ -283,33 +284,61 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) head_nms_kernel(HeadArgs a)
             const int j = cs + cj_local;
             const bool have = cj_local < chn;
             const float4 bj = have ? s.box[j] : make_float4(0, 0, 0, 0);
-            const float aj = have ? s.area[j] : 0.f;
+            const float aj = have ? s.u.s2.area[j] : 0.f;
             if (tid < NMS_CHUNK / 32) { s.chunk_dead[tid] = 0; s.row_nonempty[tid] = 0; }
             for (int i = tid; i < NMS_CHUNK * (NMS_CHUNK / 32); i += NMS_THREADS) (&s.u.s2.mask[0][0])[i] = 0;
             __syncthreads();
-            // 4a. against the kept list of this segment
+            // Two-sided area bound: IoU <= min(area)/max(area), so a pair can only matter when ai lies in
+            // [thr_lo * aj, aj / thr_lo] (bounds widened by 1e-5; disabled for tiny thresholds and for the C head).
+            const bool bound_on = PY && thr_lo > 0.f;
+            const float a_lo = bound_on ? __fmul_rn(aj, thr_lo) : -INFINITY;
+            const float a_hi = bound_on ? __fmul_rn(__fdiv_rn(aj, thr_lo), 1.00001f) : INFINITY;
+            // 4a. against the kept list of this segment: slice 0 takes the first half, slice 1 the second, in 4-aligned blocks
             bool dead = false;
-            if (have) {
-                for (int i = seg_b + slice; i < seg_b + K; i += NMS_SLICES) {
-                    const float ai = s.area[i];
-                    // area-ratio bound first (IoU <= min/max): rejects most pairs before the box is even loaded
-                    if (PY && thr_lo > 0.f && fminf(ai, aj) < __fmul_rn(thr_lo, fmaxf(ai, aj))) continue;
-                    if (suppresses<PY>(s.box[i], ai, bj, aj, thresh, thr_lo)) { dead = true; break; }
+            if (have && K > 0) {
+                const int lo = seg_b, hi = seg_b + K;
+                const int base4 = lo & ~3;
+                const int half = (((hi - base4 + 1) >> 1) + 3) & ~3;
+                const int beg = base4 + slice * half, end = min(hi, beg + half);
+                for (int i4 = beg; i4 < end; i4 += 4) {
+                    const float4 a4 = *reinterpret_cast<const float4 *>(&s.u.s2.area[i4]);
+                    const float av[4] = { a4.x, a4.y, a4.z, a4.w };
+                    unsigned pass = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        pass |= (unsigned)(i4 + k >= lo && i4 + k < hi && !(av[k] < a_lo) && !(av[k] > a_hi)) << k;
+                    if (pass) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if ((pass >> k) & 1u) dead |= suppresses<PY>(s.box[i4 + k], av[k], bj, aj, thresh, thr_lo);
+                        if (dead) break;
+                    }
                 }
             }
             unsigned db = __ballot_sync(0xffffffffu, dead);
             if (lane == 0 && db) atomicOr(&s.chunk_dead[cj_local >> 5], db);
-            __syncthreads();
-            // 4b. bit-rows: which later candidates of this chunk would j suppress (skipped when j is already dead)
-            const bool jdead = (s.chunk_dead[cj_local >> 5] >> (cj_local & 31)) & 1u;
-            if (have && !jdead) {
+            // 4b. bit-rows: which later candidates of this chunk would j suppress.  The warp walks the chunk from its first
+            // candidate on (uniform addresses = broadcasts); rows of candidates that die in 4a are ignored by 4c.
+            if (have && !dead) {
+                const int cj0 = cj_local & ~31;                                  // first candidate of this warp
+                const int base4 = (cs + cj0 + 1) & ~3;
+                const int hi = cs + chn;
                 bool any = false;
-                for (int t = cj_local + 1 + slice; t < chn; t += NMS_SLICES) {
-                    const float at = s.area[cs + t];
-                    if (PY && thr_lo > 0.f && fminf(at, aj) < __fmul_rn(thr_lo, fmaxf(at, aj))) continue;
-                    if (suppresses<PY>(bj, aj, s.box[cs + t], at, thresh, thr_lo)) {
-                        atomicOr(&s.u.s2.mask[cj_local][t >> 5], 1u << (t & 31));
-                        any = true;
+                for (int i4 = base4 + 4 * slice; i4 < hi; i4 += 4 * NMS_SLICES) {
+                    const float4 a4 = *reinterpret_cast<const float4 *>(&s.u.s2.area[i4]);
+                    const float av[4] = { a4.x, a4.y, a4.z, a4.w };
+                    unsigned pass = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        pass |= (unsigned)(i4 + k > j && i4 + k < hi && !(av[k] < a_lo) && !(av[k] > a_hi)) << k;
+                    if (pass) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (((pass >> k) & 1u) && suppresses<PY>(bj, aj, s.box[i4 + k], av[k], thresh, thr_lo)) {
+                                const int t = i4 + k - cs;
+                                atomicOr(&s.u.s2.mask[cj_local][t >> 5], 1u << (t & 31));
+                                any = true;
+                            }
                     }
                 }
                 if (any) atomicOr(&s.row_nonempty[cj_local >> 5], 1u << (cj_local & 31));
@@ -341,7 +370,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) head_nms_kernel(HeadArgs a)
             int off = block_scan_flag(alive, s.warp_sums, &tot);     // contains the barriers that order reads before writes
             if (alive) {
                 const int d = seg_b + K + off;
-                s.box[d] = bj; s.area[d] = aj; s.u.s2.idx[d] = my; s.cls[d] = mc;
+                s.box[d] = bj; s.u.s2.area[d] = aj; s.u.s2.idx[d] = my; s.cls[d] = mc;
                 if (PY) atomicOr(&s.keepmap[my >> 5], 1u << (my & 31));
             }
             K += tot;
@@ -387,7 +416,12 @@ cudaError_t head_init(void)
 {
     cudaError_t e = cudaFuncSetAttribute(head_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(head_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    e = cudaFuncSetAttribute(head_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    if (e != cudaSuccess) return e;
+    // two frames per SM: ask for the full shared-memory carve-out
+    e = cudaFuncSetAttribute(head_nms_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(head_nms_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
