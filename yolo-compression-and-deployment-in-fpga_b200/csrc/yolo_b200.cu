@@ -57,6 +57,10 @@ struct yolo_b200_ctx {
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     int ev_used = 0;
+    // host-buffer entry points: copies of chunk k+1 / k-1 overlap the kernels of chunk k
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    int host_chunk = 128;                // frames per chunk
 };
 
 static std::mutex g_default_mu;
@@ -139,6 +143,10 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     cudaFree(c->lut_dev); cudaFree(c->ovf_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
     cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
     for (auto e : c->ev) cudaEventDestroy(e);
+    for (auto e : c->ev_in) cudaEventDestroy(e);
+    for (auto e : c->ev_done) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -287,6 +295,14 @@ int yolo_b200_set_conv_backend(yolo_b200_ctx *c, int backend)
     if (!c) return fail(E_ARG, "null ctx");
     if (backend < 0 || backend > 5) return fail(E_ARG, "backend %d", backend);
     c->conv_backend = backend;
+    return 0;
+}
+
+int yolo_b200_set_host_chunk(yolo_b200_ctx *c, int frames)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (frames < 0) return fail(E_ARG, "chunk %d", frames);
+    c->host_chunk = frames;
     return 0;
 }
 
@@ -503,7 +519,9 @@ int yolo_b200_sync(yolo_b200_ctx *c)
     return 0;
 }
 
-// host-buffer variants: H2D of the frames, forward, D2H of detections + counts, all on the context stream
+// host-buffer variants: H2D of the frames, forward, D2H of detections + counts.  Batches larger than one chunk are
+// pipelined over three streams: while chunk k computes on the context stream, chunk k+1 is copied in and the detections
+// of chunk k-1 are copied out (frames are independent, so chunking does not change any result).
 static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
                         yolo_b200_det *dets, int32_t *counts)
 {
@@ -511,16 +529,39 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     if (n == 0) return 0;
     if (!host_in || !dets || !counts) return fail(E_ARG, "null buffer");
     rc = ensure(&c->stage_in, &c->stage_in_cap, in_bytes); if (rc) return rc;
-    size_t det_bytes = (size_t)n * c->prm.max_det * sizeof(yolo_b200_det);
-    rc = ensure((void **)&c->d_dets, &c->dets_cap, det_bytes); if (rc) return rc;
+    const size_t md = (size_t)c->prm.max_det;
+    rc = ensure((void **)&c->d_dets, &c->dets_cap, (size_t)n * md * sizeof(yolo_b200_det)); if (rc) return rc;
     rc = ensure((void **)&c->d_counts, &c->counts_cap, (size_t)n * sizeof(int32_t)); if (rc) return rc;
-    CU(cudaMemcpyAsync(c->stage_in, host_in, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    if (kind == 0) rc = yolo_b200_forward_rgb444_dev(c, (const uint16_t *)c->stage_in, n, h, w, c->d_dets, c->d_counts);
-    else if (kind == 1) rc = yolo_b200_forward_int8_dev(c, (const int8_t *)c->stage_in, n, h, w, c->d_dets, c->d_counts);
-    else rc = yolo_b200_forward_f32_dev(c, (const float *)c->stage_in, n, h, w, c->d_dets, c->d_counts);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(counts, c->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(dets, c->d_dets, det_bytes, cudaMemcpyDeviceToHost, c->stream));
+    const int chunk = c->host_chunk > 0 ? c->host_chunk : n;
+    const int nchunks = (n + chunk - 1) / chunk;
+    const size_t frame_bytes = in_bytes / (size_t)n;
+    if (!c->s_in) { CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
+    while ((int)c->ev_in.size() < nchunks) {
+        cudaEvent_t e1, e2;
+        CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        c->ev_in.push_back(e1); c->ev_done.push_back(e2);
+    }
+    // the staging buffers may still be read by work queued earlier on the context stream
+    CU(cudaEventRecord(c->ev_done[0], c->stream));
+    CU(cudaStreamWaitEvent(c->s_in, c->ev_done[0], 0));
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = k * chunk, nk = (n - f0) < chunk ? (n - f0) : chunk;
+        char *stage = (char *)c->stage_in + (size_t)f0 * frame_bytes;
+        CU(cudaMemcpyAsync(stage, (const char *)host_in + (size_t)f0 * frame_bytes, (size_t)nk * frame_bytes, cudaMemcpyHostToDevice, c->s_in));
+        CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        yolo_b200_det *dd = c->d_dets + (size_t)f0 * md;
+        int32_t *dc = c->d_counts + f0;
+        if (kind == 0) rc = yolo_b200_forward_rgb444_dev(c, (const uint16_t *)stage, nk, h, w, dd, dc);
+        else if (kind == 1) rc = yolo_b200_forward_int8_dev(c, (const int8_t *)stage, nk, h, w, dd, dc);
+        else rc = yolo_b200_forward_f32_dev(c, (const float *)stage, nk, h, w, dd, dc);
+        if (rc) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
+        CU(cudaEventRecord(c->ev_done[k], c->stream));
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
+        CU(cudaMemcpyAsync(counts + f0, dc, (size_t)nk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+        CU(cudaMemcpyAsync(dets + (size_t)f0 * md, dd, (size_t)nk * md * sizeof(yolo_b200_det), cudaMemcpyDeviceToHost, c->s_out));
+    }
+    CU(cudaStreamSynchronize(c->s_out));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -190,8 +190,30 @@ def synthetic_frames_f32(n: int, h: int, w: int, seed: int = 0) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
 
 
+def rgb444_lut(sa: int = 0) -> np.ndarray:
+    """pixel_norm_quantize (c_embedding/yolo_forward.c:57-85) for all 4096 RGB444 codes -> int8 [4096][4] (R,G,B,0):
+    mask WITHOUT shifting (R in 0..15, G in {0,16..240}, B in {0,256..3840}), /255., -mean, /std in the reference's
+    float/double mix, * 2^sa, truncation toward zero, low byte kept.  Host replica used to build calibration frames;
+    the device table is built by the C library (yolo_b200_rgb444_lut) and tests compare the two."""
+    codes = np.arange(4096, dtype=np.int64)
+    out = np.zeros((4096, 4), dtype=np.int8)
+    for ch, (mask, mean, sd) in enumerate(((0x000f, 0.485, 0.229), (0x00f0, 0.456, 0.224), (0x0f00, 0.406, 0.225))):
+        v = (codes & mask).astype(np.float32)
+        v = (v.astype(np.float64) / 255.).astype(np.float32)
+        v = (v.astype(np.float64) - mean).astype(np.float32)
+        v = (v.astype(np.float64) / sd).astype(np.float32)
+        t = np.trunc(v.astype(np.float64) * 2.0 ** sa).astype(np.int64)
+        out[:, ch] = (t & 0xff).astype(np.uint8).view(np.int8)
+    return out
+
+
+def synthetic_frames_rgb444(n: int, h: int, w: int, seed: int = 0) -> np.ndarray:
+    """Synthetic camera frames in the C path's input format: uint16 [n][h][w], 0x0BGR (ov7670.h:203-230)."""
+    return np.random.default_rng(seed).integers(0, 4096, size=(n, h, w), dtype=np.uint16)
+
+
 def random_quantnet(seed: int = 0, calib_hw=(416, 416), calib_frames: int = 2, head_bias_shift: float = 0.0,
-                    anchors=None) -> QuantNet:
+                    anchors=None, calib_input: str = "f32") -> QuantNet:
     """Random-init slim_yolo_v2 of the named architecture, quantised and calibrated by the reference's rules
     (SURVEY.md 8d 'Weights for all configs').  head_bias_shift is added to the 5 objectness biases of `pred`
     BEFORE quantisation: random init otherwise puts most anchors above the threshold (dense NMS worst case);
@@ -200,7 +222,13 @@ def random_quantnet(seed: int = 0, calib_hw=(416, 416), calib_frames: int = 2, h
     if head_bias_shift:
         bs[-1] = bs[-1].clone()
         bs[-1][:5] += head_bias_shift
-    frames = synthetic_frames_f32(calib_frames, calib_hw[0], calib_hw[1], seed=1000 + seed)
+    if calib_input == "rgb444":
+        # calibrate on what the RGB444 front end delivers at scale_a[0] = 0 (the shipped table): integers in [-2, 65]
+        u16 = synthetic_frames_rgb444(calib_frames, calib_hw[0], calib_hw[1], seed=1000 + seed)
+        q = rgb444_lut(0)[u16.astype(np.int64)][..., :3].astype(np.float32)
+        frames = torch.from_numpy(np.ascontiguousarray(q.transpose(0, 3, 1, 2)))
+    else:
+        frames = synthetic_frames_f32(calib_frames, calib_hw[0], calib_hw[1], seed=1000 + seed)
     return build_quantnet(ws, bs, frames, anchors=anchors)
 
 

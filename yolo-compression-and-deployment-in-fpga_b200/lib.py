@@ -24,7 +24,7 @@ HEAD_PYTHON, HEAD_C = 0, 1
 EXPORTS = [
     "yolo_b200_abi_version", "yolo_b200_last_error", "yolo_b200_cstride", "yolo_b200_default_params",
     "yolo_b200_create", "yolo_b200_destroy", "yolo_b200_set_stream", "yolo_b200_load", "yolo_b200_set_thresholds",
-    "yolo_b200_set_conv_backend", "yolo_b200_debug_requant",
+    "yolo_b200_set_conv_backend", "yolo_b200_set_host_chunk", "yolo_b200_debug_requant",
     "yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32",
     "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev", "yolo_b200_sync",
     "yolo_b200_quantize_rgb444", "yolo_b200_quantize_f32", "yolo_b200_rgb444_lut", "yolo_b200_conv_layer",
@@ -86,6 +86,7 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_load.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(Params), i32]
     L.yolo_b200_set_thresholds.argtypes = [vp, C.c_float, C.c_float]
     L.yolo_b200_set_conv_backend.argtypes = [vp, i32]
+    L.yolo_b200_set_host_chunk.argtypes = [vp, i32]
     L.yolo_b200_debug_requant.argtypes = [vp, i32, vp, C.c_size_t, vp, i32]
     for name in ("yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32",
                  "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev"):
@@ -195,6 +196,10 @@ class Context:
     def set_conv_backend(self, backend: int):
         """0 auto, 1 integer dot-product kernels only, 2 tcgen05 only."""
         self._check(self.L.yolo_b200_set_conv_backend(self._h, backend))
+
+    def set_host_chunk(self, frames: int):
+        """Frames per chunk of the pipelined host-buffer entry points (0 = no chunking)."""
+        self._check(self.L.yolo_b200_set_host_chunk(self._h, frames))
 
     def debug_requant(self, layer, d_acc, count, d_out, force_generic=False) -> int:
         rc = self.L.yolo_b200_debug_requant(self._h, layer, _ptr(d_acc), count, _ptr(d_out), int(force_generic))

@@ -21,18 +21,22 @@ def shard_range(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
 
 def gather_detections(dets: torch.Tensor, counts: torch.Tensor, n_frames: int, group=None):
     """dets: [local_frames, max_det, 8] int32 view of yolo_b200_det records, counts: [local_frames] int32.
-    Returns (all_dets [n_frames, max_det, 8], all_counts [n_frames]) on every rank, in global frame order.
+    Returns (all_dets [n_frames, md, 8], all_counts [n_frames]) on every rank, in global frame order, where md is the
+    largest detection count of any frame (the lists are trimmed to their filled part before they travel).
     Ragged shards are padded to the largest shard for the collective and trimmed afterwards."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return dets, counts
     rank = dist.get_rank(group)
     max_local = shard_range(n_frames, 0, world)[1]            # rank 0 always has the largest shard
-    md = dets.shape[1]
+    # only the filled part of the fixed-capacity lists travels: trim to the largest count of any frame on any rank
+    mc = counts.max().to(torch.int64).reshape(1) if counts.numel() else torch.zeros(1, dtype=torch.int64, device=counts.device)
+    dist.all_reduce(mc, op=dist.ReduceOp.MAX, group=group)
+    md = max(1, min(int(mc.item()), dets.shape[1]))
     pad_d = torch.zeros((max_local, md, 8), dtype=dets.dtype, device=dets.device)
     pad_c = torch.zeros((max_local,), dtype=counts.dtype, device=counts.device)
     lo, hi = shard_range(n_frames, rank, world)
-    pad_d[:hi - lo] = dets
+    pad_d[:hi - lo] = dets[:, :md]
     pad_c[:hi - lo] = counts
     out_d = [torch.empty_like(pad_d) for _ in range(world)]
     out_c = [torch.empty_like(pad_c) for _ in range(world)]
