@@ -140,30 +140,26 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *warp_sums, int *t
 
 __device__ __forceinline__ float area_py(float4 a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
 
-// python: overlap as in slim_yolo_v2.py:159-169, suppress when NOT (ovr <= thresh).
-// thr_lo = thresh*(1-1e-5) when the shortcuts are usable (thresh > 1e-6), else a negative number (shortcuts off).
-__device__ __forceinline__ bool suppress_py(float4 a, float areaa, float4 b, float areab, float thresh, float thr_lo)
+// python: overlap as in slim_yolo_v2.py:159-169, suppress when NOT (ovr <= thresh): the reference's fp32 expression,
+// every operation rounded separately.  Only pairs the cheap screen below cannot decide get here.
+__device__ __noinline__ bool suppress_py_exact(float4 a, float4 b, float thresh)
 {
-    float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
-    float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
-    float asum = __fadd_rn(areaa, areab);
-    if (thr_lo > 0.f) {
-        // disjoint boxes: the reference clamps w,h to 1e-28, so inter <= 1e-28 and ovr is ~0 (or negative) unless both
-        // areas are ~zero (then it can be 0/0 = NaN, which the reference drops): only that case needs the full formula
-        if ((w <= 0.f || h <= 0.f) && asum > 1e-20f) return false;
-        // inter <= min(area) and union >= max(area) (fp32 rounding is monotone): IoU <= min/max
-        if (fminf(areaa, areab) < __fmul_rn(thr_lo, fmaxf(areaa, areab))) return false;
-    }
-    w = fmaxf(1e-28f, w); h = fmaxf(1e-28f, h);
+    float w = fmaxf(1e-28f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    float h = fmaxf(1e-28f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     float inter = __fmul_rn(w, h);
-    float den = __fsub_rn(asum, inter);
-    if (thr_lo > 0.f && den > 1e-20f) {
-        float p = __fmul_rn(thresh, den);
-        if (inter < __fmul_rn(p, 0.99999f)) return false;          // quotient clearly below the threshold
-        if (inter > __fmul_rn(p, 1.00001f)) return true;           // clearly above
-    }
-    float ovr = __fdiv_rn(inter, den);
+    float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_py(a), area_py(b)), inter));
     return !(ovr <= thresh);
+}
+
+// Screen: inter/(ai+aj-inter) > t  <=>  inter > t/(1+t) * (ai+aj).  The pair loops store ca = t/(1+t)*(1-1e-5) * area per box
+// and evaluate, branch-free, max(iw,0)*ih > ca_i + ca_j: false means "certainly kept" (the 1e-5 slack covers every
+// rounding difference, and the reference's 1e-28 clamps only matter for degenerate boxes, which the screen passes on as
+// they make the right-hand side ~0); true sends the pair to suppress_py_exact.
+__device__ __forceinline__ bool screen_py(float4 a, float ca, float4 b, float cb)
+{
+    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    return fmaxf(iw, 0.f) * ih >= ca + cb;
 }
 
 // C: integer boxes, overlap()/box_intersection()/box_union() of yolo_forward.c:1000-1036, suppress iou >= thresh
@@ -180,14 +176,30 @@ __device__ __forceinline__ bool suppress_c(float4 a, float4 b, float thresh)
     return iou >= thresh;
 }
 
-template <bool PY>
-__device__ __forceinline__ bool suppresses(float4 a, float areaa, float4 b, float areab, float thresh, float thr_lo)
+// One pair: does box a (kept / higher ranked) suppress box b?  FAST: screen first (python head, thresh > 1e-6).
+template <bool PY, bool FAST>
+__device__ __forceinline__ bool suppresses(float4 a, float ca, float4 b, float cb, float thresh)
 {
-    if (PY) return suppress_py(a, areaa, b, areab, thresh, thr_lo);
-    return suppress_c(a, b, thresh);
+    if (!PY) return suppress_c(a, b, thresh);
+    if (FAST && !screen_py(a, ca, b, cb)) return false;
+    return suppress_py_exact(a, b, thresh);
 }
 
-template <bool PY>
+// Four boxes of the sorted/kept array against box bj: bit k of the result = "entry i4+k may matter" (screen, or simply
+// valid when there is no screen).  vm masks the entries that belong to the range.  Branch-free: the four screens are
+// independent instruction streams; the caller branches once per block.
+template <bool PY, bool FAST>
+__device__ __forceinline__ unsigned screen4(const float4 *box, const float *carea, int i4, unsigned vm, float4 bj, float cj)
+{
+    if (!(PY && FAST)) return vm;
+    const float4 c4 = *reinterpret_cast<const float4 *>(carea + i4);
+    const float4 b0 = box[i4], b1 = box[i4 + 1], b2 = box[i4 + 2], b3 = box[i4 + 3];
+    unsigned m = (unsigned)screen_py(b0, c4.x, bj, cj) | ((unsigned)screen_py(b1, c4.y, bj, cj) << 1) |
+                 ((unsigned)screen_py(b2, c4.z, bj, cj) << 2) | ((unsigned)screen_py(b3, c4.w, bj, cj) << 3);
+    return m & vm;
+}
+
+template <bool PY, bool FAST>
 __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     const float4 *boxes = a.boxes + (size_t)f * N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float thresh = a.nms_thresh;
-    const float thr_lo = thresh > 1e-6f ? thresh * 0.99999f : -1.f;
+    const float cfac = FAST ? thresh / (1.f + thresh) * 0.99999f : 1.f;     // screen factor (see screen_py)
 
     // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
     //    key = class | score bits | tie-break: python sorts per class, ties -> higher anchor index first (reversed stable
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             float4 b = boxes[idx];
             s.u.s2.idx[i] = (unsigned short)idx;
             s.box[i] = b;
-            s.u.s2.area[i] = area_py(b);
+            s.u.s2.area[i] = cfac * area_py(b);
             s.cls[i] = (unsigned char)cls[idx];
         }
     }
@@ -288,12 +300,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             if (tid < NMS_CHUNK / 32) { s.chunk_dead[tid] = 0; s.row_nonempty[tid] = 0; }
             for (int i = tid; i < NMS_CHUNK * (NMS_CHUNK / 32); i += NMS_THREADS) (&s.u.s2.mask[0][0])[i] = 0;
             __syncthreads();
-            // Two-sided area bound: IoU <= min(area)/max(area), so a pair can only matter when ai lies in
-            // [thr_lo * aj, aj / thr_lo] (bounds widened by 1e-5; disabled for tiny thresholds and for the C head).
-            const bool bound_on = PY && thr_lo > 0.f;
-            const float a_lo = bound_on ? __fmul_rn(aj, thr_lo) : -INFINITY;
-            const float a_hi = bound_on ? __fmul_rn(__fdiv_rn(aj, thr_lo), 1.00001f) : INFINITY;
-            // 4a. against the kept list of this segment: slice 0 takes the first half, slice 1 the second, in 4-aligned blocks
+            // 4a. against the kept list of this segment: slice 0 takes the first half, slice 1 the second, in 4-aligned
+            //     blocks; every lane of a warp reads the same kept boxes (shared-memory broadcasts)
             bool dead = false;
             if (have && K > 0) {
                 const int lo = seg_b, hi = seg_b + K;
@@ -301,16 +309,16 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                 const int half = (((hi - base4 + 1) >> 1) + 3) & ~3;
                 const int beg = base4 + slice * half, end = min(hi, beg + half);
                 for (int i4 = beg; i4 < end; i4 += 4) {
-                    const float4 a4 = *reinterpret_cast<const float4 *>(&s.u.s2.area[i4]);
-                    const float av[4] = { a4.x, a4.y, a4.z, a4.w };
-                    unsigned pass = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        pass |= (unsigned)(i4 + k >= lo && i4 + k < hi && !(av[k] < a_lo) && !(av[k] > a_hi)) << k;
-                    if (pass) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if ((pass >> k) & 1u) dead |= suppresses<PY>(s.box[i4 + k], av[k], bj, aj, thresh, thr_lo);
+                    unsigned vm = 0xfu;                                         // which of the 4 entries belong to the list
+                    if (i4 < lo) vm &= 0xfu << (lo - i4);
+                    if (i4 + 4 > hi) vm &= 0xfu >> (i4 + 4 - hi);
+                    unsigned mk = screen4<PY, FAST>(s.box, s.u.s2.area, i4, vm, bj, aj);
+                    if (mk) {                                                    // rare: exact evaluation of the flagged pairs
+                        while (mk) {
+                            const int k = __ffs(mk) - 1;
+                            mk &= mk - 1;
+                            if (PY ? suppress_py_exact(s.box[i4 + k], bj, thresh) : suppress_c(s.box[i4 + k], bj, thresh)) dead = true;
+                        }
                         if (dead) break;
                     }
                 }
@@ -325,20 +333,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                 const int hi = cs + chn;
                 bool any = false;
                 for (int i4 = base4 + 4 * slice; i4 < hi; i4 += 4 * NMS_SLICES) {
-                    const float4 a4 = *reinterpret_cast<const float4 *>(&s.u.s2.area[i4]);
-                    const float av[4] = { a4.x, a4.y, a4.z, a4.w };
-                    unsigned pass = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        pass |= (unsigned)(i4 + k > j && i4 + k < hi && !(av[k] < a_lo) && !(av[k] > a_hi)) << k;
-                    if (pass) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (((pass >> k) & 1u) && suppresses<PY>(bj, aj, s.box[i4 + k], av[k], thresh, thr_lo)) {
-                                const int t = i4 + k - cs;
-                                atomicOr(&s.u.s2.mask[cj_local][t >> 5], 1u << (t & 31));
-                                any = true;
-                            }
+                    unsigned vm = 0xfu;                                         // entries after j and inside the chunk
+                    if (i4 <= j) vm &= 0xfu << min(j + 1 - i4, 4);
+                    if (i4 + 4 > hi) vm &= 0xfu >> (i4 + 4 - hi);
+                    unsigned mk = vm ? screen4<PY, FAST>(s.box, s.u.s2.area, i4, vm, bj, aj) : 0u;
+                    while (mk) {
+                        const int k = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        if (PY ? suppress_py_exact(bj, s.box[i4 + k], thresh) : suppress_c(bj, s.box[i4 + k], thresh)) {
+                            const int t = i4 + k - cs;
+                            atomicOr(&s.u.s2.mask[cj_local][t >> 5], 1u << (t & 31));
+                            any = true;
+                        }
                     }
                 }
                 if (any) atomicOr(&s.row_nonempty[cj_local >> 5], 1u << (cj_local & 31));
@@ -412,24 +418,30 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     }
 }
 
-cudaError_t head_init(void)
+template <bool PY, bool FAST>
+static cudaError_t nms_attrs()
 {
-    cudaError_t e = cudaFuncSetAttribute(head_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(head_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
+    cudaError_t e = cudaFuncSetAttribute(head_nms_kernel<PY, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem));
     if (e != cudaSuccess) return e;
     // two frames per SM: ask for the full shared-memory carve-out
-    e = cudaFuncSetAttribute(head_nms_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(head_nms_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(head_nms_kernel<PY, FAST>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t head_init(void)
+{
+    cudaError_t e = nms_attrs<true, true>();
+    if (e == cudaSuccess) e = nms_attrs<true, false>();
+    if (e == cudaSuccess) e = nms_attrs<false, false>();
+    return e;
 }
 
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     if (a.gh * a.gw * a.A > HEAD_MAX_CAND || a.C > NMS_MAX_CLASSES) return cudaErrorInvalidValue;
-    if (a.head_mode == YOLO_B200_HEAD_PYTHON) head_nms_kernel<true><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
-    else head_nms_kernel<false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
+    if (a.head_mode != YOLO_B200_HEAD_PYTHON) head_nms_kernel<false, false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
+    else if (a.nms_thresh > 1e-6f) head_nms_kernel<true, true><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
+    else head_nms_kernel<true, false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
     return cudaGetLastError();
 }
 
