@@ -20,22 +20,32 @@
 //     lane i of the four accumulators holds the four members of pooled pixel i and the max-pool happens in registers.
 //     Requantisation is monotone, so max-then-requantise == requantise-then-max (slim_yolo_v2.py:229-231).
 //
-// Warp roles (544 threads): warp 0 = TMEM allocator + MMA issuer (one lane), warps 1-8 = cp.async producers (one halo
-// row per warp at a time), warps 9-16 = epilogue (two warps per TMEM lane quarter, each half of the columns).
+// Warp roles (640 threads): warp 0 = TMEM allocator + MMA issuer (one lane), warps 1-3 = cp.async producers (one halo
+// row per warp at a time), warps 4-19 = two epilogue groups of 8 warps (two warps per TMEM lane quarter, each half of the
+// columns); group g drains accumulator buffer g, so the epilogues of two consecutive tiles run concurrently (a single
+// group is latency-bound: ~0.2 instructions per cycle per warp, measured with clock64 stamps, tools/ws_timeline.py).
 // The MMA warp stays converged and elects one lane per tile to issue (elect.sync): with `if (lane == 0)` the issue interval
 // is ~80-120 cycles per MMA, with an elected lane ~42 (tools/micro/umma_issue.cu), which is what the thin layers need.
 #include "kernels.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
 #include <climits>
+#include <cstdio>
 
 namespace yb {
 
-constexpr int WS_PROD_WARPS = 8;
+#ifdef YB_WS_TIMELINE
+#define WS_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + (slot)] = clock64(); } while (0)
+#else
+#define WS_STAMP(slot) do { } while (0)
+#endif
+
+constexpr int WS_PROD_WARPS = 3;                        // 1 + 3 + 16 = 20 warps: registers are allocated per 4 warps, 20 x 96 x 32 fits
 constexpr int WS_PROD_THREADS = WS_PROD_WARPS * 32;
-constexpr int WS_EPI_WARPS = 8;
+constexpr int WS_EPI_WARPS = 8;                         // per group: two warps per TMEM lane quarter
 constexpr int WS_EPI_THREADS = WS_EPI_WARPS * 32;
-constexpr int WS_THREADS = 32 + WS_PROD_THREADS + WS_EPI_THREADS;
+constexpr int WS_EPI_GROUPS = 2;                        // group g drains accumulator buffer g: two tiles' epilogues overlap
+constexpr int WS_THREADS = 32 + WS_PROD_THREADS + WS_EPI_GROUPS * WS_EPI_THREADS;
 constexpr int WS_MAX_STAGES = 4;
 
 struct WsParams {
@@ -64,6 +74,7 @@ struct WsParams {
     const int *bias_sh;
     int8_t *out;
     unsigned *ovf;
+    long long *dbg;              // optional timeline (YB_WS_TIMELINE builds): [cta][tile][8] clock64 stamps
 };
 
 // tile geometry
@@ -225,7 +236,10 @@ __device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t 
     }
 }
 
-template <bool PHASE, int EPI>
+// KHALF = cs_in / 32 (0 for 16 input channels) is a template parameter so that each kernel holds exactly one fully
+// unrolled issue sequence with compile-time operand offsets (a run-time switch over all five kept their descriptor words
+// live at once and spilled ~1.5 KB in the issuing lane: 72 cycles per MMA instead of the ~45 the hardware needs).
+template <bool PHASE, int EPI, int KHALF>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParams p)
 {
     using G = WsGeom<PHASE>;
@@ -280,7 +294,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const uint32_t plane16 = p.plane_stride >> 4;             // LBO of A: the next 16-byte channel plane
         const uint32_t half16 = p.plane_stride >> 5;              // PHASE: x-parity half-plane, in 16-byte units
         const uint32_t cstep16 = p.plane_stride >> 3;             // two channel planes = one K = 32 step
-        const int khalf = p.nplanes >> 1;
         mbar_wait(bar_w, 0);
         int it = 0, s = 0;
         uint32_t ph = 0;
@@ -288,23 +301,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             const int buf = it & 1;
             const uint32_t bph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(bar_tempty(buf), bph ^ 1u);                 // epilogue has drained this accumulator buffer
+            WS_STAMP(0);
             mbar_wait(bar_full(s), ph);                           // the haloed tile is in shared memory
+            WS_STAMP(1);
             tc_fence_after();
             const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
             if (elect_one()) {
                 const uint32_t d0 = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
                 const uint32_t sa16 = sa >> 4;
-                switch (khalf) {
-                case 0: ws_issue_tile<PHASE, 0>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
-                case 1: ws_issue_tile<PHASE, 1>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
-                case 2: ws_issue_tile<PHASE, 2>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
-                case 4: ws_issue_tile<PHASE, 4>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
-                default: ws_issue_tile<PHASE, 8>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc); break;
-                }
+                ws_issue_tile<PHASE, KHALF>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc);
                 umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
                 umma_commit(bar_tfull(buf));                       // accumulators complete
             }
             __syncwarp();
+            WS_STAMP(2);
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp <= WS_PROD_WARPS) {
@@ -315,37 +325,86 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const int pw = warp - 1;
         const int row_pieces = G::HW << p.nplanes_log2;
         const int lag = p.stages >= 3 ? p.stages - 2 : 1;          // tiles in flight per thread before their arrival is signalled
+        // Everything about a lane's pieces except the row is tile-invariant: piece qr = lane + 32 t of a row is halo pixel
+        // hx = qr / nplanes, channel chunk c = qr % nplanes.
+        constexpr int MAXIT = 5;                                    // ceil(10 * 16 / 32): 256 input channels, un-phased tile
+        int hxv[MAXIT];
+        uint32_t dof[MAXIT];                                        // shared-memory offset inside the stage, without the row part
+#pragma unroll
+        for (int t = 0; t < MAXIT; ++t) {
+            const int qr = lane + 32 * t;
+            const int hx = qr >> p.nplanes_log2, c = qr & (p.nplanes - 1);
+            hxv[t] = qr < row_pieces ? hx : 0x40000000;            // out of range: fails the x test below
+            dof[t] = (uint32_t)c * p.plane_stride + (PHASE ? (uint32_t)(hx & 1) * (p.plane_stride >> 1) + (uint32_t)(hx >> 1) * 16u : (uint32_t)hx * 16u);
+        }
+        const int gut = p.period - p.H;
+        const int cs_shift = 4 + p.nplanes_log2;                    // log2(cs_in)
+        // thin rows: per-lane piece slots for the whole tile (tile-invariant), piece q = pt + 96 t
+        constexpr int LIN_SLOTS = (G::HH * 32 + WS_PROD_THREADS - 1) / WS_PROD_THREADS;
+        const bool linear = row_pieces <= 32 && G::HH * row_pieces <= LIN_SLOTS * WS_PROD_THREADS;
+        int lin_hy[LIN_SLOTS], lin_hx[LIN_SLOTS], lin_c16[LIN_SLOTS];
+        uint32_t lin_dst[LIN_SLOTS];
+#pragma unroll
+        for (int t = 0; t < LIN_SLOTS; ++t) {
+            const int q = (threadIdx.x - 32) + WS_PROD_THREADS * t;
+            const int hy = q / row_pieces, qr = q - hy * row_pieces;
+            const int hx = qr >> p.nplanes_log2, c = qr & (p.nplanes - 1);
+            lin_hy[t] = (linear && hy < G::HH) ? hy : -1;
+            lin_hx[t] = hx; lin_c16[t] = 16 * c;
+            lin_dst[t] = (uint32_t)(hy * G::PITCH) * 16u + (uint32_t)c * p.plane_stride +
+                         (PHASE ? (uint32_t)(hx & 1) * (p.plane_stride >> 1) + (uint32_t)(hx >> 1) * 16u : (uint32_t)hx * 16u);
+        }
         int it = 0, s = 0, s_arrive = 0;
         uint32_t ph = 0;
         int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int tx0 = tx * G::TW, ty0 = ty * G::TH;
             mbar_wait(bar_empty(s), ph ^ 1u);
+            if (pw == 0) WS_STAMP(3);
             const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
+            if (linear) {
+                // thin rows (<= 32 pieces): pieces are dealt to the producer lanes across the whole tile
+#pragma unroll
+                for (int t = 0; t < LIN_SLOTS; ++t) {
+                    if (lin_hy[t] >= 0) {
+                        const int cy = ty0 - 1 + lin_hy[t];
+                        const int n = (int)__umulhi((unsigned)max(cy, 0), p.period_magic);
+                        const int y = cy - n * p.period;
+                        const bool ok = cy >= 0 && cy < p.canvas_rows && y < p.H && (unsigned)(tx0 - 1 + lin_hx[t]) < (unsigned)p.W;
+                        const int off = (((cy - n * gut) * p.W + (tx0 - 1 + lin_hx[t])) << cs_shift) + lin_c16[t];
+                        cp_async16(sa + lin_dst[t], p.in + (ok ? off : 0), ok ? 16u : 0u);
+                    }
+                }
+            } else {
 #pragma unroll 2
             for (int hy = pw; hy < G::HH; hy += WS_PROD_WARPS) {
                 const int cy = ty0 - 1 + hy;
                 const int n = (int)__umulhi((unsigned)max(cy, 0), p.period_magic);
                 const int y = cy - n * p.period;
                 const bool rowok = cy >= 0 && cy < p.canvas_rows && y < p.H;
-                const int8_t *row_src = p.in + (((long long)n * p.H + y) * p.W + (tx0 - 1)) * (long long)p.cs_in;
+                // byte offset of halo pixel hx = 0 of this row (32-bit: the host checks the map is < 2 GB); image row index
+                // = canvas row minus the gutter rows before it
+                const int row_off = ((cy - n * gut) * p.W + (tx0 - 1)) << cs_shift;
                 const uint32_t row_dst = sa + (uint32_t)(hy * G::PITCH) * 16u;
-                for (int qr = lane; qr < row_pieces; qr += 32) {
-                    const int hx = qr >> p.nplanes_log2, c = qr & (p.nplanes - 1);
-                    const bool ok = rowok && (unsigned)(tx0 - 1 + hx) < (unsigned)p.W;
-                    uint32_t dst = row_dst + (uint32_t)c * p.plane_stride;
-                    if (PHASE) dst += (uint32_t)(hx & 1) * (p.plane_stride >> 1) + (uint32_t)(hx >> 1) * 16u;
-                    else dst += (uint32_t)hx * 16u;
-                    cp_async16(dst, ok ? row_src + 16 * qr : p.in, ok ? 16u : 0u);
+#pragma unroll
+                for (int t = 0; t < MAXIT; ++t) {
+                    if (t * 32 < row_pieces) {
+                        const bool ok = rowok && (unsigned)(tx0 - 1 + hxv[t]) < (unsigned)p.W;
+                        const int8_t *src = p.in + (ok ? row_off + 16 * (lane + 32 * t) : 0);
+                        if (hxv[t] < 0x40000000) cp_async16(row_dst + dof[t], src, ok ? 16u : 0u);
+                    }
                 }
             }
+            }
             cp_async_commit();
+            if (pw == 0) WS_STAMP(4);
             if (it >= lag) {
                 if (lag == 1) cp_async_wait<1>(); else cp_async_wait<2>();
                 fence_proxy_async();
                 mbar_arrive(bar_full(s_arrive));
                 if (++s_arrive == p.stages) s_arrive = 0;
             }
+            if (pw == 0) WS_STAMP(5);
             if (++s == p.stages) { s = 0; ph ^= 1u; }
             tx += p.step_x; ty += p.step_y;
             if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
@@ -359,24 +418,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         }
     } else {
         // ===================== epilogue warps =====================
-        const int ew = warp - (1 + WS_PROD_WARPS);
+        const int ew_all = warp - (1 + WS_PROD_WARPS);
+        const int grp = ew_all / WS_EPI_WARPS;                     // = accumulator buffer this group drains
+        const int ew = ew_all % WS_EPI_WARPS;
         const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
         const int cmid = ((p.N / 16 + 1) / 2) * 16;                // column split between the two warps of a quarter
         const int cbeg = ew < 4 ? 0 : cmid, cend = ew < 4 ? cmid : p.N;
         unsigned ovf = 0;
-        int it = 0;
+        // tiles blockIdx.x + (grp + 2k) * gridDim.x: advance the tile coordinates two grid strides at a time
         int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
+        if (grp) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
+        const int buf = grp;
+        int it = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
             const uint32_t bph = (uint32_t)(it >> 1) & 1u;
             const int tx0 = tx * G::TW, ty0 = ty * G::TH;
-            tx += p.step_x; ty += p.step_y;
-            if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
             mbar_wait(bar_tfull(buf), bph);
+            if (ew_all == 0) WS_STAMP(6);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * p.tmem_buf_stride + ((uint32_t)(q4 * 32) << 16);
             if (p.q.activ) ws_epilogue_tile<PHASE, EPI, true>(p, taddr, cbeg, cend, lane, q4, tx0, ty0, s_bias, bar_tempty(buf), ovf);
             else ws_epilogue_tile<PHASE, EPI, false>(p, taddr, cbeg, cend, lane, q4, tx0, ty0, s_bias, bar_tempty(buf), ovf);
+            if (ew_all == 0) WS_STAMP(7);
         }
         if (p.q.contract == CONTRACT_P) {
             ovf = __reduce_add_sync(0xffffffffu, ovf);
@@ -442,6 +507,7 @@ static bool ws_shape_ok(const ConvArgs &a)
     if (a.cs_out < 16 || a.cs_out > 256 || a.cs_out % 16) return false;
     if (a.q.pool && (a.H < 2 || a.W < 2)) return false;
     if ((long long)a.n * (a.H + 2) * (a.H + 2) >= (1ll << 32)) return false;   // exactness range of the multiply-high division by H + gut
+    if ((long long)a.n * a.H * a.W * a.cs_in >= (1ll << 31)) return false;     // the producers use 32-bit byte offsets
     return true;
 }
 
@@ -452,8 +518,8 @@ bool conv3x3_ws_supported(const ConvArgs &a)
     return ws_plan(a, false, &p) || (a.q.pool && ws_plan(a, true, &p));
 }
 
-template <bool PHASE, int EPI>
-static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
+template <bool PHASE, int EPI, int KHALF>
+static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
 {
     using G = WsGeom<PHASE>;
     const int gut = a.q.pool ? ((a.H & 1) ? 1 : 2) : 1;                  // pooled: image origins stay on even canvas rows
@@ -465,19 +531,52 @@ static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, in
     p.num_tiles = p.tiles_x * ((p.canvas_rows + G::TH - 1) / G::TH);
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
     p.q = a.q; p.wimg = a.wimg; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
+#ifdef YB_WS_TIMELINE
+    {   // debug builds only: stamps of CTA 0's first 64 tiles, printed after the launch (synchronises)
+        static long long *dbg = nullptr;
+        if (!dbg) cudaMalloc(&dbg, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(dbg, 0, 64 * 8 * sizeof(long long), st);
+        p.dbg = dbg;
+    }
+#endif
     const uint32_t smem_bytes = p.off_bar + 256u + 128u;
-    static bool attr_set[64] = {};
+    static bool attr_set[64] = {};     // per instantiation
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI, KHALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     p.step_x = grid % p.tiles_x; p.step_y = grid / p.tiles_x;
-    conv3x3_ws_kernel<PHASE, EPI><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+    conv3x3_ws_kernel<PHASE, EPI, KHALF><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+#ifdef YB_WS_TIMELINE
+    {
+        long long h[64 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.dbg, sizeof h, cudaMemcpyDeviceToHost);
+        const long long t0 = h[3] ? h[3] : h[0];
+        printf("WS timeline PHASE=%d N=%d nplanes=%d stages=%d tiles=%d (cycles since first stamp): tile | mma: tempty_ok full_ok issued | prod: empty_ok loads_issued arrived | epi: tfull_ok done\n",
+               (int)PHASE, p.N, p.nplanes, p.stages, p.num_tiles);
+        for (int i = 0; i < 24; ++i)
+            printf("  %2d | %7lld %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld\n", i, h[i*8]-t0, h[i*8+1]-t0, h[i*8+2]-t0, h[i*8+3]-t0, h[i*8+4]-t0, h[i*8+5]-t0, h[i*8+6]-t0, h[i*8+7]-t0);
+    }
+#endif
     return cudaGetLastError();
+}
+
+template <bool PHASE, int EPI>
+static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
+{
+    switch (p.nplanes >> 1) {
+    case 0: return launch_ws_k<PHASE, EPI, 0>(a, p, st, sm_count);
+    case 1: return launch_ws_k<PHASE, EPI, 1>(a, p, st, sm_count);
+    case 2: return launch_ws_k<PHASE, EPI, 2>(a, p, st, sm_count);
+    case 4: return launch_ws_k<PHASE, EPI, 4>(a, p, st, sm_count);
+    case 8: return launch_ws_k<PHASE, EPI, 8>(a, p, st, sm_count);
+    default: return cudaErrorInvalidConfiguration;
+    }
 }
 
 template <bool PHASE>
