@@ -276,6 +276,33 @@ def test_c_head_mode_against_oracle(ctx):
                 assert abs(int(counts[i]) - ocnt) <= 3
 
 
+@pytest.mark.parametrize("sa_pred", [2, 4, 6])
+@pytest.mark.parametrize("nms_thresh", [0.3, 0.5, 0.7])
+def test_python_head_random_prediction_maps_against_oracle(ctx, sa_pred, nms_thresh):
+    """Decode + per-class greedy NMS on random prediction maps (dense, heavily overlapping boxes of every size, both the
+    spatially indexed and the exhaustive suppression paths) against the oracle: identical kept sets, classes, order."""
+    import copy
+    g, qnet, frames = gu.load("ref_p_64x96")
+    q = copy.deepcopy(qnet)
+    q.sa = list(q.sa)
+    q.sa[10] = sa_pred
+    rng = np.random.default_rng(1000 * sa_pred + int(nms_thresh * 10))
+    ctx.load_quantnet(q, contract=lib.CONTRACT_F, head_mode=lib.HEAD_PYTHON, conf_thresh=0.05, nms_thresh=nms_thresh, max_det=4096)
+    for (n, gh, gw) in ((2, 26, 26), (3, 13, 13), (2, 15, 20)):
+        pred = np.zeros((n, gh, gw, 48), dtype=np.int8)
+        pred[..., :35] = rng.integers(-128, 128, (n, gh, gw, 35), dtype=np.int8)
+        pred[0, : gh // 2, :, 25:35:4] = -128          # a region of tiny boxes
+        dets, counts = det_arrays(ctx, dev(pred), n, gh, gw, gh * 16, gw * 16)
+        for i in range(n):
+            (ob, os_, oc, oidx), ocnt = ol.head_python(pred[i], 5, 2, sa_pred, q.anchors, 16, gh * 16, gw * 16, 0.05, nms_thresh)
+            b, s_, c, idx = lib.dets_to_arrays(dets[i], int(counts[i]))
+            assert counts[i] == ocnt, "frame %d of %s: %d kept, oracle %d" % (i, (n, gh, gw), counts[i], ocnt)
+            np.testing.assert_array_equal(idx, oidx)
+            np.testing.assert_array_equal(c, oc)
+            np.testing.assert_allclose(s_, os_, atol=1e-6, rtol=0)
+            np.testing.assert_allclose(b, ob, atol=1e-6, rtol=0)
+
+
 # ---- batch semantics / edge cases --------------------------------------------------------------------
 
 def test_empty_batch_and_errors(ctx):

@@ -95,6 +95,13 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 //   b. every candidate records, as bit-rows, which later candidates of the same chunk it would suppress;
 //   c. one warp resolves the chunk in score order from the (rarely non-empty) bit-rows;
 //   d. the chunk's survivors are appended to the kept list (in place: kept count <= processed count).
+// Python head with thresh > 1e-6: the kept list also carries a SPATIAL INDEX so that step a visits only boxes that can
+// matter.  IoU > t implies (i) area ratio within [t, 1/t] and (ii) |dcx| < (1-t) max(w_i,w_j), |dcy| < (1-t) max(h_i,h_j)
+// (the x-overlap must exceed t times the wider box).  Kept boxes are therefore filed, as linked lists, under
+// (area bucket by binary exponent, 8x8 centre cell); a candidate walks only the lists of compatible buckets and of the
+// cells its window covers (with slack for rounding; every visited pair still goes through the screen and the exact test,
+// so pruning can only skip pairs that could not suppress).  Candidates with a degenerate area scan the whole list: the
+// reference's 0/0 = NaN quirk makes zero-area boxes suppress each other at any distance.
 // The decisions are those of sequential greedy NMS: a candidate is dropped iff a KEPT higher-ranked candidate of its
 // segment overlaps it beyond the threshold.  Most pairs are rejected without a division: disjoint boxes, boxes whose
 // area ratio already bounds the IoU below the threshold, and quotients clearly away from the threshold; only
@@ -104,6 +111,9 @@ constexpr int NMS_THREADS = 512;
 constexpr int NMS_CHUNK = 256;
 constexpr int NMS_SLICES = NMS_THREADS / NMS_CHUNK;
 constexpr int NMS_MAX_CLASSES = 64;
+constexpr int NMS_BUCKETS = 12;          // area buckets by binary exponent: bucket b = areas in [2^(b-11), 2^(b-10)), bucket 0 also everything smaller
+constexpr int NMS_GRID = 8;              // centre cells per axis over [0,1]
+constexpr unsigned NMS_END = 0xffffu;
 
 struct NmsSmem {
     union {
@@ -120,6 +130,10 @@ struct NmsSmem {
     unsigned chunk_dead[NMS_CHUNK / 32];
     unsigned row_nonempty[NMS_CHUNK / 32];
     int warp_sums[NMS_THREADS / 32];
+    // spatial index of the kept list (python head): linked lists per (area bucket, centre cell)
+    unsigned ghead[NMS_BUCKETS * NMS_GRID * NMS_GRID];             // first kept entry of the list, NMS_END = empty
+    unsigned short gnext[HEAD_MAX_CAND];                           // next entry of the same list
+    float gw[NMS_BUCKETS], gh[NMS_BUCKETS];                        // widest / tallest kept box of the bucket (-1 = empty)
 };
 
 // block-wide exclusive scan of a 0/1 flag; returns this thread's offset, *total = sum over the block
@@ -199,6 +213,13 @@ __device__ __forceinline__ unsigned screen4(const float4 *box, const float *care
     return m & vm;
 }
 
+__device__ __forceinline__ int nms_bucket(float area)
+{
+    const int e = (int)((__float_as_uint(area) >> 23) & 0xffu) - 127;     // binary exponent (area >= 0)
+    return min(max(e + (NMS_BUCKETS - 1), 0), NMS_BUCKETS - 1);
+}
+__device__ __forceinline__ int nms_cell(float c) { return min(max((int)(c * (float)NMS_GRID), 0), NMS_GRID - 1); }
+
 template <bool PY, bool FAST>
 __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 {
@@ -212,6 +233,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float thresh = a.nms_thresh;
     const float cfac = FAST ? thresh / (1.f + thresh) * 0.99999f : 1.f;     // screen factor (see screen_py)
+    constexpr bool GRID = PY && FAST;
+    // spatial-index bounds with slack: IoU > t needs area ratio >= t (bucket distance <= grid_d) and centre distance
+    // < (1 - t) * max extent per axis
+    const float t_lo = thresh * 0.999f;
+    const int grid_d = GRID ? (int)floorf(log2f(1.f / t_lo)) + 1 : 0;
+    const float grid_q = fmaxf(1.f - t_lo, 0.f) * 1.0001f;
 
     // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
     //    key = class | score bits | tie-break: python sorts per class, ties -> higher anchor index first (reversed stable
@@ -290,6 +317,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
         }
         if (seg_b == seg_e) continue;
 
+        if (GRID) {                                  // empty spatial index for this segment (the chunk loop starts with a barrier)
+            for (int i = tid; i < NMS_BUCKETS * NMS_GRID * NMS_GRID; i += NMS_THREADS) s.ghead[i] = NMS_END;
+            if (tid < NMS_BUCKETS) { s.gw[tid] = -1.f; s.gh[tid] = -1.f; }
+        }
         int K = 0;                                   // kept in this segment: entries [seg_b, seg_b + K)
         for (int cs = seg_b; cs < seg_e; cs += NMS_CHUNK) {
             const int chn = min(NMS_CHUNK, seg_e - cs);
@@ -303,7 +334,29 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             // 4a. against the kept list of this segment: slice 0 takes the first half, slice 1 the second, in 4-aligned
             //     blocks; every lane of a warp reads the same kept boxes (shared-memory broadcasts)
             bool dead = false;
-            if (have && K > 0) {
+            const float area_j = GRID ? area_py(bj) : 0.f;
+            if (GRID && have && K > 0 && area_j >= 1e-20f) {
+                // walk only the lists that can hold a suppressor of j; the two slices take alternate cells
+                const float wj = bj.z - bj.x, hj = bj.w - bj.y;
+                const float cxj = 0.5f * (bj.x + bj.z), cyj = 0.5f * (bj.y + bj.w);
+                const int bk = nms_bucket(area_j);
+                int cnt = 0;
+                for (int b = max(bk - grid_d, 0); b <= min(bk + grid_d, NMS_BUCKETS - 1) && !dead; ++b) {
+                    const float wm = s.gw[b];
+                    if (wm < 0.f) continue;                                      // nothing kept in this bucket yet
+                    const float rx = grid_q * fmaxf(wj, wm) + 1e-6f, ry = grid_q * fmaxf(hj, s.gh[b]) + 1e-6f;
+                    const int x0 = nms_cell(cxj - rx), x1 = nms_cell(cxj + rx), y0 = nms_cell(cyj - ry), y1 = nms_cell(cyj + ry);
+                    for (int yc = y0; yc <= y1 && !dead; ++yc)
+                        for (int xc = x0; xc <= x1 && !dead; ++xc) {
+                            if (((cnt++) & (NMS_SLICES - 1)) != slice) continue;
+                            unsigned e = s.ghead[(b * NMS_GRID + yc) * NMS_GRID + xc];
+                            while (e != NMS_END) {
+                                if (suppresses<PY, FAST>(s.box[e], s.u.s2.area[e], bj, aj, thresh)) { dead = true; break; }
+                                e = s.gnext[e];
+                            }
+                        }
+                }
+            } else if (have && K > 0) {
                 const int lo = seg_b, hi = seg_b + K;
                 const int base4 = lo & ~3;
                 const int half = (((hi - base4 + 1) >> 1) + 3) & ~3;
@@ -378,6 +431,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                 const int d = seg_b + K + off;
                 s.box[d] = bj; s.u.s2.area[d] = aj; s.u.s2.idx[d] = my; s.cls[d] = mc;
                 if (PY) atomicOr(&s.keepmap[my >> 5], 1u << (my & 31));
+                if (GRID) {                                                      // file it in the spatial index
+                    const int b = nms_bucket(area_j);
+                    const int cell = (b * NMS_GRID + nms_cell(0.5f * (bj.y + bj.w))) * NMS_GRID + nms_cell(0.5f * (bj.x + bj.z));
+                    s.gnext[d] = (unsigned short)atomicExch(&s.ghead[cell], (unsigned)d);
+                    atomicMax(reinterpret_cast<int *>(&s.gw[b]), __float_as_int(bj.z - bj.x));      // widths are >= 0: integer order = float order
+                    atomicMax(reinterpret_cast<int *>(&s.gh[b]), __float_as_int(bj.w - bj.y));
+                }
             }
             K += tot;
             __syncthreads();
