@@ -19,7 +19,9 @@
 namespace yb {
 
 struct FirstParams {
-    const int8_t *in;          // [n][H][W][4]
+    const int8_t *in;          // [n][H][W][4]  (RGB444 = false)
+    const uint16_t *in16;      // [n][H][W] 0x0BGR camera pixels (RGB444 = true): quantised on the fly through the LUT
+    const int *lut;            // 4096 packed (R,G,B,0) words = pixel_norm_quantize for every code (yolo_forward.c:57-85)
     int n_img, H, W;
     int OH, OW;
     int cs_out;                // 16
@@ -49,24 +51,63 @@ __device__ __forceinline__ void mma_s8_k16(int (&c)[4], unsigned a0, unsigned a1
 
 // POOL: CTA = 32 x 16 pre-pool pixels -> 16 x 8 pooled; warp w = pooled rows 2*(w>>1), +1 and pooled columns 8*(w&1)..+7.
 // !POOL: CTA = 32 x 16 pixels; warp w = rows 2w, 2w+1 and four column groups of 8 (four M=16 tiles, rows g / g+8 = the two rows).
-template <bool POOL, int EPI, bool ACT>
+// RGB444: the input is the camera frame itself; the RGB444 -> int8 quantiser (camera_to_inpBuf + pixel_norm_quantize,
+// yolo_forward.c:57-123) is applied while the halo tile is staged.  The 4096-entry table is separable (each colour is
+// masked and normalised on its own), so three 16-entry byte tables in shared memory reproduce it exactly.
+template <bool POOL, int EPI, bool ACT, bool RGB444>
 __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstParams p)
 {
     __shared__ unsigned s_in[F_HROWS * F_PITCH];
+    __shared__ unsigned char s_lut[3][16];
     const int tiles_x = (p.W + F_TW - 1) / F_TW;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, img = blockIdx.y;
     const int x0 = tx * F_TW, y0 = ty * F_TH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    // haloed input tile, zero outside the image (= the convolution's zero padding)
-    const unsigned *gin = reinterpret_cast<const unsigned *>(p.in) + (size_t)img * p.H * p.W;
-    for (int i = threadIdx.x; i < F_HROWS * (F_TW + 2); i += F_THREADS) {
-        const int hy = i / (F_TW + 2), hx = i - hy * (F_TW + 2);
-        const int y = y0 - 1 + hy, x = x0 - 1 + hx;
-        unsigned v = 0;
-        if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) v = __ldg(gin + (size_t)y * p.W + x);
-        s_in[hy * F_PITCH + hx] = v;
+    // haloed input tile, zero outside the image (= the convolution's zero padding): warp w stages halo rows w, w+8, w+16;
+    // lane l takes column l, lanes 0 and 1 also columns 32 and 33
+    // (global loads are issued first, for all rows of this warp; the table lookups follow once the table is in place)
+    constexpr int ROWS_PER_WARP = (F_HROWS + F_THREADS / 32 - 1) / (F_THREADS / 32);
+    unsigned raw[ROWS_PER_WARP][2];
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_WARP; ++k) {
+        const int hy = warp + k * (F_THREADS / 32);
+        const int y = y0 - 1 + hy;
+        const bool rowok = hy < F_HROWS && (unsigned)y < (unsigned)p.H;
+        const size_t rowbase = ((size_t)img * p.H + (rowok ? y : 0)) * p.W;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int hx = lane + 32 * r;
+            const int x = x0 - 1 + hx;
+            unsigned v = RGB444 ? 0xffffu : 0u;                    // RGB444: 0xffff marks "outside the image"
+            if (rowok && hx < F_TW + 2 && (unsigned)x < (unsigned)p.W)
+                v = RGB444 ? (unsigned)__ldg(p.in16 + rowbase + x) : __ldg(reinterpret_cast<const unsigned *>(p.in) + rowbase + x);
+            raw[k][r] = v;
+        }
+    }
+    if (RGB444) {
+        if (threadIdx.x < 48) {
+            const int ch = threadIdx.x >> 4, i = threadIdx.x & 15;
+            s_lut[ch][i] = (unsigned char)((unsigned)__ldg(p.lut + (i << (4 * ch))) >> (8 * ch));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS_PER_WARP; ++k) {
+        const int hy = warp + k * (F_THREADS / 32);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int hx = lane + 32 * r;
+            if (hy < F_HROWS && hx < F_TW + 2) {
+                unsigned v = raw[k][r];
+                if (RGB444) {
+                    const unsigned c = v;
+                    v = c == 0xffffu ? 0u : ((unsigned)s_lut[0][c & 15u] | ((unsigned)s_lut[1][(c >> 4) & 15u] << 8) | ((unsigned)s_lut[2][(c >> 8) & 15u] << 16));
+                }
+                s_in[hy * F_PITCH + hx] = v;
+            }
+        }
     }
 
     // B fragments.  N-tile n, column c <-> output channel 4*(c>>1) + 2*n + (c&1), so that the C fragment of thread t
@@ -173,8 +214,13 @@ static cudaError_t launch_first2(const FirstParams &p, cudaStream_t st)
 {
     const int tiles = ((p.W + F_TW - 1) / F_TW) * ((p.H + F_TH - 1) / F_TH);
     dim3 grid(tiles, p.n_img);
-    if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true><<<grid, F_THREADS, 0, st>>>(p);
-    else conv3x3_first_kernel<POOL, EPI, false><<<grid, F_THREADS, 0, st>>>(p);
+    if (p.in16) {
+        if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, true><<<grid, F_THREADS, 0, st>>>(p);
+        else conv3x3_first_kernel<POOL, EPI, false, true><<<grid, F_THREADS, 0, st>>>(p);
+    } else {
+        if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, false><<<grid, F_THREADS, 0, st>>>(p);
+        else conv3x3_first_kernel<POOL, EPI, false, false><<<grid, F_THREADS, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 
@@ -189,13 +235,14 @@ static cudaError_t launch_first(const ConvArgs &a, FirstParams &p, cudaStream_t 
     }
 }
 
-cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st)
+// frames16 != nullptr: fused RGB444 front end (a.in is ignored), lut = the context's 4096-word table
+cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, const uint16_t *frames16, const int *lut)
 {
     if (a.n == 0) return cudaSuccess;
     if (!conv3x3_first_supported(a)) return cudaErrorInvalidValue;
     FirstParams p;
     memset(&p, 0, sizeof p);
-    p.in = a.in; p.n_img = a.n; p.H = a.H; p.W = a.W;
+    p.in = a.in; p.in16 = frames16; p.lut = lut; p.n_img = a.n; p.H = a.H; p.W = a.W;
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
     p.cs_out = a.cs_out; p.wgt = a.wgt; p.bias_sh = a.bias_sh; p.q = a.q; p.out = a.out; p.ovf = a.ovf;
     return a.q.pool ? launch_first<true>(a, p, st) : launch_first<false>(a, p, st);

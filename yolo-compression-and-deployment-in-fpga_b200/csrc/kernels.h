@@ -28,7 +28,7 @@ cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
 
 // conv_first.cu (first layer: NHWC4 input, <= 16 output channels, warp-level integer MMAs)
 bool conv3x3_first_supported(const ConvArgs &a);
-cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st);
+cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, const uint16_t *frames16 = nullptr, const int *lut = nullptr);
 
 // conv_umma.cu (tcgen05 / TMEM / TMA implicit GEMM)
 bool conv3x3_umma_supported(const ConvArgs &a);

@@ -368,14 +368,20 @@ int yolo_b200_quantize_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, 
     return 0;
 }
 
-static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out)
+static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out, ConvArgs &a)
 {
     LayerDev &L = c->layers[l];
-    ConvArgs a;
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
     a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
+}
+
+static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out)
+{
+    LayerDev &L = c->layers[l];
+    ConvArgs a;
+    fill_args(c, l, d_in, n, h, w, d_out, a);
     const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
     const bool umma_ok = aligned && conv3x3_umma_supported(a);
     const bool ws_ok = aligned && conv3x3_ws_supported(a);
@@ -419,14 +425,11 @@ int yolo_b200_conv_layer(yolo_b200_ctx *c, int layer, const int8_t *d_in, int n,
     return run_layer(c, layer, d_in, n, h, w, d_out);
 }
 
-int yolo_b200_backbone(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw)
+// Layers first..last on the context stream.  `cur` is the input of layer `first` (h x w).
+static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *cur, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw)
 {
-    int rc = check_ready(c, n, h, w); if (rc) return rc;
-    if (!d_nhwc4 && n > 0) return fail(E_ARG, "null input");
-    const int8_t *cur = d_nhwc4;
-    c->ev_used = 0;
-    tick(c);
-    for (size_t l = 0; l < c->layers.size(); ++l) {
+    int rc;
+    for (size_t l = first; l < c->layers.size(); ++l) {
         LayerDev &L = c->layers[l];
         if (L.q.pool && (h < 2 || w < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, h, w);
         int oh = L.q.pool ? h / 2 : h, ow = L.q.pool ? w / 2 : w;
@@ -442,6 +445,15 @@ int yolo_b200_backbone(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, in
     if (gh) *gh = h;
     if (gw) *gw = w;
     return 0;
+}
+
+int yolo_b200_backbone(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_nhwc4 && n > 0) return fail(E_ARG, "null input");
+    c->ev_used = 0;
+    tick(c);
+    return backbone_from(c, 0, d_nhwc4, n, h, w, d_pred, gh, gw);
 }
 
 int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, size_t bytes)
@@ -498,6 +510,26 @@ int yolo_b200_forward_int8_dev(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, i
 int yolo_b200_forward_rgb444_dev(yolo_b200_ctx *c, const uint16_t *d_frames, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
 {
     int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_frames && n > 0) return fail(E_ARG, "null input");
+    // Auto back end: the RGB444 -> int8 quantiser (camera_to_inpBuf + pixel_norm_quantize, yolo_forward.c:57-123) is fused
+    // into the first layer's tile load, so the quantised frame never exists in HBM.
+    LayerDev &L0 = c->layers[0];
+    ConvArgs a0;
+    fill_args(c, 0, nullptr, n, h, w, nullptr, a0);
+    if (n > 0 && c->conv_backend == 0 && conv3x3_first_supported(a0) && (((uintptr_t)d_frames) & 1) == 0 && !(L0.q.pool && (h < 2 || w < 2))) {
+        const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
+        rc = ensure((void **)&L0.out, &L0.out_cap, (size_t)n * oh * ow * L0.cs_out); if (rc) return rc;
+        L0.oh = oh; L0.ow = ow;
+        a0.out = L0.out;
+        c->ev_used = 0;
+        tick(c);
+        CU(conv3x3_first(a0, c->stream, d_frames, c->lut_dev));
+        c->launches++;
+        tick(c);
+        const int8_t *pred; int gh, gw;
+        rc = backbone_from(c, 1, L0.out, n, oh, ow, &pred, &gh, &gw); if (rc) return rc;
+        return yolo_b200_detect(c, pred, n, gh, gw, h, w, d_dets, d_counts);
+    }
     rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
     rc = yolo_b200_quantize_rgb444(c, d_frames, n, h, w, c->in_q); if (rc) return rc;
     return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
