@@ -96,8 +96,8 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 //   c. one warp resolves the chunk in score order from the (rarely non-empty) bit-rows;
 //   d. the chunk's survivors are appended to the kept list (in place: kept count <= processed count).
 // Python head with thresh > 1e-6: the kept list also carries a SPATIAL INDEX so that step a visits only boxes that can
-// matter.  IoU > t implies (i) area ratio within [t, 1/t] and (ii) |dcx| < (1-t) max(w_i,w_j), |dcy| < (1-t) max(h_i,h_j)
-// (the x-overlap must exceed t times the wider box).  Kept boxes are therefore filed, as linked lists, under
+// matter.  IoU > t implies (i) area ratio within [t, 1/t] and (ii) |dcx| < (1-t)/(1+t) max(w_i,w_j), likewise in y
+// (from inter > t/(1+t) (a_i + a_j): the x-overlap must exceed t/(1+t) times the sum of the widths).  Kept boxes are therefore filed, as linked lists, under
 // (area bucket by binary exponent, 8x8 centre cell); a candidate walks only the lists of compatible buckets and of the
 // cells its window covers (with slack for rounding; every visited pair still goes through the screen and the exact test,
 // so pruning can only skip pairs that could not suppress).  Candidates with a degenerate area scan the whole list: the
@@ -234,11 +234,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     const float thresh = a.nms_thresh;
     const float cfac = FAST ? thresh / (1.f + thresh) * 0.99999f : 1.f;     // screen factor (see screen_py)
     constexpr bool GRID = PY && FAST;
-    // spatial-index bounds with slack: IoU > t needs area ratio >= t (bucket distance <= grid_d) and centre distance
-    // < (1 - t) * max extent per axis
+    // spatial-index bounds with slack: IoU > t needs area ratio >= t (bucket distance <= grid_d) and, per axis, centre
+    // distance < (1 - t)/(1 + t) * max extent:  inter > t/(1+t) (a_i + a_j) and ih <= min(h) give
+    // iw > t/(1+t) (w_i + w_j), and iw <= (w_i + w_j)/2 - |dcx|
     const float t_lo = thresh * 0.999f;
     const int grid_d = GRID ? (int)floorf(log2f(1.f / t_lo)) + 1 : 0;
-    const float grid_q = fmaxf(1.f - t_lo, 0.f) * 1.0001f;
+    const float grid_q = fmaxf(1.f - t_lo, 0.f) / (1.f + t_lo) * 1.0001f;
 
     // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
     //    key = class | score bits | tie-break: python sorts per class, ties -> higher anchor index first (reversed stable
