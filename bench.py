@@ -212,16 +212,19 @@ def main():
     n_sets = 3
     host_sets = [torch.from_numpy(ex.synthetic_frames_rgb444(B, H, W, seed=100 * rank + s).view(np.int16)).pin_memory() for s in range(n_sets)]
     dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
-    d_dets = torch.zeros((B, MAXDET, 8), dtype=torch.int32, device="cuda")
-    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    n_anchors = (H // 16) * (W // 16) * 5                       # bounds any per-frame detection count
+    gath = runner.DetectionGatherer(B, MAXDET, n_anchors, torch.device("cuda", local))
+    d_dets, d_counts = gath.bufs[0].dets, gath.bufs[0].counts
     torch.cuda.synchronize()
 
     def step(i):
-        ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, d_dets, d_counts)
-        if world > 1:
-            runner.gather_detections(d_dets, d_counts, B * world)
+        # detections of every rank are all-gathered asynchronously (double-buffered): the gather of step i overlaps step i+1
+        buf = gath.buffers(i)
+        ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, buf.dets, buf.counts)
+        gath.launch(i)
 
     def barrier():
+        gath.finish()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

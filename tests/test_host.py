@@ -128,3 +128,35 @@ print("rank", rank, "ok")
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_async_detection_gatherer_gloo_world2(tmp_path):
+    """The double-buffered asynchronous gather the bench uses at N > 1 (here over gloo on CPU, world size 2)."""
+    script = tmp_path / "g.py"
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import yolo_b200
+from yolo_b200 import runner
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = runner.DetectionGatherer(local_frames=3, max_det=6, cap=4, device=torch.device("cpu"))
+for step in range(5):
+    b = g.buffers(step)
+    b.dets[:] = 100 * step + 10 * rank + torch.arange(6, dtype=torch.int32).view(1, 6, 1)
+    b.counts[:] = torch.tensor([1, 2, 3], dtype=torch.int32) + rank
+    g.launch(step)
+g.finish()
+b = g.bufs[4 %% 2]
+assert b.all_dets.shape == (6, 4, 8) and b.all_counts.tolist() == [1, 2, 3, 2, 3, 4]
+for r in range(world):
+    assert b.all_dets[3 * r, :, 0].tolist() == [400 + 10 * r + k for k in range(4)]
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+''' % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

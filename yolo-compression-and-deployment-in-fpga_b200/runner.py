@@ -49,3 +49,49 @@ def gather_detections(dets: torch.Tensor, counts: torch.Tensor, n_frames: int, g
         ds.append(out_d[r][:h - l])
         cs.append(out_c[r][:h - l])
     return torch.cat(ds), torch.cat(cs)
+
+
+class DetectionGatherer:
+    """Asynchronous, double-buffered all-gather of the per-rank detection lists (NCCL over NVLink on GPUs).
+
+    The gather of step i runs on the collective's own stream while step i+1 computes, so it costs the hot path nothing;
+    `finish()` (or the next use of the same buffer) waits for it.  No host synchronisation: the lists travel at a fixed
+    capacity `cap` <= max_det (callers pass the number of anchors per frame, which bounds any count), so no count has to
+    reach the host first.  Usage per step:  buf = g.buffers(i); <write detections into buf.dets / buf.counts>; g.launch(i)."""
+
+    class _Buf:
+        def __init__(self, local_frames, max_det, cap, world, device):
+            self.dets = torch.zeros((local_frames, max_det, 8), dtype=torch.int32, device=device)
+            self.counts = torch.zeros((local_frames,), dtype=torch.int32, device=device)
+            self.send = torch.zeros((local_frames, cap, 8), dtype=torch.int32, device=device)
+            self.all_dets = torch.zeros((world * local_frames, cap, 8), dtype=torch.int32, device=device)
+            self.all_counts = torch.zeros((world * local_frames,), dtype=torch.int32, device=device)
+            self.work = []
+
+    def __init__(self, local_frames: int, max_det: int, cap: int, device, group=None, depth: int = 2):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cap = min(cap, max_det)
+        self.bufs = [self._Buf(local_frames, max_det, self.cap, self.world, device) for _ in range(depth)]
+
+    def buffers(self, step: int):
+        b = self.bufs[step % len(self.bufs)]
+        for w in b.work:            # the gather that last used this buffer must have read it (stream-side wait, host does not block)
+            w.wait()
+        b.work = []
+        return b
+
+    def launch(self, step: int):
+        b = self.bufs[step % len(self.bufs)]
+        if self.world == 1:
+            return b
+        b.send.copy_(b.dets[:, :self.cap])
+        b.work = [dist.all_gather_into_tensor(b.all_dets, b.send, group=self.group, async_op=True),
+                  dist.all_gather_into_tensor(b.all_counts, b.counts, group=self.group, async_op=True)]
+        return b
+
+    def finish(self):
+        for b in self.bufs:
+            for w in b.work:
+                w.wait()
+            b.work = []
