@@ -245,7 +245,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,6 +329,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_fps = world * B * e2e_steps / e2e_s
+    # clocks / throttle reasons sampled from the start of the timed region to the end of the e2e region (the timed region
+    # alone lasts only tens of milliseconds: too short for nvidia-smi's sampling period)
+    clocks = sampler.stop() if rank == 0 else None
     assert int(h_counts.sum()) > 0 or mean_dets == 0
 
     # ---- secondary: the same network with a trained-like sparse head (objectness bias - 5)
