@@ -156,6 +156,13 @@ int yolo_b200_forward_rgb444(yolo_b200_ctx *ctx, const uint16_t *frames, int n, 
 int yolo_b200_forward_int8(yolo_b200_ctx *ctx, const int8_t *nhwc4, int n, int h, int w,
                            yolo_b200_det *dets, int32_t *counts);
 
+/* Replaces the image front end of the Python path for images already at network size: BaseTransform without the resize
+ * (data/__init__.py:30-56: /255, -mean, /std on the BGR bytes cv2 delivers), the BGR->RGB / CHW swap of test.py:79 and
+ * a_tracker_in's quantisation (slim_yolo_v2.py:218,35), then the forward pass.  bgr: uint8 [n][h][w][3].
+ * The three steps are a pure function of one byte per channel and run as a table lookup fused into the first layer. */
+int yolo_b200_forward_u8bgr(yolo_b200_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
+                            yolo_b200_det *dets, int32_t *counts);
+
 /* Replaces SlimYOLOv2_quantize_bnfuse.forward(x, quantization=True) inference branch,
  * slim_yolo_v2.py:212-358, for a float NCHW batch (input quantised by a_tracker_in, :218). */
 int yolo_b200_forward_f32(yolo_b200_ctx *ctx, const float *nchw, int n, int h, int w,
@@ -169,6 +176,8 @@ int yolo_b200_forward_int8_dev(yolo_b200_ctx *ctx, const int8_t *d_nhwc4, int n,
                                yolo_b200_det *d_dets, int32_t *d_counts);
 int yolo_b200_forward_f32_dev(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w,
                               yolo_b200_det *d_dets, int32_t *d_counts);
+int yolo_b200_forward_u8bgr_dev(yolo_b200_ctx *ctx, const uint8_t *d_bgr, int n, int h, int w,
+                                yolo_b200_det *d_dets, int32_t *d_counts);
 /* Block until everything queued on the context stream is done. */
 int yolo_b200_sync(yolo_b200_ctx *ctx);
 
@@ -180,6 +189,10 @@ int yolo_b200_quantize_rgb444(yolo_b200_ctx *ctx, const uint16_t *d_frames, int 
                               int8_t *d_nhwc4);
 int yolo_b200_quantize_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w,
                            int8_t *d_nhwc4);
+/* uint8 BGR image -> int8 NHWC4 (the front end of yolo_b200_forward_u8bgr as a stage), and its table for tests:
+ * lut[ch*256 + v], ch 0..2 = R,G,B of the network input (R comes from BGR byte 2). */
+int yolo_b200_quantize_u8bgr(yolo_b200_ctx *ctx, const uint8_t *d_bgr, int n, int h, int w, int8_t *d_nhwc4);
+int yolo_b200_u8bgr_lut(yolo_b200_ctx *ctx, int8_t *lut_host);
 /* The 4096 x 4 byte table itself (host copy), for tests: lut[code*4 + {0,1,2}] = R,G,B. */
 int yolo_b200_rgb444_lut(yolo_b200_ctx *ctx, int8_t *lut_host);
 

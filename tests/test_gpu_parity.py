@@ -358,6 +358,77 @@ def test_frames_are_independent_at_full_size(ctx):
     np.testing.assert_array_equal(pred_all[2:3], ref)
 
 
+def test_pipelined_host_entry_points_do_not_depend_on_the_chunk_size(ctx):
+    """yolo_b200_forward_rgb444 / _int8 (host buffers; copies overlapped with compute chunk by chunk) return the same
+    detections for every chunk size, and the same as the device-buffer entry point."""
+    qnet = ex.random_quantnet(seed=3, calib_hw=(64, 96), calib_frames=2, calib_input="rgb444")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    n, h, w = 7, 64, 96
+    frames = ex.synthetic_frames_rgb444(n, h, w, seed=9)
+    d_dets = torch.zeros((n, 512, 8), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    ctx.forward_rgb444_dev(dev(frames.view(np.int16)), n, h, w, d_dets, d_counts)
+    ctx.sync()
+    ref_d, ref_c = d_dets.cpu().numpy(), d_counts.cpu().numpy()
+    assert ref_c.sum() > 0
+    x8 = ol.quantize_rgb444(frames, qnet.sa[0])
+    try:
+        for chunk in (0, 1, 2, 3, 128):
+            ctx.set_host_chunk(chunk)
+            dets, counts = ctx.forward_rgb444(frames)
+            np.testing.assert_array_equal(counts, ref_c)
+            dets8, counts8 = ctx.forward_int8(x8)
+            np.testing.assert_array_equal(counts8, ref_c)
+            for i in range(n):
+                k = int(ref_c[i])
+                np.testing.assert_array_equal(dets[i][:k].view(np.int32).reshape(k, 8), ref_d[i, :k])
+                np.testing.assert_array_equal(dets8[i][:k].view(np.int32).reshape(k, 8), ref_d[i, :k])
+    finally:
+        ctx.set_host_chunk(128)
+
+
+def test_uint8_image_front_end_matches_basetransform_and_f32_path(ctx):
+    """yolo_b200_forward_u8bgr: BaseTransform (without resize) + BGR->RGB + tracker quantiser as a fused table lookup.
+    The table equals the reference's float32 arithmetic evaluated in numpy; the quantised map equals the f32 front end
+    on the transformed image; detections equal the f32 entry point's."""
+    g, qnet, frames = gu.load("ref_p_64x96")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_P, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    rng = np.random.default_rng(21)
+    n, h, w = 3, 64, 96
+    img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)                 # BGR, as cv2.imread delivers
+    # data/__init__.py:44-52 in numpy float32, then test.py:79 (BGR -> RGB, HWC -> CHW)
+    x = img.astype(np.float32)
+    x /= 255.
+    x -= np.array((0.406, 0.456, 0.485), dtype=np.float32)
+    x /= np.array((0.225, 0.224, 0.229), dtype=np.float32)
+    x = np.ascontiguousarray(x[..., (2, 1, 0)].transpose(0, 3, 1, 2))
+    ref8, ovf = ol.quantize_f32(x, qnet.sa[0])
+    assert ovf == 0
+    lut = ctx.u8bgr_lut()
+    v = np.arange(256, dtype=np.float32)
+    for ch, (mean, sd) in enumerate(((0.485, 0.229), (0.456, 0.224), (0.406, 0.225))):
+        t = v / np.float32(255.)
+        t = (t - np.float32(mean)) / np.float32(sd)
+        np.testing.assert_array_equal(lut[ch], np.rint(t * np.float32(2.0 ** qnet.sa[0])).astype(np.int8))
+    d_q = torch.zeros((n, h, w, 4), dtype=torch.int8, device="cuda")
+    ctx.quantize_u8bgr(dev(img), n, h, w, d_q)
+    ctx.sync()
+    np.testing.assert_array_equal(d_q.cpu().numpy(), ref8)
+    dets_u8, counts_u8 = ctx.forward_u8bgr(img)                              # fused into the first layer
+    dets_f, counts_f = ctx.forward_f32(x)
+    np.testing.assert_array_equal(counts_u8, counts_f)
+    assert counts_f.sum() > 0
+    for i in range(n):
+        k = int(counts_f[i])
+        np.testing.assert_array_equal(dets_u8[i][:k].view(np.int32), dets_f[i][:k].view(np.int32))
+    ctx.set_conv_backend(1)                                                  # un-fused path (stand-alone quantiser + dp4a)
+    try:
+        dets_b, counts_b = ctx.forward_u8bgr(img)
+    finally:
+        ctx.set_conv_backend(0)
+    np.testing.assert_array_equal(counts_b, counts_f)
+
+
 def test_legacy_yolo_forward_symbol(ctx):
     """yolo_forward(18,22,16,20,32,16, camera, vga) as main.c:44-49 calls it: detections are drawn into the camera
     buffer and the frame is copied to the VGA buffer (yolo_forward.c:1280-1281)."""

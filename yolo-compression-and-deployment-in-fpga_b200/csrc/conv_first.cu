@@ -22,6 +22,8 @@ struct FirstParams {
     const int8_t *in;          // [n][H][W][4]  (RGB444 = false)
     const uint16_t *in16;      // [n][H][W] 0x0BGR camera pixels (RGB444 = true): quantised on the fly through the LUT
     const int *lut;            // 4096 packed (R,G,B,0) words = pixel_norm_quantize for every code (yolo_forward.c:57-85)
+    const uint8_t *in8;        // [n][H][W][3] BGR bytes (SRC = 2): BaseTransform-without-resize + tracker quantiser through lut8
+    const uint8_t *lut8;       // [3][256]: R (from byte 2), G, B
     int n_img, H, W;
     int OH, OW;
     int cs_out;                // 16
@@ -54,11 +56,13 @@ __device__ __forceinline__ void mma_s8_k16(int (&c)[4], unsigned a0, unsigned a1
 // RGB444: the input is the camera frame itself; the RGB444 -> int8 quantiser (camera_to_inpBuf + pixel_norm_quantize,
 // yolo_forward.c:57-123) is applied while the halo tile is staged.  The 4096-entry table is separable (each colour is
 // masked and normalised on its own), so three 16-entry byte tables in shared memory reproduce it exactly.
-template <bool POOL, int EPI, bool ACT, bool RGB444>
+// SRC: 0 = int8 NHWC4, 1 = RGB444, 2 = uint8 BGR image (three 256-entry tables, see quantize.cu)
+template <bool POOL, int EPI, bool ACT, int SRC>
 __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstParams p)
 {
+    constexpr bool RGB444 = SRC == 1, U8 = SRC == 2;
     __shared__ unsigned s_in[F_HROWS * F_PITCH];
-    __shared__ unsigned char s_lut[3][16];
+    __shared__ unsigned char s_lut[U8 ? 768 : 48];
     const int tiles_x = (p.W + F_TW - 1) / F_TW;
     const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, img = blockIdx.y;
     const int x0 = tx * F_TW, y0 = ty * F_TH;
@@ -80,17 +84,23 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
         for (int r = 0; r < 2; ++r) {
             const int hx = lane + 32 * r;
             const int x = x0 - 1 + hx;
-            unsigned v = RGB444 ? 0xffffu : 0u;                    // RGB444: 0xffff marks "outside the image"
-            if (rowok && hx < F_TW + 2 && (unsigned)x < (unsigned)p.W)
-                v = RGB444 ? (unsigned)__ldg(p.in16 + rowbase + x) : __ldg(reinterpret_cast<const unsigned *>(p.in) + rowbase + x);
+            unsigned v = SRC ? 0xffffffffu : 0u;                   // table sources: all ones marks "outside the image"
+            if (rowok && hx < F_TW + 2 && (unsigned)x < (unsigned)p.W) {
+                if (RGB444) v = (unsigned)__ldg(p.in16 + rowbase + x);
+                else if (U8) { const uint8_t *px = p.in8 + 3 * (rowbase + x); v = (unsigned)__ldg(px) | ((unsigned)__ldg(px + 1) << 8) | ((unsigned)__ldg(px + 2) << 16); }
+                else v = __ldg(reinterpret_cast<const unsigned *>(p.in) + rowbase + x);
+            }
             raw[k][r] = v;
         }
     }
     if (RGB444) {
         if (threadIdx.x < 48) {
             const int ch = threadIdx.x >> 4, i = threadIdx.x & 15;
-            s_lut[ch][i] = (unsigned char)((unsigned)__ldg(p.lut + (i << (4 * ch))) >> (8 * ch));
+            s_lut[16 * ch + i] = (unsigned char)((unsigned)__ldg(p.lut + (i << (4 * ch))) >> (8 * ch));
         }
+        __syncthreads();
+    } else if (U8) {
+        for (int i = threadIdx.x; i < 768 / 4; i += F_THREADS) reinterpret_cast<unsigned *>(s_lut)[i] = __ldg(reinterpret_cast<const unsigned *>(p.lut8) + i);
         __syncthreads();
     }
 #pragma unroll
@@ -103,7 +113,10 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
                 unsigned v = raw[k][r];
                 if (RGB444) {
                     const unsigned c = v;
-                    v = c == 0xffffu ? 0u : ((unsigned)s_lut[0][c & 15u] | ((unsigned)s_lut[1][(c >> 4) & 15u] << 8) | ((unsigned)s_lut[2][(c >> 8) & 15u] << 16));
+                    v = c == 0xffffffffu ? 0u : ((unsigned)s_lut[c & 15u] | ((unsigned)s_lut[16 + ((c >> 4) & 15u)] << 8) | ((unsigned)s_lut[32 + ((c >> 8) & 15u)] << 16));
+                } else if (U8) {
+                    const unsigned c = v;      // B | G << 8 | R << 16
+                    v = c == 0xffffffffu ? 0u : ((unsigned)s_lut[(c >> 16) & 255u] | ((unsigned)s_lut[256 + ((c >> 8) & 255u)] << 8) | ((unsigned)s_lut[512 + (c & 255u)] << 16));
                 }
                 s_in[hy * F_PITCH + hx] = v;
             }
@@ -209,19 +222,22 @@ bool conv3x3_first_supported(const ConvArgs &a)
     return true;
 }
 
-template <bool POOL, int EPI>
-static cudaError_t launch_first2(const FirstParams &p, cudaStream_t st)
+template <bool POOL, int EPI, int SRC>
+static cudaError_t launch_first3(const FirstParams &p, cudaStream_t st)
 {
     const int tiles = ((p.W + F_TW - 1) / F_TW) * ((p.H + F_TH - 1) / F_TH);
     dim3 grid(tiles, p.n_img);
-    if (p.in16) {
-        if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, true><<<grid, F_THREADS, 0, st>>>(p);
-        else conv3x3_first_kernel<POOL, EPI, false, true><<<grid, F_THREADS, 0, st>>>(p);
-    } else {
-        if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, false><<<grid, F_THREADS, 0, st>>>(p);
-        else conv3x3_first_kernel<POOL, EPI, false, false><<<grid, F_THREADS, 0, st>>>(p);
-    }
+    if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, SRC><<<grid, F_THREADS, 0, st>>>(p);
+    else conv3x3_first_kernel<POOL, EPI, false, SRC><<<grid, F_THREADS, 0, st>>>(p);
     return cudaGetLastError();
+}
+
+template <bool POOL, int EPI>
+static cudaError_t launch_first2(const FirstParams &p, cudaStream_t st)
+{
+    if (p.in16) return launch_first3<POOL, EPI, 1>(p, st);
+    if (p.in8) return launch_first3<POOL, EPI, 2>(p, st);
+    return launch_first3<POOL, EPI, 0>(p, st);
 }
 
 template <bool POOL>
@@ -235,14 +251,16 @@ static cudaError_t launch_first(const ConvArgs &a, FirstParams &p, cudaStream_t 
     }
 }
 
-// frames16 != nullptr: fused RGB444 front end (a.in is ignored), lut = the context's 4096-word table
-cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, const uint16_t *frames16, const int *lut)
+// src_kind 1 / 2: fused RGB444 / uint8-BGR front end (a.in is ignored); lut = the context's table for that source
+cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind, const void *src, const void *lut)
 {
     if (a.n == 0) return cudaSuccess;
     if (!conv3x3_first_supported(a)) return cudaErrorInvalidValue;
     FirstParams p;
     memset(&p, 0, sizeof p);
-    p.in = a.in; p.in16 = frames16; p.lut = lut; p.n_img = a.n; p.H = a.H; p.W = a.W;
+    p.in = a.in; p.n_img = a.n; p.H = a.H; p.W = a.W;
+    if (src_kind == 1) { p.in16 = (const uint16_t *)src; p.lut = (const int *)lut; }
+    else if (src_kind == 2) { p.in8 = (const uint8_t *)src; p.lut8 = (const uint8_t *)lut; }
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
     p.cs_out = a.cs_out; p.wgt = a.wgt; p.bias_sh = a.bias_sh; p.q = a.q; p.out = a.out; p.ovf = a.ovf;
     return a.q.pool ? launch_first<true>(a, p, st) : launch_first<false>(a, p, st);

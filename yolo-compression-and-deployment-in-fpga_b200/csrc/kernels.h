@@ -28,7 +28,8 @@ cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
 
 // conv_first.cu (first layer: NHWC4 input, <= 16 output channels, warp-level integer MMAs)
 bool conv3x3_first_supported(const ConvArgs &a);
-cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, const uint16_t *frames16 = nullptr, const int *lut = nullptr);
+// src_kind: 0 = a.in (int8 NHWC4), 1 = RGB444 uint16 frames + 4096-word table, 2 = uint8 BGR images + 3x256-byte table
+cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind = 0, const void *src = nullptr, const void *lut = nullptr);
 
 // conv_umma.cu (tcgen05 / TMEM / TMA implicit GEMM)
 bool conv3x3_umma_supported(const ConvArgs &a);
@@ -41,6 +42,7 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // quantize.cu
 cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st);
+cudaError_t quantize_u8bgr(const uint8_t *bgr, size_t npix, const uint8_t *lut8_dev, int8_t *nhwc4, unsigned *ovf, cudaStream_t st);
 cudaError_t quantize_f32(const float *nchw, int n, int h, int w, int sa, int8_t *nhwc4, unsigned *ovf, cudaStream_t st);
 
 // head.cu

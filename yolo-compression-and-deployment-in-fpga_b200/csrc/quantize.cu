@@ -40,6 +40,38 @@ cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_
     return cudaGetLastError();
 }
 
+// BaseTransform without the resize (data/__init__.py:30-56: /255, -mean, /std on the BGR bytes cv2 delivers), test.py:79's
+// BGR -> RGB swap and a_tracker_in's quantisation (slim_yolo_v2.py:218,35) are a pure function of one byte per channel:
+// the host evaluates the reference's float32 arithmetic once per byte value into three 256-entry tables
+// (yolo_b200.cu: build_u8_lut); lut8[0..255] = R (from BGR byte 2), [256..511] = G, [512..767] = B.
+// lut8[768..1535] flags the byte values whose quantised value had to be saturated (the reference never clamps): counted.
+__global__ void __launch_bounds__(256) quantize_u8bgr_kernel(const uint8_t *__restrict__ bgr, size_t npix,
+                                                             const uint8_t *__restrict__ lut8, int *__restrict__ out,
+                                                             unsigned *__restrict__ ovf_counter)
+{
+    __shared__ uint8_t s_lut[1536];
+    for (int i = threadIdx.x; i < 1536; i += blockDim.x) s_lut[i] = lut8[i];
+    __syncthreads();
+    unsigned ovf = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t *px = bgr + 3 * i;
+        const unsigned r = px[2], g = 256u + px[1], b = 512u + px[0];
+        out[i] = (int)((unsigned)s_lut[r] | ((unsigned)s_lut[g] << 8) | ((unsigned)s_lut[b] << 16));
+        ovf += s_lut[768 + r] + s_lut[768 + g] + s_lut[768 + b];
+    }
+    ovf = __reduce_add_sync(0xffffffffu, ovf);
+    if ((threadIdx.x & 31) == 0 && ovf) atomicAdd(ovf_counter, ovf);
+}
+
+cudaError_t quantize_u8bgr(const uint8_t *bgr, size_t npix, const uint8_t *lut8_dev, int8_t *nhwc4, unsigned *ovf, cudaStream_t st)
+{
+    int blocks = (int)((npix + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    quantize_u8bgr_kernel<<<blocks, 256, 0, st>>>(bgr, npix, lut8_dev, reinterpret_cast<int *>(nhwc4), ovf);
+    return cudaGetLastError();
+}
+
 // a_tracker_in.quantize_activation with a frozen power-of-two scale (models/slim_yolo_v2.py:33-35):
 // q = round-half-even(x * 2^sa).  The reference does not clamp; int8 storage saturates and counts.
 // float NCHW (3 planes) -> int8 NHWC4, 4 pixels per thread (3 x 16 B loads, one 16 B store).

@@ -45,6 +45,9 @@ struct yolo_b200_ctx {
     std::vector<LayerDev> layers;
     int *lut_dev = nullptr;              // 4096 packed (R,G,B,0) words
     int8_t lut_host[4096 * 4];
+    uint8_t *lut8_dev = nullptr;         // uint8 BGR front end: [3][256] quantised bytes (R,G,B) + [3][256] saturation flags
+    uint8_t lut8_host[1536];
+    bool lut8_saturates = false;
     unsigned *ovf_dev = nullptr;
     int8_t *in_q = nullptr; size_t in_q_cap = 0;        // quantised NHWC4 input
     void *stage_in = nullptr; size_t stage_in_cap = 0;  // device staging of host inputs
@@ -119,6 +122,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
     CU(cudaMalloc(&c->ovf_dev, sizeof(unsigned)));
     CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));
     CU(cudaMalloc(&c->lut_dev, 4096 * sizeof(int)));
+    CU(cudaMalloc(&c->lut8_dev, 1536));
     CU(head_init());
     *out = c;
     return 0;
@@ -140,7 +144,7 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_layers(c);
-    cudaFree(c->lut_dev); cudaFree(c->ovf_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
+    cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
     cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
     for (auto e : c->ev) cudaEventDestroy(e);
     for (auto e : c->ev_in) cudaEventDestroy(e);
@@ -177,6 +181,31 @@ static void build_rgb444_lut(int sa, int8_t *lut)
         }
         lut[code * 4 + 3] = 0;
     }
+}
+
+// BaseTransform without the resize + a_tracker_in, per byte value and channel (see quantize.cu).  numpy evaluates
+// x /= 255.; x -= mean; x /= std in float32 (data/__init__.py:44-46,50-52); the tracker rounds x * 2^sa half-to-even
+// (slim_yolo_v2.py:35).  Network channel order is RGB (test.py:79), the image is BGR.
+static bool build_u8_lut(int sa, uint8_t *lut)
+{
+    const float mean_bgr[3] = { 0.406f, 0.456f, 0.485f }, std_bgr[3] = { 0.225f, 0.224f, 0.229f };
+    const float s = ldexpf(1.0f, sa);
+    bool sat = false;
+    for (int ch = 0; ch < 3; ++ch) {              // ch: 0 = R, 1 = G, 2 = B of the network input = BGR byte 2 - ch
+        const float mean = mean_bgr[2 - ch], sd = std_bgr[2 - ch];
+        for (int v = 0; v < 256; ++v) {
+            volatile float x = (float)v;
+            x = x / 255.0f;
+            x = x - mean;
+            x = x / sd;
+            float q = nearbyintf(x * s);          // default rounding mode: to nearest even
+            int qi = q < -128.f ? -128 : q > 127.f ? 127 : (int)q;
+            lut[ch * 256 + v] = (uint8_t)(int8_t)qi;
+            lut[768 + ch * 256 + v] = (q < -128.f || q > 127.f) ? 1 : 0;
+            sat |= (q < -128.f || q > 127.f);
+        }
+    }
+    return sat;
 }
 
 static int host_shr_round(int x, int n, int mode)
@@ -286,6 +315,8 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
     CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));      // the saturation counter belongs to the loaded network
     build_rgb444_lut(p->scale_a[0], c->lut_host);
     CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
+    c->lut8_saturates = build_u8_lut(p->scale_a[0], c->lut8_host);
+    CU(cudaMemcpy(c->lut8_dev, c->lut8_host, sizeof c->lut8_host, cudaMemcpyHostToDevice));
     c->loaded = true;
     return 0;
 }
@@ -365,6 +396,23 @@ int yolo_b200_quantize_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, 
     if (((size_t)h * w) % 4) return fail(E_UNSUPPORTED, "h*w must be a multiple of 4");
     CU(quantize_f32(d_nchw, n, h, w, c->prm.scale_a[0], d_nhwc4, c->ovf_dev, c->stream));
     c->launches++;
+    return 0;
+}
+
+int yolo_b200_quantize_u8bgr(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int h, int w, int8_t *d_nhwc4)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (n == 0) return 0;
+    CU(quantize_u8bgr(d_bgr, (size_t)n * h * w, c->lut8_dev, d_nhwc4, c->ovf_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int yolo_b200_u8bgr_lut(yolo_b200_ctx *c, int8_t *lut_host)
+{
+    if (!c || !lut_host) return fail(E_ARG, "null argument");
+    if (!c->loaded) return fail(E_STATE, "no network loaded");
+    memcpy(lut_host, c->lut8_host, 768);
     return 0;
 }
 
@@ -507,31 +555,53 @@ int yolo_b200_forward_int8_dev(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, i
     return yolo_b200_detect(c, pred, n, gh, gw, h, w, d_dets, d_counts);
 }
 
+// Camera / image front ends fused into the first layer (auto back end): the quantised frame never exists in HBM.
+// kind 1 = RGB444 (camera_to_inpBuf + pixel_norm_quantize, yolo_forward.c:57-123), 2 = uint8 BGR (BaseTransform + tracker).
+static int forward_fused_front(yolo_b200_ctx *c, int kind, const void *d_src, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts, bool *done)
+{
+    *done = false;
+    LayerDev &L0 = c->layers[0];
+    ConvArgs a0;
+    fill_args(c, 0, nullptr, n, h, w, nullptr, a0);
+    if (!(n > 0 && c->conv_backend == 0 && conv3x3_first_supported(a0) && !(L0.q.pool && (h < 2 || w < 2)))) return 0;
+    if (kind == 1 && (((uintptr_t)d_src) & 1)) return 0;
+    if (kind == 2 && c->lut8_saturates) return 0;              // saturated inputs must be counted: the stand-alone quantiser does
+    const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
+    int rc = ensure((void **)&L0.out, &L0.out_cap, (size_t)n * oh * ow * L0.cs_out); if (rc) return rc;
+    L0.oh = oh; L0.ow = ow;
+    a0.out = L0.out;
+    c->ev_used = 0;
+    tick(c);
+    CU(conv3x3_first(a0, c->stream, kind, d_src, kind == 1 ? (const void *)c->lut_dev : (const void *)c->lut8_dev));
+    c->launches++;
+    tick(c);
+    const int8_t *pred; int gh, gw;
+    rc = backbone_from(c, 1, L0.out, n, oh, ow, &pred, &gh, &gw); if (rc) return rc;
+    *done = true;
+    return yolo_b200_detect(c, pred, n, gh, gw, h, w, d_dets, d_counts);
+}
+
 int yolo_b200_forward_rgb444_dev(yolo_b200_ctx *c, const uint16_t *d_frames, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
 {
     int rc = check_ready(c, n, h, w); if (rc) return rc;
     if (!d_frames && n > 0) return fail(E_ARG, "null input");
-    // Auto back end: the RGB444 -> int8 quantiser (camera_to_inpBuf + pixel_norm_quantize, yolo_forward.c:57-123) is fused
-    // into the first layer's tile load, so the quantised frame never exists in HBM.
-    LayerDev &L0 = c->layers[0];
-    ConvArgs a0;
-    fill_args(c, 0, nullptr, n, h, w, nullptr, a0);
-    if (n > 0 && c->conv_backend == 0 && conv3x3_first_supported(a0) && (((uintptr_t)d_frames) & 1) == 0 && !(L0.q.pool && (h < 2 || w < 2))) {
-        const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
-        rc = ensure((void **)&L0.out, &L0.out_cap, (size_t)n * oh * ow * L0.cs_out); if (rc) return rc;
-        L0.oh = oh; L0.ow = ow;
-        a0.out = L0.out;
-        c->ev_used = 0;
-        tick(c);
-        CU(conv3x3_first(a0, c->stream, d_frames, c->lut_dev));
-        c->launches++;
-        tick(c);
-        const int8_t *pred; int gh, gw;
-        rc = backbone_from(c, 1, L0.out, n, oh, ow, &pred, &gh, &gw); if (rc) return rc;
-        return yolo_b200_detect(c, pred, n, gh, gw, h, w, d_dets, d_counts);
-    }
+    bool done;
+    rc = forward_fused_front(c, 1, d_frames, n, h, w, d_dets, d_counts, &done);
+    if (rc || done) return rc;
     rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
     rc = yolo_b200_quantize_rgb444(c, d_frames, n, h, w, c->in_q); if (rc) return rc;
+    return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
+}
+
+int yolo_b200_forward_u8bgr_dev(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_bgr && n > 0) return fail(E_ARG, "null input");
+    bool done;
+    rc = forward_fused_front(c, 2, d_bgr, n, h, w, d_dets, d_counts, &done);
+    if (rc || done) return rc;
+    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
+    rc = yolo_b200_quantize_u8bgr(c, d_bgr, n, h, w, c->in_q); if (rc) return rc;
     return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
 }
 
@@ -586,6 +656,7 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         int32_t *dc = c->d_counts + f0;
         if (kind == 0) rc = yolo_b200_forward_rgb444_dev(c, (const uint16_t *)stage, nk, h, w, dd, dc);
         else if (kind == 1) rc = yolo_b200_forward_int8_dev(c, (const int8_t *)stage, nk, h, w, dd, dc);
+        else if (kind == 3) rc = yolo_b200_forward_u8bgr_dev(c, (const uint8_t *)stage, nk, h, w, dd, dc);
         else rc = yolo_b200_forward_f32_dev(c, (const float *)stage, nk, h, w, dd, dc);
         if (rc) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
         CU(cudaEventRecord(c->ev_done[k], c->stream));
@@ -602,6 +673,8 @@ int yolo_b200_forward_rgb444(yolo_b200_ctx *c, const uint16_t *frames, int n, in
 { return forward_host(c, frames, (size_t)n * h * w * 2, 0, n, h, w, dets, counts); }
 int yolo_b200_forward_int8(yolo_b200_ctx *c, const int8_t *nhwc4, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
 { return forward_host(c, nhwc4, (size_t)n * h * w * 4, 1, n, h, w, dets, counts); }
+int yolo_b200_forward_u8bgr(yolo_b200_ctx *c, const uint8_t *bgr, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{ return forward_host(c, bgr, (size_t)n * h * w * 3, 3, n, h, w, dets, counts); }
 int yolo_b200_forward_f32(yolo_b200_ctx *c, const float *nchw, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
 { return forward_host(c, nchw, (size_t)n * h * w * 12, 2, n, h, w, dets, counts); }
 

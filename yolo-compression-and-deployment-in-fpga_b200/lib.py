@@ -25,7 +25,8 @@ EXPORTS = [
     "yolo_b200_abi_version", "yolo_b200_last_error", "yolo_b200_cstride", "yolo_b200_default_params",
     "yolo_b200_create", "yolo_b200_destroy", "yolo_b200_set_stream", "yolo_b200_load", "yolo_b200_set_thresholds",
     "yolo_b200_set_conv_backend", "yolo_b200_set_host_chunk", "yolo_b200_debug_requant",
-    "yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32",
+    "yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32", "yolo_b200_forward_u8bgr",
+    "yolo_b200_forward_u8bgr_dev", "yolo_b200_quantize_u8bgr", "yolo_b200_u8bgr_lut",
     "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev", "yolo_b200_sync",
     "yolo_b200_quantize_rgb444", "yolo_b200_quantize_f32", "yolo_b200_rgb444_lut", "yolo_b200_conv_layer",
     "yolo_b200_backbone", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
@@ -88,13 +89,15 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_set_conv_backend.argtypes = [vp, i32]
     L.yolo_b200_set_host_chunk.argtypes = [vp, i32]
     L.yolo_b200_debug_requant.argtypes = [vp, i32, vp, C.c_size_t, vp, i32]
-    for name in ("yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32",
-                 "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev"):
+    for name in ("yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32", "yolo_b200_forward_u8bgr",
+                 "yolo_b200_forward_u8bgr_dev", "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.yolo_b200_sync.argtypes = [vp]
     L.yolo_b200_quantize_rgb444.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_quantize_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_rgb444_lut.argtypes = [vp, vp]
+    L.yolo_b200_quantize_u8bgr.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.yolo_b200_u8bgr_lut.argtypes = [vp, vp]
     L.yolo_b200_conv_layer.argtypes = [vp, i32, i8p, i32, i32, i32, i8p]
     L.yolo_b200_backbone.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
     L.yolo_b200_get_layer_output.argtypes = [vp, i32, vp, C.c_size_t]
@@ -223,6 +226,14 @@ class Context:
         n, h, w = f.shape
         return self._forward_host(self.L.yolo_b200_forward_rgb444, f, n, h, w)
 
+    def forward_u8bgr(self, images: np.ndarray):
+        """uint8 BGR images [n][h][w][3] at network size (what cv2 delivers): BaseTransform arithmetic + tracker quantiser
+        + forward pass, all on the GPU."""
+        f = np.ascontiguousarray(images, dtype=np.uint8)
+        n, h, w, c = f.shape
+        assert c == 3
+        return self._forward_host(self.L.yolo_b200_forward_u8bgr, f, n, h, w)
+
     def forward_int8(self, nhwc4: np.ndarray):
         x = np.ascontiguousarray(nhwc4, dtype=np.int8)
         n, h, w, c = x.shape
@@ -244,6 +255,17 @@ class Context:
 
     def forward_f32_dev(self, d_in, n, h, w, d_dets, d_counts):
         self._check(self.L.yolo_b200_forward_f32_dev(self._h, _ptr(d_in), n, h, w, _ptr(d_dets), _ptr(d_counts)))
+
+    def forward_u8bgr_dev(self, d_in, n, h, w, d_dets, d_counts):
+        self._check(self.L.yolo_b200_forward_u8bgr_dev(self._h, _ptr(d_in), n, h, w, _ptr(d_dets), _ptr(d_counts)))
+
+    def quantize_u8bgr(self, d_bgr, n, h, w, d_out):
+        self._check(self.L.yolo_b200_quantize_u8bgr(self._h, _ptr(d_bgr), n, h, w, _ptr(d_out)))
+
+    def u8bgr_lut(self) -> np.ndarray:
+        lut = np.zeros((3, 256), dtype=np.int8)
+        self._check(self.L.yolo_b200_u8bgr_lut(self._h, lut.ctypes.data))
+        return lut
 
     def quantize_rgb444(self, d_frames, n, h, w, d_out):
         self._check(self.L.yolo_b200_quantize_rgb444(self._h, _ptr(d_frames), n, h, w, _ptr(d_out)))
