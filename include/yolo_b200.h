@@ -213,6 +213,14 @@ int yolo_b200_debug_requant(yolo_b200_ctx *ctx, int layer, const int32_t *d_acc,
  * valid until the next call) and its grid size. */
 int yolo_b200_backbone(yolo_b200_ctx *ctx, const int8_t *d_nhwc4, int n, int h, int w,
                        const int8_t **d_pred, int *gh, int *gw);
+/* Calibration on the GPU: one forward pass over a float NCHW calibration batch with fresh trackers.  Replaces the
+ * calibration call of retune_bias_quantize.py -q (AveragedRangeTracker first-call rule, slim_yolo_v2.py:22-27,33:
+ * scale_a = floor(log2(127 / max|a|)) per activation) and the overflow search of retune_bias_quantize_findbest.py
+ * (retune[l] = largest r with max|y_l| * 2^r < 2^15, slim_yolo_v2.py:222-227).  Updates the context's tables and epilogue
+ * programmes in place and returns them (scale_a_out: num_layers + 1 entries, retune_out: num_layers; either may be NULL). */
+int yolo_b200_calibrate_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w,
+                            int32_t *scale_a_out, int32_t *retune_out);
+
 /* Copy layer l's output of the most recent backbone call to the host (debug / parity). */
 int yolo_b200_get_layer_output(yolo_b200_ctx *ctx, int layer, int8_t *host_out, size_t bytes);
 

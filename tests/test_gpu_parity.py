@@ -429,6 +429,30 @@ def test_uint8_image_front_end_matches_basetransform_and_f32_path(ctx):
     np.testing.assert_array_equal(counts_b, counts_f)
 
 
+@pytest.mark.parametrize("contract", [lib.CONTRACT_P, lib.CONTRACT_F])
+def test_gpu_calibration_matches_the_reference_rule(ctx, contract):
+    """yolo_b200_calibrate_f32 (tracker first-call rule + overflow guard, on the GPU) derives the same exponent tables as
+    the exporter's float32 restatement of the reference's calibration call, from deliberately wrong starting tables,
+    and the re-programmed context then reproduces the exporter-calibrated network bit for bit."""
+    import copy
+    ws, bs = ex.random_float_convs(seed=4)
+    frames = ex.synthetic_frames_f32(2, 64, 96, seed=77)
+    ref = ex.build_quantnet(ws, bs, frames)                       # CPU: quantise weights, calibrate on `frames`
+    wrong = copy.deepcopy(ref)
+    wrong.sa = [max(0, e - 1) for e in ref.sa]
+    wrong.retune = [r - 1 for r in ref.retune]
+    ctx.load_quantnet(wrong, contract=contract, conf_thresh=0.1, nms_thresh=0.5)
+    sa, rt = ctx.calibrate_f32(frames.cuda(), 2, 64, 96)
+    assert sa == list(ref.sa), (sa, ref.sa)
+    assert rt == list(ref.retune), (rt, ref.retune)
+    test = ex.synthetic_frames_f32(2, 64, 96, seed=78)
+    x8, _ = ol.quantize_f32(test.numpy(), ref.sa[0])
+    outs, _ = run_backbone(ctx, x8)
+    want, _ = ol.backbone(ref, x8, contract=contract)
+    for l, (a_, b_) in enumerate(zip(outs, want)):
+        np.testing.assert_array_equal(a_, b_, err_msg="layer %d after GPU calibration" % l)
+
+
 def test_legacy_yolo_forward_symbol(ctx):
     """yolo_forward(18,22,16,20,32,16, camera, vga) as main.c:44-49 calls it: detections are drawn into the camera
     buffer and the frame is copied to the VGA buffer (yolo_forward.c:1280-1281)."""

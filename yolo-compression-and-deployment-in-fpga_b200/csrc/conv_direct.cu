@@ -12,6 +12,7 @@
 // staged in shared memory with their 1-pixel halo (zero filled = the convolution's zero padding).
 #include "common.cuh"
 #include "kernels.h"
+#include <climits>
 
 namespace yb {
 
@@ -25,7 +26,8 @@ __global__ void __launch_bounds__(QUADS *(COT / 8))
 conv3x3_direct_kernel(const int8_t *__restrict__ in, int n_img, int H, int W, int cs_in,   // cs_in: channel stride (bytes)
                       const int8_t *__restrict__ wgt,                                      // [cout_pad][9][cs_in]
                       const int *__restrict__ bias_sh,                                     // [cout_pad]
-                      int cout, int cs_out, LayerQ q, int8_t *__restrict__ out, unsigned *__restrict__ ovf_counter)
+                      int cout, int cs_out, LayerQ q, int8_t *__restrict__ out, unsigned *__restrict__ ovf_counter,
+                      int *__restrict__ stats)
 {
     constexpr int PH = TILE_H + 2, PW = TILE_W + 2;
     constexpr int WPC = CK / 4;                       // 32-bit words per pixel per chunk
@@ -91,6 +93,22 @@ conv3x3_direct_kernel(const int8_t *__restrict__ in, int n_img, int H, int W, in
     int bsh[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) bsh[c] = bias_sh[co0 + c];
+    if (stats) {
+        // calibration pass (yolo_b200_calibrate_f32): no output; stats[0] = max, stats[1] = min over every pre-pool
+        // element of the layer numerator num = (acc << la) + (b << lb), the real-valued activation at scale 2^-E
+        int mx = INT_MIN, mn = INT_MAX;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int oy = y0 + 2 * qy + (p >> 1), ox = x0 + 2 * qx + (p & 1);
+            if (oy < H && ox < W)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (co0 + c < cout) { const int num = (acc[p][c] << q.la) + bsh[c]; mx = max(mx, num); mn = min(mn, num); }
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx); mn = __reduce_min_sync(0xffffffffu, mn);
+        if ((threadIdx.x & 31) == 0) { atomicMax(&stats[0], mx); atomicMin(&stats[1], mn); }
+        return;
+    }
     int o[4][8];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
@@ -140,7 +158,7 @@ static cudaError_t launch(const ConvArgs &a, cudaStream_t st)
     int tiles = ((a.H + TILE_H - 1) / TILE_H) * ((a.W + TILE_W - 1) / TILE_W);
     dim3 grid(tiles, (a.cs_out + COT - 1) / COT, a.n);
     conv3x3_direct_kernel<CK, COT><<<grid, QUADS *(COT / 8), 0, st>>>(a.in, a.n, a.H, a.W, a.cs_in, a.wgt, a.bias_sh,
-                                                                       a.cout, a.cs_out, a.q, a.out, a.ovf);
+                                                                       a.cout, a.cs_out, a.q, a.out, a.ovf, a.stats);
     return cudaGetLastError();
 }
 

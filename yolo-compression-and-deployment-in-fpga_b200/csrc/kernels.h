@@ -21,6 +21,7 @@ struct ConvArgs {
     LayerQ q;
     int8_t *out;           // [n][H'][W'][cs_out]
     unsigned *ovf;         // contract-P saturation counter
+    int *stats = nullptr;  // conv3x3_direct only: calibration pass, see conv_direct.cu (bias_sh then holds b << lb, q.la the shift)
 };
 
 // conv_direct.cu
@@ -43,6 +44,7 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
 // quantize.cu
 cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st);
 cudaError_t quantize_u8bgr(const uint8_t *bgr, size_t npix, const uint8_t *lut8_dev, int8_t *nhwc4, unsigned *ovf, cudaStream_t st);
+cudaError_t absmax_f32(const float *x, size_t count, unsigned *out_bits, cudaStream_t st);   // max |x| as float bits (atomicMax)
 cudaError_t quantize_f32(const float *nchw, int n, int h, int w, int sa, int8_t *nhwc4, unsigned *ovf, cudaStream_t st);
 
 // head.cu

@@ -72,6 +72,26 @@ cudaError_t quantize_u8bgr(const uint8_t *bgr, size_t npix, const uint8_t *lut8_
     return cudaGetLastError();
 }
 
+// max |x| over a float tensor (AveragedRangeTracker's min/max, slim_yolo_v2.py:22-23): non-negative floats order like their
+// bit patterns, so the reduction is an integer atomicMax.  *out_bits must be zeroed by the caller.
+__global__ void __launch_bounds__(256) absmax_f32_kernel(const float *__restrict__ x, size_t count, unsigned *__restrict__ out_bits)
+{
+    unsigned m = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(x[i])));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, m);
+}
+
+cudaError_t absmax_f32(const float *x, size_t count, unsigned *out_bits, cudaStream_t st)
+{
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    absmax_f32_kernel<<<blocks, 256, 0, st>>>(x, count, out_bits);
+    return cudaGetLastError();
+}
+
 // a_tracker_in.quantize_activation with a frozen power-of-two scale (models/slim_yolo_v2.py:33-35):
 // q = round-half-even(x * 2^sa).  The reference does not clamp; int8 storage saturates and counts.
 // float NCHW (3 planes) -> int8 NHWC4, 4 pixels per thread (3 x 16 B loads, one 16 B store).

@@ -27,6 +27,7 @@ enum { E_ARG = -1, E_STATE = -2, E_UNSUPPORTED = -3, E_NOMEM = -4, E_CUDA = -5 }
 struct LayerDev {
     int cin, cout, cs_in, cs_out, cout_pad;
     int bias_abs_max = 0;
+    std::vector<int8_t> bias_host;   // int8 biases as loaded (the epilogue programme is re-derived when the tables change)
     LayerQ q;
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
@@ -49,6 +50,7 @@ struct yolo_b200_ctx {
     uint8_t lut8_host[1536];
     bool lut8_saturates = false;
     unsigned *ovf_dev = nullptr;
+    int *stats_dev = nullptr;            // calibration: {max, min} of a layer's numerator / abs-max bits of the input
     int8_t *in_q = nullptr; size_t in_q_cap = 0;        // quantised NHWC4 input
     void *stage_in = nullptr; size_t stage_in_cap = 0;  // device staging of host inputs
     float *h_scores = nullptr; int *h_cls = nullptr; float4 *h_boxes = nullptr; size_t head_cap = 0;
@@ -121,6 +123,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->ovf_dev, sizeof(unsigned)));
     CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));
+    CU(cudaMalloc(&c->stats_dev, 2 * sizeof(int)));
     CU(cudaMalloc(&c->lut_dev, 4096 * sizeof(int)));
     CU(cudaMalloc(&c->lut8_dev, 1536));
     CU(head_init());
@@ -144,7 +147,7 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_layers(c);
-    cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
+    cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->stats_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
     cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
     for (auto e : c->ev) cudaEventDestroy(e);
     for (auto e : c->ev_in) cudaEventDestroy(e);
@@ -218,6 +221,39 @@ static int host_shr_round(int x, int n, int mode)
     return fl + (fl & 1);
 }
 
+// Epilogue programme of layer l from the context's tables (set_quantize_scale, yolo_forward.c:235-254, for contract F;
+// slim_yolo_v2.py:33-38 for contract P) and the pre-shifted biases; uploads the biases.
+static int derive_layer(yolo_b200_ctx *c, int l)
+{
+    const yolo_b200_params *p = &c->prm;
+    const yolo_b200_layer &L = p->layers[l];
+    LayerDev &d = c->layers[l];
+    LayerQ &q = d.q;
+    memset(&q, 0, sizeof q);
+    q.contract = p->contract; q.round_mode = p->round_mode; q.activ = L.activ; q.pool = L.pool;
+    const int sa_i = p->scale_a[l], sw = p->scale_w[l], sb = p->scale_b[l], rt = p->retune[l], sa_o = p->scale_a[l + 1];
+    std::vector<int> bsh(d.cout_pad, 0);
+    const int8_t *b = d.bias_host.data();
+    if (p->contract == YOLO_B200_CONTRACT_F) {
+        int iofs = sa_i + sw - rt, bofs = sb - rt, oofs = rt - sa_o, bdir = 0;
+        q.idir = iofs < 0; q.iofs = abs(iofs);
+        bdir = bofs < 0; bofs = abs(bofs);
+        q.odir = oofs < 0; q.oofs = abs(oofs);
+        if (q.iofs > 24 || bofs > 20 || q.oofs > 24) return fail(E_UNSUPPORTED, "layer %d: shift out of range (iofs %d bofs %d oofs %d)", l, q.iofs, bofs, q.oofs);
+        for (int o = 0; o < L.cout; ++o)
+            bsh[o] = bdir ? (int)b[o] * (1 << bofs) : host_shr_round(b[o], bofs, p->round_mode);
+    } else if (p->contract == YOLO_B200_CONTRACT_P) {
+        int ea = sa_i + sw, E = ea > sb ? ea : sb;
+        q.la = E - ea; q.sh = E - sa_o;
+        if (q.la > 4 || E - sb > 22 || q.sh > 24 || q.sh < -8) return fail(E_UNSUPPORTED, "layer %d: exponents out of range (la %d lb %d sh %d)", l, q.la, E - sb, q.sh);
+        for (int o = 0; o < L.cout; ++o) bsh[o] = (int)b[o] * (1 << (E - sb));
+    } else return fail(E_ARG, "contract %d", p->contract);
+    d.bias_abs_max = 0;
+    for (int o = 0; o < L.cout; ++o) d.bias_abs_max = abs(bsh[o]) > d.bias_abs_max ? abs(bsh[o]) : d.bias_abs_max;
+    CU(cudaMemcpy(d.bias_sh, bsh.data(), bsh.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t *const *biases,
                    const yolo_b200_params *p, int layout)
 {
@@ -246,28 +282,7 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
         d.cin = L.cin; d.cout = L.cout;
         d.cs_in = yolo_b200_cstride(L.cin); d.cs_out = yolo_b200_cstride(L.cout);
         d.cout_pad = (d.cs_out + 31) / 32 * 32;
-        LayerQ &q = d.q;
-        memset(&q, 0, sizeof q);
-        q.contract = p->contract; q.round_mode = p->round_mode; q.activ = L.activ; q.pool = L.pool;
-        const int sa_i = p->scale_a[l], sw = p->scale_w[l], sb = p->scale_b[l], rt = p->retune[l], sa_o = p->scale_a[l + 1];
-        std::vector<int> bsh(d.cout_pad, 0);
-        if (p->contract == YOLO_B200_CONTRACT_F) {
-            // set_quantize_scale, yolo_forward.c:235-254
-            int iofs = sa_i + sw - rt, bofs = sb - rt, oofs = rt - sa_o, bdir = 0;
-            q.idir = iofs < 0; q.iofs = abs(iofs);
-            bdir = bofs < 0; bofs = abs(bofs);
-            q.odir = oofs < 0; q.oofs = abs(oofs);
-            if (q.iofs > 24 || bofs > 20 || q.oofs > 24) return fail(E_UNSUPPORTED, "layer %d: shift out of range (iofs %d bofs %d oofs %d)", l, q.iofs, bofs, q.oofs);
-            for (int o = 0; o < L.cout; ++o)
-                bsh[o] = bdir ? (int)biases[l][o] * (1 << bofs) : host_shr_round(biases[l][o], bofs, p->round_mode);
-        } else if (p->contract == YOLO_B200_CONTRACT_P) {
-            int ea = sa_i + sw, E = ea > sb ? ea : sb;
-            q.la = E - ea; q.sh = E - sa_o;
-            if (q.la > 4 || E - sb > 22 || q.sh > 24 || q.sh < -8) return fail(E_UNSUPPORTED, "layer %d: exponents out of range (la %d lb %d sh %d)", l, q.la, E - sb, q.sh);
-            for (int o = 0; o < L.cout; ++o) bsh[o] = (int)biases[l][o] * (1 << (E - sb));
-        } else return fail(E_ARG, "contract %d", p->contract);
-
-        for (int o = 0; o < L.cout; ++o) d.bias_abs_max = abs(bsh[o]) > d.bias_abs_max ? abs(bsh[o]) : d.bias_abs_max;
+        d.bias_host.assign(biases[l], biases[l] + L.cout);
         // repack to [cout_pad][tap][cs_in], zero padded
         std::vector<int8_t> wp((size_t)d.cout_pad * 9 * d.cs_in, 0);
         const int8_t *w = weights[l];
@@ -308,9 +323,9 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
             CU(cudaMalloc(&d.wimg, img.size()));
             CU(cudaMemcpy(d.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
         }
-        CU(cudaMalloc(&d.bias_sh, bsh.size() * sizeof(int)));
-        CU(cudaMemcpy(d.bias_sh, bsh.data(), bsh.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&d.bias_sh, (size_t)d.cout_pad * sizeof(int)));
         c->layers.push_back(d);
+        { int rc = derive_layer(c, l); if (rc) return rc; }
     }
     CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));      // the saturation counter belongs to the loaded network
     build_rgb444_lut(p->scale_a[0], c->lut_host);
@@ -502,6 +517,81 @@ int yolo_b200_backbone(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, in
     c->ev_used = 0;
     tick(c);
     return backbone_from(c, 0, d_nhwc4, n, h, w, d_pred, gh, gw);
+}
+
+// Calibration on the GPU.  One forward pass over a calibration batch with FRESH trackers: every
+// AveragedRangeTracker takes scale = 127 / max|a| on its first call and the power of two below it
+// (slim_yolo_v2.py:22-27,33); retune[l] is the largest r that keeps max|y_l| * 2^r below 2^15, the overflow guard of
+// find=True (slim_yolo_v2.py:222-227; retune_bias_quantize_findbest.py:115-148).  The activations are exact dyadic
+// rationals y = num * 2^-E, so their maxima come from integer max/min reductions of the layer numerators: each layer is run
+// twice, once to reduce (conv_direct.cu statistics mode) and once, with the exponents just derived, to produce the
+// quantised map the next layer calibrates on.  Updates the context's tables and epilogue programmes in place.
+int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, int32_t *scale_a_out, int32_t *retune_out)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_nchw || n < 1) return fail(E_ARG, "calibration needs at least one frame");
+    if (((size_t)h * w) % 4) return fail(E_UNSUPPORTED, "h*w must be a multiple of 4");
+    yolo_b200_params &p = c->prm;
+    int hs[2];
+    // input tracker
+    CU(cudaMemsetAsync(c->stats_dev, 0, 2 * sizeof(int), c->stream));
+    CU(absmax_f32(d_nchw, (size_t)n * 3 * h * w, reinterpret_cast<unsigned *>(c->stats_dev), c->stream));
+    c->launches++;
+    CU(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float m32; memcpy(&m32, &hs[0], 4);
+    if (!(m32 > 0.f) || !isfinite(m32)) return fail(E_ARG, "calibration input is all zero or not finite");
+    p.scale_a[0] = (int)floorf(log2f(127.0f / m32));
+    build_rgb444_lut(p.scale_a[0], c->lut_host);
+    CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
+    c->lut8_saturates = build_u8_lut(p.scale_a[0], c->lut8_host);
+    CU(cudaMemcpy(c->lut8_dev, c->lut8_host, sizeof c->lut8_host, cudaMemcpyHostToDevice));
+    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)n * h * w * 4); if (rc) return rc;
+    rc = yolo_b200_quantize_f32(c, d_nchw, n, h, w, c->in_q); if (rc) return rc;
+    const int8_t *cur = c->in_q;
+    for (size_t l = 0; l < c->layers.size(); ++l) {
+        LayerDev &L = c->layers[l];
+        const yolo_b200_layer &Lp = p.layers[l];
+        if (Lp.pool && (h < 2 || w < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, h, w);
+        // statistics pass: numerator at scale E = max(sa_i + sw, sb), biases shifted accordingly
+        const int ea = p.scale_a[l] + p.scale_w[l], E = ea > p.scale_b[l] ? ea : p.scale_b[l];
+        const int la = E - ea, lb = E - p.scale_b[l];
+        if (la > 6 || lb > 22 || la < 0) return fail(E_UNSUPPORTED, "layer %zu: exponents out of range during calibration (la %d lb %d)", l, la, lb);
+        std::vector<int> bp(L.cout_pad, 0);
+        for (int o = 0; o < L.cout; ++o) bp[o] = (int)L.bias_host[o] * (1 << lb);
+        CU(cudaMemcpy(L.bias_sh, bp.data(), bp.size() * sizeof(int), cudaMemcpyHostToDevice));
+        const int init[2] = { INT32_MIN, INT32_MAX };
+        CU(cudaMemcpyAsync(c->stats_dev, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+        ConvArgs a;
+        fill_args(c, (int)l, cur, n, h, w, nullptr, a);
+        a.q.la = la; a.stats = c->stats_dev;
+        CU(conv3x3_direct(a, c->stream));
+        c->launches++;
+        CU(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const float pos = hs[0] > 0 ? (float)hs[0] : 0.f;
+        float neg = hs[1] < 0 ? -(float)hs[1] : 0.f;
+        if (Lp.activ) neg *= 0.125f;                                   // leaky-ReLU before the tracker (slim_yolo_v2.py:220-229)
+        const float my = ldexpf(pos > neg ? pos : neg, -E);            // max |y|, exact
+        if (!(my > 0.f)) return fail(E_ARG, "layer %zu produces only zeros on the calibration batch", l);
+        const double md = (double)my;
+        int r = (int)floor(log2(32768.0 / md));
+        while (md * ldexp(1.0, r) >= 32768.0) --r;
+        p.retune[l] = r;
+        p.scale_a[l + 1] = (int)floorf(log2f(127.0f / my));
+        rc = derive_layer(c, (int)l); if (rc) return rc;
+        // the layer itself, with the exponents just derived
+        const int oh = Lp.pool ? h / 2 : h, ow = Lp.pool ? w / 2 : w;
+        rc = ensure((void **)&L.out, &L.out_cap, (size_t)n * oh * ow * L.cs_out); if (rc) return rc;
+        L.oh = oh; L.ow = ow;
+        rc = run_layer(c, (int)l, cur, n, h, w, L.out); if (rc) return rc;
+        cur = L.out; h = oh; w = ow;
+    }
+    c->last_n = n;
+    CU(cudaStreamSynchronize(c->stream));
+    if (scale_a_out) for (int l = 0; l <= p.num_layers; ++l) scale_a_out[l] = p.scale_a[l];
+    if (retune_out) for (int l = 0; l < p.num_layers; ++l) retune_out[l] = p.retune[l];
+    return 0;
 }
 
 int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, size_t bytes)

@@ -29,7 +29,7 @@ EXPORTS = [
     "yolo_b200_forward_u8bgr_dev", "yolo_b200_quantize_u8bgr", "yolo_b200_u8bgr_lut",
     "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev", "yolo_b200_sync",
     "yolo_b200_quantize_rgb444", "yolo_b200_quantize_f32", "yolo_b200_rgb444_lut", "yolo_b200_conv_layer",
-    "yolo_b200_backbone", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
+    "yolo_b200_backbone", "yolo_b200_calibrate_f32", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
     "yolo_b200_launch_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
     "yolo_forward", "yolo_b200_set_default_context",
 ]
@@ -97,6 +97,7 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_quantize_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_rgb444_lut.argtypes = [vp, vp]
     L.yolo_b200_quantize_u8bgr.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.yolo_b200_calibrate_f32.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.yolo_b200_u8bgr_lut.argtypes = [vp, vp]
     L.yolo_b200_conv_layer.argtypes = [vp, i32, i8p, i32, i32, i32, i8p]
     L.yolo_b200_backbone.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
@@ -258,6 +259,18 @@ class Context:
 
     def forward_u8bgr_dev(self, d_in, n, h, w, d_dets, d_counts):
         self._check(self.L.yolo_b200_forward_u8bgr_dev(self._h, _ptr(d_in), n, h, w, _ptr(d_dets), _ptr(d_counts)))
+
+    def calibrate_f32(self, d_nchw, n, h, w):
+        """Derive scale_a / retune on the GPU from a float NCHW calibration batch (device tensor) by the reference's
+        first-call tracker rule and overflow guard; the context is re-programmed in place.  Returns (scale_a, retune)."""
+        nl = self.params.num_layers
+        sa = np.zeros(nl + 1, dtype=np.int32)
+        rt = np.zeros(nl, dtype=np.int32)
+        self._check(self.L.yolo_b200_calibrate_f32(self._h, _ptr(d_nchw), n, h, w, sa.ctypes.data, rt.ctypes.data))
+        for l in range(nl):
+            self.params.scale_a[l] = int(sa[l]); self.params.retune[l] = int(rt[l])
+        self.params.scale_a[nl] = int(sa[nl])
+        return sa.tolist(), rt.tolist()
 
     def quantize_u8bgr(self, d_bgr, n, h, w, d_out):
         self._check(self.L.yolo_b200_quantize_u8bgr(self._h, _ptr(d_bgr), n, h, w, _ptr(d_out)))
