@@ -624,3 +624,14 @@ def test_epilogue_arithmetic_against_oracle(ctx, contract, tables):
                 np.testing.assert_array_equal(fast, out, err_msg="fp32 and integer epilogues differ, layer %d" % layer)
     if tables in ("calibrated",):
         assert fast_seen >= 9, "the exact-fp32 epilogue should apply to calibrated tables"
+
+
+def test_detect_cli_on_synthetic_images(tmp_path):
+    """tools/detect.py (the test.py / demo.py counterpart) runs end to end and writes one annotated image per input."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "detect.py"), "--trained_model", "random", "--images", "synthetic:3",
+                        "-size", "160", "--out", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".jpg")]) == 3
+    assert "3 images" in r.stdout
