@@ -241,6 +241,7 @@ def main():
     e0.record(stream)
     for i in range(args.steps):
         step(i)
+    gath.finish()                      # the stream waits for the outstanding gathers: they are inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
