@@ -148,7 +148,8 @@ int yolo_b200_set_thresholds(yolo_b200_ctx *ctx, float conf_thresh, float nms_th
 /* ---- whole-frame forward, HOST buffers (copies are part of the call) -------------------- */
 
 /* Replaces yolo_forward() body, yolo_forward.c:1181-1279, for n frames of h x w RGB444.
- * dets: [n][max_det], counts: [n]. */
+ * dets: [n][max_det], counts: [n].  Only the filled part of each list is copied back: entries of frame i at index
+ * >= counts[i] are unspecified (all host-buffer entry points). */
 int yolo_b200_forward_rgb444(yolo_b200_ctx *ctx, const uint16_t *frames, int n, int h, int w,
                              yolo_b200_det *dets, int32_t *counts);
 

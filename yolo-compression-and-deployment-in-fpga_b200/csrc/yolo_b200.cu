@@ -64,7 +64,7 @@ struct yolo_b200_ctx {
     int ev_used = 0;
     // host-buffer entry points: copies of chunk k+1 / k-1 overlap the kernels of chunk k
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_done;
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_cnt;
     int host_chunk = 128;                // frames per chunk
 };
 
@@ -152,6 +152,7 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     for (auto e : c->ev) cudaEventDestroy(e);
     for (auto e : c->ev_in) cudaEventDestroy(e);
     for (auto e : c->ev_done) cudaEventDestroy(e);
+    for (auto e : c->ev_cnt) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     cudaStreamDestroy(c->own_stream);
@@ -729,9 +730,10 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     const size_t frame_bytes = in_bytes / (size_t)n;
     if (!c->s_in) { CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
     while ((int)c->ev_in.size() < nchunks) {
-        cudaEvent_t e1, e2;
+        cudaEvent_t e1, e2, e3;
         CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-        c->ev_in.push_back(e1); c->ev_done.push_back(e2);
+        CU(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming));
+        c->ev_in.push_back(e1); c->ev_done.push_back(e2); c->ev_cnt.push_back(e3);
     }
     // the staging buffers may still be read by work queued earlier on the context stream
     CU(cudaEventRecord(c->ev_done[0], c->stream));
@@ -752,7 +754,19 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         CU(cudaEventRecord(c->ev_done[k], c->stream));
         CU(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
         CU(cudaMemcpyAsync(counts + f0, dc, (size_t)nk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
-        CU(cudaMemcpyAsync(dets + (size_t)f0 * md, dd, (size_t)nk * md * sizeof(yolo_b200_det), cudaMemcpyDeviceToHost, c->s_out));
+        CU(cudaEventRecord(c->ev_cnt[k], c->s_out));
+    }
+    // detections: only the filled part of each frame's list travels (one strided copy per chunk, as wide as the chunk's
+    // largest count), issued as soon as that chunk's counts have reached the host; later chunks keep computing meanwhile
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = k * chunk, nk = (n - f0) < chunk ? (n - f0) : chunk;
+        CU(cudaEventSynchronize(c->ev_cnt[k]));
+        int maxc = 0;
+        for (int i = 0; i < nk; ++i) maxc = counts[f0 + i] > maxc ? counts[f0 + i] : maxc;
+        if (maxc > (int)md) maxc = (int)md;
+        if (maxc > 0)
+            CU(cudaMemcpy2DAsync(dets + (size_t)f0 * md, md * sizeof(yolo_b200_det), c->d_dets + (size_t)f0 * md, md * sizeof(yolo_b200_det),
+                                 (size_t)maxc * sizeof(yolo_b200_det), (size_t)nk, cudaMemcpyDeviceToHost, c->s_out));
     }
     CU(cudaStreamSynchronize(c->s_out));
     CU(cudaStreamSynchronize(c->stream));
