@@ -137,9 +137,9 @@ int yolo_b200_load(yolo_b200_ctx *ctx, const int8_t *const *weights, const int8_
  * integer epilogue forced.  All are CUDA; results are identical. */
 int yolo_b200_set_conv_backend(yolo_b200_ctx *ctx, int backend);
 
-/* Host-buffer entry points (yolo_b200_forward_rgb444 / _int8 / _f32) split a batch into chunks of `frames` frames and
- * overlap the host-to-device copy of chunk k+1 and the device-to-host copy of chunk k-1 with the kernels of chunk k.
- * Default 128 (the per-frame NMS kernel needs about one frame per SM to fill the GPU); 0 = one chunk (no overlap).  Results do not depend on it (frames are independent). */
+/* Host-buffer entry points (yolo_b200_forward_rgb444 / _int8 / _f32 / _u8bgr) split a batch into chunks of `frames` frames
+ * and overlap the host-to-device copy of chunk k+1 with the convolution layers of chunk k; decode + NMS run once over the
+ * whole batch.  Default 64; 0 = one chunk (no overlap).  Results do not depend on it (frames are independent). */
 int yolo_b200_set_host_chunk(yolo_b200_ctx *ctx, int frames);
 
 /* Change thresholds / head mode after load (test.py --conf_thresh / --nms_thresh). */

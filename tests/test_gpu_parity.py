@@ -384,7 +384,7 @@ def test_pipelined_host_entry_points_do_not_depend_on_the_chunk_size(ctx):
                 np.testing.assert_array_equal(dets[i][:k].view(np.int32).reshape(k, 8), ref_d[i, :k])
                 np.testing.assert_array_equal(dets8[i][:k].view(np.int32).reshape(k, 8), ref_d[i, :k])
     finally:
-        ctx.set_host_chunk(128)
+        ctx.set_host_chunk(64)
 
 
 def test_uint8_image_front_end_matches_basetransform_and_f32_path(ctx):

@@ -65,7 +65,8 @@ struct yolo_b200_ctx {
     // host-buffer entry points: copies of chunk k+1 / k-1 overlap the kernels of chunk k
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done, ev_cnt;
-    int host_chunk = 128;                // frames per chunk
+    int host_chunk = 64;                 // frames per chunk (measured best at 416x416: tools/t_e2e.py)
+    int8_t *pred_all = nullptr; size_t pred_all_cap = 0;   // batch-wide prediction map of the host-buffer entry points
 };
 
 static std::mutex g_default_mu;
@@ -147,6 +148,7 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_layers(c);
+    cudaFree(c->pred_all);
     cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->stats_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
     cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
     for (auto e : c->ev) cudaEventDestroy(e);
@@ -490,19 +492,26 @@ int yolo_b200_conv_layer(yolo_b200_ctx *c, int layer, const int8_t *d_in, int n,
 }
 
 // Layers first..last on the context stream.  `cur` is the input of layer `first` (h x w).
-static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *cur, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw)
+// `last_out` != nullptr: the last layer writes there instead of into its own buffer (a slot of a batch-wide prediction map).
+static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *cur, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw,
+                         int8_t *last_out = nullptr)
 {
     int rc;
     for (size_t l = first; l < c->layers.size(); ++l) {
         LayerDev &L = c->layers[l];
         if (L.q.pool && (h < 2 || w < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, h, w);
         int oh = L.q.pool ? h / 2 : h, ow = L.q.pool ? w / 2 : w;
-        size_t bytes = (size_t)(n > 0 ? n : 1) * oh * ow * L.cs_out;
-        rc = ensure((void **)&L.out, &L.out_cap, bytes); if (rc) return rc;
-        L.oh = oh; L.ow = ow;
-        if (n > 0) { rc = run_layer(c, (int)l, cur, n, h, w, L.out); if (rc) return rc; }
+        int8_t *dst = L.out;
+        if (last_out && l + 1 == c->layers.size()) dst = last_out;
+        else {
+            size_t bytes = (size_t)(n > 0 ? n : 1) * oh * ow * L.cs_out;
+            rc = ensure((void **)&L.out, &L.out_cap, bytes); if (rc) return rc;
+            dst = L.out;
+            L.oh = oh; L.ow = ow;
+        }
+        if (n > 0) { rc = run_layer(c, (int)l, cur, n, h, w, dst); if (rc) return rc; }
         tick(c);
-        cur = L.out; h = oh; w = ow;
+        cur = dst; h = oh; w = ow;
     }
     c->last_n = n;
     if (d_pred) *d_pred = cur;
@@ -648,13 +657,14 @@ int yolo_b200_forward_int8_dev(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, i
 
 // Camera / image front ends fused into the first layer (auto back end): the quantised frame never exists in HBM.
 // kind 1 = RGB444 (camera_to_inpBuf + pixel_norm_quantize, yolo_forward.c:57-123), 2 = uint8 BGR (BaseTransform + tracker).
-static int forward_fused_front(yolo_b200_ctx *c, int kind, const void *d_src, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts, bool *done)
+static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, int n, int h, int w, int8_t *last_out,
+                                const int8_t **pred, int *gh, int *gw, bool *done)
 {
     *done = false;
     LayerDev &L0 = c->layers[0];
     ConvArgs a0;
     fill_args(c, 0, nullptr, n, h, w, nullptr, a0);
-    if (!(n > 0 && c->conv_backend == 0 && conv3x3_first_supported(a0) && !(L0.q.pool && (h < 2 || w < 2)))) return 0;
+    if (!(n > 0 && c->conv_backend == 0 && c->layers.size() > 1 && conv3x3_first_supported(a0) && !(L0.q.pool && (h < 2 || w < 2)))) return 0;
     if (kind == 1 && (((uintptr_t)d_src) & 1)) return 0;
     if (kind == 2 && c->lut8_saturates) return 0;              // saturated inputs must be counted: the stand-alone quantiser does
     const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
@@ -666,43 +676,51 @@ static int forward_fused_front(yolo_b200_ctx *c, int kind, const void *d_src, in
     CU(conv3x3_first(a0, c->stream, kind, d_src, kind == 1 ? (const void *)c->lut_dev : (const void *)c->lut8_dev));
     c->launches++;
     tick(c);
-    const int8_t *pred; int gh, gw;
-    rc = backbone_from(c, 1, L0.out, n, oh, ow, &pred, &gh, &gw); if (rc) return rc;
+    rc = backbone_from(c, 1, L0.out, n, oh, ow, pred, gh, gw, last_out); if (rc) return rc;
     *done = true;
+    return 0;
+}
+
+// Front end + all convolution layers for one of the four input kinds (0 RGB444, 1 int8 NHWC4, 2 float NCHW, 3 uint8 BGR).
+static int features_dev(yolo_b200_ctx *c, int kind, const void *d_src, int n, int h, int w, int8_t *last_out,
+                        const int8_t **pred, int *gh, int *gw)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_src && n > 0) return fail(E_ARG, "null input");
+    if (kind == 0 || kind == 3) {
+        bool done;
+        rc = fused_front_features(c, kind == 0 ? 1 : 2, d_src, n, h, w, last_out, pred, gh, gw, &done);
+        if (rc || done) return rc;
+    }
+    const int8_t *x8 = (const int8_t *)d_src;
+    if (kind != 1) {
+        rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
+        if (kind == 0) rc = yolo_b200_quantize_rgb444(c, (const uint16_t *)d_src, n, h, w, c->in_q);
+        else if (kind == 3) rc = yolo_b200_quantize_u8bgr(c, (const uint8_t *)d_src, n, h, w, c->in_q);
+        else rc = yolo_b200_quantize_f32(c, (const float *)d_src, n, h, w, c->in_q);
+        if (rc) return rc;
+        x8 = c->in_q;
+    }
+    c->ev_used = 0;
+    tick(c);
+    return backbone_from(c, 0, x8, n, h, w, pred, gh, gw, last_out);
+}
+
+static int forward_dev(yolo_b200_ctx *c, int kind, const void *d_src, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    const int8_t *pred; int gh, gw;
+    int rc = features_dev(c, kind, d_src, n, h, w, nullptr, &pred, &gh, &gw); if (rc) return rc;
     return yolo_b200_detect(c, pred, n, gh, gw, h, w, d_dets, d_counts);
 }
 
 int yolo_b200_forward_rgb444_dev(yolo_b200_ctx *c, const uint16_t *d_frames, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
-{
-    int rc = check_ready(c, n, h, w); if (rc) return rc;
-    if (!d_frames && n > 0) return fail(E_ARG, "null input");
-    bool done;
-    rc = forward_fused_front(c, 1, d_frames, n, h, w, d_dets, d_counts, &done);
-    if (rc || done) return rc;
-    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
-    rc = yolo_b200_quantize_rgb444(c, d_frames, n, h, w, c->in_q); if (rc) return rc;
-    return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
-}
+{ return forward_dev(c, 0, d_frames, n, h, w, d_dets, d_counts); }
 
 int yolo_b200_forward_u8bgr_dev(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
-{
-    int rc = check_ready(c, n, h, w); if (rc) return rc;
-    if (!d_bgr && n > 0) return fail(E_ARG, "null input");
-    bool done;
-    rc = forward_fused_front(c, 2, d_bgr, n, h, w, d_dets, d_counts, &done);
-    if (rc || done) return rc;
-    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
-    rc = yolo_b200_quantize_u8bgr(c, d_bgr, n, h, w, c->in_q); if (rc) return rc;
-    return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
-}
+{ return forward_dev(c, 3, d_bgr, n, h, w, d_dets, d_counts); }
 
 int yolo_b200_forward_f32_dev(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
-{
-    int rc = check_ready(c, n, h, w); if (rc) return rc;
-    rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)(n > 0 ? n : 1) * h * w * 4); if (rc) return rc;
-    rc = yolo_b200_quantize_f32(c, d_nchw, n, h, w, c->in_q); if (rc) return rc;
-    return yolo_b200_forward_int8_dev(c, c->in_q, n, h, w, d_dets, d_counts);
-}
+{ return forward_dev(c, 2, d_nchw, n, h, w, d_dets, d_counts); }
 
 int yolo_b200_sync(yolo_b200_ctx *c)
 {
@@ -712,9 +730,11 @@ int yolo_b200_sync(yolo_b200_ctx *c)
     return 0;
 }
 
-// host-buffer variants: H2D of the frames, forward, D2H of detections + counts.  Batches larger than one chunk are
-// pipelined over three streams: while chunk k computes on the context stream, chunk k+1 is copied in and the detections
-// of chunk k-1 are copied out (frames are independent, so chunking does not change any result).
+// host-buffer variants: H2D of the frames, forward, D2H of detections + counts.  The frames travel and are convolved chunk
+// by chunk over two streams (the copy of chunk k+1 overlaps the convolution layers of chunk k; frames are independent, so
+// chunking changes no result); every chunk's prediction map lands in one batch-wide buffer and decode + NMS then run once
+// over the whole batch (a per-chunk NMS launch cannot fill the GPU: it is one CTA per frame).  Only the filled part of the
+// detection lists is copied back.
 static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
                         yolo_b200_det *dets, int32_t *counts)
 {
@@ -725,50 +745,47 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     const size_t md = (size_t)c->prm.max_det;
     rc = ensure((void **)&c->d_dets, &c->dets_cap, (size_t)n * md * sizeof(yolo_b200_det)); if (rc) return rc;
     rc = ensure((void **)&c->d_counts, &c->counts_cap, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+    // prediction map of the whole batch
+    int gh = h, gw = w;
+    for (auto &L : c->layers) {
+        if (L.q.pool && (gh < 2 || gw < 2)) return fail(E_ARG, "input too small for the pooling layers");
+        if (L.q.pool) { gh /= 2; gw /= 2; }
+    }
+    const size_t pred_frame = (size_t)gh * gw * c->layers.back().cs_out;
+    rc = ensure((void **)&c->pred_all, &c->pred_all_cap, (size_t)n * pred_frame); if (rc) return rc;
     const int chunk = c->host_chunk > 0 ? c->host_chunk : n;
     const int nchunks = (n + chunk - 1) / chunk;
     const size_t frame_bytes = in_bytes / (size_t)n;
     if (!c->s_in) { CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
-    while ((int)c->ev_in.size() < nchunks) {
-        cudaEvent_t e1, e2, e3;
-        CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming));
-        c->ev_in.push_back(e1); c->ev_done.push_back(e2); c->ev_cnt.push_back(e3);
+    while ((int)c->ev_in.size() < nchunks + 1) {
+        cudaEvent_t e1;
+        CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        c->ev_in.push_back(e1);
     }
     // the staging buffers may still be read by work queued earlier on the context stream
-    CU(cudaEventRecord(c->ev_done[0], c->stream));
-    CU(cudaStreamWaitEvent(c->s_in, c->ev_done[0], 0));
+    CU(cudaEventRecord(c->ev_in[nchunks], c->stream));
+    CU(cudaStreamWaitEvent(c->s_in, c->ev_in[nchunks], 0));
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, nk = (n - f0) < chunk ? (n - f0) : chunk;
         char *stage = (char *)c->stage_in + (size_t)f0 * frame_bytes;
         CU(cudaMemcpyAsync(stage, (const char *)host_in + (size_t)f0 * frame_bytes, (size_t)nk * frame_bytes, cudaMemcpyHostToDevice, c->s_in));
         CU(cudaEventRecord(c->ev_in[k], c->s_in));
         CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
-        yolo_b200_det *dd = c->d_dets + (size_t)f0 * md;
-        int32_t *dc = c->d_counts + f0;
-        if (kind == 0) rc = yolo_b200_forward_rgb444_dev(c, (const uint16_t *)stage, nk, h, w, dd, dc);
-        else if (kind == 1) rc = yolo_b200_forward_int8_dev(c, (const int8_t *)stage, nk, h, w, dd, dc);
-        else if (kind == 3) rc = yolo_b200_forward_u8bgr_dev(c, (const uint8_t *)stage, nk, h, w, dd, dc);
-        else rc = yolo_b200_forward_f32_dev(c, (const float *)stage, nk, h, w, dd, dc);
-        if (rc) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
-        CU(cudaEventRecord(c->ev_done[k], c->stream));
-        CU(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
-        CU(cudaMemcpyAsync(counts + f0, dc, (size_t)nk * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
-        CU(cudaEventRecord(c->ev_cnt[k], c->s_out));
+        const int8_t *pred; int g1, g2;
+        rc = features_dev(c, kind, stage, nk, h, w, c->pred_all + (size_t)f0 * pred_frame, &pred, &g1, &g2);
+        if (rc) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); return rc; }
     }
-    // detections: only the filled part of each frame's list travels (one strided copy per chunk, as wide as the chunk's
-    // largest count), issued as soon as that chunk's counts have reached the host; later chunks keep computing meanwhile
-    for (int k = 0; k < nchunks; ++k) {
-        const int f0 = k * chunk, nk = (n - f0) < chunk ? (n - f0) : chunk;
-        CU(cudaEventSynchronize(c->ev_cnt[k]));
-        int maxc = 0;
-        for (int i = 0; i < nk; ++i) maxc = counts[f0 + i] > maxc ? counts[f0 + i] : maxc;
-        if (maxc > (int)md) maxc = (int)md;
-        if (maxc > 0)
-            CU(cudaMemcpy2DAsync(dets + (size_t)f0 * md, md * sizeof(yolo_b200_det), c->d_dets + (size_t)f0 * md, md * sizeof(yolo_b200_det),
-                                 (size_t)maxc * sizeof(yolo_b200_det), (size_t)nk, cudaMemcpyDeviceToHost, c->s_out));
-    }
-    CU(cudaStreamSynchronize(c->s_out));
+    rc = yolo_b200_detect(c, c->pred_all, n, gh, gw, h, w, c->d_dets, c->d_counts);
+    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    CU(cudaMemcpyAsync(counts, c->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // detections: one strided copy as wide as the largest count
+    int maxc = 0;
+    for (int i = 0; i < n; ++i) maxc = counts[i] > maxc ? counts[i] : maxc;
+    if (maxc > (int)md) maxc = (int)md;
+    if (maxc > 0)
+        CU(cudaMemcpy2DAsync(dets, md * sizeof(yolo_b200_det), c->d_dets, md * sizeof(yolo_b200_det),
+                             (size_t)maxc * sizeof(yolo_b200_det), (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
