@@ -47,6 +47,7 @@ struct UmmaParams {
     const int *bias_sh;
     int8_t *out;
     unsigned *ovf;
+    const uint8_t *w_swz;        // CB == 128: weights pre-swizzled into the shared-memory image of every (tap, chunk) block
 };
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
@@ -190,7 +191,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         else { tap = kb; c0 = 0; }
                         const int kh = tap / 3, kw = tap % 3;
                         tma_load_4d(sa + (uint32_t)(kb - kb0) * A_BOX, &map_a, bar_full(s), c0, x0 + kw - 1, y0 + kh - 1, n0);
-                        tma_load_2d(sb + (uint32_t)(kb - kb0) * B_BOX, &map_b, bar_full(s), kb * CB, 0);
+                        // B: the TMA unit spends ~4 cycles per box ROW whatever its length, and the N rows of a weight block
+                        // are 2/3 of all rows of a stage; when the host has laid the block out exactly as the 128B-swizzled
+                        // shared-memory image, one 1-D bulk copy replaces the N-row box
+                        if (CB == 128 && p.w_swz) bulk_load_1d(sb + (uint32_t)(kb - kb0) * B_BOX, p.w_swz + (size_t)kb * B_BOX, B_BOX, bar_full(s));
+                        else tma_load_2d(sb + (uint32_t)(kb - kb0) * B_BOX, &map_b, bar_full(s), kb * CB, 0);
                     }
                 }
             }
@@ -366,6 +371,7 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
     uint32_t nb = 32; while (nb < (uint32_t)p.N) nb <<= 1;
     p.tmem_buf_stride = nb; p.tmem_cols = 2 * nb;
     p.q = a.q; p.k = kc; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
+    p.w_swz = (CB == 128 && a.cs_out == a.wgt_swz_rows) ? a.wgt_swz : nullptr;
 
     CUtensorMap map_a, map_b;
     {

@@ -12,6 +12,8 @@ struct ConvArgs {
     int n, H, W, cs_in;
     const int8_t *wgt;     // [cout_pad][9][cs_in]  (cout_pad: multiple of 32, zero padded)
     const int8_t *wgt_k160; // cs_in == 16 only: [cout_pad][10][16], 10th tap all zero (two taps per K=32 MMA)
+    const uint8_t *wgt_swz = nullptr;  // cs_in % 128 == 0: [9*cs_in/128][cs_out][128 B] blocks in the 128B-swizzled smem layout (conv_umma.cu)
+    int wgt_swz_rows = 0;              // rows per block of wgt_swz (= cs_out)
     const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
     int w_rows;            // cout_pad
     int bias_abs_max;      // max |bias_sh[c]| (decides whether the exact fp32 epilogue applies)

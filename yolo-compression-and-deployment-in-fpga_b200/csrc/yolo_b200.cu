@@ -32,6 +32,7 @@ struct LayerDev {
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
+    uint8_t *w_swz = nullptr;  // cs_in % 128 == 0: 128B-swizzled blocks [9*cs_in/128][cs_out][128] (conv_umma.cu B operand)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
     size_t out_cap = 0;
@@ -134,7 +135,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.bias_sh); cudaFree(l.out); }
+    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); }
     c->layers.clear();
 }
 
@@ -326,6 +327,21 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
             CU(cudaMalloc(&d.wimg, img.size()));
             CU(cudaMemcpy(d.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
         }
+        if (d.cs_in % 128 == 0) {
+            // conv_umma.cu: block kb = (tap, 128-byte channel chunk) as it must sit in shared memory for a K-major
+            // SWIZZLE_128B operand: row r (output channel) is 128 bytes, its 16-byte chunk c lives at chunk c ^ (r & 7)
+            const int per = d.cs_in / 128, nkb = 9 * per;
+            std::vector<uint8_t> sw((size_t)nkb * d.cs_out * 128, 0);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int tap = kb / per, c0 = (kb % per) * 128;
+                for (int r = 0; r < d.cs_out; ++r)
+                    for (int ch = 0; ch < 8; ++ch)
+                        memcpy(&sw[((size_t)kb * d.cs_out + r) * 128 + (size_t)((ch ^ (r & 7)) * 16)],
+                               &wp[((size_t)r * 9 + tap) * d.cs_in + c0 + 16 * ch], 16);
+            }
+            CU(cudaMalloc(&d.w_swz, sw.size()));
+            CU(cudaMemcpy(d.w_swz, sw.data(), sw.size(), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&d.bias_sh, (size_t)d.cout_pad * sizeof(int)));
         c->layers.push_back(d);
         { int rc = derive_layer(c, l); if (rc) return rc; }
@@ -440,6 +456,7 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
     a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
 }
 
