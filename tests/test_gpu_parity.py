@@ -635,3 +635,12 @@ def test_detect_cli_on_synthetic_images(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert len([f for f in os.listdir(tmp_path) if f.endswith(".jpg")]) == 3
     assert "3 images" in r.stdout
+
+
+def test_graft_entry_smoke_runs():
+    """__graft_entry__.smoke() (what the driver runs on the GPU box): host entry point + layer read-back + oracle check."""
+    import importlib, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    g = importlib.import_module("__graft_entry__")
+    g.smoke()

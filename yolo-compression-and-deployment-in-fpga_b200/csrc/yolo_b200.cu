@@ -35,6 +35,7 @@ struct LayerDev {
     uint8_t *w_swz = nullptr;  // cs_in % 128 == 0: 128B-swizzled blocks [9*cs_in/128][cs_out][128] (conv_umma.cu B operand)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
+    int8_t *view = nullptr;    // where the most recent output actually lives (out, or a slot of the batch-wide prediction map)
     size_t out_cap = 0;
     int oh = 0, ow = 0;
 };
@@ -135,7 +136,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); }
     c->layers.clear();
 }
 
@@ -524,8 +525,8 @@ static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *cur, int 
             size_t bytes = (size_t)(n > 0 ? n : 1) * oh * ow * L.cs_out;
             rc = ensure((void **)&L.out, &L.out_cap, bytes); if (rc) return rc;
             dst = L.out;
-            L.oh = oh; L.ow = ow;
         }
+        L.oh = oh; L.ow = ow; L.view = dst;
         if (n > 0) { rc = run_layer(c, (int)l, cur, n, h, w, dst); if (rc) return rc; }
         tick(c);
         cur = dst; h = oh; w = ow;
@@ -610,7 +611,7 @@ int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h,
         // the layer itself, with the exponents just derived
         const int oh = Lp.pool ? h / 2 : h, ow = Lp.pool ? w / 2 : w;
         rc = ensure((void **)&L.out, &L.out_cap, (size_t)n * oh * ow * L.cs_out); if (rc) return rc;
-        L.oh = oh; L.ow = ow;
+        L.oh = oh; L.ow = ow; L.view = L.out;
         rc = run_layer(c, (int)l, cur, n, h, w, L.out); if (rc) return rc;
         cur = L.out; h = oh; w = ow;
     }
@@ -629,7 +630,7 @@ int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, si
     size_t have = (size_t)c->last_n * L.oh * L.ow * L.cs_out;
     if (bytes != have) return fail(E_ARG, "layer %d output is %zu bytes, caller passed %zu", layer, have, bytes);
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(host_out, L.out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(host_out, L.view ? L.view : L.out, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -686,7 +687,7 @@ static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, i
     if (kind == 2 && c->lut8_saturates) return 0;              // saturated inputs must be counted: the stand-alone quantiser does
     const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
     int rc = ensure((void **)&L0.out, &L0.out_cap, (size_t)n * oh * ow * L0.cs_out); if (rc) return rc;
-    L0.oh = oh; L0.ow = ow;
+    L0.oh = oh; L0.ow = ow; L0.view = L0.out;
     a0.out = L0.out;
     c->ev_used = 0;
     tick(c);
