@@ -26,6 +26,7 @@ struct FirstParams {
     const uint8_t *lut8;       // [3][256]: R (from byte 2), G, B
     int n_img, H, W;
     int OH, OW;
+    size_t out_img_bytes;      // OH * OW * cs_out
     int cs_out;                // 16
     const int8_t *wgt;         // [cout_pad][9][4]
     const int *bias_sh;
@@ -56,18 +57,32 @@ __device__ __forceinline__ void mma_s8_k16(int (&c)[4], unsigned a0, unsigned a1
 // SRC: 0 = int8 NHWC4; 1 = RGB444 camera frames: the RGB444 -> int8 quantiser (camera_to_inpBuf + pixel_norm_quantize,
 // yolo_forward.c:57-123) is applied while the halo tile is staged, one lookup in the 4096-entry table per pixel;
 // 2 = uint8 BGR image (three 256-entry tables, see quantize.cu).
-// Persistent: a CTA loads the table(s), its B fragments and biases once and then walks tiles blockIdx.x, +gridDim.x, ...
-// (per-tile work is then only the halo staging, the MMAs and the epilogue: ~300 instead of ~460 instructions per warp).
+//
+// Persistent and software-pipelined: a CTA loads the table(s), its B fragments and biases once and then walks tiles
+// blockIdx.x, +gridDim.x, ...  The halo tile lives in two shared-memory buffers: the global load of tile k+1 is issued
+// before the MMAs and the epilogue of tile k (its latency hides behind that work; what stays live is the raw pixels and a
+// validity word per thread), is converted through the table into the other buffer afterwards, and ONE barrier per tile
+// separates the generations.  The halo is fetched as aligned pixel QUADS (columns x0-4 .. x0+35, 10 quads per row, 180 per
+// tile: one per thread), so an RGB444 quad is one 64-bit load (W % 4 == 0 and an aligned frame pointer are required, see
+// conv3x3_first_supported / conv3x3_first_src_ok); tile coordinates advance incrementally (no per-tile divisions).
+constexpr int F_QUADS_ROW = (F_TW + 8) / 4;                           // 10
+constexpr int F_NQUAD = F_HROWS * F_QUADS_ROW;                        // 180 <= F_THREADS
+constexpr int F_COL0 = 3;                                             // halo column of x = x0 - 1
+static_assert(F_NQUAD <= F_THREADS && 4 * F_QUADS_ROW <= F_PITCH, "one quad per thread");
+
+__device__ __forceinline__ int keep(int v) { asm volatile("" : "+r"(v)); return v; }   // stops the compiler re-deriving v from tid per tile
+
 template <bool POOL, int EPI, bool ACT, int SRC>
-__global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstParams p)
+__global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const FirstParams p)
 {
     constexpr bool RGB444 = SRC == 1, U8 = SRC == 2;
-    __shared__ unsigned s_in[F_HROWS * F_PITCH];
-    __shared__ unsigned s_lut[RGB444 ? 4096 : U8 ? 192 : 1];
+    constexpr int RAWN = RGB444 ? 2 : U8 ? 3 : 4;                     // 32-bit words per pixel quad
+    __shared__ unsigned s_in[2][F_HROWS * F_PITCH];                   // column c of a row <-> x = x0 - 4 + c
+    __shared__ unsigned s_lut[RGB444 ? 4097 : U8 ? 192 : 1];          // RGB444: entry 4096 = 0 = "outside the image"
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    if (RGB444) for (int i = threadIdx.x; i < 4096; i += F_THREADS) s_lut[i] = (unsigned)__ldg(p.lut + i);
+    if (RGB444) { for (int i = threadIdx.x; i < 4096; i += F_THREADS) s_lut[i] = (unsigned)__ldg(p.lut + i); if (threadIdx.x == 0) s_lut[4096] = 0u; }
     if (U8) for (int i = threadIdx.x; i < 192; i += F_THREADS) s_lut[i] = __ldg(reinterpret_cast<const unsigned *>(p.lut8) + i);
     const unsigned char *s_lut8 = reinterpret_cast<const unsigned char *>(s_lut);
 
@@ -87,72 +102,91 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
     if (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI)
         bw = make_int4(__float_as_int((float)bias.x), __float_as_int((float)bias.y), __float_as_int((float)bias.z), __float_as_int((float)bias.w));
 
-    // tap offsets (words) of this thread's A registers: tap t, tap 4+t, tap 8
-    const int o_a = (t / 3) * F_PITCH + (t % 3);
-    const int o_b = ((4 + t) / 3) * F_PITCH + ((4 + t) % 3);
-    const int o_c = 2 * F_PITCH + 2;
+    // Word offsets of this thread's A registers inside a halo buffer: tile-invariant origin + tap t, tap 4+t, tap 8
+    const int a_org = POOL ? (4 * (warp >> 1)) * F_PITCH + 2 * (8 * (warp & 1) + g) + F_COL0
+                           : (2 * warp) * F_PITCH + g + F_COL0;
+    const int o_a = keep(a_org + (t / 3) * F_PITCH + (t % 3));
+    const int o_b = keep(a_org + ((4 + t) / 3) * F_PITCH + ((4 + t) % 3));
+    const int o_c = keep(a_org + 2 * F_PITCH + 2);
+    // this thread's output pixel inside a tile (rows oy_t, oy_t + 1; column ox_t [+ 8 cg]) and its byte offset
+    const int oy_t = keep(POOL ? 2 * (warp >> 1) : 2 * warp), ox_t = keep(POOL ? 8 * (warp & 1) + g : g);
+    const int o_thr = keep((oy_t * (POOL ? p.OW : p.W) + ox_t) * 16 + 4 * t);     // cs_out == 16 (conv3x3_first_supported)
     unsigned ovf = 0;
 
     const int tiles_x = (p.W + F_TW - 1) / F_TW, tiles_y = (p.H + F_TH - 1) / F_TH;
     const int tiles_img = tiles_x * tiles_y;
-    const long long total = (long long)tiles_img * p.n_img;
-    // haloed input tile, zero outside the image (= the convolution's zero padding): warp w stages halo rows w, w+8, w+16;
-    // lane l takes column l, lanes 0 and 1 also columns 32 and 33.  (Prefetching tile k+1 through registers during the MMAs
-    // of tile k was tried: +14 registers cost a resident CTA per SM and made the kernel 15 % slower.)
-    constexpr int ROWS_PER_WARP = (F_HROWS + F_THREADS / 32 - 1) / (F_THREADS / 32);
-    unsigned raw[ROWS_PER_WARP][2];
-    auto fetch = [&](long long tile) {
-        const int img = (int)(tile / tiles_img), tin = (int)(tile - (long long)img * tiles_img);
-        const int ty = tin / tiles_x, tx = tin - ty * tiles_x;
-        const int x0 = tx * F_TW, y0 = ty * F_TH;
+    // one grid stride, decomposed into (images, tile rows, tile columns)
+    const int s_img = (int)gridDim.x / tiles_img;
+    const int s_y = ((int)gridDim.x - s_img * tiles_img) / tiles_x, s_x = (int)gridDim.x - s_img * tiles_img - s_y * tiles_x;
+    int img = (int)blockIdx.x / tiles_img;
+    int ty = ((int)blockIdx.x - img * tiles_img) / tiles_x, tx = (int)blockIdx.x - img * tiles_img - ty * tiles_x;
+
+    // this thread's halo quad: halo row tid / 10, columns 4 (tid % 10) .. +3
+    const bool has_quad = threadIdx.x < F_NQUAD;
+    const int q_hy = has_quad ? (int)threadIdx.x / F_QUADS_ROW : -0x1000000;  // no quad: fails the row test
+    const int q_hx = 4 * ((int)threadIdx.x % F_QUADS_ROW);
+    const int q_goff = keep(has_quad ? q_hy * p.W + q_hx : 0);               // pixel offset from the halo's top-left corner
+    const int q_soff = keep(has_quad ? q_hy * F_PITCH + q_hx : 0);
+    unsigned raw[RAWN];
+    unsigned oob = 0;              // RGB444: 0x1000 in both half-words when the quad lies outside the image (table entry 4096 = 0)
+    auto fetch = [&](int im, int y0, int x0) {
+        const int y = y0 - 1 + q_hy, x = x0 - 4 + q_hx;
+        const bool ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;   // W % 4 == 0: a quad is all in or all out
+        const int e = (im * p.H + (y0 - 1)) * p.W + (x0 - 4) + q_goff;  // pixel index (host: n*H*W < 2^31)
 #pragma unroll
-        for (int k = 0; k < ROWS_PER_WARP; ++k) {
-            const int hy = warp + k * (F_THREADS / 32);
-            const int y = y0 - 1 + hy;
-            const bool rowok = hy < F_HROWS && (unsigned)y < (unsigned)p.H;
-            const size_t rowbase = ((size_t)img * p.H + (rowok ? y : 0)) * p.W;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int hx = lane + 32 * r;
-                const int x = x0 - 1 + hx;
-                unsigned v = SRC ? 0xffffffffu : 0u;                   // table sources: all ones marks "outside the image"
-                if (rowok && hx < F_TW + 2 && (unsigned)x < (unsigned)p.W) {
-                    if (RGB444) v = (unsigned)__ldg(p.in16 + rowbase + x);
-                    else if (U8) { const uint8_t *px = p.in8 + 3 * (rowbase + x); v = (unsigned)__ldg(px) | ((unsigned)__ldg(px + 1) << 8) | ((unsigned)__ldg(px + 2) << 16); }
-                    else v = __ldg(reinterpret_cast<const unsigned *>(p.in) + rowbase + x);
-                }
-                raw[k][r] = v;
-            }
+        for (int i = 0; i < RAWN; ++i) raw[i] = 0u;
+        if (RGB444) {
+            if (ok) { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p.in16 + e)); raw[0] = v.x; raw[1] = v.y; }
+            oob = ok ? 0u : 0x10001000u;
+        } else if (U8) {
+            if (ok) { const unsigned *px = reinterpret_cast<const unsigned *>(p.in8 + 3 * (size_t)e); raw[0] = __ldg(px); raw[1] = __ldg(px + 1); raw[2] = __ldg(px + 2); }
+            oob = ok ? 0u : 1u;
+        } else {
+            if (ok) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned *>(p.in) + e)); raw[0] = v.x; raw[1] = v.y; raw[2] = v.z; raw[3] = v.w; }
         }
     };
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int img = (int)(tile / tiles_img), tin = (int)(tile - (long long)img * tiles_img);
-        const int ty = tin / tiles_x, tx = tin - ty * tiles_x;
-        const int x0 = tx * F_TW, y0 = ty * F_TH;
-        fetch(tile);                                                   // global loads first, then the barrier
-        __syncthreads();                                               // previous tile fully consumed (first pass: tables loaded)
-#pragma unroll
-        for (int k = 0; k < ROWS_PER_WARP; ++k) {
-            const int hy = warp + k * (F_THREADS / 32);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int hx = lane + 32 * r;
-                if (hy < F_HROWS && hx < F_TW + 2) {
-                    unsigned v = raw[k][r];
-                    if (RGB444) {
-                        v = v == 0xffffffffu ? 0u : s_lut[v & 0xfffu];
-                    } else if (U8) {
-                        const unsigned c = v;      // B | G << 8 | R << 16
-                        v = c == 0xffffffffu ? 0u : ((unsigned)s_lut8[(c >> 16) & 255u] | ((unsigned)s_lut8[256 + ((c >> 8) & 255u)] << 8) | ((unsigned)s_lut8[512 + (c & 255u)] << 16));
-                    }
-                    s_in[hy * F_PITCH + hx] = v;
-                }
-            }
+    // table lookups + stores of the fetched quad; zero outside the image (= the convolution's zero padding)
+    auto u8px = [&](unsigned c) {                                      // c = B | G << 8 | R << 16
+        return (unsigned)s_lut8[(c >> 16) & 255u] | ((unsigned)s_lut8[256 + ((c >> 8) & 255u)] << 8) | ((unsigned)s_lut8[512 + (c & 255u)] << 16);
+    };
+    auto stage = [&](unsigned *dst) {
+        if (has_quad) {
+            unsigned v[4];
+            if (RGB444) {
+                const unsigned r0 = (raw[0] & 0x0fff0fffu) | oob, r1 = (raw[1] & 0x0fff0fffu) | oob;
+                v[0] = s_lut[r0 & 0xffffu]; v[1] = s_lut[r0 >> 16]; v[2] = s_lut[r1 & 0xffffu]; v[3] = s_lut[r1 >> 16];
+            } else if (U8) {
+                // bytes: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+                v[0] = u8px(raw[0]);
+                v[1] = u8px((raw[0] >> 24) | (raw[1] << 8));
+                v[2] = u8px((raw[1] >> 16) | (raw[2] << 16));
+                v[3] = u8px(raw[2] >> 8);
+                if (oob) { v[0] = 0u; v[1] = 0u; v[2] = 0u; v[3] = 0u; }
+            } else { v[0] = raw[0]; v[1] = raw[1]; v[2] = raw[2]; v[3] = raw[3]; }
+            unsigned *d = dst + q_soff;
+            d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
         }
-        __syncthreads();
+    };
+    auto advance = [&](int &im, int &y, int &x) {
+        x += s_x; if (x >= tiles_x) { x -= tiles_x; ++y; }
+        y += s_y; if (y >= tiles_y) { y -= tiles_y; ++im; }
+        im += s_img;
+    };
+
+    __syncthreads();                                                   // tables loaded
+    fetch(img, ty * F_TH, tx * F_TW);
+    stage(s_in[0]);
+    __syncthreads();
+    int buf = 0;
+    while (img < p.n_img) {
+        int nimg = img, nty = ty, ntx = tx;
+        advance(nimg, nty, ntx);
+        const bool has_next = nimg < p.n_img;
+        if (has_next) fetch(nimg, nty * F_TH, ntx * F_TW);             // in flight during this tile's MMAs and epilogue
+        const unsigned *tile_in = s_in[buf];
+        const int x0 = tx * F_TW, y0 = ty * F_TH;
 
         if (POOL) {
-            const int pr0 = 2 * (warp >> 1), pc0 = 8 * (warp & 1);           // pooled row / column origin inside the tile
             int acc[4][2][4];
 #pragma unroll
             for (int ph = 0; ph < 4; ++ph)
@@ -164,7 +198,7 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
             for (int ph = 0; ph < 4; ++ph) {
                 const int dy = ph >> 1, dx = ph & 1;
                 // rows g / g+8 of the M=16 tile: pooled pixel (pr0, pc0+g) / (pr0+1, pc0+g), member (dy,dx)
-                const unsigned *r0 = s_in + (2 * pr0 + dy) * F_PITCH + 2 * (pc0 + g) + dx;
+                const unsigned *r0 = tile_in + dy * F_PITCH + dx;
                 const unsigned *r1 = r0 + 2 * F_PITCH;
                 const unsigned a0 = r0[o_a], a1 = r1[o_a], a2 = r0[o_b], a3 = r1[o_b], a4 = r0[o_c], a5 = r1[o_c];
 #pragma unroll
@@ -173,6 +207,8 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
                     mma_s8_k16(acc[ph][n], a4, a5, b2[n]);
                 }
             }
+            // this thread's 4 channels of pooled pixel (oy, ox)
+            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + ((((y0 >> 1) * p.OW + (x0 >> 1)) * 16) + o_thr);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 int m[4];
@@ -181,13 +217,13 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
                         m[2 * n + c] = max(max(acc[0][n][2 * h + c], acc[1][n][2 * h + c]), max(acc[2][n][2 * h + c], acc[3][n][2 * h + c]));
-                const int oy = (y0 >> 1) + pr0 + h, ox = (x0 >> 1) + pc0 + g;
+                const int oy = (y0 >> 1) + oy_t + h, ox = (x0 >> 1) + ox_t;
                 const bool valid = oy < p.OH && ox < p.OW;
                 const unsigned w = requant4v<EPI, ACT>(m, bw, p, ovf, valid);
-                if (valid) *reinterpret_cast<unsigned *>(p.out + (((size_t)img * p.OH + oy) * p.OW + ox) * p.cs_out + 4 * t) = w;
+                if (valid) *reinterpret_cast<unsigned *>(out_px + h * p.OW * 16) = w;
             }
         } else {
-            const int r = 2 * warp;                                            // rows r, r+1 of the tile
+            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + (((y0 * p.W + x0) * 16) + o_thr);
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
                 int acc[2][4];
@@ -195,7 +231,7 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
                 for (int n = 0; n < 2; ++n)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[n][j] = 0;
-                const unsigned *r0 = s_in + r * F_PITCH + 8 * cg + g;
+                const unsigned *r0 = tile_in + 8 * cg;                     // rows 2 warp, 2 warp + 1 of the tile
                 const unsigned *r1 = r0 + F_PITCH;
                 const unsigned a0 = r0[o_a], a1 = r1[o_a], a2 = r0[o_b], a3 = r1[o_b], a4 = r0[o_c], a5 = r1[o_c];
 #pragma unroll
@@ -206,13 +242,17 @@ __global__ void __launch_bounds__(F_THREADS) conv3x3_first_kernel(const FirstPar
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int m[4] = { acc[0][2 * h], acc[0][2 * h + 1], acc[1][2 * h], acc[1][2 * h + 1] };
-                    const int y = y0 + r + h, x = x0 + 8 * cg + g;
+                    const int y = y0 + oy_t + h, x = x0 + 8 * cg + ox_t;
                     const bool valid = y < p.H && x < p.W;
                     const unsigned w = requant4v<EPI, ACT>(m, bw, p, ovf, valid);
-                    if (valid) *reinterpret_cast<unsigned *>(p.out + (((size_t)img * p.H + y) * p.W + x) * p.cs_out + 4 * t) = w;
+                    if (valid) *reinterpret_cast<unsigned *>(out_px + (h * p.W + 8 * cg) * 16) = w;
                 }
             }
         }
+
+        if (has_next) stage(s_in[buf ^ 1]);
+        __syncthreads();                                               // tile k+1 staged; tile k's buffer free for tile k+2
+        buf ^= 1; img = nimg; ty = nty; tx = ntx;
     }
     if (p.q.contract == CONTRACT_P) {
         ovf = __reduce_add_sync(0xffffffffu, ovf);
@@ -224,7 +264,15 @@ bool conv3x3_first_supported(const ConvArgs &a)
 {
     if (a.cs_in != 4 || a.cs_out != 16 || a.w_rows < 16) return false;
     if (a.q.pool && (a.H < 2 || a.W < 2)) return false;
+    if (a.W % 4) return false;                                                     // the halo is fetched as aligned pixel quads
+    if ((long long)a.n * a.H * a.W >= (1ll << 31) - (1ll << 20)) return false;     // 32-bit pixel offsets in the halo fetch
     return true;
+}
+
+// alignment the quad loads need from the source pointer (frames are W*H pixels with W % 4 == 0, so every quad inherits it)
+bool conv3x3_first_src_ok(int src_kind, const void *src)
+{
+    return ((uintptr_t)src % (src_kind == 1 ? 8 : src_kind == 2 ? 4 : 16)) == 0;
 }
 
 template <bool POOL, int EPI, int SRC>
@@ -276,7 +324,10 @@ cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind, cons
     p.in = a.in; p.n_img = a.n; p.H = a.H; p.W = a.W;
     if (src_kind == 1) { p.in16 = (const uint16_t *)src; p.lut = (const int *)lut; }
     else if (src_kind == 2) { p.in8 = (const uint8_t *)src; p.lut8 = (const uint8_t *)lut; }
+    // a pixel quad = 8 bytes of RGB444, 12 of BGR bytes (three word loads), 16 of NHWC4
+    if (!conv3x3_first_src_ok(src_kind, src_kind ? src : (const void *)a.in)) return cudaErrorInvalidValue;
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
+    p.out_img_bytes = (size_t)p.OH * p.OW * a.cs_out;
     p.cs_out = a.cs_out; p.wgt = a.wgt; p.bias_sh = a.bias_sh; p.q = a.q; p.out = a.out; p.ovf = a.ovf;
     return a.q.pool ? launch_first<true>(a, p, st) : launch_first<false>(a, p, st);
 }

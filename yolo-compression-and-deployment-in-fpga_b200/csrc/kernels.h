@@ -31,6 +31,7 @@ cudaError_t conv3x3_direct(const ConvArgs &a, cudaStream_t st);
 
 // conv_first.cu (first layer: NHWC4 input, <= 16 output channels, warp-level integer MMAs)
 bool conv3x3_first_supported(const ConvArgs &a);
+bool conv3x3_first_src_ok(int src_kind, const void *src);      // pointer alignment the first-layer kernel needs (0 int8 NHWC4, 1 RGB444, 2 BGR bytes)
 // src_kind: 0 = a.in (int8 NHWC4), 1 = RGB444 uint16 frames + 4096-word table, 2 = uint8 BGR images + 3x256-byte table
 cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind = 0, const void *src = nullptr, const void *lut = nullptr);
 

@@ -472,7 +472,7 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     const int be = c->conv_backend;
     if ((be == 2 || be == 3) && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
     if ((be == 4 || be == 5) && !ws_ok) return fail(E_UNSUPPORTED, "layer %d does not fit the weight-stationary kernel (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
-    const bool first_ok = (((uintptr_t)d_in | (uintptr_t)d_out) & 3) == 0 && conv3x3_first_supported(a);
+    const bool first_ok = ((uintptr_t)d_out & 3) == 0 && conv3x3_first_src_ok(0, d_in) && conv3x3_first_supported(a);
     if (be == 1) CU(conv3x3_direct(a, c->stream));
     else if (be == 0 && first_ok) CU(conv3x3_first(a, c->stream));
     else if (be == 2 || be == 3) CU(conv3x3_umma(a, c->stream, c->sm_count));
@@ -682,7 +682,7 @@ static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, i
     LayerDev &L0 = c->layers[0];
     ConvArgs a0;
     fill_args(c, 0, nullptr, n, h, w, nullptr, a0);
-    if (!(n > 0 && c->conv_backend == 0 && c->layers.size() > 1 && conv3x3_first_supported(a0) && !(L0.q.pool && (h < 2 || w < 2)))) return 0;
+    if (!(n > 0 && c->conv_backend == 0 && c->layers.size() > 1 && conv3x3_first_supported(a0) && conv3x3_first_src_ok(kind, d_src) && !(L0.q.pool && (h < 2 || w < 2)))) return 0;
     if (kind == 1 && (((uintptr_t)d_src) & 1)) return 0;
     if (kind == 2 && c->lut8_saturates) return 0;              // saturated inputs must be counted: the stand-alone quantiser does
     const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
