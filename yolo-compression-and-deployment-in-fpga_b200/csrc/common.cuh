@@ -95,6 +95,7 @@ enum { EPI_GENERIC = 0, EPI_F_RNE = 1, EPI_P = 2, EPI_F_RNE_NOHI = 3 };
 
 struct EpiConst {
     float s_in;       // F: 2^(-iofs) or 2^(+iofs) ; P: 2^(-sh)
+    float in_add;     // F: MAGIC * (1 - s_in): first addend when the accumulators already carry MAGIC (conv_first)
     float s_in2;      // P: 2^(-(sh+3)) (leaky branch)
     float leak_add;   // F: MAGIC * 7/8
     float s_out;      // F: 2^(-oofs) or 2^(+oofs)

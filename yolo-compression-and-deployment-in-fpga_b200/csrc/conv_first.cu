@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
 {
     constexpr bool RGB444 = SRC == 1, U8 = SRC == 2;
     constexpr int RAWN = RGB444 ? 2 : U8 ? 3 : 4;                     // 32-bit words per pixel quad
+    // fp32 epilogues: the accumulators start at the bit pattern of 1.5 * 2^23, so that read as fp32 they are MAGIC + sum
+    // (|sum| <= 27 * 128 * 128 < 2^22) and the epilogue needs no int -> float conversion (requant_f_rne_x2, PRE)
+    constexpr bool PRE = EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI;
+    constexpr int ACC0 = PRE ? YB_MAGIC_BITS : 0;
     __shared__ unsigned s_in[2][F_HROWS * F_PITCH];                   // column c of a row <-> x = x0 - 4 + c
     __shared__ unsigned s_lut[RGB444 ? 4097 : U8 ? 192 : 1];          // RGB444: entry 4096 = 0 = "outside the image"
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
 #pragma unroll
                 for (int n = 0; n < 2; ++n)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[ph][n][j] = 0;
+                    for (int j = 0; j < 4; ++j) acc[ph][n][j] = ACC0;
 #pragma unroll
             for (int ph = 0; ph < 4; ++ph) {
                 const int dy = ph >> 1, dx = ph & 1;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
                         m[2 * n + c] = max(max(acc[0][n][2 * h + c], acc[1][n][2 * h + c]), max(acc[2][n][2 * h + c], acc[3][n][2 * h + c]));
                 const int oy = (y0 >> 1) + oy_t + h, ox = (x0 >> 1) + ox_t;
                 const bool valid = oy < p.OH && ox < p.OW;
-                const unsigned w = requant4v<EPI, ACT>(m, bw, p, ovf, valid);
+                const unsigned w = requant4v<EPI, ACT, FirstParams, PRE>(m, bw, p, ovf, valid);
                 if (valid) *reinterpret_cast<unsigned *>(out_px + h * p.OW * 16) = w;
             }
         } else {
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
 #pragma unroll
                 for (int n = 0; n < 2; ++n)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[n][j] = 0;
+                    for (int j = 0; j < 4; ++j) acc[n][j] = ACC0;
                 const unsigned *r0 = tile_in + 8 * cg;                     // rows 2 warp, 2 warp + 1 of the tile
                 const unsigned *r1 = r0 + F_PITCH;
                 const unsigned a0 = r0[o_a], a1 = r1[o_a], a2 = r0[o_b], a3 = r1[o_b], a4 = r0[o_c], a5 = r1[o_c];
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
                     const int m[4] = { acc[0][2 * h], acc[0][2 * h + 1], acc[1][2 * h], acc[1][2 * h + 1] };
                     const int y = y0 + oy_t + h, x = x0 + 8 * cg + ox_t;
                     const bool valid = y < p.H && x < p.W;
-                    const unsigned w = requant4v<EPI, ACT>(m, bw, p, ovf, valid);
+                    const unsigned w = requant4v<EPI, ACT, FirstParams, PRE>(m, bw, p, ovf, valid);
                     if (valid) *reinterpret_cast<unsigned *>(out_px + (h * p.W + 8 * cg) * 16) = w;
                 }
             }

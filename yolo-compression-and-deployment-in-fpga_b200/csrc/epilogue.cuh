@@ -47,19 +47,27 @@ __device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c)
 // Contract F, round-half-even, two channels at a time.  fb = (float)sh(bias).  Returns o as an integer that is
 // exact inside [-128,127] and on the correct side outside it (the pack saturates).  See requant_f_rne in common.cuh for
 // the arithmetic; HI16 = false drops the upper 16-bit clamp when the host proved it cannot change the result.
-// The LOWER 16-bit clamp always runs: it keeps every float positive, which the integer view of the result needs.
-template <bool ACT, bool HI16>
+// The LOWER 16-bit clamp always runs: it keeps the final float positive, which the integer view of the result needs.
+// With the leaky-ReLU it is folded into the same 3-input maximum: l = rne(v / 8) is taken from the UNclamped v, and
+// max(v, l, MAGIC - 4096) equals leaky(max(v, MAGIC - 32768)) because rne(./8) is monotone and leaky(-32768) = -4096
+// (one FMNMX3 instead of two FMNMX; the float min/max share the half-rate ALU pipe with the integer work).
+// PRE: the accumulators were started at YB_MAGIC_BITS, so their bit pattern read as fp32 is MAGIC + sum exactly
+// (|sum| < 2^22); the int->float conversion disappears and the first FMA's addend becomes MAGIC * (1 - s_in), which
+// gives the same real number sum * s_in + MAGIC before the FMA's single rounding.
+template <bool ACT, bool HI16, bool PRE = false>
 __device__ __forceinline__ int2 requant_f_rne_x2(int a0, int a1, float2 fb, const EpiConst &k)
 {
-    const float2 magic = make_float2(YB_MAGIC, YB_MAGIC);
-    float2 v = ffma2(make_float2(__int2float_rn(a0), __int2float_rn(a1)), make_float2(k.s_in, k.s_in), magic);
+    float2 v;
+    if (PRE) v = ffma2(make_float2(__int_as_float(a0), __int_as_float(a1)), make_float2(k.s_in, k.s_in), make_float2(k.in_add, k.in_add));
+    else v = ffma2(make_float2(__int2float_rn(a0), __int2float_rn(a1)), make_float2(k.s_in, k.s_in), make_float2(YB_MAGIC, YB_MAGIC));
     v = fadd2(v, fb);
-    v.x = fmaxf(v.x, YB_MAGIC - 32768.f); v.y = fmaxf(v.y, YB_MAGIC - 32768.f);
-    if (HI16) { v.x = fminf(v.x, YB_MAGIC + 32767.f); v.y = fminf(v.y, YB_MAGIC + 32767.f); }
     if (ACT) {
         const float2 l = ffma2(v, make_float2(0.125f, 0.125f), make_float2(k.leak_add, k.leak_add));
-        v.x = fmaxf(v.x, l.x); v.y = fmaxf(v.y, l.y);
+        v.x = fmaxf(fmaxf(v.x, l.x), YB_MAGIC - 4096.f); v.y = fmaxf(fmaxf(v.y, l.y), YB_MAGIC - 4096.f);
+    } else {
+        v.x = fmaxf(v.x, YB_MAGIC - 32768.f); v.y = fmaxf(v.y, YB_MAGIC - 32768.f);
     }
+    if (HI16) { v.x = fminf(v.x, YB_MAGIC + 32767.f); v.y = fminf(v.y, YB_MAGIC + 32767.f); }
     v = ffma2(v, make_float2(k.s_out, k.s_out), make_float2(k.out_add, k.out_add));
     return make_int2(__float_as_int(v.x) - YB_MAGIC_BITS, __float_as_int(v.y) - YB_MAGIC_BITS);
 }
@@ -81,13 +89,15 @@ __device__ __forceinline__ int2 requant_p_x2(int a0, int a1, int bp0, int bp1, c
 
 // Requantise 4 accumulators with per-channel words b (fp32 bias bits for the F fast paths, int otherwise) and pack them
 // into one word.  EPI_F_RNE_NOHI is EPI_F_RNE without the upper 16-bit clamp.
-template <int EPI, bool ACT, class P>
+// PRE (F fast paths only): acc[] started at YB_MAGIC_BITS, see requant_f_rne_x2.
+template <int EPI, bool ACT, class P, bool PRE = false>
 __device__ __forceinline__ unsigned requant4v(const int *acc, int4 b, const P &p, unsigned &ovf, bool count)
 {
+    static_assert(!PRE || EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI, "pre-biased accumulators: contract F fast paths only");
     if (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) {
         constexpr bool HI = EPI == EPI_F_RNE;
-        const int2 lo = requant_f_rne_x2<ACT, HI>(acc[0], acc[1], make_float2(__int_as_float(b.x), __int_as_float(b.y)), p.k);
-        const int2 hi = requant_f_rne_x2<ACT, HI>(acc[2], acc[3], make_float2(__int_as_float(b.z), __int_as_float(b.w)), p.k);
+        const int2 lo = requant_f_rne_x2<ACT, HI, PRE>(acc[0], acc[1], make_float2(__int_as_float(b.x), __int_as_float(b.y)), p.k);
+        const int2 hi = requant_f_rne_x2<ACT, HI, PRE>(acc[2], acc[3], make_float2(__int_as_float(b.z), __int_as_float(b.w)), p.k);
         return pack_sat_s8(lo.x, lo.y, pack_sat_s8(hi.x, hi.y, 0u));
     } else if (EPI == EPI_P) {
         const int2 lo = requant_p_x2<ACT>(acc[0], acc[1], b.x, b.y, p.k);
@@ -154,6 +164,7 @@ static inline int epi_mode_for(const ConvArgs &a, EpiConst *k)
         const bool in_ok = q.idir ? q.iofs <= 20 : (q.iofs <= 20 && ((32769LL + bmax) << q.iofs) <= (1LL << 24));
         if (!in_ok || bmax >= (1 << 21) || q.oofs > 20 || (q.odir && q.oofs > 8)) return EPI_GENERIC;
         k->s_in = ldexpf(1.0f, q.idir ? q.iofs : -q.iofs);
+        k->in_add = (float)((double)YB_MAGIC * (1.0 - (double)k->s_in));     // exact: 3 * 2^22 * (1 - 2^+-iofs), iofs <= 20
         k->leak_add = YB_MAGIC * 0.875f;
         k->s_out = ldexpf(1.0f, q.odir ? q.oofs : -q.oofs);
         k->out_add = (float)((double)YB_MAGIC * (1.0 - (double)k->s_out));
