@@ -47,6 +47,7 @@ constexpr int WS_EPI_THREADS = WS_EPI_WARPS * 32;
 constexpr int WS_EPI_GROUPS = 2;                        // group g drains accumulator buffer g: two tiles' epilogues overlap
 constexpr int WS_THREADS = 32 + WS_PROD_THREADS + WS_EPI_GROUPS * WS_EPI_THREADS;
 constexpr int WS_MAX_STAGES = 4;
+constexpr int WS_MAX_TBUF = 4;                          // TMEM accumulator buffers (2 when 4 of them exceed 512 columns)
 
 struct WsParams {
     const int8_t *in;
@@ -67,6 +68,7 @@ struct WsParams {
     uint32_t w_bytes;
     uint32_t off_stage, off_bias, off_bar;
     uint32_t tmem_cols, tmem_buf_stride;
+    int tbufs, tbufs_log2;       // accumulator buffers in TMEM: 4 when they fit 512 columns, else 2
     int OH, OW;                  // output map (pooled when q.pool)
     LayerQ q;
     EpiConst k;
@@ -252,18 +254,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     const uint32_t stage0 = base + p.off_stage;
     int *s_bias = reinterpret_cast<int *>(base_ptr + p.off_bias);
     const uint32_t bar0 = base + p.off_bar;
-    // barrier layout: full[MAX], empty[MAX], tmem_full[2], tmem_empty[2], weights, then the TMEM address slot
+    // barrier layout: full[MAX], empty[MAX], tmem_full[TBUF], tmem_empty[TBUF], weights, then the TMEM address slot
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (WS_MAX_STAGES + s); };
     auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * WS_MAX_STAGES + b); };
-    auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * WS_MAX_STAGES + 2 + b); };
-    const uint32_t bar_w = bar0 + 8u * (2 * WS_MAX_STAGES + 4);
-    const uint32_t tmem_slot = bar0 + 8u * (2 * WS_MAX_STAGES + 5);
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * WS_MAX_STAGES + 5));
+    auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * WS_MAX_STAGES + WS_MAX_TBUF + b); };
+    const uint32_t bar_w = bar0 + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 1);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 1));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(bar_full(s), WS_PROD_THREADS); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), WS_EPI_THREADS); }
+        for (int b = 0; b < WS_MAX_TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), WS_EPI_THREADS); }
         mbar_init(bar_w, 1);
         fence_barrier_init();
         // the whole layer's weights, once
@@ -298,8 +300,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         int it = 0, s = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+            const int buf = it & (p.tbufs - 1);
+            const uint32_t bph = (uint32_t)(it >> p.tbufs_log2) & 1u;
             mbar_wait(bar_tempty(buf), bph ^ 1u);                 // epilogue has drained this accumulator buffer
             WS_STAMP(0);
             mbar_wait(bar_full(s), ph);                           // the haloed tile is in shared memory
@@ -428,10 +430,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         // tiles blockIdx.x + (grp + 2k) * gridDim.x: advance the tile coordinates two grid strides at a time
         int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
         if (grp) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
-        const int buf = grp;
+        // tile it of this CTA: accumulator buffer it % tbufs (2 or 4), drained by group it % 2.  With four buffers the MMA
+        // warp runs up to three tiles ahead of a group's epilogue instead of waiting for "its" buffer every other tile.
         int it = grp;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
-            const uint32_t bph = (uint32_t)(it >> 1) & 1u;
+            const int buf = it & (p.tbufs - 1);
+            const uint32_t bph = (uint32_t)(it >> p.tbufs_log2) & 1u;
             const int tx0 = tx * G::TW, ty0 = ty * G::TH;
 #pragma unroll
             for (int r = 0; r < 2; ++r) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
@@ -486,7 +490,8 @@ static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p)
     p->stage_bytes = ((uint32_t)nplanes * p->plane_stride + 127u) & ~127u;
     uint32_t nb = 32; while (nb < (uint32_t)(nacc * p->N)) nb <<= 1;
     if (2 * nb > 512) return false;
-    p->tmem_buf_stride = nb; p->tmem_cols = 2 * nb;
+    p->tbufs = 4 * nb <= 512 ? 4 : 2; p->tbufs_log2 = p->tbufs == 4 ? 2 : 1;
+    p->tmem_buf_stride = nb; p->tmem_cols = (uint32_t)p->tbufs * nb;
     const uint32_t fixed = ((p->w_bytes + 127u) & ~127u) + (uint32_t)p->N * 4u + 256u + 128u /*alignment slack*/;
     const uint32_t budget = 227u * 1024u;
     if (fixed + 2 * p->stage_bytes > budget) return false;
