@@ -8,6 +8,7 @@
 // compare against the threshold bit-for-bit.
 #include "kernels.h"
 #include <math.h>
+#include <cstdio>
 
 namespace yb {
 
@@ -128,7 +129,6 @@ struct NmsSmem {
     unsigned char cls[HEAD_MAX_CAND];
     unsigned keepmap[HEAD_MAX_CAND / 32];                          // by anchor index (python mode output order)
     unsigned chunk_dead[NMS_CHUNK / 32];
-    unsigned row_nonempty[NMS_CHUNK / 32];
     int warp_sums[NMS_THREADS / 32];
     // spatial index of the kept list (python head): linked lists per (area bucket, centre cell)
     unsigned ghead[NMS_BUCKETS * NMS_GRID * NMS_GRID];             // first kept entry of the list, NMS_END = empty
@@ -220,9 +220,18 @@ __device__ __forceinline__ int nms_bucket(float area)
 }
 __device__ __forceinline__ int nms_cell(float c) { return min(max((int)(c * (float)NMS_GRID), 0), NMS_GRID - 1); }
 
+#ifdef YB_NMS_TIMELINE
+#define NMS_T(k) do { if (tid == 0) { long long c_ = clock64(); tacc[k] += c_ - tlast; tlast = c_; } } while (0)
+#else
+#define NMS_T(k) do { } while (0)
+#endif
+
 template <bool PY, bool FAST>
 __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 {
+#ifdef YB_NMS_TIMELINE
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
     const int f = blockIdx.x;
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     for (int i = m + tid; i < P; i += NMS_THREADS) s.u.key[i] = 0ull;
     __syncthreads();
 
+    NMS_T(0);
     // 2. bitonic sort, descending
     for (int k = 2; k <= P; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -277,6 +287,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             __syncthreads();
         }
 
+    NMS_T(1);
     // 3. sorted order -> anchor index, box, area, class (keys are dead after this; their storage is reused)
     constexpr int PER = HEAD_MAX_CAND / NMS_THREADS;
     unsigned short my_idx[PER];
@@ -300,6 +311,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
         }
     }
     __syncthreads();
+    NMS_T(2);
     // 4. greedy suppression, segment by segment, chunk by chunk
     const int cj_local = tid & (NMS_CHUNK - 1);      // candidate within the chunk
     const int slice = tid / NMS_CHUNK;               // warp-uniform
@@ -323,14 +335,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             if (tid < NMS_BUCKETS) { s.gw[tid] = -1.f; s.gh[tid] = -1.f; }
         }
         int K = 0;                                   // kept in this segment: entries [seg_b, seg_b + K)
-        for (int cs = seg_b; cs < seg_e; cs += NMS_CHUNK) {
-            const int chn = min(NMS_CHUNK, seg_e - cs);
+        // chunks start on 4-aligned positions (screen4 reads 4-aligned blocks); the first may begin before the segment
+        for (int cs = seg_b & ~3; cs < seg_e; cs += NMS_CHUNK) {
+            const int hi = min(cs + NMS_CHUNK, seg_e);             // end of the chunk's candidates
             const int j = cs + cj_local;
-            const bool have = cj_local < chn;
+            const bool have = j >= seg_b && j < hi;
             const float4 bj = have ? s.box[j] : make_float4(0, 0, 0, 0);
             const float aj = have ? s.u.s2.area[j] : 0.f;
-            if (tid < NMS_CHUNK / 32) { s.chunk_dead[tid] = 0; s.row_nonempty[tid] = 0; }
-            for (int i = tid; i < NMS_CHUNK * (NMS_CHUNK / 32); i += NMS_THREADS) (&s.u.s2.mask[0][0])[i] = 0;
+            if (tid < NMS_CHUNK / 32) s.chunk_dead[tid] = 0;
             __syncthreads();
             // 4a. against the kept list of this segment: slice 0 takes the first half, slice 1 the second, in 4-aligned
             //     blocks; every lane of a warp reads the same kept boxes (shared-memory broadcasts)
@@ -358,14 +370,14 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                         }
                 }
             } else if (have && K > 0) {
-                const int lo = seg_b, hi = seg_b + K;
+                const int lo = seg_b, khi = seg_b + K;
                 const int base4 = lo & ~3;
-                const int half = (((hi - base4 + 1) >> 1) + 3) & ~3;
-                const int beg = base4 + slice * half, end = min(hi, beg + half);
+                const int half = (((khi - base4 + 1) >> 1) + 3) & ~3;
+                const int beg = base4 + slice * half, end = min(khi, beg + half);
                 for (int i4 = beg; i4 < end; i4 += 4) {
                     unsigned vm = 0xfu;                                         // which of the 4 entries belong to the list
                     if (i4 < lo) vm &= 0xfu << (lo - i4);
-                    if (i4 + 4 > hi) vm &= 0xfu >> (i4 + 4 - hi);
+                    if (i4 + 4 > khi) vm &= 0xfu >> (i4 + 4 - khi);
                     unsigned mk = screen4<PY, FAST>(s.box, s.u.s2.area, i4, vm, bj, aj);
                     if (mk) {                                                    // rare: exact evaluation of the flagged pairs
                         while (mk) {
@@ -377,53 +389,81 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                     }
                 }
             }
-            unsigned db = __ballot_sync(0xffffffffu, dead);
+            NMS_T(3);
+            unsigned db = __ballot_sync(0xffffffffu, dead || !have);
             if (lane == 0 && db) atomicOr(&s.chunk_dead[cj_local >> 5], db);
-            // 4b. bit-rows: which later candidates of this chunk would j suppress.  The warp walks the chunk from its first
-            // candidate on (uniform addresses = broadcasts); rows of candidates that die in 4a are ignored by 4c.
-            if (have && !dead) {
-                const int cj0 = cj_local & ~31;                                  // first candidate of this warp
-                const int base4 = (cs + cj0 + 1) & ~3;
-                const int hi = cs + chn;
-                bool any = false;
-                for (int i4 = base4 + 4 * slice; i4 < hi; i4 += 4 * NMS_SLICES) {
-                    unsigned vm = 0xfu;                                         // entries after j and inside the chunk
-                    if (i4 <= j) vm &= 0xfu << min(j + 1 - i4, 4);
-                    if (i4 + 4 > hi) vm &= 0xfu >> (i4 + 4 - hi);
-                    unsigned mk = vm ? screen4<PY, FAST>(s.box, s.u.s2.area, i4, vm, bj, aj) : 0u;
-                    while (mk) {
-                        const int k = __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        if (PY ? suppress_py_exact(bj, s.box[i4 + k], thresh) : suppress_c(bj, s.box[i4 + k], thresh)) {
-                            const int t = i4 + k - cs;
-                            atomicOr(&s.u.s2.mask[cj_local][t >> 5], 1u << (t & 31));
-                            any = true;
+            __syncthreads();                                                    // chunk_dead = dropped by the kept list (or no candidate)
+            // 4b. predecessor rows: pred[c][w] = which candidates of word w of this chunk (ranked before c) would suppress c.
+            // The work per candidate grows with its rank, so candidate words wb and 7 - wb form a team (9 words to scan
+            // whatever wb is); a team has NMS_THREADS / 32 / 4 = 4 warps, which take the scanned words round-robin, so each
+            // pred word has one writer.  All lanes walk the same entries (shared-memory broadcasts).
+            constexpr int NB = NMS_CHUNK / 32, NSUB = (NMS_THREADS / 32) / (NB / 2);
+            const int team = wid % (NB / 2), sub = wid / (NB / 2);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int wb = pass ? NB - 1 - team : team;
+                const int c = wb * 32 + lane;                                   // candidate inside the chunk
+                const bool act = !((s.chunk_dead[wb] >> lane) & 1u);
+                if (!__any_sync(0xffffffffu, act)) continue;
+                const float4 bc = act ? s.box[cs + c] : make_float4(0, 0, 0, 0);
+                const float ac = act ? s.u.s2.area[cs + c] : 0.f;
+                for (int w = sub; w <= wb; w += NSUB) {
+                    unsigned word = 0;
+                    const int wbeg = cs + 32 * w;
+                    if (wbeg >= hi) break;
+                    const unsigned before = w < wb ? 0xffffffffu : (1u << lane) - 1u;   // entries ranked before c
+                    const unsigned alivew = ~s.chunk_dead[w];                          // entries that can still suppress
+#pragma unroll 2
+                    for (int q = 0; q < 8; ++q) {
+                        const int i4 = wbeg + 4 * q;
+                        if (i4 >= hi) break;
+                        const unsigned vm = act ? ((before & alivew) >> (4 * q)) & 0xfu : 0u;
+                        unsigned mk = __any_sync(0xffffffffu, vm != 0u) ? screen4<PY, FAST>(s.box, s.u.s2.area, i4, vm, bc, ac) : 0u;
+                        while (mk) {
+                            const int k = __ffs(mk) - 1;
+                            mk &= mk - 1;
+                            if (PY ? suppress_py_exact(s.box[i4 + k], bc, thresh) : suppress_c(s.box[i4 + k], bc, thresh)) word |= 1u << (4 * q + k);
                         }
                     }
+                    if (act) s.u.s2.mask[c][w] = word;
                 }
-                if (any) atomicOr(&s.row_nonempty[cj_local >> 5], 1u << (cj_local & 31));
             }
+            NMS_T(4);
             __syncthreads();
-            // 4c. one warp resolves the chunk in order; lane w owns dead word w
+            NMS_T(5);
+            // 4c. one warp resolves the chunk word by word: lane l <-> candidate 32 w + l.  A candidate survives iff no
+            // SURVIVING predecessor suppresses it; predecessors in earlier words are final, those in the same word are
+            // resolved in rank order, but only for the candidates that have a possibly-surviving predecessor there.
             if (wid == 0) {
-                unsigned dw = lane < NMS_CHUNK / 32 ? s.chunk_dead[lane] : 0u;
+                unsigned alive_w[NMS_CHUNK / 32];
+#pragma unroll
                 for (int w = 0; w < NMS_CHUNK / 32; ++w) {
-                    unsigned pending = s.row_nonempty[w];
-                    while (pending) {
-                        int b = __ffs(pending) - 1;
-                        pending &= pending - 1;
-                        unsigned cur = __shfl_sync(0xffffffffu, dw, w);          // dead word of row (w*32+b) as of now
-                        if (!((cur >> b) & 1u)) {
-                            unsigned mrow = lane < NMS_CHUNK / 32 ? s.u.s2.mask[w * 32 + b][lane] : 0u;
-                            dw |= mrow;
+                    alive_w[w] = 0u;
+                    if (cs + 32 * w < hi) {                                      // warp-uniform
+                        const int c = 32 * w + lane;
+                        bool pre = !((s.chunk_dead[w] >> lane) & 1u);
+#pragma unroll
+                        for (int v = 0; v < w; ++v)
+                            if (pre && (s.u.s2.mask[c][v] & alive_w[v])) pre = false;
+                        const unsigned inw = pre ? s.u.s2.mask[c][w] : 0u;
+                        const unsigned cand = __ballot_sync(0xffffffffu, pre);
+                        unsigned need = __ballot_sync(0xffffffffu, (inw & cand) != 0u);
+                        unsigned aw = cand & ~need;
+                        while (need) {
+                            const int b = __ffs(need) - 1;
+                            need &= need - 1;
+                            const unsigned inb = __shfl_sync(0xffffffffu, inw, b);
+                            if (!(inb & aw)) aw |= 1u << b;
                         }
+                        alive_w[w] = aw;
+                        if (lane == 0) s.chunk_dead[w] = ~aw;
                     }
                 }
-                if (lane < NMS_CHUNK / 32) s.chunk_dead[lane] = dw;
             }
             __syncthreads();
+            NMS_T(6);
             // 4d. append the survivors to the kept list (registers first: the list grows into this chunk's storage)
-            const bool alive = tid < NMS_CHUNK && have && !((s.chunk_dead[cj_local >> 5] >> (cj_local & 31)) & 1u);
+            const bool alive = tid < NMS_CHUNK && !((s.chunk_dead[cj_local >> 5] >> (cj_local & 31)) & 1u);   // dead covers !have
             const unsigned short my = have ? s.u.s2.idx[j] : 0;
             const unsigned char mc = have ? s.cls[j] : 0;
             int tot;
@@ -442,11 +482,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             }
             K += tot;
             __syncthreads();
+            NMS_T(7);
         }
         out_count = K;
     }
 
     // 5. output
+#ifdef YB_NMS_TIMELINE
+    if (tid == 0 && f < 2) printf("NMS frame %d m=%d: compact %lld sort %lld gather %lld | 4a %lld 4b %lld wait %lld 4c %lld 4d %lld\n", f, m, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+#endif
     yolo_b200_det *dets = a.dets + (size_t)f * a.max_det;
     if (PY) {
         // ascending anchor order (np.where(keep > 0), slim_yolo_v2.py:205)
