@@ -88,14 +88,15 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 //
 // One CTA of 512 threads per frame, two CTAs per SM (so that one frame's serial phases overlap the other's pair loops).  Candidates over the threshold are compacted and sorted once by
 // (class, score desc, tie-break) with a shared-memory bitonic sort.  Greedy suppression then runs per class segment
-// (python head; the C head is class-agnostic = one segment) in chunks of 256 sorted candidates, against a COMPACTED
-// list of the candidates kept so far (which is also the output list):
-//   a. every candidate of the chunk is tested against the kept list; 2 threads share one candidate, each taking half of
-//      the list, four kept boxes at a time (all lanes of a warp read the same kept boxes: shared-memory broadcasts);
-//      a two-sided area bound (IoU <= min/max of the areas) rejects ~99 % of the pairs with two compares each;
-//   b. every candidate records, as bit-rows, which later candidates of the same chunk it would suppress;
-//   c. one warp resolves the chunk in score order from the (rarely non-empty) bit-rows;
-//   d. the chunk's survivors are appended to the kept list (in place: kept count <= processed count).
+// (python head; the C head is class-agnostic = one segment) in chunks of 128 sorted candidates, against a COMPACTED
+// list of the candidates kept so far (which is also the output list); four barriers + one per chunk:
+//   a. every candidate of the chunk is tested against the kept list; 4 threads share one candidate, each taking a part
+//      of the list / of the index cells; then the chunk is squeezed to the candidates that are still alive;
+//   b. every candidate records, as bit-rows, which EARLIER candidates of the chunk would suppress it; the triangle of
+//      pairs is cut into (candidate word, scanned half-word) items dealt round-robin to the 16 warps;
+//   c. one warp resolves the chunk word by word (ballots; rank order only inside a 32-candidate word and only for the
+//      candidates that have a possibly-surviving predecessor there) and leaves per-word survivor counts;
+//   d. the chunk's survivors are appended to the kept list (in place: kept count <= processed count; no scan).
 // Python head with thresh > 1e-6: the kept list also carries a SPATIAL INDEX so that step a visits only boxes that can
 // matter.  IoU > t implies (i) area ratio within [t, 1/t] and (ii) |dcx| < (1-t)/(1+t) max(w_i,w_j), likewise in y
 // (from inter > t/(1+t) (a_i + a_j): the x-overlap must exceed t/(1+t) times the sum of the widths).  Kept boxes are therefore filed, as linked lists, under
@@ -109,8 +110,9 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 // borderline pairs evaluate the reference's exact fp32 expression.
 
 constexpr int NMS_THREADS = 512;
-constexpr int NMS_CHUNK = 256;
+constexpr int NMS_CHUNK = 128;
 constexpr int NMS_SLICES = NMS_THREADS / NMS_CHUNK;
+constexpr int NB = NMS_CHUNK / 32;                           // candidate words per chunk
 constexpr int NMS_MAX_CLASSES = 64;
 constexpr int NMS_BUCKETS = 12;          // area buckets by binary exponent: bucket b = areas in [2^(b-11), 2^(b-10)), bucket 0 also everything smaller
 constexpr int NMS_GRID = 8;              // centre cells per axis over [0,1]
@@ -128,8 +130,8 @@ struct NmsSmem {
     float4 box[HEAD_MAX_CAND];                                     // sorted candidates; kept list compacted in place
     unsigned char cls[HEAD_MAX_CAND];
     unsigned keepmap[HEAD_MAX_CAND / 32];                          // by anchor index (python mode output order)
-    unsigned chunk_dead[NMS_CHUNK / 32];
-    int warp_sums[NMS_THREADS / 32];
+    unsigned chunk_dead[2][NMS_CHUNK / 32];                       // per chunk: dropped / no candidate (double-buffered)
+    int warp_sums[NMS_THREADS / 32 + 1];
     // spatial index of the kept list (python head): linked lists per (area bucket, centre cell)
     unsigned ghead[NMS_BUCKETS * NMS_GRID * NMS_GRID];             // first kept entry of the list, NMS_END = empty
     unsigned short gnext[HEAD_MAX_CAND];                           // next entry of the same list
@@ -213,10 +215,13 @@ __device__ __forceinline__ unsigned screen4(const float4 *box, const float *care
     return m & vm;
 }
 
-__device__ __forceinline__ int nms_bucket(float area)
+// Area bucket: floor(log_{1/t'}(area)) counted down from area = 1, t' = the slackened threshold.  Two boxes whose area
+// ratio is at least t' are then at most ONE bucket apart (bscale = 1 / log2(1/t'); the error of log2f is orders of
+// magnitude below the slack built into t').  Bucket 0 also takes everything smaller, the last one areas >= 1/t'.
+__device__ __forceinline__ int nms_bucket(float area, float bscale)
 {
-    const int e = (int)((__float_as_uint(area) >> 23) & 0xffu) - 127;     // binary exponent (area >= 0)
-    return min(max(e + (NMS_BUCKETS - 1), 0), NMS_BUCKETS - 1);
+    const float l = log2f(fmaxf(area, 1e-30f)) * bscale;                  // <= 0 for areas <= 1
+    return min(max((int)floorf(l) + (NMS_BUCKETS - 1), 0), NMS_BUCKETS - 1);
 }
 __device__ __forceinline__ int nms_cell(float c) { return min(max((int)(c * (float)NMS_GRID), 0), NMS_GRID - 1); }
 
@@ -230,7 +235,8 @@ template <bool PY, bool FAST>
 __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 {
 #ifdef YB_NMS_TIMELINE
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    int dbg_s4 = 0, dbg_ex = 0;
 #endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NmsSmem &s = *reinterpret_cast<NmsSmem *>(smem_raw);
@@ -246,8 +252,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     // spatial-index bounds with slack: IoU > t needs area ratio >= t (bucket distance <= grid_d) and, per axis, centre
     // distance < (1 - t)/(1 + t) * max extent:  inter > t/(1+t) (a_i + a_j) and ih <= min(h) give
     // iw > t/(1+t) (w_i + w_j), and iw <= (w_i + w_j)/2 - |dcx|
-    const float t_lo = thresh * 0.999f;
-    const int grid_d = GRID ? (int)floorf(log2f(1.f / t_lo)) + 1 : 0;
+    const float t_lo = fminf(thresh * 0.999f, 0.97f);                     // (buckets no finer than 3 % steps)
+    const float bscale = GRID ? 1.f / log2f(1.f / t_lo) : 1.f;
+    constexpr int grid_d = 1;
+    const float inv_t = 1.f / t_lo * 1.0001f;                            // a suppressor is at most this much wider / taller
     const float grid_q = fmaxf(1.f - t_lo, 0.f) / (1.f + t_lo) * 1.0001f;
 
     // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
@@ -330,49 +338,62 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
         }
         if (seg_b == seg_e) continue;
 
-        if (GRID) {                                  // empty spatial index for this segment (the chunk loop starts with a barrier)
+        if (GRID) {                                  // empty spatial index for this segment
             for (int i = tid; i < NMS_BUCKETS * NMS_GRID * NMS_GRID; i += NMS_THREADS) s.ghead[i] = NMS_END;
             if (tid < NMS_BUCKETS) { s.gw[tid] = -1.f; s.gh[tid] = -1.f; }
         }
+        // per-chunk scratch is cleared one chunk ahead (dead words are double-buffered), so a chunk needs four barriers
+        if (tid < 2 * NB) (&s.chunk_dead[0][0])[tid] = 0;
+        for (int i = tid; i < NMS_CHUNK * NB; i += NMS_THREADS) (&s.u.s2.mask[0][0])[i] = 0;
+        __syncthreads();
         int K = 0;                                   // kept in this segment: entries [seg_b, seg_b + K)
+        int par = 0;                                 // which set of dead words this chunk uses
         // chunks start on 4-aligned positions (screen4 reads 4-aligned blocks); the first may begin before the segment
-        for (int cs = seg_b & ~3; cs < seg_e; cs += NMS_CHUNK) {
+        for (int cs = seg_b & ~3; cs < seg_e; cs += NMS_CHUNK, par ^= 1) {
+            NMS_T(9);
+            unsigned *dead_w = s.chunk_dead[par];
             const int hi = min(cs + NMS_CHUNK, seg_e);             // end of the chunk's candidates
             const int j = cs + cj_local;
             const bool have = j >= seg_b && j < hi;
+            // everything of candidate j that 4d needs is read here: the kept list grows into this chunk's storage
             const float4 bj = have ? s.box[j] : make_float4(0, 0, 0, 0);
             const float aj = have ? s.u.s2.area[j] : 0.f;
-            if (tid < NMS_CHUNK / 32) s.chunk_dead[tid] = 0;
-            __syncthreads();
+            const unsigned short my = have ? s.u.s2.idx[j] : 0;
+            const unsigned char mc = have ? s.cls[j] : 0;
+            if (tid < NB) s.chunk_dead[par ^ 1][tid] = 0;          // for the next chunk (last read before this chunk began)
             // 4a. against the kept list of this segment: slice 0 takes the first half, slice 1 the second, in 4-aligned
             //     blocks; every lane of a warp reads the same kept boxes (shared-memory broadcasts)
             bool dead = false;
             const float area_j = GRID ? area_py(bj) : 0.f;
             if (GRID && have && K > 0 && area_j >= 1e-20f) {
-                // walk only the lists that can hold a suppressor of j; the two slices take alternate cells
+                // walk only the lists that can hold a suppressor of j; the slices take alternate cells
                 const float wj = bj.z - bj.x, hj = bj.w - bj.y;
                 const float cxj = 0.5f * (bj.x + bj.z), cyj = 0.5f * (bj.y + bj.w);
-                const int bk = nms_bucket(area_j);
+                const int bk = nms_bucket(area_j, bscale);
+                const float wcap = wj * inv_t, hcap = hj * inv_t;
                 int cnt = 0;
                 for (int b = max(bk - grid_d, 0); b <= min(bk + grid_d, NMS_BUCKETS - 1) && !dead; ++b) {
                     const float wm = s.gw[b];
                     if (wm < 0.f) continue;                                      // nothing kept in this bucket yet
-                    const float rx = grid_q * fmaxf(wj, wm) + 1e-6f, ry = grid_q * fmaxf(hj, s.gh[b]) + 1e-6f;
+                    // centre window: the partner's extent is bounded by the bucket's maximum AND by extent_j / t
+                    // (IoU > t needs both the width and the height ratio above t)
+                    const float rx = grid_q * fmaxf(wj, fminf(wm, wcap)) + 1e-6f, ry = grid_q * fmaxf(hj, fminf(s.gh[b], hcap)) + 1e-6f;
                     const int x0 = nms_cell(cxj - rx), x1 = nms_cell(cxj + rx), y0 = nms_cell(cyj - ry), y1 = nms_cell(cyj + ry);
                     for (int yc = y0; yc <= y1 && !dead; ++yc)
                         for (int xc = x0; xc <= x1 && !dead; ++xc) {
                             if (((cnt++) & (NMS_SLICES - 1)) != slice) continue;
                             unsigned e = s.ghead[(b * NMS_GRID + yc) * NMS_GRID + xc];
                             while (e != NMS_END) {
+                                const unsigned nx = s.gnext[e];                  // fetched alongside the box, not after the test
                                 if (suppresses<PY, FAST>(s.box[e], s.u.s2.area[e], bj, aj, thresh)) { dead = true; break; }
-                                e = s.gnext[e];
+                                e = nx;
                             }
                         }
                 }
             } else if (have && K > 0) {
                 const int lo = seg_b, khi = seg_b + K;
                 const int base4 = lo & ~3;
-                const int half = (((khi - base4 + 1) >> 1) + 3) & ~3;
+                const int half = (((khi - base4 + NMS_SLICES - 1) / NMS_SLICES) + 3) & ~3;      // one part per slice
                 const int beg = base4 + slice * half, end = min(khi, beg + half);
                 for (int i4 = beg; i4 < end; i4 += 4) {
                     unsigned vm = 0xfu;                                         // which of the 4 entries belong to the list
@@ -389,43 +410,78 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                     }
                 }
             }
-            NMS_T(3);
             unsigned db = __ballot_sync(0xffffffffu, dead || !have);
-            if (lane == 0 && db) atomicOr(&s.chunk_dead[cj_local >> 5], db);
-            __syncthreads();                                                    // chunk_dead = dropped by the kept list (or no candidate)
+            if (lane == 0 && db) atomicOr(&dead_w[cj_local >> 5], db);
+            __syncthreads();                                                    // dead_w = dropped by the kept list (or no candidate)
+            NMS_T(3);
+            // 4a'. squeeze the candidates the kept list dropped out of the chunk (in place, rank order preserved; offsets
+            // from the dead words, no scan): the pairwise work of 4b is quadratic in what is left.  From here on the chunk
+            // is entries [cs, cs + n1); a writer may overwrite another candidate's slot, whose owner read it at the top.
+            int n1 = 0;
+            {
+                int before = 0;
+#pragma unroll
+                for (int v = 0; v < NB; ++v) {
+                    const int pc = __popc(~dead_w[v]);
+                    if (v < (cj_local >> 5)) before += pc;
+                    n1 += pc;
+                }
+                const unsigned dwj = dead_w[cj_local >> 5];
+                if (tid < NMS_CHUNK && !((dwj >> lane) & 1u)) {
+                    const int d = cs + before + __popc(~dwj & ((1u << lane) - 1u));
+                    s.box[d] = bj; s.u.s2.area[d] = aj; s.u.s2.idx[d] = my; s.cls[d] = mc;
+                }
+            }
+            __syncthreads();
+            // the squeezed entry this thread appends in 4d if it survives (read before anything is appended)
+            const bool have2 = tid < n1;
+            const float4 b2 = have2 ? s.box[cs + tid] : make_float4(0, 0, 0, 0);
+            const float a2 = have2 ? s.u.s2.area[cs + tid] : 0.f;
+            const unsigned short my2 = have2 ? s.u.s2.idx[cs + tid] : 0;
+            const unsigned char mc2 = have2 ? s.cls[cs + tid] : 0;
+            const int nb1 = (n1 + 31) >> 5, hi1 = cs + n1;
+            NMS_T(8);
             // 4b. predecessor rows: pred[c][w] = which candidates of word w of this chunk (ranked before c) would suppress c.
-            // The work per candidate grows with its rank, so candidate words wb and 7 - wb form a team (9 words to scan
-            // whatever wb is); a team has NMS_THREADS / 32 / 4 = 4 warps, which take the scanned words round-robin, so each
-            // pred word has one writer.  All lanes walk the same entries (shared-memory broadcasts).
-            constexpr int NB = NMS_CHUNK / 32, NSUB = (NMS_THREADS / 32) / (NB / 2);
-            const int team = wid % (NB / 2), sub = wid / (NB / 2);
+            // Work item = (candidate word wb, scanned word w <= wb, half h of w = four blocks of 4 entries):
+            // nb1 (nb1 + 1) items, dealt round-robin to the 16 warps (the triangle of pairs is spread evenly whatever nb1
+            // is).  The lanes of a warp are the 32 candidates of wb and read the same entries (shared-memory broadcasts);
+            // hits are rare and go to the zero-initialised rows with one atomic OR per item.
+            {
+                const int nitems = nb1 * (nb1 + 1);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                const int wb = pass ? NB - 1 - team : team;
-                const int c = wb * 32 + lane;                                   // candidate inside the chunk
-                const bool act = !((s.chunk_dead[wb] >> lane) & 1u);
-                if (!__any_sync(0xffffffffu, act)) continue;
-                const float4 bc = act ? s.box[cs + c] : make_float4(0, 0, 0, 0);
-                const float ac = act ? s.u.s2.area[cs + c] : 0.f;
-                for (int w = sub; w <= wb; w += NSUB) {
-                    unsigned word = 0;
-                    const int wbeg = cs + 32 * w;
-                    if (wbeg >= hi) break;
-                    const unsigned before = w < wb ? 0xffffffffu : (1u << lane) - 1u;   // entries ranked before c
-                    const unsigned alivew = ~s.chunk_dead[w];                          // entries that can still suppress
-#pragma unroll 2
-                    for (int q = 0; q < 8; ++q) {
-                        const int i4 = wbeg + 4 * q;
-                        if (i4 >= hi) break;
-                        const unsigned vm = act ? ((before & alivew) >> (4 * q)) & 0xfu : 0u;
-                        unsigned mk = __any_sync(0xffffffffu, vm != 0u) ? screen4<PY, FAST>(s.box, s.u.s2.area, i4, vm, bc, ac) : 0u;
-                        while (mk) {
-                            const int k = __ffs(mk) - 1;
-                            mk &= mk - 1;
-                            if (PY ? suppress_py_exact(s.box[i4 + k], bc, thresh) : suppress_c(s.box[i4 + k], bc, thresh)) word |= 1u << (4 * q + k);
+                for (int it = wid; it < nitems; it += NMS_THREADS / 32) {
+                    const int wi = it >> 1, h = it & 1;
+                    int wb = 0, wbase = 0;
+                    while (wbase + wb + 1 <= wi) { wbase += wb + 1; ++wb; }     // wi -> (wb, w): wi = wb (wb + 1) / 2 + w
+                    const int w = wi - wbase;
+                    const int i0 = cs + 32 * w + 16 * h;
+                    if (i0 >= hi1) continue;
+                    const int c = wb * 32 + lane;                               // candidate inside the chunk
+                    const bool act = c < n1;
+                    // entries of this half that are ranked before c and inside the chunk
+                    unsigned vm16 = w < wb ? 0xffffu : (((1u << lane) - 1u) >> (16 * h)) & 0xffffu;
+                    if (i0 + 16 > hi1) vm16 &= 0xffffu >> (i0 + 16 - hi1);
+                    if (!act) vm16 = 0u;
+                    if (!__any_sync(0xffffffffu, vm16 != 0u)) continue;
+                    const float4 bc = act ? s.box[cs + c] : make_float4(0, 0, 0, 0);
+                    const float ac = act ? s.u.s2.area[cs + c] : 0.f;
+                    unsigned bits = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i4 = i0 + 4 * q;
+                        if (i4 < hi1) {                                          // warp-uniform
+                            unsigned mk = screen4<PY, FAST>(s.box, s.u.s2.area, i4, (vm16 >> (4 * q)) & 0xfu, bc, ac);
+#ifdef YB_NMS_TIMELINE
+                            dbg_s4++; dbg_ex += __popc(__ballot_sync(0xffffffffu, mk != 0u)) ? 1 : 0;
+#endif
+                            while (mk) {
+                                const int k = __ffs(mk) - 1;
+                                mk &= mk - 1;
+                                if (PY ? suppress_py_exact(s.box[i4 + k], bc, thresh) : suppress_c(s.box[i4 + k], bc, thresh)) bits |= 1u << (4 * q + k);
+                            }
                         }
                     }
-                    if (act) s.u.s2.mask[c][w] = word;
+                    if (bits) atomicOr(&s.u.s2.mask[c][w], bits << (16 * h));
                 }
             }
             NMS_T(4);
@@ -434,14 +490,16 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
             // 4c. one warp resolves the chunk word by word: lane l <-> candidate 32 w + l.  A candidate survives iff no
             // SURVIVING predecessor suppresses it; predecessors in earlier words are final, those in the same word are
             // resolved in rank order, but only for the candidates that have a possibly-surviving predecessor there.
+            // It also leaves, per word, the number of survivors before it (4d needs no scan).
             if (wid == 0) {
-                unsigned alive_w[NMS_CHUNK / 32];
+                unsigned alive_w[NB];
+                int run = 0;
 #pragma unroll
-                for (int w = 0; w < NMS_CHUNK / 32; ++w) {
+                for (int w = 0; w < NB; ++w) {
                     alive_w[w] = 0u;
-                    if (cs + 32 * w < hi) {                                      // warp-uniform
+                    if (w < nb1) {                                               // warp-uniform
                         const int c = 32 * w + lane;
-                        bool pre = !((s.chunk_dead[w] >> lane) & 1u);
+                        bool pre = c < n1;
 #pragma unroll
                         for (int v = 0; v < w; ++v)
                             if (pre && (s.u.s2.mask[c][v] & alive_w[v])) pre = false;
@@ -456,30 +514,32 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                             if (!(inb & aw)) aw |= 1u << b;
                         }
                         alive_w[w] = aw;
-                        if (lane == 0) s.chunk_dead[w] = ~aw;
                     }
+                    if (lane == 0) { dead_w[w] = ~alive_w[w]; s.warp_sums[w] = run; }
+                    run += __popc(alive_w[w]);
                 }
+                if (lane == 0) s.warp_sums[NB] = run;
             }
             __syncthreads();
             NMS_T(6);
-            // 4d. append the survivors to the kept list (registers first: the list grows into this chunk's storage)
-            const bool alive = tid < NMS_CHUNK && !((s.chunk_dead[cj_local >> 5] >> (cj_local & 31)) & 1u);   // dead covers !have
-            const unsigned short my = have ? s.u.s2.idx[j] : 0;
-            const unsigned char mc = have ? s.cls[j] : 0;
-            int tot;
-            int off = block_scan_flag(alive, s.warp_sums, &tot);     // contains the barriers that order reads before writes
+            // 4d. append the survivors to the kept list (the squeezed entries have been in registers since before 4b)
+            const unsigned dw = tid < NMS_CHUNK ? dead_w[cj_local >> 5] : 0xffffffffu;
+            const bool alive = !((dw >> lane) & 1u);
+            const int tot = s.warp_sums[NB];
             if (alive) {
-                const int d = seg_b + K + off;
-                s.box[d] = bj; s.u.s2.area[d] = aj; s.u.s2.idx[d] = my; s.cls[d] = mc;
-                if (PY) atomicOr(&s.keepmap[my >> 5], 1u << (my & 31));
+                const int d = seg_b + K + s.warp_sums[cj_local >> 5] + __popc(~dw & ((1u << lane) - 1u));
+                s.box[d] = b2; s.u.s2.area[d] = a2; s.u.s2.idx[d] = my2; s.cls[d] = mc2;
+                if (PY) atomicOr(&s.keepmap[my2 >> 5], 1u << (my2 & 31));
                 if (GRID) {                                                      // file it in the spatial index
-                    const int b = nms_bucket(area_j);
-                    const int cell = (b * NMS_GRID + nms_cell(0.5f * (bj.y + bj.w))) * NMS_GRID + nms_cell(0.5f * (bj.x + bj.z));
+                    const int b = nms_bucket(area_py(b2), bscale);
+                    const int cell = (b * NMS_GRID + nms_cell(0.5f * (b2.y + b2.w))) * NMS_GRID + nms_cell(0.5f * (b2.x + b2.z));
                     s.gnext[d] = (unsigned short)atomicExch(&s.ghead[cell], (unsigned)d);
-                    atomicMax(reinterpret_cast<int *>(&s.gw[b]), __float_as_int(bj.z - bj.x));      // widths are >= 0: integer order = float order
-                    atomicMax(reinterpret_cast<int *>(&s.gh[b]), __float_as_int(bj.w - bj.y));
+                    atomicMax(reinterpret_cast<int *>(&s.gw[b]), __float_as_int(b2.z - b2.x));      // widths are >= 0: integer order = float order
+                    atomicMax(reinterpret_cast<int *>(&s.gh[b]), __float_as_int(b2.w - b2.y));
                 }
             }
+            // rows of the next chunk (this chunk's were last read in 4c)
+            for (int i = tid; i < NMS_CHUNK * NB; i += NMS_THREADS) (&s.u.s2.mask[0][0])[i] = 0;
             K += tot;
             __syncthreads();
             NMS_T(7);
@@ -489,7 +549,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 
     // 5. output
 #ifdef YB_NMS_TIMELINE
-    if (tid == 0 && f < 2) printf("NMS frame %d m=%d: compact %lld sort %lld gather %lld | 4a %lld 4b %lld wait %lld 4c %lld 4d %lld\n", f, m, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+    if (tid == 0 && f < 2) printf("NMS frame %d m=%d, warp0: screen4 %d with-exact %d: compact %lld sort %lld gather %lld | 4a %lld squeeze %lld 4b %lld wait %lld 4c %lld 4d %lld other %lld\n", f, m, dbg_s4, dbg_ex, tacc[0], tacc[1], tacc[2], tacc[3], tacc[8], tacc[4], tacc[5], tacc[6], tacc[7], tacc[9]);
 #endif
     yolo_b200_det *dets = a.dets + (size_t)f * a.max_det;
     if (PY) {
