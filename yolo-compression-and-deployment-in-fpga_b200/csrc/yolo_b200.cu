@@ -65,7 +65,8 @@ struct yolo_b200_ctx {
     std::vector<cudaEvent_t> ev;
     int ev_used = 0;
     // host-buffer entry points: copies of chunk k+1 / k-1 overlap the kernels of chunk k
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_head = nullptr;
+    int32_t *counts_pinned = nullptr; size_t counts_pinned_cap = 0;   // counts land here first: the caller's array may be pageable
     std::vector<cudaEvent_t> ev_in, ev_done, ev_cnt;
     int host_chunk = 64;                 // frames per chunk (measured best at 416x416: tools/t_e2e.py)
     int8_t *pred_all = nullptr; size_t pred_all_cap = 0;   // batch-wide prediction map of the host-buffer entry points
@@ -159,6 +160,8 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     for (auto e : c->ev_cnt) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_head) cudaStreamDestroy(c->s_head);
+    if (c->counts_pinned) cudaFreeHost(c->counts_pinned);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -635,33 +638,48 @@ int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, si
     return 0;
 }
 
-int yolo_b200_detect(yolo_b200_ctx *c, const int8_t *d_pred, int n, int gh, int gw, int in_h, int in_w,
+// scratch of the head (scores, classes, boxes of every anchor) for `frames` frames
+static int ensure_head(yolo_b200_ctx *c, size_t frames, size_t N)
+{
+    if (c->head_cap >= frames * N) return 0;
+    cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes);
+    c->h_scores = nullptr; c->h_cls = nullptr; c->h_boxes = nullptr; c->head_cap = 0;
+    CU(cudaMalloc(&c->h_scores, frames * N * sizeof(float)));
+    CU(cudaMalloc(&c->h_cls, frames * N * sizeof(int)));
+    CU(cudaMalloc(&c->h_boxes, frames * N * sizeof(float4)));
+    c->head_cap = frames * N;
+    return 0;
+}
+
+// decode + NMS of n frames on stream st; the frames use the scratch slots [slot0, slot0 + n) (ensure_head first)
+static int detect_on(yolo_b200_ctx *c, cudaStream_t st, size_t slot0, const int8_t *d_pred, int n, int gh, int gw, int in_h, int in_w,
                      yolo_b200_det *d_dets, int32_t *d_counts)
 {
-    int rc = check_ready(c, n, gh, gw); if (rc) return rc;
-    if (n == 0) return 0;
-    if (!d_pred || !d_dets || !d_counts) return fail(E_ARG, "null buffer");
     const yolo_b200_params &p = c->prm;
-    size_t N = (size_t)gh * gw * p.num_anchors;
-    if (N > (size_t)HEAD_MAX_CAND) return fail(E_UNSUPPORTED, "grid %dx%d x %d anchors exceeds %d candidates per frame", gh, gw, p.num_anchors, HEAD_MAX_CAND);
-    if (c->head_cap < (size_t)n * N) {
-        cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes);
-        c->h_scores = nullptr; c->h_cls = nullptr; c->h_boxes = nullptr; c->head_cap = 0;
-        CU(cudaMalloc(&c->h_scores, (size_t)n * N * sizeof(float)));
-        CU(cudaMalloc(&c->h_cls, (size_t)n * N * sizeof(int)));
-        CU(cudaMalloc(&c->h_boxes, (size_t)n * N * sizeof(float4)));
-        c->head_cap = (size_t)n * N;
-    }
+    const size_t N = (size_t)gh * gw * p.num_anchors;
     HeadArgs a;
     a.pred = d_pred; a.n = n; a.gh = gh; a.gw = gw; a.cs = yolo_b200_cstride(p.num_anchors * (5 + p.num_classes));
     a.A = p.num_anchors; a.C = p.num_classes; a.sa_pred = p.scale_a[p.num_layers];
     for (int i = 0; i < YOLO_B200_MAX_ANCHORS; ++i) { a.anchors[i][0] = p.anchors[i][0]; a.anchors[i][1] = p.anchors[i][1]; }
     a.stride = p.stride; a.in_h = in_h; a.in_w = in_w; a.conf_thresh = p.conf_thresh; a.nms_thresh = p.nms_thresh;
     a.head_mode = p.head_mode; a.max_det = p.max_det;
-    a.scores = c->h_scores; a.cls = c->h_cls; a.boxes = c->h_boxes; a.dets = d_dets; a.counts = d_counts;
-    CU(head_decode(a, c->stream));
-    CU(head_nms(a, c->stream));
+    a.scores = c->h_scores + slot0 * N; a.cls = c->h_cls + slot0 * N; a.boxes = c->h_boxes + slot0 * N; a.dets = d_dets; a.counts = d_counts;
+    CU(head_decode(a, st));
+    CU(head_nms(a, st));
     c->launches += 2;
+    return 0;
+}
+
+int yolo_b200_detect(yolo_b200_ctx *c, const int8_t *d_pred, int n, int gh, int gw, int in_h, int in_w,
+                     yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    int rc = check_ready(c, n, gh, gw); if (rc) return rc;
+    if (n == 0) return 0;
+    if (!d_pred || !d_dets || !d_counts) return fail(E_ARG, "null buffer");
+    const size_t N = (size_t)gh * gw * c->prm.num_anchors;
+    if (N > (size_t)HEAD_MAX_CAND) return fail(E_UNSUPPORTED, "grid %dx%d x %d anchors exceeds %d candidates per frame", gh, gw, c->prm.num_anchors, HEAD_MAX_CAND);
+    rc = ensure_head(c, (size_t)n, N); if (rc) return rc;
+    rc = detect_on(c, c->stream, 0, d_pred, n, gh, gw, in_h, in_w, d_dets, d_counts); if (rc) return rc;
     tick(c);
     return 0;
 }
@@ -774,15 +792,41 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     const int chunk = c->host_chunk > 0 ? c->host_chunk : n;
     const int nchunks = (n + chunk - 1) / chunk;
     const size_t frame_bytes = in_bytes / (size_t)n;
-    if (!c->s_in) { CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
-    while ((int)c->ev_in.size() < nchunks + 1) {
-        cudaEvent_t e1;
-        CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-        c->ev_in.push_back(e1);
+    const size_t N = (size_t)gh * gw * c->prm.num_anchors;
+    if (N > (size_t)HEAD_MAX_CAND) return fail(E_UNSUPPORTED, "grid %dx%d x %d anchors exceeds %d candidates per frame", gh, gw, c->prm.num_anchors, HEAD_MAX_CAND);
+    rc = ensure_head(c, (size_t)n, N); if (rc) return rc;
+    if (c->counts_pinned_cap < (size_t)n) {
+        if (c->counts_pinned) cudaFreeHost(c->counts_pinned);
+        c->counts_pinned = nullptr; c->counts_pinned_cap = 0;
+        CU(cudaHostAlloc((void **)&c->counts_pinned, (size_t)n * sizeof(int32_t), cudaHostAllocDefault));
+        c->counts_pinned_cap = (size_t)n;
     }
+    if (!c->s_in) {
+        CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->s_head, cudaStreamNonBlocking));
+    }
+    auto grow = [](std::vector<cudaEvent_t> &v, int want) -> cudaError_t {
+        while ((int)v.size() < want) {
+            cudaEvent_t e1;
+            cudaError_t e = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            v.push_back(e1);
+        }
+        return cudaSuccess;
+    };
+    CU(grow(c->ev_in, nchunks + 1)); CU(grow(c->ev_done, nchunks)); CU(grow(c->ev_cnt, nchunks));
+    auto drain = [&]() { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_head); cudaStreamSynchronize(c->s_out); };
     // the staging buffers may still be read by work queued earlier on the context stream
     CU(cudaEventRecord(c->ev_in[nchunks], c->stream));
     CU(cudaStreamWaitEvent(c->s_in, c->ev_in[nchunks], 0));
+    CU(cudaStreamWaitEvent(c->s_head, c->ev_in[nchunks], 0));
+    // Three stages, all queued up front: chunk k's frames are copied in on s_in, its convolution layers run on the
+    // context stream, decode + NMS and the copy of the counts on s_head.  The head runs twice: once for all chunks but the
+    // last, as soon as the second-to-last chunk's layers are done (it then overlaps the last chunk's copy, which the GPU
+    // would otherwise wait for), and once for the last chunk.  (A head per chunk was measured slower: the NMS CTAs hold
+    // shared memory the persistent convolution CTAs of the next chunk need, so the two serialise.)
+    int head_f0 = 0, ngroups = 0, grp_f0[2] = {0, 0}, grp_n[2] = {0, 0};
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, nk = (n - f0) < chunk ? (n - f0) : chunk;
         char *stage = (char *)c->stage_in + (size_t)f0 * frame_bytes;
@@ -791,19 +835,33 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
         const int8_t *pred; int g1, g2;
         rc = features_dev(c, kind, stage, nk, h, w, c->pred_all + (size_t)f0 * pred_frame, &pred, &g1, &g2);
-        if (rc) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); return rc; }
+        if (rc) { drain(); return rc; }
+        if (k == nchunks - 2 || k == nchunks - 1) {
+            const int hn = f0 + nk - head_f0;                                  // frames [head_f0, f0 + nk)
+            CU(cudaEventRecord(c->ev_done[ngroups], c->stream));
+            CU(cudaStreamWaitEvent(c->s_head, c->ev_done[ngroups], 0));
+            rc = detect_on(c, c->s_head, (size_t)head_f0, c->pred_all + (size_t)head_f0 * pred_frame, hn, gh, gw, h, w,
+                           c->d_dets + (size_t)head_f0 * md, c->d_counts + head_f0);
+            if (rc) { drain(); return rc; }
+            CU(cudaMemcpyAsync(c->counts_pinned + head_f0, c->d_counts + head_f0, (size_t)hn * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_head));
+            CU(cudaEventRecord(c->ev_cnt[ngroups], c->s_head));
+            grp_f0[ngroups] = head_f0; grp_n[ngroups] = hn; ++ngroups;
+            head_f0 = f0 + nk;
+        }
     }
-    rc = yolo_b200_detect(c, c->pred_all, n, gh, gw, h, w, c->d_dets, c->d_counts);
-    if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-    CU(cudaMemcpyAsync(counts, c->d_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    // detections: one strided copy as wide as the largest count
-    int maxc = 0;
-    for (int i = 0; i < n; ++i) maxc = counts[i] > maxc ? counts[i] : maxc;
-    if (maxc > (int)md) maxc = (int)md;
-    if (maxc > 0)
-        CU(cudaMemcpy2DAsync(dets, md * sizeof(yolo_b200_det), c->d_dets, md * sizeof(yolo_b200_det),
-                             (size_t)maxc * sizeof(yolo_b200_det), (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    // detections: per head launch, one strided copy as wide as its largest count, as soon as its counts are here
+    for (int k = 0; k < ngroups; ++k) {
+        const int f0 = grp_f0[k], nk = grp_n[k];
+        cudaError_t e = cudaEventSynchronize(c->ev_cnt[k]);
+        if (e != cudaSuccess) { drain(); return fail(E_CUDA, "%s", cudaGetErrorString(e)); }
+        int maxc = 0;
+        for (int i = 0; i < nk; ++i) { counts[f0 + i] = c->counts_pinned[f0 + i]; maxc = counts[f0 + i] > maxc ? counts[f0 + i] : maxc; }
+        if (maxc > (int)md) maxc = (int)md;
+        if (maxc > 0)
+            CU(cudaMemcpy2DAsync(dets + (size_t)f0 * md, md * sizeof(yolo_b200_det), c->d_dets + (size_t)f0 * md, md * sizeof(yolo_b200_det),
+                                 (size_t)maxc * sizeof(yolo_b200_det), (size_t)nk, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    CU(cudaStreamSynchronize(c->s_out));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
