@@ -11,6 +11,7 @@
 #include <string.h>
 #include <mutex>
 #include <vector>
+#include <string>
 
 using namespace yb;
 
@@ -771,6 +772,23 @@ int yolo_b200_sync(yolo_b200_ctx *c)
 // chunking changes no result); every chunk's prediction map lands in one batch-wide buffer and decode + NMS then run once
 // over the whole batch (a per-chunk NMS launch cannot fill the GPU: it is one CTA per frame).  Only the filled part of the
 // detection lists is copied back.
+// YOLO_B200_TRACE_HOST=1: timeline of one host-buffer call (ms since its start), printed to stderr
+struct HostTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    void mark(const char *what, int k, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        ev.push_back({std::string(what) + " " + std::to_string(k), e});
+    }
+    void dump() {
+        if (!on) return;
+        for (auto &p : ev) { float ms = 0; cudaEventSynchronize(p.second); cudaEventElapsedTime(&ms, t0, p.second); fprintf(stderr, "  %-22s %7.3f ms\n", p.first.c_str(), ms); cudaEventDestroy(p.second); }
+        cudaEventDestroy(t0);
+    }
+};
+
 static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
                         yolo_b200_det *dets, int32_t *counts)
 {
@@ -790,7 +808,19 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     const size_t pred_frame = (size_t)gh * gw * c->layers.back().cs_out;
     rc = ensure((void **)&c->pred_all, &c->pred_all_cap, (size_t)n * pred_frame); if (rc) return rc;
     const int chunk = c->host_chunk > 0 ? c->host_chunk : n;
-    const int nchunks = (n + chunk - 1) / chunk;
+    std::vector<int> cf0, cnk;                                   // first frame / frames of each chunk
+    if (const char *sched = getenv("YOLO_B200_CHUNKS")) {        // experiment hook: explicit chunk sizes, the last one repeats
+        int f = 0, last = chunk;
+        while (f < n) {
+            if (sched && *sched) { last = atoi(sched); sched = strchr(sched, ','); if (sched) ++sched; }
+            if (last < 1) last = chunk;
+            const int nk = (n - f) < last ? (n - f) : last;
+            cf0.push_back(f); cnk.push_back(nk); f += nk;
+        }
+    } else {
+        for (int f = 0; f < n; f += chunk) { cf0.push_back(f); cnk.push_back((n - f) < chunk ? (n - f) : chunk); }
+    }
+    const int nchunks = (int)cf0.size();
     const size_t frame_bytes = in_bytes / (size_t)n;
     const size_t N = (size_t)gh * gw * c->prm.num_anchors;
     if (N > (size_t)HEAD_MAX_CAND) return fail(E_UNSUPPORTED, "grid %dx%d x %d anchors exceeds %d candidates per frame", gh, gw, c->prm.num_anchors, HEAD_MAX_CAND);
@@ -817,6 +847,9 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     };
     CU(grow(c->ev_in, nchunks + 1)); CU(grow(c->ev_done, nchunks)); CU(grow(c->ev_cnt, nchunks));
     auto drain = [&]() { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_head); cudaStreamSynchronize(c->s_out); };
+    HostTrace tr;
+    tr.on = getenv("YOLO_B200_TRACE_HOST") != nullptr;
+    if (tr.on) { cudaEventCreate(&tr.t0); cudaEventRecord(tr.t0, c->stream); }
     // the staging buffers may still be read by work queued earlier on the context stream
     CU(cudaEventRecord(c->ev_in[nchunks], c->stream));
     CU(cudaStreamWaitEvent(c->s_in, c->ev_in[nchunks], 0));
@@ -828,14 +861,16 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     // shared memory the persistent convolution CTAs of the next chunk need, so the two serialise.)
     int head_f0 = 0, ngroups = 0, grp_f0[2] = {0, 0}, grp_n[2] = {0, 0};
     for (int k = 0; k < nchunks; ++k) {
-        const int f0 = k * chunk, nk = (n - f0) < chunk ? (n - f0) : chunk;
+        const int f0 = cf0[k], nk = cnk[k];
         char *stage = (char *)c->stage_in + (size_t)f0 * frame_bytes;
         CU(cudaMemcpyAsync(stage, (const char *)host_in + (size_t)f0 * frame_bytes, (size_t)nk * frame_bytes, cudaMemcpyHostToDevice, c->s_in));
         CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        tr.mark("h2d done", k, c->s_in);
         CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
         const int8_t *pred; int g1, g2;
         rc = features_dev(c, kind, stage, nk, h, w, c->pred_all + (size_t)f0 * pred_frame, &pred, &g1, &g2);
         if (rc) { drain(); return rc; }
+        tr.mark("layers done", k, c->stream);
         if (k == nchunks - 2 || k == nchunks - 1) {
             const int hn = f0 + nk - head_f0;                                  // frames [head_f0, f0 + nk)
             CU(cudaEventRecord(c->ev_done[ngroups], c->stream));
@@ -845,6 +880,7 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
             if (rc) { drain(); return rc; }
             CU(cudaMemcpyAsync(c->counts_pinned + head_f0, c->d_counts + head_f0, (size_t)hn * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_head));
             CU(cudaEventRecord(c->ev_cnt[ngroups], c->s_head));
+            tr.mark("head+counts done", ngroups, c->s_head);
             grp_f0[ngroups] = head_f0; grp_n[ngroups] = hn; ++ngroups;
             head_f0 = f0 + nk;
         }
@@ -860,9 +896,11 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         if (maxc > 0)
             CU(cudaMemcpy2DAsync(dets + (size_t)f0 * md, md * sizeof(yolo_b200_det), c->d_dets + (size_t)f0 * md, md * sizeof(yolo_b200_det),
                                  (size_t)maxc * sizeof(yolo_b200_det), (size_t)nk, cudaMemcpyDeviceToHost, c->s_out));
+        tr.mark("dets d2h done", k, c->s_out);
     }
     CU(cudaStreamSynchronize(c->s_out));
     CU(cudaStreamSynchronize(c->stream));
+    tr.dump();
     return 0;
 }
 
