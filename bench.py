@@ -378,7 +378,7 @@ def main():
                        "parallelism": "frames sharded over %d GPU(s), detections all-gathered" % world},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(host_sets[0].numel() * 2),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "api": "yolo_b200_forward_rgb444 (pinned host buffers; H2D of 64-frame chunks overlapped with the convolution layers, decode + NMS once per batch, filled part of the lists copied back)",
+                    "api": "yolo_b200_forward_rgb444 (pinned host buffers; H2D of 64-frame chunks overlapped with the convolution layers; decode + NMS on a second stream: all chunks but the last while the last is copied in, then the last; filled part of the lists copied back)",
                     "gpu_launches": int(e2e_launches)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sparse_head": sparse,
         }))
