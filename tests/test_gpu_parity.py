@@ -387,6 +387,32 @@ def test_pipelined_host_entry_points_do_not_depend_on_the_chunk_size(ctx):
         ctx.set_host_chunk(64)
 
 
+def test_fused_rgb444_front_end_edge_cases(ctx):
+    """The first layer with the camera quantiser fused in: upper nibble of the pixels ignored (camera_to_inpBuf masks
+    it, yolo_forward.c:87-123), frame widths that are / are not a multiple of 4 and a frame pointer that is only 2-byte
+    aligned (both fall back to quantiser + generic first layer): always the layer-1 map of the oracle."""
+    qnet = ex.random_quantnet(seed=5, calib_hw=(64, 96), calib_frames=2, calib_input="rgb444")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    rng = np.random.default_rng(11)
+    for (n, h, w) in ((3, 64, 96), (2, 34, 52), (2, 40, 98), (1, 33, 47)):
+        clean = rng.integers(0, 4096, (n, h, w), dtype=np.uint16)
+        dirty = clean | (rng.integers(0, 16, (n, h, w), dtype=np.uint16) << 12)
+        x8 = ol.quantize_rgb444(clean, qnet.sa[0])
+        ref, _ = ol.backbone(qnet, x8, contract=0)
+        for frames, shift in ((clean, 0), (dirty, 0), (dirty, 1)):
+            buf = torch.zeros((n * h * w + 4,), dtype=torch.int16, device="cuda")
+            view = buf[shift:shift + n * h * w]
+            view.copy_(torch.from_numpy(frames.reshape(-1).view(np.int16)))
+            d_dets = torch.zeros((n, 512, 8), dtype=torch.int32, device="cuda")
+            d_counts = torch.zeros((n,), dtype=torch.int32, device="cuda")
+            ctx.forward_rgb444_dev(view, n, h, w, d_dets, d_counts)
+            ctx.sync()
+            for l in (0, 1, 9):
+                shp = ref[l].shape
+                np.testing.assert_array_equal(ctx.layer_output(l, shp[0], shp[1], shp[2]), ref[l],
+                                              err_msg="shape %s shift %d layer %d" % ((n, h, w), shift, l))
+
+
 def test_uint8_image_front_end_matches_basetransform_and_f32_path(ctx):
     """yolo_b200_forward_u8bgr: BaseTransform (without resize) + BGR->RGB + tracker quantiser as a fused table lookup.
     The table equals the reference's float32 arithmetic evaluated in numpy; the quantised map equals the f32 front end
@@ -538,7 +564,8 @@ def test_first_layer_kernel_against_oracle(ctx, pool):
     cin, cout, activ, _ = qnet.layers[0]
     qnet.layers[0] = (cin, cout, activ, pool)
     rng = np.random.default_rng(7 + pool)
-    for (n, h, w) in ((2, 33, 47), (3, 16, 32), (1, 50, 70)):
+    # widths that are not a multiple of 4 fall back to the dp4a kernel (the mma kernel fetches aligned pixel quads)
+    for (n, h, w) in ((2, 33, 47), (3, 16, 32), (1, 50, 70), (2, 33, 44), (1, 50, 68), (2, 5, 4), (1, 18, 100)):
         x = np.zeros((n, h, w, 4), dtype=np.int8)
         x[..., :3] = rng.integers(-128, 128, (n, h, w, 3), dtype=np.int8)
         for contract in (lib.CONTRACT_F, lib.CONTRACT_P):

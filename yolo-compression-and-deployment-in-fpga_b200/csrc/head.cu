@@ -379,9 +379,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                     // (IoU > t needs both the width and the height ratio above t)
                     const float rx = grid_q * fmaxf(wj, fminf(wm, wcap)) + 1e-6f, ry = grid_q * fmaxf(hj, fminf(s.gh[b], hcap)) + 1e-6f;
                     const int x0 = nms_cell(cxj - rx), x1 = nms_cell(cxj + rx), y0 = nms_cell(cyj - ry), y1 = nms_cell(cyj + ry);
-                    for (int yc = y0; yc <= y1 && !dead; ++yc)
+                    for (int yc = y0; yc <= y1 && !dead; ++yc) {
+                        if (((cnt++) & (NMS_SLICES - 1)) != slice) continue;     // the slices take alternate cell rows
                         for (int xc = x0; xc <= x1 && !dead; ++xc) {
-                            if (((cnt++) & (NMS_SLICES - 1)) != slice) continue;
                             unsigned e = s.ghead[(b * NMS_GRID + yc) * NMS_GRID + xc];
                             while (e != NMS_END) {
                                 const unsigned nx = s.gnext[e];                  // fetched alongside the box, not after the test
@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                                 e = nx;
                             }
                         }
+                    }
                 }
             } else if (have && K > 0) {
                 const int lo = seg_b, khi = seg_b + K;
