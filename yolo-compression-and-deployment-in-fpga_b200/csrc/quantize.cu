@@ -12,8 +12,8 @@ __global__ void __launch_bounds__(256) quantize_rgb444_kernel(const uint16_t *__
     __shared__ int s_lut[4096];
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
-    // 8 pixels (16 B in, 32 B out) per thread per step
-    size_t nvec = npix / 8;
+    // 8 pixels (16 B in, 32 B out) per thread per step; a frame pointer that is not 16-byte aligned takes the scalar loop
+    size_t nvec = (reinterpret_cast<uintptr_t>(frames) & 15) ? 0 : npix / 8;
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
         uint4 p = reinterpret_cast<const uint4 *>(frames)[v];
         unsigned w[4] = { p.x, p.y, p.z, p.w };
@@ -26,13 +26,12 @@ __global__ void __launch_bounds__(256) quantize_rgb444_kernel(const uint16_t *__
         reinterpret_cast<int4 *>(out)[2 * v + 1] = o1;
     }
     // tail
-    if (blockIdx.x == 0)
-        for (size_t i = nvec * 8 + threadIdx.x; i < npix; i += blockDim.x) out[i] = s_lut[frames[i] & 0xfff];
+    for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) out[i] = s_lut[frames[i] & 0xfff];
 }
 
 cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st)
 {
-    size_t nvec = npix / 8;
+    size_t nvec = ((uintptr_t)frames & 15) ? (npix + 7) / 8 : npix / 8;      // sizes the grid only
     int blocks = (int)((nvec + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
