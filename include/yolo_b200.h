@@ -185,7 +185,9 @@ int yolo_b200_sync(yolo_b200_ctx *ctx);
 /* ---- per-stage entry points (device buffers) -------------------------------------------- */
 
 /* Input quantisers: pixel_norm_quantize (yolo_forward.c:57-85) as a 4096-entry table, and
- * a_tracker_in.quantize_activation (slim_yolo_v2.py:35: round-half-even of x*2^scale_a[0]). */
+ * a_tracker_in.quantize_activation (slim_yolo_v2.py:35: round-half-even of x*2^scale_a[0]).
+ * Alignment of device buffers: int8 maps 16 bytes, fp32 input 16 bytes (error otherwise); camera frames 2 bytes
+ * (frames that are not 16-byte aligned, or whose width is not a multiple of 4, take slower kernels, same results). */
 int yolo_b200_quantize_rgb444(yolo_b200_ctx *ctx, const uint16_t *d_frames, int n, int h, int w,
                               int8_t *d_nhwc4);
 int yolo_b200_quantize_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w,

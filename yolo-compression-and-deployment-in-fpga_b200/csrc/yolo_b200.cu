@@ -433,6 +433,7 @@ int yolo_b200_quantize_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, 
     int rc = check_ready(c, n, h, w); if (rc) return rc;
     if (n == 0) return 0;
     if (((size_t)h * w) % 4) return fail(E_UNSUPPORTED, "h*w must be a multiple of 4");
+    if (((uintptr_t)d_nchw | (uintptr_t)d_nhwc4) & 15) return fail(E_ARG, "fp32 front end: device buffers must be 16-byte aligned");
     CU(quantize_f32(d_nchw, n, h, w, c->prm.scale_a[0], d_nhwc4, c->ovf_dev, c->stream));
     c->launches++;
     return 0;
