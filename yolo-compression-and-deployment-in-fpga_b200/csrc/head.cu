@@ -500,19 +500,24 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
                     alive_w[w] = 0u;
                     if (w < nb1) {                                               // warp-uniform
                         const int c = 32 * w + lane;
-                        bool pre = c < n1;
+                        // rows of this candidate for all earlier words at once (independent loads), then one test
+                        unsigned hit = 0u;
 #pragma unroll
-                        for (int v = 0; v < w; ++v)
-                            if (pre && (s.u.s2.mask[c][v] & alive_w[v])) pre = false;
+                        for (int v = 0; v < w; ++v) hit |= s.u.s2.mask[c & (NMS_CHUNK - 1)][v] & alive_w[v];
+                        const bool pre = c < n1 && hit == 0u;
                         const unsigned inw = pre ? s.u.s2.mask[c][w] : 0u;
                         const unsigned cand = __ballot_sync(0xffffffffu, pre);
-                        unsigned need = __ballot_sync(0xffffffffu, (inw & cand) != 0u);
-                        unsigned aw = cand & ~need;
-                        while (need) {
-                            const int b = __ffs(need) - 1;
-                            need &= need - 1;
-                            const unsigned inb = __shfl_sync(0xffffffffu, inw, b);
-                            if (!(inb & aw)) aw |= 1u << b;
+                        // in-word fixpoint: `und` = undecided candidates, `aw` = survivors so far.  An undecided candidate
+                        // with a surviving predecessor is dropped; one whose predecessors are all decided survives.  The
+                        // lowest undecided candidate is always decided, and typically most are after two or three rounds.
+                        unsigned und = __ballot_sync(0xffffffffu, (inw & cand) != 0u);
+                        unsigned aw = cand & ~und;
+                        while (und) {
+                            const bool mine = (und >> lane) & 1u;
+                            const bool drop = mine && (inw & aw) != 0u;
+                            const bool keep = mine && !drop && (inw & und) == 0u;
+                            const unsigned d = __ballot_sync(0xffffffffu, drop), k = __ballot_sync(0xffffffffu, keep);
+                            aw |= k; und &= ~(d | k);
                         }
                         alive_w[w] = aw;
                     }
