@@ -355,6 +355,14 @@ def main():
         sparse = {"value": B * 10 / (s0.elapsed_time(s1) / 1e3), "unit": "frames/s",
                   "mean_detections_per_frame": float(d_counts.float().mean().item()),
                   "note": "same step with pred objectness bias - 5 before quantisation (sparse detections of a trained network)"}
+        for i in range(2):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        sparse["e2e"] = B * e2e_steps / (time.perf_counter() - t0)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
