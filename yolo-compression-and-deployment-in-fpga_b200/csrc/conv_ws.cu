@@ -79,6 +79,14 @@ struct WsParams {
     long long *dbg;              // optional timeline (YB_WS_TIMELINE builds): [cta][tile][8] clock64 stamps
 };
 
+// TMA-fed variant (TMAIN, un-phased tiles with 32 / 64 / 128 input channels): the halo tile is pixel-major
+// [18 rows][WS_TMA_PITCH(cs_in) pixels][cs_in bytes], written by swizzled TMA boxes (one swizzle row = one pixel), and the 9
+// taps are row-shifted descriptor starts into it (tools/micro/umma_swz_shift.cu: the swizzle is a function of the absolute
+// shared-memory address, so shifted starts read the right bytes with descriptor base offset 0).  Boxes have a fixed height,
+// so there is one tensor map per power of two and a run of rows (a tile can straddle images of the canvas) is cut into them.
+struct WsMaps { CUtensorMap m[5]; };                                    // box heights 1, 2, 4, 8, 16
+__host__ __device__ constexpr int ws_tma_pitch(int cs_in) { return cs_in == 32 ? 12 : 10; }   // rows of 384 / 640 / 1280 B: 128-byte multiples
+
 // tile geometry
 //   !PHASE: 8 x 16 pixels; halo 10 x 18, plane = [18][10] pixels, tap (kh,kw) -> +(kh*10+kw) pixels, row group stride 10
 //    PHASE: 16 x 32 pre-pool pixels; halo 18 x 34, planes split by x parity: [par][34][9], accumulator (dy,dx) and tap
@@ -178,12 +186,15 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
 // All MMAs of one tile, fully unrolled (KHALF = channel-plane pairs per tap = cs_in / 32; 0 = the 16-channel case).
 // Descriptor words: lo = start>>4 | LBO>>4 << 16, hi = SBO>>4 | version | layout.  Everything except the stage base
 // (sa16), the parity half-plane (half16) and the plane-pair step (cstep16) is a compile-time constant.
-template <bool PHASE, int KHALF>
+template <bool PHASE, int KHALF, bool TMAIN = false>
 __device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t sa16, uint32_t plane16, uint32_t half16, uint32_t cstep16,
                                               uint32_t b16, uint32_t bhi, uint32_t idesc)
 {
     using G = WsGeom<PHASE>;
-    const uint32_t ahi = (G::SBO >> 4) | (1u << 14);
+    static_assert(!TMAIN || (!PHASE && (KHALF == 1 || KHALF == 2 || KHALF == 4)), "TMA-fed tiles: un-phased, 32 / 64 / 128 input channels");
+    constexpr uint32_t T_CIN = 32u * (KHALF ? KHALF : 1), T_PITCH = (uint32_t)ws_tma_pitch((int)T_CIN);
+    constexpr uint32_t T_LAYOUT = T_CIN == 128 ? 2u : T_CIN == 64 ? 4u : 6u;          // swizzle 128B / 64B / 32B
+    const uint32_t ahi = TMAIN ? (((T_PITCH * T_CIN) >> 4) | (1u << 14) | (T_LAYOUT << 29)) : ((G::SBO >> 4) | (1u << 14));
     const uint32_t blo0 = b16 | (8u << 16);                         // LBO = 128 B between the two K halves of the weights
 #pragma unroll
     for (int acc = 0; acc < G::NACC; ++acc) {
@@ -219,16 +230,17 @@ __device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t 
                 else umma_i8_lohi<true>(d, alo, ahi, blo, bhi, idesc);
             }
         } else {
-            const uint32_t a_lbo = plane16 << 16;
+            const uint32_t a_lbo = TMAIN ? (1u << 16) : (plane16 << 16);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const int kh = tap / 3, kw = tap % 3;
                 uint32_t abase;
-                if (PHASE) abase = sa16 + (((dx + kw) & 1) ? half16 : 0u) + (uint32_t)((dy + kh) * G::PITCH + ((dx + kw) >> 1));
+                if (TMAIN) abase = sa16 + (uint32_t)(kh * (int)T_PITCH + kw) * (T_CIN >> 4);   // one pixel = T_CIN bytes
+                else if (PHASE) abase = sa16 + (((dx + kw) & 1) ? half16 : 0u) + (uint32_t)((dy + kh) * G::PITCH + ((dx + kw) >> 1));
                 else abase = sa16 + (uint32_t)(kh * G::PITCH + kw);
 #pragma unroll
                 for (int c2 = 0; c2 < KHALF; ++c2) {
-                    const uint32_t alo = (abase + (uint32_t)c2 * cstep16) | a_lbo;
+                    const uint32_t alo = (abase + (uint32_t)c2 * (TMAIN ? 2u : cstep16)) | a_lbo;   // TMAIN: 32 bytes on inside the pixel
                     const uint32_t blo = blo0 + (uint32_t)(tap * KHALF + c2) * 16u;            // 256 B of weights per K = 32
                     if (tap == 0 && c2 == 0) umma_i8_lohi<false>(d, alo, ahi, blo, bhi, idesc);
                     else umma_i8_lohi<true>(d, alo, ahi, blo, bhi, idesc);
@@ -241,12 +253,12 @@ __device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t 
 // KHALF = cs_in / 32 (0 for 16 input channels) is a template parameter so that each kernel holds exactly one fully
 // unrolled issue sequence with compile-time operand offsets (a run-time switch over all five kept their descriptor words
 // live at once and spilled ~1.5 KB in the issuing lane: 72 cycles per MMA instead of the ~45 the hardware needs).
-template <bool PHASE, int EPI, int KHALF>
-__global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParams p)
+template <bool PHASE, int EPI, int KHALF, bool TMAIN = false>
+__global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps)
 {
     using G = WsGeom<PHASE>;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t base = TMAIN ? (smem_u32(smem_raw) + 1023u) & ~1023u : (smem_u32(smem_raw) + 127u) & ~127u;   // swizzle atoms: 1024 B
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 1));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(bar_full(s), WS_PROD_THREADS); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(bar_full(s), TMAIN ? 1 : WS_PROD_THREADS); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < WS_MAX_TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), WS_EPI_THREADS); }
         mbar_init(bar_w, 1);
         fence_barrier_init();
@@ -311,13 +323,46 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             if (elect_one()) {
                 const uint32_t d0 = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
                 const uint32_t sa16 = sa >> 4;
-                ws_issue_tile<PHASE, KHALF>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc);
+                ws_issue_tile<PHASE, KHALF, TMAIN>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc);
                 umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
                 umma_commit(bar_tfull(buf));                       // accumulators complete
             }
             __syncwarp();
             WS_STAMP(2);
             if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+    } else if (TMAIN && warp <= WS_PROD_WARPS) {
+        // ===================== TMA producer: one thread =====================
+        if (warp == 1 && lane == 0) {
+            constexpr int CIN = 32 * (KHALF ? KHALF : 1), PITCHPX = ws_tma_pitch(CIN);
+            constexpr uint32_t ROW_BYTES = (uint32_t)(PITCHPX * CIN);
+            int it = 0, s = 0;
+            uint32_t ph = 0;
+            int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int tx0 = tx * G::TW, ty0 = ty * G::TH;
+                mbar_wait(bar_empty(s), ph ^ 1u);
+                WS_STAMP(3);
+                const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
+                mbar_expect_tx(bar_full(s), (uint32_t)G::HH * ROW_BYTES);
+                // the 18 halo rows = canvas rows ty0-1 .. ty0+16: runs of rows of one image (its gutter rows and the rows
+                // above / below the canvas are out of bounds for the box = zero filled = the convolution's padding)
+                int r = 0, cy = ty0 - 1;
+                while (r < G::HH) {
+                    const int n = cy < 0 ? 0 : (int)__umulhi((unsigned)cy, p.period_magic);
+                    int y = cy - n * p.period;
+                    int run = min(G::HH - r, p.period - y);
+                    while (run > 0) {
+                        const int lg = run >= 16 ? 4 : run >= 8 ? 3 : run >= 4 ? 2 : run >= 2 ? 1 : 0, h = 1 << lg;
+                        tma_load_4d(sa + (uint32_t)r * ROW_BYTES, &maps.m[lg], bar_full(s), 0, tx0 - 1, y, n);
+                        r += h; y += h; cy += h; run -= h;
+                    }
+                }
+                WS_STAMP(4);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+                tx += p.step_x; ty += p.step_y;
+                if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+            }
         }
     } else if (warp <= WS_PROD_WARPS) {
         // ===================== cp.async producers =====================
@@ -464,8 +509,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // Shared-memory plan; returns false when the layer does not fit this kernel.
-static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p)
+static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p, bool tma = false)
 {
+    if (tma && (phase || (a.cs_in != 32 && a.cs_in != 64 && a.cs_in != 128))) return false;
     const int nplanes = a.cs_in / 16;
     const int pix = phase ? WsGeom<true>::PIX : WsGeom<false>::PIX;
     const int nacc = phase ? 4 : 1;
@@ -488,17 +534,19 @@ static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p)
     p->N = a.cs_out; p->cs_out = a.cs_out;
     p->w_bytes = (uint32_t)p->N * (uint32_t)p->kc * 16u;
     p->stage_bytes = ((uint32_t)nplanes * p->plane_stride + 127u) & ~127u;
+    if (tma) p->stage_bytes = ((uint32_t)(WsGeom<false>::HH * ws_tma_pitch(a.cs_in) * a.cs_in) + 1023u) & ~1023u;
     uint32_t nb = 32; while (nb < (uint32_t)(nacc * p->N)) nb <<= 1;
     if (2 * nb > 512) return false;
     p->tbufs = 4 * nb <= 512 ? 4 : 2; p->tbufs_log2 = p->tbufs == 4 ? 2 : 1;
     p->tmem_buf_stride = nb; p->tmem_cols = (uint32_t)p->tbufs * nb;
-    const uint32_t fixed = ((p->w_bytes + 127u) & ~127u) + (uint32_t)p->N * 4u + 256u + 128u /*alignment slack*/;
+    const uint32_t walign = tma ? 1023u : 127u;                           // swizzled stages start on 1024-byte boundaries
+    const uint32_t fixed = ((p->w_bytes + walign) & ~walign) + (uint32_t)p->N * 4u + 256u + walign + 1u /*alignment slack*/;
     const uint32_t budget = 227u * 1024u;
     if (fixed + 2 * p->stage_bytes > budget) return false;
     int stages = (int)((budget - fixed) / p->stage_bytes);
     if (stages > WS_MAX_STAGES) stages = WS_MAX_STAGES;
     p->stages = stages;
-    p->off_stage = (p->w_bytes + 127u) & ~127u;
+    p->off_stage = (p->w_bytes + walign) & ~walign;
     p->off_bias = p->off_stage + (uint32_t)stages * p->stage_bytes;
     p->off_bar = (p->off_bias + (uint32_t)p->N * 4u + 15u) & ~15u;
     return true;
@@ -523,9 +571,40 @@ bool conv3x3_ws_supported(const ConvArgs &a)
     return ws_plan(a, false, &p) || (a.q.pool && ws_plan(a, true, &p));
 }
 
-template <bool PHASE, int EPI, int KHALF>
+// ---- tensor maps of the TMA-fed variant ----
+typedef CUresult (*WsEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cudaError_t ws_make_maps(const ConvArgs &a, WsMaps *maps)
+{
+    static WsEncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        enc = (WsEncodeTiledFn)fn;
+    }
+    const CUtensorMapSwizzle sw = a.cs_in == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : a.cs_in == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    cuuint64_t dims[4] = { (cuuint64_t)a.cs_in, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n };
+    cuuint64_t strides[3] = { (cuuint64_t)a.cs_in, (cuuint64_t)a.cs_in * a.W, (cuuint64_t)a.cs_in * a.W * a.H };
+    cuuint32_t es[4] = { 1, 1, 1, 1 };
+    for (int i = 0; i < 5; ++i) {
+        cuuint32_t box[4] = { (cuuint32_t)a.cs_in, (cuuint32_t)ws_tma_pitch(a.cs_in), (cuuint32_t)(1 << i), 1 };
+        CUresult r = enc(&maps->m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
+}
+
+template <bool PHASE, int EPI, int KHALF, bool TMAIN = false>
 static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
 {
+    WsMaps maps;
+    memset(&maps, 0, sizeof maps);
+    if (TMAIN) { cudaError_t e = ws_make_maps(a, &maps); if (e != cudaSuccess) return e; }
     using G = WsGeom<PHASE>;
     const int gut = a.q.pool ? ((a.H & 1) ? 1 : 2) : 1;                  // pooled: image origins stay on even canvas rows
     p.in = a.in; p.n_img = a.n; p.H = a.H; p.W = a.W; p.cs_in = a.cs_in;
@@ -544,18 +623,18 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
         p.dbg = dbg;
     }
 #endif
-    const uint32_t smem_bytes = p.off_bar + 256u + 128u;
+    const uint32_t smem_bytes = p.off_bar + 256u + (TMAIN ? 1024u : 128u);
     static bool attr_set[64] = {};     // per instantiation
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI, KHALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     p.step_x = grid % p.tiles_x; p.step_y = grid / p.tiles_x;
-    conv3x3_ws_kernel<PHASE, EPI, KHALF><<<grid, WS_THREADS, smem_bytes, st>>>(p);
+    conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN><<<grid, WS_THREADS, smem_bytes, st>>>(p, maps);
 #ifdef YB_WS_TIMELINE
     {
         long long h[64 * 8];
@@ -572,8 +651,15 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
 }
 
 template <bool PHASE, int EPI>
-static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
+static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count, bool tma)
 {
+    if (!PHASE && tma)
+        switch (p.nplanes >> 1) {
+        case 1: return launch_ws_k<false, EPI, 1, true>(a, p, st, sm_count);
+        case 2: return launch_ws_k<false, EPI, 2, true>(a, p, st, sm_count);
+        case 4: return launch_ws_k<false, EPI, 4, true>(a, p, st, sm_count);
+        default: return cudaErrorInvalidConfiguration;
+        }
     switch (p.nplanes >> 1) {
     case 0: return launch_ws_k<PHASE, EPI, 0>(a, p, st, sm_count);
     case 1: return launch_ws_k<PHASE, EPI, 1>(a, p, st, sm_count);
@@ -585,13 +671,13 @@ static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, in
 }
 
 template <bool PHASE>
-static cudaError_t launch_ws_epi(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
+static cudaError_t launch_ws_epi(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count, bool tma = false)
 {
     switch (epi_mode_for(a, &p.k)) {
-    case EPI_F_RNE: return launch_ws<PHASE, EPI_F_RNE>(a, p, st, sm_count);
-    case EPI_F_RNE_NOHI: return launch_ws<PHASE, EPI_F_RNE_NOHI>(a, p, st, sm_count);
-    case EPI_P:     return launch_ws<PHASE, EPI_P>(a, p, st, sm_count);
-    default:        return launch_ws<PHASE, EPI_GENERIC>(a, p, st, sm_count);
+    case EPI_F_RNE: return launch_ws<PHASE, EPI_F_RNE>(a, p, st, sm_count, tma);
+    case EPI_F_RNE_NOHI: return launch_ws<PHASE, EPI_F_RNE_NOHI>(a, p, st, sm_count, tma);
+    case EPI_P:     return launch_ws<PHASE, EPI_P>(a, p, st, sm_count, tma);
+    default:        return launch_ws<PHASE, EPI_GENERIC>(a, p, st, sm_count, tma);
     }
 }
 
@@ -602,6 +688,10 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count)
     WsParams p;
     memset(&p, 0, sizeof p);
     if (a.q.pool && ws_plan(a, true, &p)) return launch_ws_epi<true>(a, p, st, sm_count);
+    // un-phased tiles: TMA-fed halo where the channel count allows it (YOLO_B200_WS_TMA=0 keeps the cp.async producers)
+    static const bool use_tma = [] { const char *e = getenv("YOLO_B200_WS_TMA"); return e ? atoi(e) != 0 : true; }();
+    memset(&p, 0, sizeof p);
+    if (use_tma && ((uintptr_t)a.in & 15) == 0 && ws_plan(a, false, &p, true)) return launch_ws_epi<false>(a, p, st, sm_count, true);
     memset(&p, 0, sizeof p);
     if (ws_plan(a, false, &p)) return launch_ws_epi<false>(a, p, st, sm_count);
     return cudaErrorInvalidConfiguration;
