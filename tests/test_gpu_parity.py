@@ -2,6 +2,7 @@
 (1) the golden vectors of the unmodified reference module (tests/golden) and (2) the CPU oracle on seeded inputs.
 Integer feature maps must be bit-exact; the float head is held to 1e-5 with identical kept sets."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -14,6 +15,7 @@ from yolo_b200 import export as ex
 from yolo_b200 import lib
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -162,7 +164,7 @@ def test_contract_f_against_oracle(ctx, mode, tables):
 
 
 @pytest.mark.parametrize("hw", [(26, 26), (13, 13), (15, 20), (30, 40), (2, 2), (1, 1), (17, 33)])
-@pytest.mark.parametrize("layer", [0, 1, 3, 5, 8, 9])
+@pytest.mark.parametrize("layer", [0, 1, 2, 3, 4, 5, 8, 9])
 def test_single_layer_ragged_shapes(ctx, hw, layer):
     """Per-layer entry point (first_conv...conv_last replacement) on odd / tiny maps, both contracts."""
     g, qnet, frames = gu.load("ref_p_64x96")
@@ -585,6 +587,37 @@ def test_first_layer_kernel_against_oracle(ctx, pool):
                                    qnet.retune[0], qnet.sa[1], activ, pool, contract)
             np.testing.assert_array_equal(outs[0], ref, err_msg="mma kernel, shape %s contract %d" % ((n, h, w), contract))
             np.testing.assert_array_equal(outs[1], ref, err_msg="dp4a kernel, shape %s contract %d" % ((n, h, w), contract))
+
+
+def test_weight_stationary_layers_with_cp_async_producers_in_a_subprocess():
+    """YOLO_B200_WS_TMA=0 (read once per process) keeps the cp.async producers for conv3_1 / conv4_1 / conv4_2: same
+    results as the oracle (the TMA-fed default is what every other test runs)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import yolo_b200
+        from yolo_b200 import lib, export as ex
+        import golden_util as gu, oracle_lib as ol
+        g, qnet, frames = gu.load("ref_p_64x96")
+        ctx = lib.Context(0)
+        rng = np.random.default_rng(3)
+        for layer in (2, 4, 5):
+            cin, cout, activ, pool = qnet.layers[layer]
+            for (n, h, w) in ((3, 14, 18), (2, 40, 20)):
+                x = np.zeros((n, h, w, ex.cstride(cin)), dtype=np.int8)
+                x[..., :cin] = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
+                ctx.load_quantnet(qnet, contract=lib.CONTRACT_F)
+                oh, ow = (h // 2, w // 2) if pool else (h, w)
+                d_out = torch.zeros((n, oh, ow, ex.cstride(cout)), dtype=torch.int8, device="cuda")
+                ctx.conv_layer(layer, torch.from_numpy(x).cuda(), n, h, w, d_out); ctx.sync()
+                ref, _ = ol.conv_layer(x, qnet.w[layer], qnet.b[layer], cin, cout, qnet.sa[layer], qnet.sw[layer], qnet.sb[layer],
+                                       qnet.retune[layer], qnet.sa[layer + 1], activ, pool, lib.CONTRACT_F)
+                assert (d_out.cpu().numpy() == ref).all(), (layer, n, h, w)
+        print("OK")
+    """) % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, YOLO_B200_WS_TMA="0"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
 
 
 def test_weight_stationary_kernel_rejects_layers_that_do_not_fit(ctx):

@@ -282,18 +282,38 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     __syncthreads();
 
     NMS_T(0);
-    // 2. bitonic sort, descending
-    for (int k = 2; k <= P; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < P / 2; t += NMS_THREADS) {
-                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));     // index with bit j clear
-                int ixj = i | j;
-                unsigned long long x = s.u.key[i], y = s.u.key[ixj];
-                bool desc = (i & k) == 0;
-                if (desc ? x < y : x > y) { s.u.key[i] = y; s.u.key[ixj] = x; }
+    // 2. bitonic sort, descending.  Two consecutive strides (j, j/2) of a stage are fused: a thread takes the four keys
+    //    i, i+j/2, i+j, i+3j/2 through both compare-exchange levels in registers (half the barriers and shared-memory
+    //    passes of the textbook loop); a stage with an odd number of strides ends with one plain pass.
+    for (int k = 2; k <= P; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 2; j >>= 2) {
+            const int h = j >> 1;
+            for (int t = tid; t < P / 4; t += NMS_THREADS) {
+                const int i = ((t & ~(h - 1)) << 2) | (t & (h - 1));             // bits h and j clear
+                unsigned long long a0 = s.u.key[i], a1 = s.u.key[i + h], a2 = s.u.key[i + j], a3 = s.u.key[i + j + h];
+                const bool desc = (i & k) == 0;                                 // k > j: the same for the four keys
+                auto cx = [&](unsigned long long &x, unsigned long long &y) {
+                    const bool sw = desc ? x < y : x > y;
+                    const unsigned long long tx = sw ? y : x, ty = sw ? x : y;
+                    x = tx; y = ty;
+                };
+                cx(a0, a2); cx(a1, a3);                                         // stride j
+                cx(a0, a1); cx(a2, a3);                                         // stride j / 2
+                s.u.key[i] = a0; s.u.key[i + h] = a1; s.u.key[i + j] = a2; s.u.key[i + j + h] = a3;
             }
             __syncthreads();
         }
+        if (j == 1) {
+            for (int t = tid; t < P / 2; t += NMS_THREADS) {
+                const int i = t << 1;
+                const unsigned long long x = s.u.key[i], y = s.u.key[i + 1];
+                const bool desc = (i & k) == 0;
+                if (desc ? x < y : x > y) { s.u.key[i] = y; s.u.key[i + 1] = x; }
+            }
+            __syncthreads();
+        }
+    }
 
     NMS_T(1);
     // 3. sorted order -> anchor index, box, area, class (keys are dead after this; their storage is reused)
