@@ -77,6 +77,11 @@ struct WsParams {
     int8_t *out;
     unsigned *ovf;
     long long *dbg;              // optional timeline (YB_WS_TIMELINE builds): [cta][tile][8] clock64 stamps
+    // weight-streaming variant (BSTREAM): the layer's weights do not fit shared memory; one tap's weights for all output
+    // channels (b_chunk_bytes = N * cs_in) travel through a ring of b_slots slots at the start of shared memory
+    const uint8_t *wtap;         // [tap][N/8][cs_in/16][8][16 B]
+    uint32_t b_chunk_bytes;
+    int b_slots;
 };
 
 // TMA-fed variant (TMAIN, un-phased tiles with 32 / 64 / 128 input channels): the halo tile is pixel-major
@@ -250,19 +255,41 @@ __device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t 
     }
 }
 
+// BSTREAM: the MMAs of ONE tap (KHALF K-steps of 32 channels) against the weight chunk at b16 (16-byte units).  The halo
+// tile is TMA-written: pixels of 128 bytes (cs_in = 256: two such planes, plane16 apart), or of cs_in bytes below that.
+template <int KHALF>
+__device__ __forceinline__ void ws_issue_tap(uint32_t d, uint32_t sa16, uint32_t plane16, int tap, uint32_t b16, bool first, uint32_t idesc)
+{
+    constexpr uint32_t CIN_PL = KHALF >= 4 ? 128u : 32u * KHALF, PITCHPX = (uint32_t)ws_tma_pitch((int)CIN_PL);
+    constexpr uint32_t LAYOUT = CIN_PL == 128 ? 2u : CIN_PL == 64 ? 4u : 6u;
+    constexpr uint32_t KC_T = 2u * KHALF;                                          // 16-byte K chunks per output channel and tap
+    const uint32_t ahi = ((PITCHPX * CIN_PL) >> 4) | (1u << 14) | (LAYOUT << 29);
+    const uint32_t bhi = (KC_T * 8u) | (1u << 14);
+    const int kh = tap / 3, kw = tap - 3 * kh;
+    const uint32_t abase = sa16 + (uint32_t)(kh * (int)PITCHPX + kw) * (CIN_PL >> 4);
+#pragma unroll
+    for (int c2 = 0; c2 < KHALF; ++c2) {
+        const uint32_t alo = (abase + (uint32_t)(c2 / 4) * plane16 + (uint32_t)(c2 % 4) * 2u) | (1u << 16);
+        const uint32_t blo = (b16 + (uint32_t)c2 * 16u) | (8u << 16);
+        if (c2 == 0 && first) umma_i8_lohi<false>(d, alo, ahi, blo, bhi, idesc);
+        else umma_i8_lohi<true>(d, alo, ahi, blo, bhi, idesc);
+    }
+}
+
 // KHALF = cs_in / 32 (0 for 16 input channels) is a template parameter so that each kernel holds exactly one fully
 // unrolled issue sequence with compile-time operand offsets (a run-time switch over all five kept their descriptor words
 // live at once and spilled ~1.5 KB in the issuing lane: 72 cycles per MMA instead of the ~45 the hardware needs).
-template <bool PHASE, int EPI, int KHALF, bool TMAIN = false>
+template <bool PHASE, int EPI, int KHALF, bool TMAIN = false, bool BSTREAM = false>
 __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps)
 {
+    static_assert(!BSTREAM || (TMAIN && !PHASE && (KHALF == 4 || KHALF == 8)), "weight streaming: TMA-fed un-phased tiles, 128 / 256 input channels");
     using G = WsGeom<PHASE>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = TMAIN ? (smem_u32(smem_raw) + 1023u) & ~1023u : (smem_u32(smem_raw) + 127u) & ~127u;   // swizzle atoms: 1024 B
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const uint32_t wsm = base;                                           // resident weight image
+    const uint32_t wsm = base;                                           // resident weight image (BSTREAM: the weight ring)
     const uint32_t stage0 = base + p.off_stage;
     int *s_bias = reinterpret_cast<int *>(base_ptr + p.off_bias);
     const uint32_t bar0 = base + p.off_bar;
@@ -273,18 +300,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * WS_MAX_STAGES + WS_MAX_TBUF + b); };
     const uint32_t bar_w = bar0 + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF);
     const uint32_t tmem_slot = bar0 + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 1);
+    auto bar_bfull = [&](int i) { return bar0 + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 2 + i); };       // BSTREAM: weight ring
+    auto bar_bempty = [&](int i) { return bar0 + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 6 + i); };
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * WS_MAX_STAGES + 2 * WS_MAX_TBUF + 1));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(bar_full(s), TMAIN ? 1 : WS_PROD_THREADS); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < WS_MAX_TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), WS_EPI_THREADS); }
         mbar_init(bar_w, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
         fence_barrier_init();
-        // the whole layer's weights, once
-        mbar_expect_tx(bar_w, p.w_bytes);
-        for (uint32_t o = 0; o < p.w_bytes; o += 32768u) {
-            const uint32_t n = p.w_bytes - o < 32768u ? p.w_bytes - o : 32768u;
-            bulk_load_1d(wsm + o, p.wimg + o, n, bar_w);
+        if (!BSTREAM) {
+            // the whole layer's weights, once
+            mbar_expect_tx(bar_w, p.w_bytes);
+            for (uint32_t o = 0; o < p.w_bytes; o += 32768u) {
+                const uint32_t n = p.w_bytes - o < 32768u ? p.w_bytes - o : 32768u;
+                bulk_load_1d(wsm + o, p.wimg + o, n, bar_w);
+            }
         }
     }
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
@@ -308,9 +340,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const uint32_t plane16 = p.plane_stride >> 4;             // LBO of A: the next 16-byte channel plane
         const uint32_t half16 = p.plane_stride >> 5;              // PHASE: x-parity half-plane, in 16-byte units
         const uint32_t cstep16 = p.plane_stride >> 3;             // two channel planes = one K = 32 step
-        mbar_wait(bar_w, 0);
-        int it = 0, s = 0;
-        uint32_t ph = 0;
+        if (!BSTREAM) mbar_wait(bar_w, 0);
+        int it = 0, s = 0, bslot = 0;
+        uint32_t ph = 0, rph = 0;                                 // stage phase, weight-ring phase
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & (p.tbufs - 1);
             const uint32_t bph = (uint32_t)(it >> p.tbufs_log2) & 1u;
@@ -320,12 +352,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             WS_STAMP(1);
             tc_fence_after();
             const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
-            if (elect_one()) {
+            if constexpr (BSTREAM) {
+                // tap by tap: each needs its weight chunk in the ring; the chunk's slot is released by a commit
                 const uint32_t d0 = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
-                const uint32_t sa16 = sa >> 4;
-                ws_issue_tile<PHASE, KHALF, TMAIN>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc);
-                umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
-                umma_commit(bar_tfull(buf));                       // accumulators complete
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(bar_bfull(bslot), rph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        ws_issue_tap<KHALF>(d0, sa >> 4, plane16, tap, (wsm + (uint32_t)bslot * p.b_chunk_bytes) >> 4, tap == 0, idesc);
+                        umma_commit(bar_bempty(bslot));
+                        if (tap == 8) { umma_commit(bar_empty(s)); umma_commit(bar_tfull(buf)); }
+                    }
+                    __syncwarp();
+                    if (++bslot == p.b_slots) { bslot = 0; rph ^= 1u; }
+                }
+            } else {
+                if (elect_one()) {
+                    const uint32_t d0 = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
+                    const uint32_t sa16 = sa >> 4;
+                    ws_issue_tile<PHASE, KHALF, TMAIN>(d0, (uint32_t)p.N, sa16, plane16, half16, cstep16, b16, bhi, idesc);
+                    umma_commit(bar_empty(s));                         // stage free once these MMAs have read it
+                    umma_commit(bar_tfull(buf));                       // accumulators complete
+                }
             }
             __syncwarp();
             WS_STAMP(2);
@@ -333,8 +381,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         }
     } else if (TMAIN && warp <= WS_PROD_WARPS) {
         // ===================== TMA producer: one thread =====================
+        if (BSTREAM && warp == 2 && lane == 0) {
+            // weight chunks: tile after tile, tap after tap
+            int slot = 0;
+            uint32_t bph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(bar_bempty(slot), bph ^ 1u);
+                    mbar_expect_tx(bar_bfull(slot), p.b_chunk_bytes);
+                    const uint32_t dst = wsm + (uint32_t)slot * p.b_chunk_bytes;
+                    const uint8_t *src = p.wtap + (size_t)tap * p.b_chunk_bytes;
+                    for (uint32_t o = 0; o < p.b_chunk_bytes; o += 32768u) {
+                        const uint32_t nb = p.b_chunk_bytes - o < 32768u ? p.b_chunk_bytes - o : 32768u;
+                        bulk_load_1d(dst + o, src + o, nb, bar_bfull(slot));
+                    }
+                    if (++slot == p.b_slots) { slot = 0; bph ^= 1u; }
+                }
+        }
         if (warp == 1 && lane == 0) {
-            constexpr int CIN = 32 * (KHALF ? KHALF : 1), PITCHPX = ws_tma_pitch(CIN);
+            constexpr int NPL = KHALF == 8 ? 2 : 1;                                // 128-byte channel planes of the tile
+            constexpr int CIN = KHALF >= 4 ? 128 : 32 * (KHALF ? KHALF : 1), PITCHPX = ws_tma_pitch(CIN);
             constexpr uint32_t ROW_BYTES = (uint32_t)(PITCHPX * CIN);
             int it = 0, s = 0;
             uint32_t ph = 0;
@@ -344,7 +410,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
                 mbar_wait(bar_empty(s), ph ^ 1u);
                 WS_STAMP(3);
                 const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
-                mbar_expect_tx(bar_full(s), (uint32_t)G::HH * ROW_BYTES);
+                mbar_expect_tx(bar_full(s), (uint32_t)(NPL * G::HH) * ROW_BYTES);
                 // the 18 halo rows = canvas rows ty0-1 .. ty0+16: runs of rows of one image (its gutter rows and the rows
                 // above / below the canvas are out of bounds for the box = zero filled = the convolution's padding)
                 int r = 0, cy = ty0 - 1;
@@ -354,7 +420,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
                     int run = min(G::HH - r, p.period - y);
                     while (run > 0) {
                         const int lg = run >= 16 ? 4 : run >= 8 ? 3 : run >= 4 ? 2 : run >= 2 ? 1 : 0, h = 1 << lg;
-                        tma_load_4d(sa + (uint32_t)r * ROW_BYTES, &maps.m[lg], bar_full(s), 0, tx0 - 1, y, n);
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl)
+                            tma_load_4d(sa + (uint32_t)(pl * G::HH + r) * ROW_BYTES, &maps.m[lg], bar_full(s), 128 * pl, tx0 - 1, y, n);
                         r += h; y += h; cy += h; run -= h;
                     }
                 }
@@ -552,6 +620,36 @@ static bool ws_plan(const ConvArgs &a, bool phase, WsParams *p, bool tma = false
     return true;
 }
 
+// Shared-memory plan of the weight-streaming variant (weights too large to stay resident): ring of per-tap weight chunks
+// at offset 0, then the TMA-written halo stages (one or two 128-byte channel planes).
+static bool ws_plan_stream(const ConvArgs &a, WsParams *p)
+{
+    if (!a.wimg_tap || (a.cs_in != 128 && a.cs_in != 256)) return false;
+    const int npl = a.cs_in / 128;
+    p->nplanes = a.cs_in / 16; p->nplanes_log2 = ilog2(p->nplanes);
+    p->kc = 9 * p->nplanes;
+    p->N = a.cs_out; p->cs_out = a.cs_out;
+    p->w_bytes = 0;
+    p->plane_stride = (uint32_t)(WsGeom<false>::HH * ws_tma_pitch(128) * 128);       // one 128-byte channel plane of a stage
+    p->stage_bytes = ((uint32_t)npl * p->plane_stride + 1023u) & ~1023u;
+    uint32_t nb = 32; while (nb < (uint32_t)p->N) nb <<= 1;
+    if (2 * nb > 512) return false;
+    p->tbufs = 4 * nb <= 512 ? 4 : 2; p->tbufs_log2 = p->tbufs == 4 ? 2 : 1;
+    p->tmem_buf_stride = nb; p->tmem_cols = (uint32_t)p->tbufs * nb;
+    p->b_chunk_bytes = (uint32_t)p->N * (uint32_t)a.cs_in;
+    const uint32_t budget = 227u * 1024u, tail = (uint32_t)p->N * 4u + 256u + 1024u + 16u;
+    if (2 * p->b_chunk_bytes + 2 * p->stage_bytes + tail > budget) return false;
+    p->stages = 2;
+    int slots = (int)((budget - tail - 2 * p->stage_bytes) / p->b_chunk_bytes);
+    p->b_slots = slots > 4 ? 4 : slots;
+    int stages = (int)((budget - tail - (uint32_t)p->b_slots * p->b_chunk_bytes) / p->stage_bytes);
+    p->stages = stages > WS_MAX_STAGES ? WS_MAX_STAGES : stages;
+    p->off_stage = ((uint32_t)p->b_slots * p->b_chunk_bytes + 1023u) & ~1023u;
+    p->off_bias = p->off_stage + (uint32_t)p->stages * p->stage_bytes;
+    p->off_bar = (p->off_bias + (uint32_t)p->N * 4u + 15u) & ~15u;
+    return true;
+}
+
 static bool ws_shape_ok(const ConvArgs &a)
 {
     if (!a.wimg) return false;
@@ -564,11 +662,17 @@ static bool ws_shape_ok(const ConvArgs &a)
     return true;
 }
 
+static bool ws_stream_enabled()
+{
+    static const bool on = [] { const char *e = getenv("YOLO_B200_WS_STREAM"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
+
 bool conv3x3_ws_supported(const ConvArgs &a)
 {
     if (!ws_shape_ok(a)) return false;
     WsParams p;
-    return ws_plan(a, false, &p) || (a.q.pool && ws_plan(a, true, &p));
+    return ws_plan(a, false, &p) || (a.q.pool && ws_plan(a, true, &p)) || (ws_stream_enabled() && ws_plan_stream(a, &p));
 }
 
 // ---- tensor maps of the TMA-fed variant ----
@@ -586,12 +690,13 @@ static cudaError_t ws_make_maps(const ConvArgs &a, WsMaps *maps)
         if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
         enc = (WsEncodeTiledFn)fn;
     }
-    const CUtensorMapSwizzle sw = a.cs_in == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : a.cs_in == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const CUtensorMapSwizzle sw = a.cs_in >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : a.cs_in == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     cuuint64_t dims[4] = { (cuuint64_t)a.cs_in, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n };
     cuuint64_t strides[3] = { (cuuint64_t)a.cs_in, (cuuint64_t)a.cs_in * a.W, (cuuint64_t)a.cs_in * a.W * a.H };
     cuuint32_t es[4] = { 1, 1, 1, 1 };
     for (int i = 0; i < 5; ++i) {
-        cuuint32_t box[4] = { (cuuint32_t)a.cs_in, (cuuint32_t)ws_tma_pitch(a.cs_in), (cuuint32_t)(1 << i), 1 };
+        const int cpl = a.cs_in > 128 ? 128 : a.cs_in;                          // bytes of a pixel in one plane of the tile
+        cuuint32_t box[4] = { (cuuint32_t)cpl, (cuuint32_t)ws_tma_pitch(cpl), (cuuint32_t)(1 << i), 1 };
         CUresult r = enc(&maps->m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
@@ -599,7 +704,7 @@ static cudaError_t ws_make_maps(const ConvArgs &a, WsMaps *maps)
     return cudaSuccess;
 }
 
-template <bool PHASE, int EPI, int KHALF, bool TMAIN = false>
+template <bool PHASE, int EPI, int KHALF, bool TMAIN = false, bool BSTREAM = false>
 static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count)
 {
     WsMaps maps;
@@ -614,7 +719,7 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
     p.tiles_x = (a.W + G::TW - 1) / G::TW;
     p.num_tiles = p.tiles_x * ((p.canvas_rows + G::TH - 1) / G::TH);
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
-    p.q = a.q; p.wimg = a.wimg; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
+    p.q = a.q; p.wimg = a.wimg; p.wtap = a.wimg_tap; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
 #ifdef YB_WS_TIMELINE
     {   // debug builds only: stamps of CTA 0's first 64 tiles, printed after the launch (synchronises)
         static long long *dbg = nullptr;
@@ -628,13 +733,13 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN, BSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     p.step_x = grid % p.tiles_x; p.step_y = grid / p.tiles_x;
-    conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN><<<grid, WS_THREADS, smem_bytes, st>>>(p, maps);
+    conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN, BSTREAM><<<grid, WS_THREADS, smem_bytes, st>>>(p, maps);
 #ifdef YB_WS_TIMELINE
     {
         long long h[64 * 8];
@@ -653,6 +758,12 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
 template <bool PHASE, int EPI>
 static cudaError_t launch_ws(const ConvArgs &a, WsParams &p, cudaStream_t st, int sm_count, bool tma)
 {
+    if (!PHASE && p.b_slots)
+        switch (p.nplanes >> 1) {
+        case 4: return launch_ws_k<false, EPI, 4, true, true>(a, p, st, sm_count);
+        case 8: return launch_ws_k<false, EPI, 8, true, true>(a, p, st, sm_count);
+        default: return cudaErrorInvalidConfiguration;
+        }
     if (!PHASE && tma)
         switch (p.nplanes >> 1) {
         case 1: return launch_ws_k<false, EPI, 1, true>(a, p, st, sm_count);
@@ -694,6 +805,9 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count)
     if (use_tma && ((uintptr_t)a.in & 15) == 0 && ws_plan(a, false, &p, true)) return launch_ws_epi<false>(a, p, st, sm_count, true);
     memset(&p, 0, sizeof p);
     if (ws_plan(a, false, &p)) return launch_ws_epi<false>(a, p, st, sm_count);
+    // weights too large to stay resident: stream them tap by tap (YOLO_B200_WS_STREAM=0: conv_umma.cu takes these layers)
+    memset(&p, 0, sizeof p);
+    if (ws_stream_enabled() && ((uintptr_t)a.in & 15) == 0 && ws_plan_stream(a, &p)) return launch_ws_epi<false>(a, p, st, sm_count, true);
     return cudaErrorInvalidConfiguration;
 }
 

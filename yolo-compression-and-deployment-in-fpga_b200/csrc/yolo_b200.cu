@@ -33,6 +33,7 @@ struct LayerDev {
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
+    uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: tap-major image [tap][cs_out/8][cs_in/16][8][16] (conv_ws.cu, streamed weights)
     uint8_t *w_swz = nullptr;  // cs_in % 128 == 0: 128B-swizzled blocks [9*cs_in/128][cs_out][128] (conv_umma.cu B operand)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
@@ -138,7 +139,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); }
     c->layers.clear();
 }
 
@@ -331,6 +332,16 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
                 }
             CU(cudaMalloc(&d.wimg, img.size()));
             CU(cudaMemcpy(d.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+            if (d.cs_in == 128 || d.cs_in == 256) {
+                std::vector<uint8_t> imt((size_t)d.cs_out * 9 * d.cs_in, 0);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int o = 0; o < d.cs_out; ++o)
+                        for (int cc = 0; cc < np; ++cc)
+                            memcpy(&imt[((((size_t)tap * (d.cs_out / 8) + o / 8) * np + cc) * 8 + (o % 8)) * 16],
+                                   &wp[((size_t)o * 9 + tap) * d.cs_in + 16 * cc], 16);
+                CU(cudaMalloc(&d.wimg_tap, imt.size()));
+                CU(cudaMemcpy(d.wimg_tap, imt.data(), imt.size(), cudaMemcpyHostToDevice));
+            }
         }
         if (d.cs_in % 128 == 0) {
             // conv_umma.cu: block kb = (tap, 128-byte channel chunk) as it must sit in shared memory for a K-major
@@ -461,7 +472,7 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     LayerDev &L = c->layers[l];
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
 }
