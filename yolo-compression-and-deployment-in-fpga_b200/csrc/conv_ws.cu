@@ -79,9 +79,16 @@ struct WsParams {
     long long *dbg;              // optional timeline (YB_WS_TIMELINE builds): [cta][tile][8] clock64 stamps
     // weight-streaming variant (BSTREAM): the layer's weights do not fit shared memory; one tap's weights for all output
     // channels (b_chunk_bytes = N * cs_in) travel through a ring of b_slots slots at the start of shared memory
-    const uint8_t *wtap;         // [tap][N/8][cs_in/16][8][16 B]
+    const uint8_t *wtap;         // [tap][128-channel plane][N/8][8][8][16 B]: one chunk = b_chunk_bytes = N * 128
     uint32_t b_chunk_bytes;
     int b_slots;
+    // flattened-raster tiles (BSTREAM, un-pooled, narrow maps): the canvas rows are W + 1 pixels wide (the extra one is out of
+    // bounds for the TMA box = zero = the horizontal padding of both neighbours), an M tile is 128 consecutive pixels of
+    // that stream, its halo is raster_rows whole rows (+ one zero pixel in front), every tap is a start offset
+    int raster;                  // 0 / 1
+    int rP;                      // W + 1
+    unsigned rP_magic;           // ceil(2^32 / rP)
+    int raster_rows;             // rows of a halo tile
 };
 
 // TMA-fed variant (TMAIN, un-phased tiles with 32 / 64 / 128 input channels): the halo tile is pixel-major
@@ -135,7 +142,12 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
         tc_fence_before();
         mbar_arrive(bar_tempty);
     } else {
-        const int cy = ty0 + g, x = tx0 + xl;
+        int cy = ty0 + g, x = tx0 + xl;
+        if (p.raster) {                                        // row r = stream pixel 128 * tile + r (ty0 = 16 * tile)
+            const int q = 8 * ty0 + r;
+            cy = (int)__umulhi((unsigned)q, p.rP_magic);
+            x = q - cy * p.rP;
+        }
         const int n = (int)__umulhi((unsigned)cy, p.period_magic);
         const int y = cy - n * p.period;
         const bool inside = cy < p.canvas_rows && y < p.H && x < p.W;
@@ -257,19 +269,22 @@ __device__ __forceinline__ void ws_issue_tile(uint32_t d0, uint32_t N, uint32_t 
 
 // BSTREAM: the MMAs of ONE tap (KHALF K-steps of 32 channels) against the weight chunk at b16 (16-byte units).  The halo
 // tile is TMA-written: pixels of 128 bytes (cs_in = 256: two such planes, plane16 apart), or of cs_in bytes below that.
+// row_px = pixels between the tile rows a tap moves over (10, or W + 1 for raster tiles); sbo_px = pixels between 8-row groups
 template <int KHALF>
-__device__ __forceinline__ void ws_issue_tap(uint32_t d, uint32_t sa16, uint32_t plane16, int tap, uint32_t b16, bool first, uint32_t idesc)
+__device__ __forceinline__ void ws_issue_tap(uint32_t d, uint32_t sa16, uint32_t plane16, int tap, int row_px, uint32_t sbo_px,
+                                             uint32_t b16, bool first, uint32_t idesc)
 {
-    constexpr uint32_t CIN_PL = KHALF >= 4 ? 128u : 32u * KHALF, PITCHPX = (uint32_t)ws_tma_pitch((int)CIN_PL);
-    constexpr uint32_t LAYOUT = CIN_PL == 128 ? 2u : CIN_PL == 64 ? 4u : 6u;
-    constexpr uint32_t KC_T = 2u * KHALF;                                          // 16-byte K chunks per output channel and tap
-    const uint32_t ahi = ((PITCHPX * CIN_PL) >> 4) | (1u << 14) | (LAYOUT << 29);
+    // one weight chunk = (tap, 128-channel plane): 4 K-steps; sa16 already points at the plane
+    constexpr uint32_t CIN_PL = 128u, LAYOUT = 2u, KC_T = 8u;                      // 16-byte K chunks per output channel and chunk
+    static_assert(KHALF == 4 || KHALF == 8, "128 / 256 input channels");
+    const uint32_t ahi = ((sbo_px * CIN_PL) >> 4) | (1u << 14) | (LAYOUT << 29);
     const uint32_t bhi = (KC_T * 8u) | (1u << 14);
     const int kh = tap / 3, kw = tap - 3 * kh;
-    const uint32_t abase = sa16 + (uint32_t)(kh * (int)PITCHPX + kw) * (CIN_PL >> 4);
+    const uint32_t abase = sa16 + (uint32_t)(kh * row_px + kw) * (CIN_PL >> 4);
+    (void)plane16;
 #pragma unroll
-    for (int c2 = 0; c2 < KHALF; ++c2) {
-        const uint32_t alo = (abase + (uint32_t)(c2 / 4) * plane16 + (uint32_t)(c2 % 4) * 2u) | (1u << 16);
+    for (int c2 = 0; c2 < 4; ++c2) {
+        const uint32_t alo = (abase + (uint32_t)c2 * 2u) | (1u << 16);
         const uint32_t blo = (b16 + (uint32_t)c2 * 16u) | (8u << 16);
         if (c2 == 0 && first) umma_i8_lohi<false>(d, alo, ahi, blo, bhi, idesc);
         else umma_i8_lohi<true>(d, alo, ahi, blo, bhi, idesc);
@@ -320,6 +335,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         }
     }
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    if (BSTREAM && p.raster) {
+        // the zero pixel in front of every plane of every stage (never written afterwards)
+        const int npl = KHALF == 8 ? 2 : 1;
+        for (int i = threadIdx.x; i < p.stages * npl * 32; i += blockDim.x) {
+            const int st_ = i / (npl * 32), rem = i - st_ * npl * 32, pl = rem / 32, wd = rem & 31;
+            reinterpret_cast<uint32_t *>(base_ptr + p.off_stage + (uint32_t)st_ * p.stage_bytes + (uint32_t)pl * p.plane_stride)[wd] = 0u;
+        }
+        fence_proxy_async();
+    }
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
         const int b = p.bias_sh[i];
         s_bias[i] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
@@ -355,13 +379,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             if constexpr (BSTREAM) {
                 // tap by tap: each needs its weight chunk in the ring; the chunk's slot is released by a commit
                 const uint32_t d0 = tmem_base + (uint32_t)buf * p.tmem_buf_stride;
-                for (int tap = 0; tap < 9; ++tap) {
+                uint32_t a16 = sa >> 4;
+                int row_px = ws_tma_pitch(128);
+                uint32_t sbo_px = (uint32_t)row_px;
+                if (p.raster) {
+                    // stream pixel 128 * tile sits toff pixels into the second halo row; tap (0,0) starts one row and one
+                    // pixel earlier, which the zero pixel in front of the plane makes a non-negative offset
+                    const int q0 = 128 * tile;
+                    const int toff = q0 - (int)__umulhi((unsigned)q0, p.rP_magic) * p.rP;
+                    a16 += (uint32_t)toff * 8u;
+                    row_px = p.rP; sbo_px = 8u;
+                }
+                constexpr int NPL = KHALF / 4;                     // 128-channel planes = weight chunks per tap
+                for (int ck = 0; ck < 9 * NPL; ++ck) {
+                    const int tap = ck / NPL, pl = ck - tap * NPL;
                     mbar_wait(bar_bfull(bslot), rph);
                     tc_fence_after();
                     if (elect_one()) {
-                        ws_issue_tap<KHALF>(d0, sa >> 4, plane16, tap, (wsm + (uint32_t)bslot * p.b_chunk_bytes) >> 4, tap == 0, idesc);
+                        ws_issue_tap<KHALF>(d0, a16 + (uint32_t)pl * plane16, plane16, tap, row_px, sbo_px,
+                                            (wsm + (uint32_t)bslot * p.b_chunk_bytes) >> 4, ck == 0, idesc);
                         umma_commit(bar_bempty(bslot));
-                        if (tap == 8) { umma_commit(bar_empty(s)); umma_commit(bar_tfull(buf)); }
+                        if (ck == 9 * NPL - 1) { umma_commit(bar_empty(s)); umma_commit(bar_tfull(buf)); }
                     }
                     __syncwarp();
                     if (++bslot == p.b_slots) { bslot = 0; rph ^= 1u; }
@@ -385,12 +423,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
             // weight chunks: tile after tile, tap after tap
             int slot = 0;
             uint32_t bph = 0;
+            const int nchunks = 9 * (KHALF / 4);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int ck = 0; ck < nchunks; ++ck) {
                     mbar_wait(bar_bempty(slot), bph ^ 1u);
                     mbar_expect_tx(bar_bfull(slot), p.b_chunk_bytes);
                     const uint32_t dst = wsm + (uint32_t)slot * p.b_chunk_bytes;
-                    const uint8_t *src = p.wtap + (size_t)tap * p.b_chunk_bytes;
+                    const uint8_t *src = p.wtap + (size_t)ck * p.b_chunk_bytes;
                     for (uint32_t o = 0; o < p.b_chunk_bytes; o += 32768u) {
                         const uint32_t nb = p.b_chunk_bytes - o < 32768u ? p.b_chunk_bytes - o : 32768u;
                         bulk_load_1d(dst + o, src + o, nb, bar_bfull(slot));
@@ -410,6 +449,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
                 mbar_wait(bar_empty(s), ph ^ 1u);
                 WS_STAMP(3);
                 const uint32_t sa = stage0 + (uint32_t)s * p.stage_bytes;
+                if (BSTREAM && p.raster) {
+                    // raster tile: raster_rows whole canvas rows from the row above stream pixel 128 * tile
+                    const uint32_t row_bytes = (uint32_t)p.rP * 128u;
+                    mbar_expect_tx(bar_full(s), (uint32_t)(NPL * p.raster_rows) * row_bytes);
+                    int r = 0, cy = (int)__umulhi((unsigned)(128 * tile), p.rP_magic) - 1;
+                    while (r < p.raster_rows) {
+                        const int n = cy < 0 ? 0 : (int)__umulhi((unsigned)cy, p.period_magic);
+                        int y = cy - n * p.period;
+                        int run = min(p.raster_rows - r, p.period - y);
+                        while (run > 0) {
+                            const int lg = run >= 16 ? 4 : run >= 8 ? 3 : run >= 4 ? 2 : run >= 2 ? 1 : 0, h = 1 << lg;
+#pragma unroll
+                            for (int pl = 0; pl < NPL; ++pl)
+                                tma_load_4d(sa + (uint32_t)pl * p.plane_stride + 128u + (uint32_t)r * row_bytes, &maps.m[lg], bar_full(s), 128 * pl, 0, y, n);
+                            r += h; y += h; cy += h; run -= h;
+                        }
+                    }
+                    WS_STAMP(4);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    tx += p.step_x; ty += p.step_y;
+                    if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+                    continue;
+                }
                 mbar_expect_tx(bar_full(s), (uint32_t)(NPL * G::HH) * ROW_BYTES);
                 // the 18 halo rows = canvas rows ty0-1 .. ty0+16: runs of rows of one image (its gutter rows and the rows
                 // above / below the canvas are out of bounds for the box = zero filled = the convolution's padding)
@@ -631,13 +693,26 @@ static bool ws_plan_stream(const ConvArgs &a, WsParams *p)
     p->N = a.cs_out; p->cs_out = a.cs_out;
     p->w_bytes = 0;
     p->plane_stride = (uint32_t)(WsGeom<false>::HH * ws_tma_pitch(128) * 128);       // one 128-byte channel plane of a stage
+    // narrow un-pooled maps: flattened-raster tiles (see WsParams) waste W+1 : W instead of up to 8 : 1 columns
+    static const bool raster_on = [] { const char *e = getenv("YOLO_B200_WS_RASTER"); return e ? atoi(e) != 0 : true; }();
+    if (raster_on && !a.q.pool && a.W % 8 != 0 && a.W + 1 <= 64) {
+        p->raster = 1; p->rP = a.W + 1;
+        p->rP_magic = (unsigned)(((1ull << 32) + (unsigned)p->rP - 1) / (unsigned)p->rP);
+        p->raster_rows = (3 * p->rP + 127) / p->rP + 1;
+        p->plane_stride = 128u + (uint32_t)(p->raster_rows * p->rP) * 128u;
+    }
     p->stage_bytes = ((uint32_t)npl * p->plane_stride + 1023u) & ~1023u;
     uint32_t nb = 32; while (nb < (uint32_t)p->N) nb <<= 1;
     if (2 * nb > 512) return false;
     p->tbufs = 4 * nb <= 512 ? 4 : 2; p->tbufs_log2 = p->tbufs == 4 ? 2 : 1;
     p->tmem_buf_stride = nb; p->tmem_cols = (uint32_t)p->tbufs * nb;
-    p->b_chunk_bytes = (uint32_t)p->N * (uint32_t)a.cs_in;
+    p->b_chunk_bytes = (uint32_t)p->N * 128u;                                        // one (tap, 128-channel plane) of the weights
     const uint32_t budget = 227u * 1024u, tail = (uint32_t)p->N * 4u + 256u + 1024u + 16u;
+    if (p->raster && 2 * p->b_chunk_bytes + 2 * p->stage_bytes + tail > budget) {     // raster tile too large: regular tile
+        p->raster = 0;
+        p->plane_stride = (uint32_t)(WsGeom<false>::HH * ws_tma_pitch(128) * 128);
+        p->stage_bytes = ((uint32_t)npl * p->plane_stride + 1023u) & ~1023u;
+    }
     if (2 * p->b_chunk_bytes + 2 * p->stage_bytes + tail > budget) return false;
     p->stages = 2;
     int slots = (int)((budget - tail - 2 * p->stage_bytes) / p->b_chunk_bytes);
@@ -679,7 +754,7 @@ bool conv3x3_ws_supported(const ConvArgs &a)
 typedef CUresult (*WsEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static cudaError_t ws_make_maps(const ConvArgs &a, WsMaps *maps)
+static cudaError_t ws_make_maps(const ConvArgs &a, WsMaps *maps, int raster_px = 0)
 {
     static WsEncodeTiledFn enc = nullptr;
     if (!enc) {
@@ -696,7 +771,7 @@ static cudaError_t ws_make_maps(const ConvArgs &a, WsMaps *maps)
     cuuint32_t es[4] = { 1, 1, 1, 1 };
     for (int i = 0; i < 5; ++i) {
         const int cpl = a.cs_in > 128 ? 128 : a.cs_in;                          // bytes of a pixel in one plane of the tile
-        cuuint32_t box[4] = { (cuuint32_t)cpl, (cuuint32_t)ws_tma_pitch(cpl), (cuuint32_t)(1 << i), 1 };
+        cuuint32_t box[4] = { (cuuint32_t)cpl, (cuuint32_t)(raster_px ? raster_px : ws_tma_pitch(cpl)), (cuuint32_t)(1 << i), 1 };
         CUresult r = enc(&maps->m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
@@ -709,7 +784,7 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
 {
     WsMaps maps;
     memset(&maps, 0, sizeof maps);
-    if (TMAIN) { cudaError_t e = ws_make_maps(a, &maps); if (e != cudaSuccess) return e; }
+    if (TMAIN) { cudaError_t e = ws_make_maps(a, &maps, p.raster ? p.rP : 0); if (e != cudaSuccess) return e; }
     using G = WsGeom<PHASE>;
     const int gut = a.q.pool ? ((a.H & 1) ? 1 : 2) : 1;                  // pooled: image origins stay on even canvas rows
     p.in = a.in; p.n_img = a.n; p.H = a.H; p.W = a.W; p.cs_in = a.cs_in;
@@ -718,6 +793,7 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
     p.canvas_rows = a.n * p.period;
     p.tiles_x = (a.W + G::TW - 1) / G::TW;
     p.num_tiles = p.tiles_x * ((p.canvas_rows + G::TH - 1) / G::TH);
+    if (p.raster) { p.tiles_x = 1; p.num_tiles = (int)(((long long)p.canvas_rows * p.rP + 127) / 128); }
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
     p.q = a.q; p.wimg = a.wimg; p.wtap = a.wimg_tap; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
 #ifdef YB_WS_TIMELINE

@@ -15,7 +15,7 @@ struct ConvArgs {
     const uint8_t *wgt_swz = nullptr;  // cs_in % 128 == 0: [9*cs_in/128][cs_out][128 B] blocks in the 128B-swizzled smem layout (conv_umma.cu)
     int wgt_swz_rows = 0;              // rows per block of wgt_swz (= cs_out)
     const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
-    const uint8_t *wimg_tap;   // cs_in 128 / 256: the same image tap-major, [tap][cs_out/8][cs_in/16][8][16 B] (conv_ws.cu, weight streaming)
+    const uint8_t *wimg_tap;   // cs_in 128 / 256: the same image tap-major, [tap][128-channel plane][cs_out/8][8][8][16 B] (conv_ws.cu, weight streaming)
     int w_rows;            // cout_pad
     int bias_abs_max;      // max |bias_sh[c]| (decides whether the exact fp32 epilogue applies)
     int force_generic_epilogue;   // tests: run the integer epilogue even where the fp32 one applies

@@ -33,7 +33,7 @@ struct LayerDev {
     int8_t *w = nullptr;       // [cout_pad][9][cs_in]
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
-    uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: tap-major image [tap][cs_out/8][cs_in/16][8][16] (conv_ws.cu, streamed weights)
+    uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: chunk-major image [tap][plane][cs_out/8][8][8][16] (conv_ws.cu, streamed weights)
     uint8_t *w_swz = nullptr;  // cs_in % 128 == 0: 128B-swizzled blocks [9*cs_in/128][cs_out][128] (conv_umma.cu B operand)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
@@ -334,10 +334,11 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
             CU(cudaMemcpy(d.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
             if (d.cs_in == 128 || d.cs_in == 256) {
                 std::vector<uint8_t> imt((size_t)d.cs_out * 9 * d.cs_in, 0);
+                // chunk = (tap, 128-channel plane): [tap][plane][cs_out/8][8 K chunks][8][16 B]
                 for (int tap = 0; tap < 9; ++tap)
                     for (int o = 0; o < d.cs_out; ++o)
                         for (int cc = 0; cc < np; ++cc)
-                            memcpy(&imt[((((size_t)tap * (d.cs_out / 8) + o / 8) * np + cc) * 8 + (o % 8)) * 16],
+                            memcpy(&imt[(((((size_t)tap * (np / 8) + cc / 8) * (d.cs_out / 8) + o / 8) * 8 + cc % 8) * 8 + (o % 8)) * 16],
                                    &wp[((size_t)o * 9 + tap) * d.cs_in + 16 * cc], 16);
                 CU(cudaMalloc(&d.wimg_tap, imt.size()));
                 CU(cudaMemcpy(d.wimg_tap, imt.data(), imt.size(), cudaMemcpyHostToDevice));
