@@ -875,6 +875,11 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count)
     WsParams p;
     memset(&p, 0, sizeof p);
     if (a.q.pool && ws_plan(a, true, &p)) return launch_ws_epi<true>(a, p, st, sm_count);
+    // 256 input channels on a narrow un-pooled map (pred): the streamed, raster-tiled variant beats resident weights with
+    // cp.async producers even though the weights would fit (the layer is MMA-bound; the raster tile wastes fewer rows)
+    memset(&p, 0, sizeof p);
+    if (ws_stream_enabled() && a.cs_in == 256 && ((uintptr_t)a.in & 15) == 0 && ws_plan_stream(a, &p) && p.raster)
+        return launch_ws_epi<false>(a, p, st, sm_count, true);
     // un-phased tiles: TMA-fed halo where the channel count allows it (YOLO_B200_WS_TMA=0 keeps the cp.async producers)
     static const bool use_tma = [] { const char *e = getenv("YOLO_B200_WS_TMA"); return e ? atoi(e) != 0 : true; }();
     memset(&p, 0, sizeof p);
