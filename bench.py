@@ -364,6 +364,52 @@ def main():
         torch.cuda.synchronize()
         sparse["e2e"] = B * e2e_steps / (time.perf_counter() - t0)
 
+    # ---- secondary: the reference's image front end on the GPU (cv2.resize of base_transform, data/__init__.py:36, on
+    #      480x640 BGR frames -> 416x416, then the fused normalise/quantise first layer): the resize kernel alone against
+    #      HBM, and the host entry point with the camera-size images in pinned memory
+    front = None
+    if rank == 0 and world == 1:
+        SH, SW = 480, 640
+        g = torch.Generator().manual_seed(5)
+        h_imgs = torch.randint(0, 256, (B, SH, SW, 3), dtype=torch.uint8, generator=g).pin_memory()
+        d_imgs = h_imgs.cuda()
+        d_small = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cuda")
+        for i in range(3):
+            ctx.resize_u8bgr(d_imgs, B, SH, SW, d_small, H, W)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for i in range(10):
+            ctx.resize_u8bgr(d_imgs, B, SH, SW, d_small, H, W)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        r_ms = s0.elapsed_time(s1) / 10
+        r_bytes = B * (SH * SW * 3 + H * W * 3)
+        for i in range(3):
+            ctx.forward_u8bgr_resize_dev(d_imgs, B, SH, SW, H, W, d_dets, d_counts)
+        s0.record(stream)
+        for i in range(10):
+            ctx.forward_u8bgr_resize_dev(d_imgs, B, SH, SW, H, W, d_dets, d_counts)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        f_ms = s0.elapsed_time(s1) / 10
+
+        def front_step():
+            rc = L.yolo_b200_forward_u8bgr_resize(ctx._h, h_imgs.data_ptr(), B, SH, SW, H, W, h_dets.data_ptr(), h_counts.data_ptr())
+            if rc:
+                raise RuntimeError(L.yolo_b200_last_error())
+        for i in range(2):
+            front_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            front_step()
+        torch.cuda.synchronize()
+        front = {"workload": "%d BGR uint8 frames of %dx%d -> bilinear resize to %dx%d (cv2.resize semantics) + forward (sparse head)" % (B, SH, SW, H, W),
+                 "resize_kernel_ms": r_ms, "resize_gbs": r_bytes / (r_ms / 1e3) / 1e9, "resize_frac_of_hbm": r_bytes / (r_ms / 1e3) / 1e9 / pk["hbm_gbs"],
+                 "value": B / (f_ms / 1e3), "unit": "frames/s",
+                 "e2e": B * e2e_steps / (time.perf_counter() - t0), "h2d_bytes_per_step": int(h_imgs.numel())}
+        del d_imgs, d_small, h_imgs
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -388,7 +434,7 @@ def main():
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "yolo_b200_forward_rgb444 (pinned host buffers; H2D of 64-frame chunks overlapped with the convolution layers; decode + NMS on a second stream: all chunks but the last while the last is copied in, then the last; filled part of the lists copied back)",
                     "gpu_launches": int(e2e_launches)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sparse_head": sparse,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sparse_head": sparse, "image_front_end": front,
         }))
     if world > 1:
         dist.barrier()

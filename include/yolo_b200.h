@@ -164,6 +164,15 @@ int yolo_b200_forward_int8(yolo_b200_ctx *ctx, const int8_t *nhwc4, int n, int h
 int yolo_b200_forward_u8bgr(yolo_b200_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
                             yolo_b200_det *dets, int32_t *counts);
 
+/* The reference's whole image front end: base_transform's `cv2.resize(image, (size[1], size[0]))` (data/__init__.py:36,
+ * default INTER_LINEAR, reached through BaseTransform.__call__ :55 from test.py:76 / demo.py:71) followed by everything
+ * yolo_b200_forward_u8bgr does.  bgr: uint8 [n][sh][sw][3] host images of one size (what cv2.imread / a capture loop
+ * delivers); they are copied to the GPU as they are, resized there to the network size h x w chunk by chunk (between the
+ * copy and the first layer) and never visit the host again.  The resize is bit-exact with OpenCV's 8-bit bilinear
+ * (11-bit fixed-point taps; exact 2x decimation = 2x2 mean as OpenCV does).  sh == h && sw == w: no resize. */
+int yolo_b200_forward_u8bgr_resize(yolo_b200_ctx *ctx, const uint8_t *bgr, int n, int sh, int sw, int h, int w,
+                                   yolo_b200_det *dets, int32_t *counts);
+
 /* Replaces SlimYOLOv2_quantize_bnfuse.forward(x, quantization=True) inference branch,
  * slim_yolo_v2.py:212-358, for a float NCHW batch (input quantised by a_tracker_in, :218). */
 int yolo_b200_forward_f32(yolo_b200_ctx *ctx, const float *nchw, int n, int h, int w,
@@ -180,6 +189,9 @@ int yolo_b200_forward_f32_dev(yolo_b200_ctx *ctx, const float *d_nchw, int n, in
 int yolo_b200_forward_u8bgr_dev(yolo_b200_ctx *ctx, const uint8_t *d_bgr, int n, int h, int w,
                                 yolo_b200_det *d_dets, int32_t *d_counts);
 /* Block until everything queued on the context stream is done. */
+int yolo_b200_forward_u8bgr_resize_dev(yolo_b200_ctx *ctx, const uint8_t *d_bgr, int n, int sh, int sw, int h, int w,
+                                       yolo_b200_det *d_dets, int32_t *d_counts);
+
 int yolo_b200_sync(yolo_b200_ctx *ctx);
 
 /* ---- per-stage entry points (device buffers) -------------------------------------------- */
@@ -196,6 +208,15 @@ int yolo_b200_quantize_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h
  * lut[ch*256 + v], ch 0..2 = R,G,B of the network input (R comes from BGR byte 2). */
 int yolo_b200_quantize_u8bgr(yolo_b200_ctx *ctx, const uint8_t *d_bgr, int n, int h, int w, int8_t *d_nhwc4);
 int yolo_b200_u8bgr_lut(yolo_b200_ctx *ctx, int8_t *lut_host);
+/* cv2.resize(image, (dw, dh)) of base_transform (data/__init__.py:36) as a stage: uint8 [n][sh][sw][3] ->
+ * uint8 [n][dh][dw][3], device buffers, any channel order (the three bytes are treated alike).  Needs no loaded network.
+ * d_dst 4-byte aligned and dw a multiple of 4 take the vectorised kernel (same results otherwise). */
+int yolo_b200_resize_u8bgr(yolo_b200_ctx *ctx, const uint8_t *d_src, int n, int sh, int sw,
+                           uint8_t *d_dst, int dh, int dw);
+/* Host only (no GPU needed), for tests: the per-index programme of that resize along one axis, taps[4*d + {0,1,2,3}] =
+ * (source index 0, source index 1, weight 0, weight 1), weights in units of 1/2048; horizontal != 0 re-anchors the tap
+ * at the image border as OpenCV's horizontal pass does. */
+int yolo_b200_resize_taps(int src, int dst, int horizontal, int32_t *taps);
 /* The 4096 x 4 byte table itself (host copy), for tests: lut[code*4 + {0,1,2}] = R,G,B. */
 int yolo_b200_rgb444_lut(yolo_b200_ctx *ctx, int8_t *lut_host);
 

@@ -691,3 +691,96 @@ def test_graft_entry_smoke_runs():
     sys.path.insert(0, root)
     g = importlib.import_module("__graft_entry__")
     g.smoke()
+
+
+# ---- image resize in front of the path (cv2.resize of base_transform, data/__init__.py:36) ---------------------------
+
+def _resize_oracle():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oracle_resize_u8", os.path.join(ROOT, "oracle", "resize_u8.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _gpu_resize(ctx, imgs, dh, dw, misalign=0):
+    n, sh, sw, _ = imgs.shape
+    buf = torch.full((n * dh * dw * 3 + 8,), 0xAB, dtype=torch.uint8, device="cuda")
+    out = buf[misalign:misalign + n * dh * dw * 3]
+    ctx.resize_u8bgr(dev(imgs), n, sh, sw, out, dh, dw)
+    ctx.sync()
+    assert int(buf[misalign + n * dh * dw * 3]) == 0xAB                      # nothing written past the end
+    return out.cpu().numpy().reshape(n, dh, dw, 3)
+
+
+@pytest.mark.gpu
+def test_resize_kernel_matches_cv2_golden_and_oracle(ctx):
+    """yolo_b200_resize_u8bgr == cv2.resize(image, (w, h)) of the reference's base_transform: bit-exact against cv2's own
+    outputs (tests/golden/resize_cv2.npz) and against the oracle on geometries that take both kernel variants
+    (4 pixels per thread / 1 pixel per thread: odd widths, unaligned destination), batches, up- and down-scaling, the
+    exact-2x case where OpenCV switches to the 2x2 mean, single-pixel sources and the reference's 480x640 -> 416x416."""
+    ro = _resize_oracle()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "resize_cv2.npz"))
+    for seed, sh, sw, dh, dw in g["cases"].tolist():
+        img = np.random.default_rng(seed).integers(0, 256, (1, sh, sw, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(_gpu_resize(ctx, img, dh, dw)[0], g["out_%d" % seed], err_msg="golden %dx%d -> %dx%d" % (sh, sw, dh, dw))
+    rng = np.random.default_rng(17)
+    cases = [(3, 48, 64, 64, 96, 0), (2, 37, 53, 33, 47, 0), (2, 37, 53, 32, 48, 1), (1, 64, 96, 32, 48, 3), (4, 5, 7, 21, 19, 0),
+             (1, 1, 1, 4, 8, 0), (2, 90, 31, 8, 100, 2), (1, 3, 200, 64, 4, 0), (2, 480, 640, 416, 416, 0), (1, 1080, 1920, 416, 416, 0),
+             (1, 832, 832, 416, 416, 0), (1, 240, 320, 416, 416, 0)]
+    for n, sh, sw, dh, dw, mis in cases:
+        imgs = rng.integers(0, 256, (n, sh, sw, 3), dtype=np.uint8)
+        got = _gpu_resize(ctx, imgs, dh, dw, misalign=mis)
+        np.testing.assert_array_equal(got, ro.resize_batch(imgs, dh, dw), err_msg="%d x %dx%d -> %dx%d (+%d)" % (n, sh, sw, dh, dw, mis))
+    # constant images stay constant (weights sum to 2048 everywhere), n = 0 is a no-op, bad shapes are errors
+    flat = np.full((1, 23, 29, 3), 255, dtype=np.uint8)
+    assert (_gpu_resize(ctx, flat, 40, 44) == 255).all()
+    ctx.resize_u8bgr(dev(flat), 0, 23, 29, torch.zeros(4, dtype=torch.uint8, device="cuda"), 4, 4)
+    with pytest.raises(Exception):
+        ctx.resize_u8bgr(dev(flat), 1, 23, 29, torch.zeros(4, dtype=torch.uint8, device="cuda"), 0, 4)
+
+
+@pytest.mark.gpu
+def test_forward_u8bgr_resize_equals_basetransform_then_forward(ctx):
+    """yolo_b200_forward_u8bgr_resize (host images of camera size -> detections) == the reference's order of operations:
+    cv2.resize on the host (oracle), then the at-network-size entry point.  Chunked host path (ragged last chunk), the
+    device entry point and the identity geometry are covered; detections must be bit-identical."""
+    ro = _resize_oracle()
+    g, qnet, frames = gu.load("ref_p_64x96")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_P, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    rng = np.random.default_rng(23)
+    n, sh, sw, h, w = 5, 48, 64, 64, 96
+    imgs = rng.integers(0, 256, (n, sh, sw, 3), dtype=np.uint8)
+    small = ro.resize_batch(imgs, h, w)
+    dets_ref, counts_ref = ctx.forward_u8bgr(small)
+    assert counts_ref.sum() > 0
+
+    def same(dets, counts):
+        np.testing.assert_array_equal(counts, counts_ref)
+        for i in range(n):
+            k = int(counts_ref[i])
+            np.testing.assert_array_equal(dets[i][:k].view(np.int32), dets_ref[i][:k].view(np.int32))
+
+    for chunk in (64, 2, 1):
+        ctx.set_host_chunk(chunk)
+        try:
+            same(*ctx.forward_u8bgr_resize(imgs, (h, w)))
+        finally:
+            ctx.set_host_chunk(64)
+    md = ctx.params.max_det
+    d_dets = torch.zeros((n, md, 8), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx.forward_u8bgr_resize_dev(dev(imgs), n, sh, sw, h, w, d_dets, d_counts)
+    ctx.sync()
+    np.testing.assert_array_equal(d_counts.cpu().numpy(), counts_ref)
+    for i in range(n):
+        k = int(counts_ref[i])
+        np.testing.assert_array_equal(d_dets[i, :k].cpu().numpy().reshape(-1), dets_ref[i][:k].view(np.int32).reshape(-1))
+    same(*ctx.forward_u8bgr_resize(small, (h, w)))                           # identity geometry: no resize
+    # a second geometry on the same context rebuilds the tap tables
+    imgs2 = rng.integers(0, 256, (2, 100, 80, 3), dtype=np.uint8)
+    d2, c2 = ctx.forward_u8bgr_resize(imgs2, (h, w))
+    d2r, c2r = ctx.forward_u8bgr(ro.resize_batch(imgs2, h, w))
+    np.testing.assert_array_equal(c2, c2r)
+    for i in range(2):
+        np.testing.assert_array_equal(d2[i][:int(c2r[i])].view(np.int32), d2r[i][:int(c2r[i])].view(np.int32))

@@ -160,3 +160,22 @@ print("rank", rank, "ok")
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_resize_taps_match_the_oracle(L):
+    """yolo_b200_resize_taps (host arithmetic of the GPU resize: OpenCV's float/double coefficient set-up) against
+    oracle/resize_u8.py's axis_table, which is pinned on cv2's own outputs (tests/test_oracle.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oracle_resize_u8", os.path.join(ROOT, "oracle", "resize_u8.py"))
+    ro = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ro)
+    rng = np.random.default_rng(3)
+    pairs = [(480, 416), (640, 416), (375, 416), (1080, 416), (1920, 416), (832, 416), (1, 7), (7, 1), (416, 416), (100, 608)]
+    pairs += [tuple(int(v) for v in rng.integers(1, 3000, 2)) for _ in range(200)]
+    for src, dst in pairs:
+        for horizontal in (0, 1):
+            taps = np.zeros((dst, 4), dtype=np.int32)
+            assert L.yolo_b200_resize_taps(src, dst, horizontal, taps.ctypes.data) == 0
+            i0, i1, c0, c1 = ro.axis_table(src, dst, bool(horizontal))
+            np.testing.assert_array_equal(taps, np.stack([i0, i1, c0, c1], axis=1), err_msg="%d -> %d h=%d" % (src, dst, horizontal))
+    assert L.yolo_b200_resize_taps(0, 4, 1, None) < 0

@@ -194,3 +194,44 @@ def test_weight_h_roundtrip(tmp_path):
         np.testing.assert_array_equal(a, b)
     for a, b in zip(bs, qnet.b):
         np.testing.assert_array_equal(a, b)
+
+
+# ---- image resize in front of the path (cv2.resize of base_transform, data/__init__.py:36) ---------------------------
+
+def _resize_oracle():
+    import importlib.util
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "resize_u8.py")
+    spec = importlib.util.spec_from_file_location("oracle_resize_u8", p)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_resize_oracle_matches_cv2_golden():
+    """oracle/resize_u8.py (restated OpenCV 8-bit bilinear) == the outputs cv2.resize itself produced
+    (tests/golden/resize_cv2.npz, written by oracle/gen_golden_resize.py), bit for bit."""
+    import os
+    ro = _resize_oracle()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_cv2.npz"))
+    assert len(g["cases"]) >= 8
+    for seed, sh, sw, dh, dw in g["cases"].tolist():
+        img = np.random.default_rng(seed).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(ro.resize_bilinear_u8(img, dh, dw), g["out_%d" % seed],
+                                      err_msg="%dx%d -> %dx%d" % (sh, sw, dh, dw))
+
+
+def test_resize_oracle_matches_live_cv2_when_present():
+    """Same check against the installed OpenCV on random geometries (up, down, mixed, exact 2x, single rows/columns)."""
+    cv2 = pytest.importorskip("cv2")
+    ro = _resize_oracle()
+    rng = np.random.default_rng(11)
+    for t in range(60):
+        sh, sw, dh, dw = [int(v) for v in rng.integers(1, 120, 4)]
+        if t % 6 == 0:
+            sh, sw = 2 * dh, 2 * dw
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(ro.resize_bilinear_u8(img, dh, dw), cv2.resize(img, (dw, dh)),
+                                      err_msg="%dx%d -> %dx%d" % (sh, sw, dh, dw))
+    img = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)                      # the size the reference's demo frames have
+    np.testing.assert_array_equal(ro.resize_bilinear_u8(img, 416, 416), cv2.resize(img, (416, 416)))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Image detection CLI for the fixed-point slim_yolo_v2 path on the GPU: the counterpart of the reference's test.py /
 demo.py image mode for `-v slim_yolo_v2_q_bf` (test.py:13-99,165-181; demo.py:99-120), with the same flags where they
-apply.  Every image goes through the whole hot path on the device: the uint8 BGR image (resized on the host by cv2, as
+apply.  Every image goes through the whole hot path on the device: the uint8 BGR image (resized on the GPU with cv2.resize semantics, as
 BaseTransform does, data/__init__.py:36) is normalised, quantised, convolved, decoded and NMS-ed by libyolo_b200.so.
 
     python tools/detect.py --trained_model slim_yolo_v2_retune_quantize1.pth --images dir/ -size 416 --out output/
@@ -75,9 +75,16 @@ def main():
     t_dev = 0.0
     for b0 in range(0, len(imgs), args.batch):
         chunk = imgs[b0:b0 + args.batch]
-        x = np.stack([cv2.resize(im, (size[1], size[0])) for im in chunk])      # data/__init__.py:36 (bilinear)
+        # data/__init__.py:36 (cv2.resize, bilinear) runs on the GPU too: images of one size go in one call
         t0 = time.time()
-        dets, counts = ctx.forward_u8bgr(x)
+        dets = np.zeros((len(chunk), 1024), dtype=lib.DET_DTYPE)
+        counts = np.zeros(len(chunk), dtype=np.int32)
+        shapes = sorted({im.shape[:2] for im in chunk})
+        for shp in shapes:
+            idx = [k for k, im in enumerate(chunk) if im.shape[:2] == shp]
+            d, c_ = ctx.forward_u8bgr_resize(np.stack([chunk[k] for k in idx]), size)
+            dets[idx] = d
+            counts[idx] = c_
         t_dev += time.time() - t0
         for k, im in enumerate(chunk):
             boxes, scores, cls, _ = lib.dets_to_arrays(dets[k], int(min(counts[k], 1024)))
@@ -86,7 +93,7 @@ def main():
             out = vis(im.copy(), boxes, scores, cls, args.visual_threshold)
             cv2.imwrite(os.path.join(args.out, names[b0 + k] + ".jpg"), out)
             print("%s: %d detections (%d above %.2f)" % (names[b0 + k], len(scores), int((scores > args.visual_threshold).sum()), args.visual_threshold))
-    print("%d images, %.1f ms in yolo_b200_forward_u8bgr" % (len(imgs), 1e3 * t_dev))
+    print("%d images, %.1f ms in yolo_b200_forward_u8bgr_resize" % (len(imgs), 1e3 * t_dev))
     ctx.close()
 
 

@@ -51,6 +51,11 @@ cudaError_t quantize_u8bgr(const uint8_t *bgr, size_t npix, const uint8_t *lut8_
 cudaError_t absmax_f32(const float *x, size_t count, unsigned *out_bits, cudaStream_t st);   // max |x| as float bits (atomicMax)
 cudaError_t quantize_f32(const float *nchw, int n, int h, int w, int sa, int8_t *nhwc4, unsigned *ovf, cudaStream_t st);
 
+// resize.cu (uint8 HxWx3 bilinear resize = cv2.resize of the reference's BaseTransform, data/__init__.py:36)
+void resize_axis_table(int src, int dst, bool clamp_weights, int index_scale, int4 *out);   // host: (tap0, tap1, weight0, weight1) per output index
+cudaError_t resize_u8bgr(const uint8_t *src, int n, int sh, int sw, uint8_t *dst, int dh, int dw,
+                         const int4 *xtab_dev, const int4 *ytab_dev, int sm_count, cudaStream_t st);
+
 // head.cu
 struct HeadArgs {
     const int8_t *pred;    // [n][gh][gw][cs]

@@ -57,6 +57,10 @@ struct yolo_b200_ctx {
     int *stats_dev = nullptr;            // calibration: {max, min} of a layer's numerator / abs-max bits of the input
     int8_t *in_q = nullptr; size_t in_q_cap = 0;        // quantised NHWC4 input
     void *stage_in = nullptr; size_t stage_in_cap = 0;  // device staging of host inputs
+    void *rs_src = nullptr; size_t rs_src_cap = 0;      // resize front end: staged source images (host entry point)
+    uint8_t *rs_out = nullptr; size_t rs_out_cap = 0;   // resize front end: resized images (device entry point)
+    int4 *rs_tab = nullptr; size_t rs_tab_cap = 0;      // [dw] column taps/weights then [dh] row taps/weights
+    int rs_key[4] = {0, 0, 0, 0};                       // (sh, sw, dh, dw) the tables were built for
     float *h_scores = nullptr; int *h_cls = nullptr; float4 *h_boxes = nullptr; size_t head_cap = 0;
     yolo_b200_det *d_dets = nullptr; int32_t *d_counts = nullptr; size_t dets_cap = 0, counts_cap = 0;
     int last_n = 0;
@@ -155,6 +159,7 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     free_layers(c);
     cudaFree(c->pred_all);
     cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->stats_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
+    cudaFree(c->rs_src); cudaFree(c->rs_out); cudaFree(c->rs_tab);
     cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
     for (auto e : c->ev) cudaEventDestroy(e);
     for (auto e : c->ev_in) cudaEventDestroy(e);
@@ -456,6 +461,45 @@ int yolo_b200_quantize_u8bgr(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int 
     int rc = check_ready(c, n, h, w); if (rc) return rc;
     if (n == 0) return 0;
     CU(quantize_u8bgr(d_bgr, (size_t)n * h * w, c->lut8_dev, d_nhwc4, c->ovf_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+// taps and weights of the bilinear resize (sh, sw) -> (dh, dw), rebuilt when the geometry changes
+static int ensure_resize_tables(yolo_b200_ctx *c, int sh, int sw, int dh, int dw)
+{
+    if (c->rs_tab && c->rs_key[0] == sh && c->rs_key[1] == sw && c->rs_key[2] == dh && c->rs_key[3] == dw) return 0;
+    int rc = ensure((void **)&c->rs_tab, &c->rs_tab_cap, (size_t)(dw + dh) * sizeof(int4)); if (rc) return rc;
+    std::vector<int4> t((size_t)dw + dh);
+    resize_axis_table(sw, dw, true, 3, t.data());            // column taps as byte offsets inside a row
+    resize_axis_table(sh, dh, false, 1, t.data() + dw);      // row taps
+    c->rs_key[0] = 0;
+    // the tables may still be read by a resize queued earlier on the context stream: stream-ordered, pageable source
+    CU(cudaMemcpyAsync(c->rs_tab, t.data(), t.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->rs_key[0] = sh; c->rs_key[1] = sw; c->rs_key[2] = dh; c->rs_key[3] = dw;
+    return 0;
+}
+
+int yolo_b200_resize_taps(int src, int dst, int horizontal, int32_t *taps)
+{
+    if (src < 1 || dst < 1 || !taps) return fail(E_ARG, "bad resize axis %d -> %d", src, dst);
+    std::vector<int4> t((size_t)dst);
+    resize_axis_table(src, dst, horizontal != 0, 1, t.data());
+    for (int d = 0; d < dst; ++d) { taps[4 * d] = t[d].x; taps[4 * d + 1] = t[d].y; taps[4 * d + 2] = t[d].z; taps[4 * d + 3] = t[d].w; }
+    return 0;
+}
+
+int yolo_b200_resize_u8bgr(yolo_b200_ctx *c, const uint8_t *d_src, int n, int sh, int sw, uint8_t *d_dst, int dh, int dw)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (n < 0 || sh < 1 || sw < 1 || dh < 1 || dw < 1) return fail(E_ARG, "bad resize shape n=%d %dx%d -> %dx%d", n, sh, sw, dh, dw);
+    if ((size_t)sh * sw * 3 > (size_t)INT32_MAX) return fail(E_UNSUPPORTED, "source image larger than 2 GiB");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    if (!d_src || !d_dst) return fail(E_ARG, "null buffer");
+    int rc = ensure_resize_tables(c, sh, sw, dh, dw); if (rc) return rc;
+    CU(resize_u8bgr(d_src, n, sh, sw, d_dst, dh, dw, c->rs_tab, c->rs_tab + dw, c->sm_count, c->stream));
     c->launches++;
     return 0;
 }
@@ -769,6 +813,16 @@ int yolo_b200_forward_rgb444_dev(yolo_b200_ctx *c, const uint16_t *d_frames, int
 int yolo_b200_forward_u8bgr_dev(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
 { return forward_dev(c, 3, d_bgr, n, h, w, d_dets, d_counts); }
 
+int yolo_b200_forward_u8bgr_resize_dev(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int sh, int sw, int h, int w,
+                                       yolo_b200_det *d_dets, int32_t *d_counts)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (sh == h && sw == w) return forward_dev(c, 3, d_bgr, n, h, w, d_dets, d_counts);     // identity resize copies the bytes
+    rc = ensure((void **)&c->rs_out, &c->rs_out_cap, (size_t)(n > 0 ? n : 1) * h * w * 3); if (rc) return rc;
+    rc = yolo_b200_resize_u8bgr(c, d_bgr, n, sh, sw, c->rs_out, h, w); if (rc) return rc;
+    return forward_dev(c, 3, c->rs_out, n, h, w, d_dets, d_counts);
+}
+
 int yolo_b200_forward_f32_dev(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, yolo_b200_det *d_dets, int32_t *d_counts)
 { return forward_dev(c, 2, d_nchw, n, h, w, d_dets, d_counts); }
 
@@ -802,13 +856,22 @@ struct HostTrace {
     }
 };
 
+// sh, sw > 0 (kind 3 only): the host images are sh x sw and are resized to h x w on the GPU chunk by chunk, between the
+// copy and the first layer (in_bytes = bytes of the source images).
 static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
-                        yolo_b200_det *dets, int32_t *counts)
+                        yolo_b200_det *dets, int32_t *counts, int sh = 0, int sw = 0)
 {
     int rc = check_ready(c, n, h, w); if (rc) return rc;
     if (n == 0) return 0;
     if (!host_in || !dets || !counts) return fail(E_ARG, "null buffer");
-    rc = ensure(&c->stage_in, &c->stage_in_cap, in_bytes); if (rc) return rc;
+    const bool resize = sh > 0 && sw > 0 && !(sh == h && sw == w);
+    const size_t net_frame_bytes = resize ? (size_t)h * w * 3 : in_bytes / (size_t)n;
+    rc = ensure(&c->stage_in, &c->stage_in_cap, (size_t)n * net_frame_bytes); if (rc) return rc;
+    if (resize) {
+        if ((size_t)sh * sw * 3 > (size_t)INT32_MAX) return fail(E_UNSUPPORTED, "source image larger than 2 GiB");
+        rc = ensure(&c->rs_src, &c->rs_src_cap, in_bytes); if (rc) return rc;
+        rc = ensure_resize_tables(c, sh, sw, h, w); if (rc) return rc;
+    }
     const size_t md = (size_t)c->prm.max_det;
     rc = ensure((void **)&c->d_dets, &c->dets_cap, (size_t)n * md * sizeof(yolo_b200_det)); if (rc) return rc;
     rc = ensure((void **)&c->d_counts, &c->counts_cap, (size_t)n * sizeof(int32_t)); if (rc) return rc;
@@ -875,11 +938,17 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     int head_f0 = 0, ngroups = 0, grp_f0[2] = {0, 0}, grp_n[2] = {0, 0};
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = cf0[k], nk = cnk[k];
-        char *stage = (char *)c->stage_in + (size_t)f0 * frame_bytes;
-        CU(cudaMemcpyAsync(stage, (const char *)host_in + (size_t)f0 * frame_bytes, (size_t)nk * frame_bytes, cudaMemcpyHostToDevice, c->s_in));
+        char *stage = (char *)c->stage_in + (size_t)f0 * net_frame_bytes;
+        char *land = resize ? (char *)c->rs_src + (size_t)f0 * frame_bytes : stage;
+        CU(cudaMemcpyAsync(land, (const char *)host_in + (size_t)f0 * frame_bytes, (size_t)nk * frame_bytes, cudaMemcpyHostToDevice, c->s_in));
         CU(cudaEventRecord(c->ev_in[k], c->s_in));
         tr.mark("h2d done", k, c->s_in);
         CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        if (resize) {
+            cudaError_t e = resize_u8bgr((const uint8_t *)land, nk, sh, sw, (uint8_t *)stage, h, w, c->rs_tab, c->rs_tab + w, c->sm_count, c->stream);
+            if (e != cudaSuccess) { drain(); return fail(E_CUDA, "resize: %s", cudaGetErrorString(e)); }
+            c->launches++;
+        }
         const int8_t *pred; int g1, g2;
         rc = features_dev(c, kind, stage, nk, h, w, c->pred_all + (size_t)f0 * pred_frame, &pred, &g1, &g2);
         if (rc) { drain(); return rc; }
@@ -925,6 +994,11 @@ int yolo_b200_forward_u8bgr(yolo_b200_ctx *c, const uint8_t *bgr, int n, int h, 
 { return forward_host(c, bgr, (size_t)n * h * w * 3, 3, n, h, w, dets, counts); }
 int yolo_b200_forward_f32(yolo_b200_ctx *c, const float *nchw, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
 { return forward_host(c, nchw, (size_t)n * h * w * 12, 2, n, h, w, dets, counts); }
+int yolo_b200_forward_u8bgr_resize(yolo_b200_ctx *c, const uint8_t *bgr, int n, int sh, int sw, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{
+    if (sh < 1 || sw < 1) return fail(E_ARG, "bad source shape %dx%d", sh, sw);
+    return forward_host(c, bgr, (size_t)n * sh * sw * 3, 3, n, h, w, dets, counts, sh, sw);
+}
 
 int yolo_b200_overflow_count(yolo_b200_ctx *c, int64_t *count)
 {

@@ -32,6 +32,7 @@ EXPORTS = [
     "yolo_b200_backbone", "yolo_b200_calibrate_f32", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
     "yolo_b200_launch_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
     "yolo_forward", "yolo_b200_set_default_context",
+    "yolo_b200_resize_taps", "yolo_b200_resize_u8bgr", "yolo_b200_forward_u8bgr_resize", "yolo_b200_forward_u8bgr_resize_dev",
 ]
 
 
@@ -93,6 +94,10 @@ def load_library(path: Optional[str] = None):
                  "yolo_b200_forward_u8bgr_dev", "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.yolo_b200_sync.argtypes = [vp]
+    L.yolo_b200_resize_u8bgr.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32]
+    L.yolo_b200_resize_taps.argtypes = [i32, i32, i32, vp]
+    L.yolo_b200_forward_u8bgr_resize.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    L.yolo_b200_forward_u8bgr_resize_dev.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     L.yolo_b200_quantize_rgb444.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_quantize_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_rgb444_lut.argtypes = [vp, vp]
@@ -235,6 +240,19 @@ class Context:
         assert c == 3
         return self._forward_host(self.L.yolo_b200_forward_u8bgr, f, n, h, w)
 
+    def forward_u8bgr_resize(self, images: np.ndarray, size):
+        """uint8 BGR images [n][sh][sw][3] of any one size: the reference's whole BaseTransform (cv2.resize bilinear to
+        size = (h, w), normalise, BGR -> RGB) + tracker quantiser + forward pass, all on the GPU."""
+        f = np.ascontiguousarray(images, dtype=np.uint8)
+        n, sh, sw, c = f.shape
+        assert c == 3
+        h, w = int(size[0]), int(size[1])
+        md = self.params.max_det
+        dets = np.zeros((n, md), dtype=DET_DTYPE)
+        counts = np.zeros(n, dtype=np.int32)
+        self._check(self.L.yolo_b200_forward_u8bgr_resize(self._h, f.ctypes.data, n, sh, sw, h, w, dets.ctypes.data, counts.ctypes.data))
+        return dets, counts
+
     def forward_int8(self, nhwc4: np.ndarray):
         x = np.ascontiguousarray(nhwc4, dtype=np.int8)
         n, h, w, c = x.shape
@@ -259,6 +277,13 @@ class Context:
 
     def forward_u8bgr_dev(self, d_in, n, h, w, d_dets, d_counts):
         self._check(self.L.yolo_b200_forward_u8bgr_dev(self._h, _ptr(d_in), n, h, w, _ptr(d_dets), _ptr(d_counts)))
+
+    def forward_u8bgr_resize_dev(self, d_in, n, sh, sw, h, w, d_dets, d_counts):
+        self._check(self.L.yolo_b200_forward_u8bgr_resize_dev(self._h, _ptr(d_in), n, sh, sw, h, w, _ptr(d_dets), _ptr(d_counts)))
+
+    def resize_u8bgr(self, d_src, n, sh, sw, d_dst, dh, dw):
+        """cv2.resize (bilinear) of n uint8 [sh][sw][3] device images into d_dst [n][dh][dw][3]."""
+        self._check(self.L.yolo_b200_resize_u8bgr(self._h, _ptr(d_src), n, sh, sw, _ptr(d_dst), dh, dw))
 
     def calibrate_f32(self, d_nchw, n, h, w):
         """Derive scale_a / retune on the GPU from a float NCHW calibration batch (device tensor) by the reference's
