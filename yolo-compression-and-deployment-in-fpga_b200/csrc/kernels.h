@@ -53,8 +53,9 @@ cudaError_t quantize_f32(const float *nchw, int n, int h, int w, int sa, int8_t 
 
 // resize.cu (uint8 HxWx3 bilinear resize = cv2.resize of the reference's BaseTransform, data/__init__.py:36)
 void resize_axis_table(int src, int dst, bool clamp_weights, int index_scale, int4 *out);   // host: (tap0, tap1, weight0, weight1) per output index
+// xtab: per column (byte offset of tap 0 in its row, weight0 | weight1 << 16), tap 1 = the next pixel; ytab: per row (row 0, row 1, weight0 << 16, weight1 << 16)
 cudaError_t resize_u8bgr(const uint8_t *src, int n, int sh, int sw, uint8_t *dst, int dh, int dw,
-                         const int4 *xtab_dev, const int4 *ytab_dev, int sm_count, cudaStream_t st);
+                         const int2 *xtab_dev, const int4 *ytab_dev, int sm_count, cudaStream_t st);
 
 // head.cu
 struct HeadArgs {

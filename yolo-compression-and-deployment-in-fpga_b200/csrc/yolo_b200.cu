@@ -59,7 +59,8 @@ struct yolo_b200_ctx {
     void *stage_in = nullptr; size_t stage_in_cap = 0;  // device staging of host inputs
     void *rs_src = nullptr; size_t rs_src_cap = 0;      // resize front end: staged source images (host entry point)
     uint8_t *rs_out = nullptr; size_t rs_out_cap = 0;   // resize front end: resized images (device entry point)
-    int4 *rs_tab = nullptr; size_t rs_tab_cap = 0;      // [dw] column taps/weights then [dh] row taps/weights
+    void *rs_tab = nullptr; size_t rs_tab_cap = 0;      // [dh] int4 row taps/weights, then [dw] int2 column offsets/weights
+    const int4 *rs_ytab = nullptr; const int2 *rs_xtab = nullptr;
     int rs_key[4] = {0, 0, 0, 0};                       // (sh, sw, dh, dw) the tables were built for
     float *h_scores = nullptr; int *h_cls = nullptr; float4 *h_boxes = nullptr; size_t head_cap = 0;
     yolo_b200_det *d_dets = nullptr; int32_t *d_counts = nullptr; size_t dets_cap = 0, counts_cap = 0;
@@ -469,14 +470,22 @@ int yolo_b200_quantize_u8bgr(yolo_b200_ctx *c, const uint8_t *d_bgr, int n, int 
 static int ensure_resize_tables(yolo_b200_ctx *c, int sh, int sw, int dh, int dw)
 {
     if (c->rs_tab && c->rs_key[0] == sh && c->rs_key[1] == sw && c->rs_key[2] == dh && c->rs_key[3] == dw) return 0;
-    int rc = ensure((void **)&c->rs_tab, &c->rs_tab_cap, (size_t)(dw + dh) * sizeof(int4)); if (rc) return rc;
-    std::vector<int4> t((size_t)dw + dh);
-    resize_axis_table(sw, dw, true, 3, t.data());            // column taps as byte offsets inside a row
-    resize_axis_table(sh, dh, false, 1, t.data() + dw);      // row taps
+    const size_t ybytes = (size_t)dh * sizeof(int4), xbytes = (size_t)dw * sizeof(int2);
+    int rc = ensure(&c->rs_tab, &c->rs_tab_cap, ybytes + xbytes); if (rc) return rc;
+    std::vector<int4> t((size_t)(dw > dh ? dw : dh));
+    std::vector<char> img(ybytes + xbytes);
+    resize_axis_table(sh, dh, false, 1, t.data());           // row taps; weights pre-shifted for the kernel's high multiply
+    for (int d = 0; d < dh; ++d) { t[d].z <<= 16; t[d].w <<= 16; }
+    memcpy(img.data(), t.data(), ybytes);
+    resize_axis_table(sw, dw, true, 3, t.data());            // column taps as byte offsets inside a row; tap 1 = the next pixel
+    int2 *xt = reinterpret_cast<int2 *>(img.data() + ybytes);
+    for (int d = 0; d < dw; ++d) xt[d] = make_int2(t[d].x, t[d].z | (t[d].w << 16));
     c->rs_key[0] = 0;
-    // the tables may still be read by a resize queued earlier on the context stream: stream-ordered, pageable source
-    CU(cudaMemcpyAsync(c->rs_tab, t.data(), t.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    // an earlier resize queued on the context stream may still read the tables: stream-ordered copy from pageable memory
+    CU(cudaMemcpyAsync(c->rs_tab, img.data(), img.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->rs_ytab = reinterpret_cast<const int4 *>(c->rs_tab);
+    c->rs_xtab = reinterpret_cast<const int2 *>(reinterpret_cast<const char *>(c->rs_tab) + ybytes);
     c->rs_key[0] = sh; c->rs_key[1] = sw; c->rs_key[2] = dh; c->rs_key[3] = dw;
     return 0;
 }
@@ -499,7 +508,7 @@ int yolo_b200_resize_u8bgr(yolo_b200_ctx *c, const uint8_t *d_src, int n, int sh
     if (n == 0) return 0;
     if (!d_src || !d_dst) return fail(E_ARG, "null buffer");
     int rc = ensure_resize_tables(c, sh, sw, dh, dw); if (rc) return rc;
-    CU(resize_u8bgr(d_src, n, sh, sw, d_dst, dh, dw, c->rs_tab, c->rs_tab + dw, c->sm_count, c->stream));
+    CU(resize_u8bgr(d_src, n, sh, sw, d_dst, dh, dw, c->rs_xtab, c->rs_ytab, c->sm_count, c->stream));
     c->launches++;
     return 0;
 }
@@ -945,7 +954,7 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         tr.mark("h2d done", k, c->s_in);
         CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
         if (resize) {
-            cudaError_t e = resize_u8bgr((const uint8_t *)land, nk, sh, sw, (uint8_t *)stage, h, w, c->rs_tab, c->rs_tab + w, c->sm_count, c->stream);
+            cudaError_t e = resize_u8bgr((const uint8_t *)land, nk, sh, sw, (uint8_t *)stage, h, w, c->rs_xtab, c->rs_ytab, c->sm_count, c->stream);
             if (e != cudaSuccess) { drain(); return fail(E_CUDA, "resize: %s", cudaGetErrorString(e)); }
             c->launches++;
         }
