@@ -179,3 +179,32 @@ def test_resize_taps_match_the_oracle(L):
             i0, i1, c0, c1 = ro.axis_table(src, dst, bool(horizontal))
             np.testing.assert_array_equal(taps, np.stack([i0, i1, c0, c1], axis=1), err_msg="%d -> %d h=%d" % (src, dst, horizontal))
     assert L.yolo_b200_resize_taps(0, 4, 1, None) < 0
+
+
+def test_bn_fold_matches_the_reference_function():
+    """export.fold_bn / fold_bn_state_dict against the reference's own `fuse_conv_and_bn` (conv+bn2conv.py:126-150) run
+    on the reference's un-fused SlimYOLOv2 (tests/golden/bnfold_ref.npz, oracle/gen_golden_bnfold.py): bit-exact weights
+    and biases, BatchNorm keys gone, the fused keys are the ones SlimYOLOv2_quantize_bnfuse loads."""
+    import hashlib
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bnfold_ref.npz"))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in/")}
+    sd["pred.weight"] = torch.zeros(35, 256, 3, 3)                         # a module without BatchNorm passes through
+    fused = ex.fold_bn_state_dict(sd)
+    assert not any(".convs.1." in k for k in fused)
+    assert "pred.weight" in fused and fused["pred.weight"] is sd["pred.weight"]
+    names = sorted({k.split("/")[1] for k in g.files if k.startswith("out/")})
+    assert len(names) == 6
+    for k in names:
+        np.testing.assert_array_equal(fused[k].numpy(), g["out/" + k], err_msg=k)
+        assert hashlib.sha256(np.ascontiguousarray(fused[k].numpy()).tobytes()).hexdigest() == str(g["sha/" + k])
+        assert k.rsplit(".", 1)[0] in ex.SLIM_CONV_KEYS
+    # nested modules (what conv+bn2conv.py:317-326 cannot reach) and members after the BatchNorm moving down one index
+    nested = {"backbone.layer1.convs.0.weight": sd["conv1.convs.0.weight"], "backbone.layer1.convs.0.bias": sd["conv1.convs.0.bias"],
+              "backbone.layer1.convs.3.weight": torch.ones(2)}
+    for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+        nested["backbone.layer1.convs.1." + k] = sd["conv1.convs.1." + k]
+    f2 = ex.fold_bn_state_dict(nested)
+    assert sorted(f2) == ["backbone.layer1.convs.0.bias", "backbone.layer1.convs.0.weight", "backbone.layer1.convs.2.weight"]
+    np.testing.assert_array_equal(f2["backbone.layer1.convs.0.weight"].numpy(), g["out/conv1.convs.0.weight"])
+    with pytest.raises(ValueError):
+        ex.fold_bn_state_dict({"bn.0.running_var": torch.ones(2)})

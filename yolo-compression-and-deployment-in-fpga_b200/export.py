@@ -3,6 +3,8 @@
 The reference has NO exporter: `c_embedding/weight.h` is produced by an unpublished step
 (`.MISSING_LARGE_BLOBS:1`).  This module is that missing link, following the reference's own rules:
 
+* BatchNorm folding ................. conv+bn2conv.py:126-150 (`fuse_conv_and_bn`), generalised to nested modules
+  (`fold_bn_state_dict`; the reference's loop :317-326 only visits top-level children).
 * weight / bias quantisation ........ retune_bias_quantize.py:73-97 (`quantize_tensor`, `quantize_tensor_b`):
   per-tensor ``s = 2**floor(log2(127 / max|t|))``, ``q = round(s * t)`` (torch.round = half-to-even).
 * activation scale calibration ...... models/slim_yolo_v2.py:16-38 (`AveragedRangeTracker`, first-call rule).
@@ -97,6 +99,53 @@ class QuantNet:
             sd[key + ".scale"] = torch.tensor([2.0 ** self.sa[l]])
             sd[key + ".first_a"] = torch.ones(1)
         return sd
+
+
+def fold_bn(conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+            mean: torch.Tensor, var: torch.Tensor, eps: float = 1e-5):
+    """Conv + BatchNorm2d (eval statistics) -> one conv: `fuse_conv_and_bn`, conv+bn2conv.py:126-150, in the same float32
+    operation order (W' = diag(gamma / sqrt(eps + var)) W; b' = b + (beta - gamma * mean / sqrt(var + eps))).  The
+    reference multiplies by the diagonal matrix with torch.mm; every other term of those dot products is an exact zero,
+    so the row-wise product below is bit-identical (tests/test_host.py checks it against the reference's own output)."""
+    with torch.no_grad():
+        cout = conv_w.shape[0]
+        scale = gamma.div(torch.sqrt(eps + var))
+        w = (scale.view(cout, 1) * conv_w.reshape(cout, -1)).view(conv_w.shape)
+        b_conv = conv_b if conv_b is not None else torch.zeros(cout, dtype=conv_w.dtype)
+        b_bn = beta - gamma.mul(mean).div(torch.sqrt(var + eps))
+        return w, b_conv + b_bn
+
+
+def fold_bn_state_dict(sd: Dict[str, torch.Tensor], eps: float = 1e-5) -> Dict[str, torch.Tensor]:
+    """state_dict of an un-fused network (SlimYOLOv2, slim_yolo_v2.py:385: blocks `X.convs = Sequential(conv, bn, act)`,
+    utils/modules.py:6-18) -> state_dict of its BN-fused twin (SlimYOLOv2_quantize_bnfuse / Conv2d_fuse: `X.convs.0` with
+    a bias, no `X.convs.1`).  Generalises the loop of conv+bn2conv.py:317-326, which only visits top-level children: every
+    BatchNorm in the dict (any nesting depth, recognised by its `running_var`) is folded into the module one index before
+    it in the same Sequential, its keys are dropped, and later indices of that Sequential move down by one — the layout
+    the reference's `nn.Sequential(fused, *rest)` produces.  Keys of modules without a BatchNorm pass through."""
+    bn_prefixes = sorted(k[:-len(".running_var")] for k in sd if k.endswith(".running_var"))
+    out = dict(sd)
+    for bp in bn_prefixes:
+        parent, _, idx = bp.rpartition(".")
+        if not idx.isdigit() or int(idx) == 0:
+            raise ValueError("BatchNorm %s does not follow a convolution inside a Sequential" % bp)
+        cp = "%s.%d" % (parent, int(idx) - 1)
+        if cp + ".weight" not in sd or sd[cp + ".weight"].dim() != 4:
+            raise ValueError("no convolution at %s for BatchNorm %s" % (cp, bp))
+        w, b = fold_bn(sd[cp + ".weight"].float(), sd[cp + ".bias"].float() if cp + ".bias" in sd else None,
+                       sd[bp + ".weight"].float(), sd[bp + ".bias"].float(), sd[bp + ".running_mean"].float(),
+                       sd[bp + ".running_var"].float(), eps)
+        out[cp + ".weight"], out[cp + ".bias"] = w, b
+        for k in [k for k in out if k.startswith(bp + ".")]:
+            del out[k]
+        # later members of the Sequential move down by one index
+        moved = {}
+        for k in [k for k in out if k.startswith(parent + ".")]:
+            head, _, rest = k[len(parent) + 1:].partition(".")
+            if head.isdigit() and int(head) > int(idx):
+                moved["%s.%d.%s" % (parent, int(head) - 1, rest)] = out.pop(k)
+        out.update(moved)
+    return out
 
 
 def _float_convs_from_state_dict(sd: Dict[str, torch.Tensor]):
