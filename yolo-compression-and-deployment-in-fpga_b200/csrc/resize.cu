@@ -47,24 +47,26 @@ void resize_axis_table(int src, int dst, bool clamp_weights, int index_scale, in
 // One source row's contribution: the six bytes (tap 0 = bytes 0..2, tap 1 = bytes 3..5) that start `off` bytes into a
 // word-aligned view of the row, fetched as three aligned 32-bit words and realigned with funnel shifts (a warp's lanes
 // are ~4.6 bytes apart for 640 -> 416, so a word load touches two 128-byte lines).  CLAMP (only the rows whose windows
-// could reach past the end of the buffer, i.e. the last source rows of the last image): word indices are clamped to
-// `lim`, the last word of the buffer relative to this row; a clamped word only ever supplies bytes whose weight is zero
-// (tap 1 of a right-border pixel).
+// could reach past the end of the buffer, i.e. the last source rows of the last image): byte loads with indices clamped
+// to `lim`, the last byte of the buffer relative to this row; a clamped byte only ever supplies a zero-weight value
+// (tap 1 of a right-border pixel).  compute-sanitizer memcheck runs clean on the GPU tests with exact-size allocations.
 template <bool CLAMP>
 __device__ __forceinline__ void resize_row_taps(const unsigned char *__restrict__ rowb, unsigned off, unsigned lim, unsigned &lo, unsigned &hi)
 {
-    const unsigned sh = (off & 3u) * 8u;
-    unsigned w0, w1, w2;
     if (CLAMP) {
-        const unsigned *roww = reinterpret_cast<const unsigned *>(rowb);
-        const unsigned wi = off >> 2;
-        w0 = __ldg(roww + wi); w1 = __ldg(roww + min(wi + 1, lim)); w2 = __ldg(roww + min(wi + 2, lim));
+        // byte loads, indices clamped to the last byte of the buffer (`lim`, relative to rowb)
+        lo = 0; hi = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 4; ++k) lo |= (unsigned)__ldg(rowb + min(off + k, lim)) << (8 * k);
+#pragma unroll
+        for (unsigned k = 0; k < 2; ++k) hi |= (unsigned)__ldg(rowb + min(off + 4 + k, lim)) << (8 * k);
     } else {
+        const unsigned sh = (off & 3u) * 8u;
         const unsigned *a = reinterpret_cast<const unsigned *>(rowb + (off & ~3u));     // one address, three immediates
-        w0 = __ldg(a); w1 = __ldg(a + 1); w2 = __ldg(a + 2);
+        const unsigned w0 = __ldg(a), w1 = __ldg(a + 1), w2 = __ldg(a + 2);
+        lo = __funnelshift_r(w0, w1, sh);          // bytes off .. off+3
+        hi = __funnelshift_r(w1, w2, sh);          // bytes off+4 .. off+7
     }
-    lo = __funnelshift_r(w0, w1, sh);          // bytes off .. off+3
-    hi = __funnelshift_r(w1, w2, sh);          // bytes off+4 .. off+7
 }
 
 // a01 = weight0 | weight1 << 16 (units of 1/2048), B0/B1 = row weights << 16.  Per channel: the horizontal pass of one
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(256, 5) resize_u8c3_kernel(const uint8_t *__re
     const size_t src_frame = (size_t)sh * sw * 3, src_row = (size_t)sw * 3;
     const size_t delta = reinterpret_cast<uintptr_t>(src) & 3;                             // word-aligned view of the source
     const unsigned char *base = src - delta;
-    const size_t last_word = (delta + src_bytes - 1) >> 2;
+    const size_t end = delta + src_bytes;                                                  // one past the last source byte
     const int p = (4 * lane) / 3;
     const unsigned rsh = 8u * (unsigned)(4 * lane - 3 * p);
     unsigned dy = row % (unsigned)dh;
@@ -144,10 +146,10 @@ __global__ void __launch_bounds__(256, 5) resize_u8c3_kernel(const uint8_t *__re
         const unsigned d0 = (unsigned)o0 & 3u, d1 = (unsigned)o1 & 3u;
         // a window reaches at most 11 bytes past the start of its pixel; rows for which that stays inside the buffer need no clamp
         const size_t omax = o0 > o1 ? o0 : o1;
-        if (omax + src_row + 12 <= (last_word + 1) * 4) {
+        if (omax + src_row + 12 <= end) {
             resize_one_row<WORD_STORE, false>(r0, r1, d0, d1, 0u, 0u, (unsigned)yt.z, (unsigned)yt.w, xtab, drow, dw, lane, 0, 1, p, rsh);
         } else {
-            const size_t room0 = last_word - (o0 >> 2), room1 = last_word - (o1 >> 2);
+            const size_t room0 = end - 1 - (o0 & ~(size_t)3), room1 = end - 1 - (o1 & ~(size_t)3);
             resize_one_row<WORD_STORE, true>(r0, r1, d0, d1, (unsigned)room0, (unsigned)room1, (unsigned)yt.z, (unsigned)yt.w, xtab, drow, dw, lane, 0, 1, p, rsh);
         }
         drow += (size_t)dw * 3;
