@@ -13,9 +13,10 @@
 // issue-bound on the 64-bit index divisions; one row per CTA iteration (grid-stride) with DP2A / high-multiply
 // arithmetic 0.376 ms -- still 200 instructions per 32-pixel chunk, 72 of them row bookkeeping repeated by every warp and
 // 24 of them 64-bit addresses of the clamped word loads; this version (one warp per run of contiguous rows, clamping only
-// in the rows that can reach the end of the buffer) 0.207 ms = 1.78 TB/s of algorithmic bytes, 98 instructions per chunk,
-// 57 % issue utilisation at 40 resident warps per SM (ncu: profiles/resize_r1_ncu.txt).  Unrolling the chunk loop by two
-// (54 registers, 32 warps per SM) measured slower: 0.233 ms.
+// in the rows that can reach the end of the buffer) 0.207 ms at 47 registers / 40 resident warps per SM (98 instructions per
+// chunk, 57 % issue utilisation, long-scoreboard stalls: latency-bound), 0.193 ms (ncu: profiles/resize_r1_ncu.txt) =
+// 1.91 TB/s of algorithmic bytes capped at 40 registers / 48 warps (what ships).  Measured slower: the chunk loop unrolled
+// by two (54 registers, 32 warps: 0.233 ms), a 32-register cap (64 warps, spills: 0.226 ms).
 #include "kernels.h"
 
 #include <cmath>
@@ -122,7 +123,7 @@ __device__ __forceinline__ void resize_one_row(const unsigned char *__restrict__
 // chunk).  Everything that depends on the row only (taps, weights, row pointers, their misalignment) is warp-uniform.
 // WORD_STORE needs dst 4-byte aligned and dw % 4 == 0, so that every row and every 32-pixel chunk starts on a word.
 template <bool WORD_STORE>
-__global__ void __launch_bounds__(256, 5) resize_u8c3_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+__global__ void __launch_bounds__(256, 6) resize_u8c3_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
                                                           const int2 *__restrict__ xtab, const int4 *__restrict__ ytab,
                                                           unsigned rows, unsigned rows_per_warp, int sh, int sw, int dh, int dw, size_t src_bytes)
 {
@@ -165,7 +166,7 @@ cudaError_t resize_u8bgr(const uint8_t *src, int n, int sh, int sw, uint8_t *dst
     if (rows > 0x7fffffffull) return cudaErrorInvalidValue;
     // one wave of resident CTAs (8 warps each), equal runs of rows per warp
     const int threads = 256;
-    const size_t max_warps = (size_t)(sm_count > 0 ? sm_count : 148) * 5 * (threads / 32);     // 5 resident CTAs per SM at 47 registers
+    const size_t max_warps = (size_t)(sm_count > 0 ? sm_count : 148) * 6 * (threads / 32);     // 6 resident CTAs per SM at 40 registers
     const unsigned rows_per_warp = (unsigned)((rows + max_warps - 1) / max_warps);
     const size_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
     const size_t blocks = (warps + threads / 32 - 1) / (threads / 32);
