@@ -784,3 +784,34 @@ def test_forward_u8bgr_resize_equals_basetransform_then_forward(ctx):
     np.testing.assert_array_equal(c2, c2r)
     for i in range(2):
         np.testing.assert_array_equal(d2[i][:int(c2r[i])].view(np.int32), d2r[i][:int(c2r[i])].view(np.int32))
+
+
+@pytest.mark.gpu
+def test_detect_cli_video_mode(tmp_path):
+    """tools/detect.py --video (demo.py's video mode, :123-158): a synthetic MJPG clip goes through the GPU front end in
+    batches (ragged last batch) and comes back as an annotated clip with the same number of frames and frame size."""
+    import subprocess
+    import sys
+    cv2 = pytest.importorskip("cv2")
+    src = str(tmp_path / "clip.avi")
+    w = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"MJPG"), 10.0, (96, 72))
+    if not w.isOpened():
+        pytest.skip("this OpenCV build cannot write MJPG")
+    rng = np.random.default_rng(2)
+    for _ in range(7):
+        w.write(rng.integers(0, 256, (72, 96, 3), dtype=np.uint8))
+    w.release()
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "detect.py"), "--trained_model", "random", "--video", src,
+                        "-size", "64", "--batch", "3", "--out", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "7 frames" in r.stdout
+    cap = cv2.VideoCapture(str(out / "detections.avi"))
+    n = 0
+    while True:
+        ok, frame = cap.read()
+        if not ok:
+            break
+        assert frame.shape == (72, 96, 3)
+        n += 1
+    assert n == 7

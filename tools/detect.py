@@ -6,6 +6,7 @@ BaseTransform does, data/__init__.py:36) is normalised, quantised, convolved, de
 
     python tools/detect.py --trained_model slim_yolo_v2_retune_quantize1.pth --images dir/ -size 416 --out output/
     python tools/detect.py --trained_model random --images synthetic:4          (no checkpoint / no images at hand)
+    python tools/detect.py --trained_model ckpt.pth --video clip.avi --batch 32  (demo.py's video / camera modes, batched)
 """
 import argparse
 import glob
@@ -38,6 +39,43 @@ def vis(img, bboxes, scores, cls_inds, thresh):
     return img
 
 
+def run_video(ctx, args, size):
+    """demo.py video / camera modes (:60-96, :123-158) with the frames batched: `--batch` frames are read, go through
+    yolo_b200_forward_u8bgr_resize in one call (resize, normalise, quantise, network, decode, NMS on the GPU), are annotated
+    and appended to <out>/detections.avi (MJPG, the source's frame size and rate)."""
+    cap = cv2.VideoCapture(int(args.video) if args.video.isdigit() else args.video)
+    if not cap.isOpened():
+        raise SystemExit("cannot open video source %s" % args.video)
+    os.makedirs(args.out, exist_ok=True)
+    fps = cap.get(cv2.CAP_PROP_FPS) or 25.0
+    writer, frames, t_dev, done = None, 0, 0.0, False
+    while not done:
+        batch = []
+        while len(batch) < args.batch:
+            ok, frame = cap.read()
+            if not ok or (args.max_frames and frames + len(batch) >= args.max_frames):
+                done = True
+                break
+            batch.append(frame)
+        if not batch:
+            break
+        t0 = time.time()
+        dets, counts = ctx.forward_u8bgr_resize(np.stack(batch), size)
+        t_dev += time.time() - t0
+        for k, im in enumerate(batch):
+            boxes, scores, cls, _ = lib.dets_to_arrays(dets[k], int(min(counts[k], 1024)))
+            h, w = im.shape[:2]
+            out = vis(im, boxes * np.array([[w, h, w, h]], dtype=np.float32), scores, cls, args.visual_threshold)   # demo.py:143-149
+            if writer is None:
+                writer = cv2.VideoWriter(os.path.join(args.out, "detections.avi"), cv2.VideoWriter_fourcc(*"MJPG"), fps, (w, h))
+            writer.write(out)
+        frames += len(batch)
+    cap.release()
+    if writer is not None:
+        writer.release()
+    print("%d frames, %.1f ms in yolo_b200_forward_u8bgr_resize (%.0f frames/s incl. copies)" % (frames, 1e3 * t_dev, frames / max(t_dev, 1e-9)))
+
+
 def main():
     ap = argparse.ArgumentParser(description="slim_yolo_v2 fixed-point detection on B200")
     ap.add_argument("-v", "--version", default="slim_yolo_v2_q_bf", help="only slim_yolo_v2_q_bf runs on this path")
@@ -48,6 +86,8 @@ def main():
     ap.add_argument("--visual_threshold", default=0.3, type=float)
     ap.add_argument("--cuda", action="store_true", default=True, help="kept for compatibility: this path always runs on CUDA")
     ap.add_argument("--images", default="synthetic:2", help="directory / glob of images, or synthetic:N")
+    ap.add_argument("--video", default=None, help="video file (demo.py --mode video, :123-158) or camera index (--mode camera, :60-96): frames are batched, detected on the GPU and written, annotated, to <out>/detections.avi")
+    ap.add_argument("--max_frames", default=0, type=int, help="stop a --video run after this many frames (0 = to the end)")
     ap.add_argument("--out", default="output")
     ap.add_argument("--batch", default=64, type=int)
     args = ap.parse_args()
@@ -62,6 +102,10 @@ def main():
     ctx = lib.Context(0)
     ctx.load_quantnet(qnet, contract=lib.CONTRACT_P, head_mode=lib.HEAD_PYTHON, conf_thresh=args.conf_thresh,
                       nms_thresh=args.nms_thresh, max_det=1024)
+    if args.video is not None:
+        run_video(ctx, args, size)
+        ctx.close()
+        return
     if args.images.startswith("synthetic:"):
         rng = np.random.default_rng(0)
         imgs = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(int(args.images.split(":")[1]))]
