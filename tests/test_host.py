@@ -62,6 +62,11 @@ def test_no_cpu_fallback(L):
     # null-argument error behaviour needs no device
     assert L.yolo_b200_default_params(None) < 0
     assert L.yolo_b200_set_stream(None, None) < 0
+    # the image front end has no host path either: without a context every entry point is an error, not a CPU resize
+    buf = np.zeros(4 * 4 * 3, dtype=np.uint8)
+    assert L.yolo_b200_resize_u8bgr(None, buf.ctypes.data, 1, 4, 4, buf.ctypes.data, 4, 4) < 0
+    assert L.yolo_b200_forward_u8bgr_resize(None, buf.ctypes.data, 1, 4, 4, 4, 4, None, None) < 0
+    assert L.yolo_b200_forward_u8bgr_resize_dev(None, None, 1, 4, 4, 4, 4, None, None) < 0
 
 
 def test_quantise_rule_is_idempotent_on_checkpoints():
