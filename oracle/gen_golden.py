@@ -75,8 +75,18 @@ def nhwc_pad(t_int: torch.Tensor) -> np.ndarray:
     return out
 
 
+def basetransform_frame(img_seed, H, W, image_kind="noise"):
+    """x = BaseTransform([H, W])(rng(seed).integers(0, 256, (480, 640, 3), u8)) through the
+    reference's own data/__init__.py (cv2.resize + normalisation), then the BGR -> RGB / CHW swap of test.py:79-80."""
+    data = importlib.import_module("data")
+    img = load_pkg().export.synthetic_image_u8(img_seed, kind=image_kind)
+    x, _, _ = data.BaseTransform([H, W])(img)
+    x = x[:, :, (2, 1, 0)]
+    return torch.from_numpy(np.ascontiguousarray(x)).permute(2, 0, 1).unsqueeze(0).contiguous()
+
+
 def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, head_bias_shift=0.0,
-             max_seed_tries=40):
+             max_seed_tries=40, frame_kind="synthetic", head_gain=1.0, image_kind="noise", weight_gain=1.0):
     refmod, quantize_tensor, quantize_tensor_b = import_reference()
     yb = load_pkg()
     ex = yb.export
@@ -88,6 +98,18 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
     net.eval()
     # our exporter must draw the same random-init weights without the reference present
     ws, bs = ex.random_float_convs(seed)
+    if weight_gain != 1.0:
+        with torch.no_grad():
+            for cname in ex.SLIM_CONV_KEYS:
+                mod = net
+                for part in cname.split("."):
+                    mod = mod[int(part)] if part.isdigit() else getattr(mod, part)
+                mod.weight *= weight_gain
+        ws = [w * weight_gain for w in ws]
+    if head_gain != 1.0:
+        with torch.no_grad():
+            net.pred.weight *= head_gain
+        ws[-1] = ws[-1] * head_gain
     if head_bias_shift:
         with torch.no_grad():
             net.pred.bias[:5] += head_bias_shift
@@ -177,7 +199,7 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
 
     out = {
         "H": H, "W": W, "seed": seed, "n_frames": n_frames, "conf_thresh": conf_thresh, "nms_thresh": nms_thresh,
-        "head_bias_shift": float(head_bias_shift),
+        "head_bias_shift": float(head_bias_shift), "frame_kind": frame_kind, "head_gain": float(head_gain), "image_kind": image_kind, "weight_gain": float(weight_gain),
         "anchors": np.asarray(anchors, dtype=np.float32),
         "sa": np.asarray(qnet.sa, np.int32), "sw": np.asarray(qnet.sw, np.int32),
         "sb": np.asarray(qnet.sb, np.int32), "retune": np.asarray(qnet.retune, np.int32),
@@ -185,16 +207,17 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
         "torch_version": torch.__version__, "numpy_version": np.__version__,
     }
     frame_seeds = []
-    fseed = 2000 + seed
+    fseed = 2000 + seed if frame_kind == "synthetic" else 0
+    fseed0 = fseed
     i = 0
     while i < n_frames:
-        frame = ex.synthetic_frames_f32(1, H, W, seed=fseed)
+        frame = ex.synthetic_frames_f32(1, H, W, seed=fseed) if frame_kind == "synthetic" else basetransform_frame(fseed, H, W, image_kind)
         captured.clear(); head_in.clear()
         with torch.no_grad():
             bboxes, scores, cls_inds = net(frame, quantization=True)
         assert len(captured) == 11
         robust = tie_robust(head_in[0][0], head_in[0][1], np.asarray(scores, np.float32))
-        if not robust and fseed - (2000 + seed) < max_seed_tries:
+        if not robust and fseed - fseed0 < max_seed_tries:
             fseed += 1          # look for a frame whose reference result does not hinge on NumPy's tie order
             continue
         # trackers sit BEFORE the pools (slim_yolo_v2.py:229-231); a layer's output map is after its pool.
@@ -225,11 +248,28 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    _generate = generate
+
+    def generate(name, *a, **k):     # noqa: F811  (python oracle/gen_golden.py [fixture ...] regenerates only those)
+        if not only or name in only:
+            _generate(name, *a, **k)
     # small, non-square, every map stored: layer-by-layer parity
     generate("ref_p_64x96", 64, 96, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=2, store_maps=True)
     # sparse head variant (few detections, exercises thresholding), odd grid (80/16 = 5)
     generate("ref_p_80x64_sparse", 80, 64, seed=1, conf_thresh=0.1, nms_thresh=0.45, n_frames=1, store_maps=True,
              head_bias_shift=-1.4)
     # BASELINE.json configs[1]: batch 1 at 416x416; digests of the maps + input/pred maps + detections
+    # SURVEY 8d config 2 literally: the frame is BaseTransform([416, 416]) of rng(0) uint8 480x640 noise through the reference's
+    # own cv2 front end.  With an 8-bit, two-class head the reference's ~3400 candidates share a few hundred distinct
+    # scores, so its kept set hinges on NumPy's unstable argsort for EVERY frame (no tie-robust seed exists: pigeonhole);
+    # the tests compare the maps bit for bit and hold the detections to "a greedy outcome of the same candidates under
+    # some order of the tied scores" (tests/golden_util.py: greedy_consistent).
     generate("ref_p_416x416", 416, 416, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=1, store_maps=False,
-             max_seed_tries=0)
+             max_seed_tries=0, frame_kind="basetransform")
+    # the same size with a trained-like network (He-like gain on every layer so that the scene survives the ten layers,
+    # objectness bias - 3, head gain 4) on a structured scene: ~440 candidates with a tie-robust reference result, so the
+    # reference's DETECTIONS are compared one by one at 416x416
+    generate("ref_p_416x416_sparse", 416, 416, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=2, store_maps=False,
+             max_seed_tries=200, frame_kind="basetransform", image_kind="scene", weight_gain=2.0, head_bias_shift=-3.0,
+             head_gain=4.0)

@@ -374,6 +374,54 @@ ORACLE_API int oracle_nms_python(const float *boxes, const float *scores, const 
  * (:1114-1126), class-agnostic NMS suppressing iou >= thresh on integer boxes (:1000-1036,1128-1147). */
 static float c_sigmoid(float x) { return (float)(1 / (exp((double)x) + 1)); }
 
+/* conf_sort: selection sort by swapping, strict '>' (yolo_forward.c:1114-1126).  The order it leaves among EQUAL scores
+ * depends on the swap history; NMS (:1128-1147) is order dependent, so the sort is restated literally. */
+static void c_conf_sort(oracle_det *b, int m)
+{
+    for (int i = 0; i < m - 1; ++i)
+        for (int j = i + 1; j < m; ++j)
+            if (b[j].score > b[i].score) { oracle_det t = b[j]; b[j] = b[i]; b[i] = t; }
+}
+
+/* NMS (:1128-1147): class-agnostic, suppress iou >= thresh, on integer boxes (box_iou :1000-1036). dead[] must be zeroed. */
+static void c_nms(const oracle_det *b, int m, float nms_thresh, char *dead)
+{
+    for (int i = 0; i < m; ++i) {
+        if (dead[i]) continue;
+        for (int j = i + 1; j < m; ++j) {
+            int ax1 = (int)b[i].x1, ax2 = (int)b[i].x2, ay1 = (int)b[i].y1, ay2 = (int)b[i].y2;
+            int bx1 = (int)b[j].x1, bx2 = (int)b[j].x2, by1 = (int)b[j].y1, by2 = (int)b[j].y2;
+            /* overlap(): sum of sides minus hull (:1000-1004) */
+            int ow = (ax2 - ax1 + bx2 - bx1) - ((ax2 > bx2 ? ax2 : bx2) - (ax1 <= bx1 ? ax1 : bx1));
+            int oh = (ay2 - ay1 + by2 - by1) - ((ay2 > by2 ? ay2 : by2) - (ay1 <= by1 ? ay1 : by1));
+            int inter = (ow <= 0 || oh <= 0) ? 0 : ow * oh;
+            int uni = (ax2 - ax1) * (ay2 - ay1) + (bx2 - bx1) * (by2 - by1) - inter;
+            float iou = (float)inter / (float)uni;
+            if (iou >= nms_thresh) dead[j] = 1;
+        }
+    }
+}
+
+/* The sort + NMS of the restated C head on caller-provided boxes {x_max, x_min, y_max, y_min} and scores (the same argument
+ * convention as oracle/tierA_shim.c: tierA_sort_nms, so tests can lay the two side by side, ties included): order[i] =
+ * original index at sorted position i, suppressed[i] = its flag.  Returns the number kept. */
+ORACLE_API int oracle_conf_sort_nms(int n, const int *boxes, const float *conf, float thresh, int *order, int *suppressed)
+{
+    oracle_det *b = (oracle_det *)malloc(sizeof(oracle_det) * (size_t)(n > 0 ? n : 1));
+    char *dead = (char *)calloc((size_t)(n > 0 ? n : 1), 1);
+    for (int i = 0; i < n; ++i) {
+        b[i].x2 = (float)boxes[4 * i]; b[i].x1 = (float)boxes[4 * i + 1]; b[i].y2 = (float)boxes[4 * i + 2]; b[i].y1 = (float)boxes[4 * i + 3];
+        b[i].score = conf[i]; b[i].cls = 0; b[i].anchor_index = i; b[i].pad_ = 0;
+    }
+    c_conf_sort(b, n);
+    c_nms(b, n, thresh, dead);
+    int kept = 0;
+    for (int i = 0; i < n; ++i) { order[i] = b[i].anchor_index; suppressed[i] = dead[i]; kept += !dead[i]; }
+    free(dead); free(b);
+    return kept;
+}
+
+
 ORACLE_API int oracle_head_c(const int8_t *pred, int gh, int gw, int cs, int A,
                              int sa_pred, const float *anchors, int stride,
                              float conf_thresh, float nms_thresh, oracle_det *dets, int max_det)
@@ -405,27 +453,14 @@ ORACLE_API int oracle_head_c(const int8_t *pred, int gh, int gw, int cs, int A,
             d->score = conf; d->cls = c; d->anchor_index = cell * A + a; d->pad_ = 0;
         }
     }
-    /* conf_sort: selection sort by swapping, strict '>' (:1114-1126) */
-    for (int i = 0; i < m - 1; ++i)
-        for (int j = i + 1; j < m; ++j)
-            if (b[j].score > b[i].score) { oracle_det t = b[j]; b[j] = b[i]; b[i] = t; }
+    c_conf_sort(b, m);
     char *dead = (char *)calloc((size_t)(m > 0 ? m : 1), 1);
+    c_nms(b, m, nms_thresh, dead);
     int cnt = 0;
     for (int i = 0; i < m; ++i) {
         if (dead[i]) continue;
         if (cnt < max_det) dets[cnt] = b[i];
         ++cnt;
-        for (int j = i + 1; j < m; ++j) {
-            int ax1 = (int)b[i].x1, ax2 = (int)b[i].x2, ay1 = (int)b[i].y1, ay2 = (int)b[i].y2;
-            int bx1 = (int)b[j].x1, bx2 = (int)b[j].x2, by1 = (int)b[j].y1, by2 = (int)b[j].y2;
-            /* overlap(): sum of sides minus hull (:1000-1004) */
-            int ow = (ax2 - ax1 + bx2 - bx1) - ((ax2 > bx2 ? ax2 : bx2) - (ax1 <= bx1 ? ax1 : bx1));
-            int oh = (ay2 - ay1 + by2 - by1) - ((ay2 > by2 ? ay2 : by2) - (ay1 <= by1 ? ay1 : by1));
-            int inter = (ow <= 0 || oh <= 0) ? 0 : ow * oh;
-            int uni = (ax2 - ax1) * (ay2 - ay1) + (bx2 - bx1) * (by2 - by1) - inter;
-            float iou = (float)inter / (float)uni;
-            if (iou >= nms_thresh) dead[j] = 1;
-        }
     }
     free(dead); free(b);
     return cnt;

@@ -88,6 +88,19 @@ def test_contract_p_against_reference_golden(ctx, name):
             np.testing.assert_array_equal(c, g["f%d_cls" % i])
             np.testing.assert_allclose(s, g["f%d_scores" % i], atol=1e-5, rtol=0)
             np.testing.assert_allclose(b, g["f%d_bboxes" % i], atol=1e-5, rtol=0)
+        else:
+            # the reference's own kept set hinges on NumPy's unstable argsort (tied scores that overlap): both lists must
+            # be greedy outcomes of the reference's candidates under some order of the ties, and agree elsewhere
+            rk, rb_, rs_, rc_ = gu.reference_kept_indices(g, i)
+            conf, nt = float(g["conf_thresh"]), float(g["nms_thresh"])
+            assert gu.greedy_consistent(rb_, rs_, rc_, rk, conf, nt) == []
+            assert gu.greedy_consistent(rb_, rs_, rc_, idx, conf, nt) == []
+            differ = sorted(set(rk.tolist()) ^ set(idx.tolist()))
+            assert len([a for a in differ if not gu.tie_affected(rb_, rs_, rc_, a, nt)]) <= len(differ) // 2
+            both = sorted(set(rk.tolist()) & set(idx.tolist()))
+            sel = np.isin(idx, both)
+            np.testing.assert_allclose(s[sel], rs_[both], atol=1e-5, rtol=0)
+            np.testing.assert_allclose(b[sel], rb_[both], atol=1e-5, rtol=0)
         # every frame: identical kept set to the oracle (same deterministic tie rule)
         (ob, os_, oc, oidx), ocnt = ol.head_python(outs[-1][0], 5, 2, qnet.sa[10], qnet.anchors, 16, H, W,
                                                    float(g["conf_thresh"]), float(g["nms_thresh"]))
@@ -253,29 +266,32 @@ def test_rgb444_frontend_and_shipped_tables_320x240(ctx):
 
 
 def test_c_head_mode_against_oracle(ctx):
+    """HEAD_C: decode, strict threshold, conf_sort's order INCLUDING the order its swap history leaves among equal scores
+    (yolo_forward.c:1114-1126; pinned on the reference's compiled function by
+    tests/test_oracle.py::test_c_sort_nms_tie_order_matches_reference_c), class-agnostic NMS: identical lists, no tolerance.
+    Narrow value ranges make most scores collide; the wide range exercises the tie-free fast path."""
     g, qnet, frames = gu.load("ref_p_64x96")
     import copy
     q = copy.deepcopy(qnet)
     q.anchors = [list(a) for a in ex.ANCHOR_SIZE_COCO]
     rng = np.random.default_rng(5)
-    for trial, thresh in enumerate((0.01, 0.2, 0.3)):
-        ctx.load_quantnet(q, contract=lib.CONTRACT_F, head_mode=lib.HEAD_C, conf_thresh=thresh, nms_thresh=0.5)
-        pred = np.zeros((2, 15, 20, 48), dtype=np.int8)
-        pred[..., :35] = rng.integers(-60, 60, (2, 15, 20, 35), dtype=np.int8)
-        dets, counts = det_arrays(ctx, dev(pred), 2, 15, 20, 240, 320)
-        for i in range(2):
-            (ob, os_, oc, oidx), ocnt = ol.head_c(pred[i], 5, q.sa[10], q.anchors, 16, thresh, 0.5)
-            b, s, c, idx = lib.dets_to_arrays(dets[i], int(counts[i]))
-            # score ties are ordered differently by the reference's swap-selection sort (oracle/DEVIATIONS.md):
-            # compare on the tie-free prefix semantics: same kept SET when all kept scores are distinct
-            if len(np.unique(os_)) == len(os_) and len(np.unique(s)) == len(s):
+    saw_ties = 0
+    for trial, (thresh, span) in enumerate(((0.01, 60), (0.2, 60), (0.3, 60), (0.01, 3), (0.05, 8), (0.1, 20), (0.0, 1))):
+        ctx.load_quantnet(q, contract=lib.CONTRACT_F, head_mode=lib.HEAD_C, conf_thresh=thresh, nms_thresh=0.5, max_det=4096)
+        for (n, gh, gw) in ((2, 15, 20), (1, 26, 26)):
+            pred = np.zeros((n, gh, gw, 48), dtype=np.int8)
+            pred[..., :35] = rng.integers(-span, span, (n, gh, gw, 35), dtype=np.int8)
+            dets, counts = det_arrays(ctx, dev(pred), n, gh, gw, gh * 16, gw * 16)
+            for i in range(n):
+                (ob, os_, oc, oidx), ocnt = ol.head_c(pred[i], 5, q.sa[10], q.anchors, 16, thresh, 0.5)
+                b, s, c, idx = lib.dets_to_arrays(dets[i], int(counts[i]))
+                saw_ties += len(set(os_.tolist())) != len(os_)
                 assert counts[i] == ocnt
                 np.testing.assert_array_equal(idx, oidx)
                 np.testing.assert_array_equal(c, oc)
                 np.testing.assert_allclose(s, os_, atol=1e-6, rtol=0)
                 np.testing.assert_array_equal(b, ob)
-            else:
-                assert abs(int(counts[i]) - ocnt) <= 3
+    assert saw_ties >= 6
 
 
 @pytest.mark.parametrize("sa_pred", [2, 4, 6])
@@ -333,6 +349,48 @@ def test_empty_batch_and_errors(ctx):
             fresh.load(qnet.w, qnet.b, bad)
     finally:
         fresh.close()
+
+
+@pytest.mark.parametrize("contract", [lib.CONTRACT_F, lib.CONTRACT_P])
+def test_bench_workload_batch256_against_oracle(ctx, contract):
+    """The configuration bench.py times (BASELINE configs[2]): 256 RGB444 camera frames of 416x416, the bench's own network
+    and first input set, through the device entry point AND the host entry point yolo_b200_forward_rgb444.  Frames 0, 1,
+    127, 254, 255 (first / last of the canvas, a middle one) are compared with the oracle: every layer's map and the
+    detection list; all 256 counts and lists must agree between the two entry points."""
+    B, H, W = 256, 416, 416
+    check = [0, 1, 127, 254, 255]
+    qnet = ex.random_quantnet(seed=0, calib_hw=(H, W), calib_frames=2, calib_input="rgb444")      # bench.make_qnet()
+    ctx.load_quantnet(qnet, contract=contract, round_mode=lib.ROUND_RNE, conf_thresh=0.1, nms_thresh=0.5, max_det=4096)
+    frames = ex.synthetic_frames_rgb444(B, H, W, seed=0)                                          # bench: seed 100 * rank + set
+    d = torch.from_numpy(frames.view(np.int16)).cuda()
+    d_dets = torch.zeros((B, 4096, 8), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    ctx.forward_rgb444_dev(d, B, H, W, d_dets, d_counts)
+    ctx.sync()
+    counts = d_counts.cpu().numpy()
+    dets = d_dets.cpu().numpy().view(lib.DET_DTYPE).reshape(B, 4096)
+    shapes = layer_shapes(qnet, H, W)
+    x8 = ol.quantize_rgb444(frames[check], qnet.sa[0])
+    ref, _ = ol.backbone(qnet, x8, contract=contract)
+    for l, (oh, ow) in enumerate(shapes):
+        got = ctx.layer_output(l, B, oh, ow)
+        for k, f in enumerate(check):
+            assert np.array_equal(got[f], ref[l][k]), "layer %d, frame %d of the 256-frame batch differs from the oracle" % (l, f)
+        del got
+    for k, f in enumerate(check):
+        (ob, os_, oc, oidx), ocnt = ol.head_python(ref[-1][k], 5, 2, qnet.sa[10], qnet.anchors, 16, H, W, 0.1, 0.5)
+        b, s_, c, idx = lib.dets_to_arrays(dets[f], int(counts[f]))
+        assert counts[f] == ocnt
+        np.testing.assert_array_equal(idx, oidx)
+        np.testing.assert_array_equal(c, oc)
+        np.testing.assert_allclose(s_, os_, atol=1e-5, rtol=0)
+        np.testing.assert_allclose(b, ob, atol=1e-5, rtol=0)
+    # the host entry point (chunked copies, head on a second stream) must return the same lists for all 256 frames
+    hdets, hcounts = ctx.forward_rgb444(frames)
+    np.testing.assert_array_equal(hcounts, counts)
+    for f in range(B):
+        n = int(counts[f])
+        assert hdets[f][:n].tobytes() == dets[f][:n].tobytes(), "host and device entry points differ on frame %d" % f
 
 
 def test_frames_are_independent_at_full_size(ctx):

@@ -55,9 +55,17 @@ def test_python_head_matches_reference(name):
             np.testing.assert_allclose(scores, g["f%d_scores" % i], atol=1e-5, rtol=0)
             np.testing.assert_allclose(boxes, g["f%d_bboxes" % i], atol=1e-5, rtol=0)
         else:
-            # tied scores: the reference's own answer depends on the NumPy build; every detection the reference
-            # kept must at least be a candidate here, and the counts must be close
-            assert abs(cnt - len(g["f%d_scores" % i])) <= max(8, len(g["f%d_scores" % i]) // 50)
+            # tied scores that matter: the reference's own answer depends on NumPy's unstable argsort (its build / CPU).
+            # Both answers must be greedy outcomes of the same candidates under some order of the ties.
+            rk, rb_, rs_, rc_ = gu.reference_kept_indices(g, i)
+            conf, nt = float(g["conf_thresh"]), float(g["nms_thresh"])
+            assert gu.greedy_consistent(rb_, rs_, rc_, rk, conf, nt) == []
+            assert gu.greedy_consistent(rb_, rs_, rc_, idx, conf, nt) == []
+            # and they may differ only on candidates that overlap an equal-score candidate: everything else is pinned
+            differ = sorted(set(rk.tolist()) ^ set(idx.tolist()))
+            chain = [a for a in differ if not gu.tie_affected(rb_, rs_, rc_, a, nt)]
+            # (a candidate next to a tie-affected one may flip with it: allow only those whose kept suppressors differ)
+            assert len(chain) <= len(differ) // 2, chain
 
 
 def test_shift_programme_matches_reference_c():
@@ -166,6 +174,76 @@ def test_c_sort_nms_matches_reference_c():
                 if iou >= 0.5:
                     dead[b_i] = True
         assert mine == ref_kept
+
+
+def test_c_sort_nms_tie_order_matches_reference_c():
+    """conf_sort is a swap-selection sort (yolo_forward.c:1114-1126): with EQUAL scores the order it leaves depends on the
+    swap history, and NMS (:1128-1147) depends on that order.  The oracle's sort + NMS must reproduce the reference's own
+    compiled functions on inputs FULL of ties (scores drawn from a handful of values): same permutation, same flags."""
+    t = ol.tierA()
+    if t is None:
+        pytest.skip("oracle/_ref/libtierA.so not built (reference absent)")
+    L = ol.lib()
+    L.oracle_conf_sort_nms.restype = C.c_int
+    L.oracle_conf_sort_nms.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        n = int(rng.integers(2, 200))
+        levels = int(rng.integers(1, 8))
+        x1 = rng.integers(0, 200, n); y1 = rng.integers(0, 150, n)
+        x2 = x1 + rng.integers(1, 120, n); y2 = y1 + rng.integers(1, 120, n)
+        boxes = np.stack([x2, x1, y2, y1], 1).astype(np.int32)
+        if len({tuple(b) for b in boxes}) != n:           # the shim maps sorted entries back by (score, box): keep boxes unique
+            continue
+        conf = (rng.integers(0, levels, n).astype(np.float32) + 1) / np.float32(levels + 1)
+        ro = (C.c_int * n)(); rs = (C.c_int * n)(); oo = (C.c_int * n)(); os_ = (C.c_int * n)()
+        bp, cp = boxes.ctypes.data_as(C.POINTER(C.c_int)), conf.ctypes.data_as(C.POINTER(C.c_float))
+        rk = t.tierA_sort_nms(n, bp, cp, C.c_float(0.5), ro, rs)
+        ok = L.oracle_conf_sort_nms(n, bp, cp, C.c_float(0.5), oo, os_)
+        assert list(ro) == list(oo), "tie order differs from conf_sort (trial %d)" % trial
+        assert [int(v != 0) for v in rs] == [int(v != 0) for v in os_]
+        assert rk == ok
+
+
+def test_tier_b_literal_first_conv_over_accelerator_model():
+    """Tier B: the reference's LITERAL first_conv (yolo_forward.c:269-418) driving a host model of the accelerator
+    (oracle/tierB_shim.c) on one 240x320 RGB444 frame with the as-shipped tables.  Pins how far the literal driver agrees
+    with the clean restatement, and the divergences ledgered in oracle/DEVIATIONS.md (B1-B5):
+      * every pixel of all 14 x 15 interior tiles is identical once the tile-row placement bug (:283, B3) is undone;
+      * literally placed, only the first tile row (minus its right-edge tile) lands where it should;
+      * right-edge tiles are garbled (fill pitch, :101-113, B2); the bottom tile row's last output row is wrong (B4);
+      * 16 zero-height remainder tiles are started (:287-289, B5)."""
+    import ctypes as C
+    import os
+    so = os.path.join(ol.ORACLE_DIR, "_ref", "libtierB.so")
+    ol.build()
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libtierB.so not built (reference absent)")
+    B = C.CDLL(so)
+    rng = np.random.default_rng(0)
+    frame = np.zeros(240 * 320 + 64 * 320, np.int16)          # slack: the driver reads one row past the frame (B4)
+    frame[:240 * 320] = rng.integers(0, 4096, 240 * 320)
+    w = rng.integers(-6, 6, (16, 3, 3, 3), dtype=np.int8)
+    b = np.zeros(32, np.int8)
+    b[:16] = rng.integers(-40, 40, 16)
+    wh = ex.pack_weight_h_order(w)
+    out = np.zeros(256 * 160 * 16, np.int8)
+    stats = (C.c_long * 6)()
+    rc = B.tierB_first_conv(frame.ctypes.data_as(C.POINTER(C.c_short)), wh.ctypes.data_as(C.POINTER(C.c_int8)),
+                            b.ctypes.data_as(C.POINTER(C.c_int8)), out.ctypes.data_as(C.POINTER(C.c_int8)), out.size, stats)
+    assert rc == 0
+    assert list(stats)[:5] == [256, 16, 0, 0, 0]              # tiles started, zero-height tiles, no out-of-range buffer access
+    x8 = ol.quantize_rgb444(frame[:240 * 320].view(np.uint16).reshape(1, 240, 320), ex.SHIPPED_SCALE_A[0])
+    ref, _ = ol.conv_layer(x8, w, b[:16], 3, 16, ex.SHIPPED_SCALE_A[0], ex.SHIPPED_SCALE_W[0], ex.SHIPPED_SCALE_B[0],
+                           ex.SHIPPED_RETUNE[0], ex.SHIPPED_SCALE_A[1], 1, 1, 0, 0)
+    got = out.reshape(256, 160, 16)
+    literal = (got[:120] == ref[0]).all(axis=2).reshape(15, 8, 16, 10).mean(axis=(1, 3))
+    assert np.all(literal[0, :15] == 1.0) and np.all(literal[1:] < 1.0)
+    fixed = np.stack([got[16 * (r // 8) + r % 8] for r in range(120)])          # tile row tr landed at PSRAM row 16 tr
+    per_tile = (fixed == ref[0]).all(axis=2).reshape(15, 8, 16, 10).mean(axis=(1, 3))
+    assert np.all(per_tile[:14, :15] == 1.0)
+    assert np.all(per_tile[:, 15] < 0.5)
+    assert np.all(per_tile[14, :15] == 0.875)
 
 
 def test_requant_properties():

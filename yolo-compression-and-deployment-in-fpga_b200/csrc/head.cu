@@ -136,6 +136,8 @@ struct NmsSmem {
     unsigned ghead[NMS_BUCKETS * NMS_GRID * NMS_GRID];             // first kept entry of the list, NMS_END = empty
     unsigned short gnext[HEAD_MAX_CAND];                           // next entry of the same list
     float gw[NMS_BUCKETS], gh[NMS_BUCKETS];                        // widest / tallest kept box of the bucket (-1 = empty)
+    unsigned long long wtot[NMS_THREADS / 32];                     // C head, conf_sort emulation: per-warp prefix maxima
+    unsigned tie_min;                                              // C head: lowest score (bits) that occurs twice
 };
 
 // block-wide exclusive scan of a 0/1 flag; returns this thread's offset, *total = sum over the block
@@ -225,6 +227,106 @@ __device__ __forceinline__ int nms_bucket(float area, float bscale)
 }
 __device__ __forceinline__ int nms_cell(float c) { return min(max((int)(c * (float)NMS_GRID), 0), NMS_GRID - 1); }
 
+
+// conf_sort (yolo_forward.c:1114-1126) is a selection sort BY SWAPPING with a strict '>': pass i walks j = i+1.. and swaps
+// src[j] into slot i whenever it beats the current occupant, so slot i ends with the first maximum of the tail and every
+// strict prefix maximum ("record") of the tail moves to the slot of the NEXT record.  The result is sorted by score, but
+// the order among EQUAL scores depends on that swap history, and NMS is order dependent.  This reproduces it exactly:
+// elements below the lowest repeated score are all distinct, never take part in a swap chain that moves a larger element
+// (a record chain only links elements of increasing score) and end in sorted order anyway, so the passes are replayed in
+// parallel (one prefix-max scan + record shift per pass) on the sub-sequence S of candidates at or above that score, in
+// their original (anchor) order.  On entry key[0..m) is sorted (score desc, anchor asc); on exit the first |S| keys are in
+// conf_sort's order.  Nothing happens (one reduction) when all scores are distinct.
+constexpr int NMS_PER = HEAD_MAX_CAND / NMS_THREADS;
+__device__ void conf_sort_tie_order(NmsSmem &s, int m, const float *scores, int N, float conf_thresh)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s.tie_min = 0xffffffffu;
+    __syncthreads();
+    unsigned mymin = 0xffffffffu;
+    for (int i = tid; i + 1 < m; i += NMS_THREADS) {
+        const unsigned a = (unsigned)(s.u.key[i] >> 12), b = (unsigned)(s.u.key[i + 1] >> 12);     // score bits (class field is 0)
+        if (a == b) mymin = min(mymin, a);
+    }
+    mymin = __reduce_min_sync(0xffffffffu, mymin);
+    if (lane == 0 && mymin != 0xffffffffu) atomicMin(&s.tie_min, mymin);
+    __syncthreads();
+    const unsigned vmin = s.tie_min;
+    if (vmin == 0xffffffffu) return;                               // block-uniform
+    // S in anchor order: (score bits << 32 | anchor index); box[] is not in use yet
+    unsigned long long *E = reinterpret_cast<unsigned long long *>(s.box);
+    int T1 = 0;
+    for (int base = 0; base < N; base += NMS_THREADS) {
+        const int i = base + tid;
+        const float sc = i < N ? scores[i] : -1.f;
+        const bool in = i < N && sc > conf_thresh && __float_as_uint(sc) >= vmin;
+        int tot;
+        const int off = block_scan_flag(in, s.warp_sums, &tot);
+        if (in) E[T1 + off] = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned)i;
+        T1 += tot;
+    }
+    __syncthreads();
+    const int per = (T1 + NMS_THREADS - 1) / NMS_THREADS;          // <= NMS_PER; thread t owns slots [t per, (t + 1) per)
+    const int p0 = tid * per;
+    constexpr unsigned long long HI = 0xffffffff00000000ull;
+    for (int i = 0; i + 1 < T1; ++i) {
+        // scan key = score bits << 32 | ~slot: the maximum is the highest score at its FIRST slot
+        unsigned long long loc = 0ull;                             // scores are > 0: every real key is > 0
+#pragma unroll
+        for (int q = 0; q < NMS_PER; ++q) {
+            const int p = p0 + q;
+            if (q < per && p >= i && p < T1) loc = max(loc, (E[p] & HI) | (unsigned long long)(0xffffffffu - (unsigned)p));
+        }
+        unsigned long long inc = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc = max(inc, o);
+        }
+        if (lane == 31) s.wtot[wid] = inc;
+        unsigned long long run = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) run = 0ull;
+        __syncthreads();
+        unsigned long long top = 0ull;
+#pragma unroll
+        for (int w = 0; w < NMS_THREADS / 32; ++w) {
+            const unsigned long long v = s.wtot[w];
+            top = max(top, v);
+            if (w < wid) run = max(run, v);
+        }
+        // own slots: a record (strictly above everything before it in the tail) takes the previous record's element;
+        // slot i takes the tail's first maximum
+        unsigned long long val[NMS_PER];
+        unsigned rec = 0u;
+#pragma unroll
+        for (int q = 0; q < NMS_PER; ++q) {
+            const int p = p0 + q;
+            val[q] = 0ull;
+            if (q < per && p >= i && p < T1) {
+                const unsigned long long e = E[p];
+                if (p == i) {
+                    const unsigned g = 0xffffffffu - (unsigned)top;
+                    if (g != (unsigned)i) { val[q] = E[g]; rec |= 1u << q; }
+                    run = (e & HI) | (unsigned long long)(0xffffffffu - (unsigned)p);
+                } else if ((unsigned)(e >> 32) > (unsigned)(run >> 32)) {
+                    val[q] = E[0xffffffffu - (unsigned)run]; rec |= 1u << q;
+                    run = (e & HI) | (unsigned long long)(0xffffffffu - (unsigned)p);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NMS_PER; ++q)
+            if ((rec >> q) & 1u) E[p0 + q] = val[q];
+        __syncthreads();
+    }
+    for (int k = tid; k < T1; k += NMS_THREADS) {
+        const unsigned long long e = E[k];
+        s.u.key[k] = ((e >> 32) << 12) | (unsigned long long)(HEAD_MAX_CAND - 1 - (unsigned)e);
+    }
+    __syncthreads();
+}
+
 #ifdef YB_NMS_TIMELINE
 #define NMS_T(k) do { if (tid == 0) { long long c_ = clock64(); tacc[k] += c_ - tlast; tlast = c_; } } while (0)
 #else
@@ -260,7 +362,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
 
     // 1. threshold + compaction (python: score >= conf, slim_yolo_v2.py:190; C: score > conf, yolo_forward.c:1077).
     //    key = class | score bits | tie-break: python sorts per class, ties -> higher anchor index first (reversed stable
-    //    ascending argsort); C is class-agnostic, ties -> lower index first.
+    //    ascending argsort); C is class-agnostic, ties -> the order conf_sort's swap history leaves (conf_sort_tie_order).
     int m = 0;
     for (int base = 0; base < N; base += NMS_THREADS) {
         int i = base + tid;
@@ -315,6 +417,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
         }
     }
 
+    if (!PY) conf_sort_tie_order(s, m, scores, N, a.conf_thresh);
     NMS_T(1);
     // 3. sorted order -> anchor index, box, area, class (keys are dead after this; their storage is reused)
     constexpr int PER = HEAD_MAX_CAND / NMS_THREADS;

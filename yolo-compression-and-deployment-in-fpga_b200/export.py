@@ -239,6 +239,29 @@ def synthetic_frames_f32(n: int, h: int, w: int, seed: int = 0) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
 
 
+def synthetic_image_u8(seed: int, h: int = 480, w: int = 640, kind: str = "noise") -> np.ndarray:
+    """Seeded uint8 BGR camera image [h][w][3].  "noise": SURVEY.md 8(d) config 2 (uniform noise: after ten layers a
+    random-init network answers almost the same value in every cell).  "scene": a smooth random field, 40 random
+    half-transparent rectangles and a little noise, so that the prediction map (and hence the scores) varies from cell to cell."""
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    # smooth random field (a coarse random grid interpolated bilinearly) + 40 random filled rectangles + a little noise
+    gy, gx = 13, 17
+    coarse = rng.integers(0, 256, size=(gy, gx, 3)).astype(np.float64)
+    yy = np.linspace(0, gy - 1, h); xx = np.linspace(0, gx - 1, w)
+    y0 = np.minimum(yy.astype(int), gy - 2); x0 = np.minimum(xx.astype(int), gx - 2)
+    fy = (yy - y0)[:, None, None]; fx = (xx - x0)[None, :, None]
+    img = ((1 - fy) * ((1 - fx) * coarse[y0][:, x0] + fx * coarse[y0][:, x0 + 1]) +
+           fy * ((1 - fx) * coarse[y0 + 1][:, x0] + fx * coarse[y0 + 1][:, x0 + 1]))
+    for _ in range(40):
+        ry, rx = int(rng.integers(0, h)), int(rng.integers(0, w))
+        hh, ww = int(rng.integers(8, h // 2)), int(rng.integers(8, w // 2))
+        img[ry:ry + hh, rx:rx + ww] = 0.5 * img[ry:ry + hh, rx:rx + ww] + 0.5 * rng.integers(0, 256, size=3)
+    img = np.rint(img).astype(np.int32) + rng.integers(-12, 13, size=(h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
 def rgb444_lut(sa: int = 0) -> np.ndarray:
     """pixel_norm_quantize (c_embedding/yolo_forward.c:57-85) for all 4096 RGB444 codes -> int8 [4096][4] (R,G,B,0):
     mask WITHOUT shifting (R in 0..15, G in {0,16..240}, B in {0,256..3840}), /255., -mean, /std in the reference's
@@ -262,12 +285,21 @@ def synthetic_frames_rgb444(n: int, h: int, w: int, seed: int = 0) -> np.ndarray
 
 
 def random_quantnet(seed: int = 0, calib_hw=(416, 416), calib_frames: int = 2, head_bias_shift: float = 0.0,
-                    anchors=None, calib_input: str = "f32") -> QuantNet:
+                    anchors=None, calib_input: str = "f32", head_gain: float = 1.0, weight_gain: float = 1.0) -> QuantNet:
     """Random-init slim_yolo_v2 of the named architecture, quantised and calibrated by the reference's rules
     (SURVEY.md 8d 'Weights for all configs').  head_bias_shift is added to the 5 objectness biases of `pred`
     BEFORE quantisation: random init otherwise puts most anchors above the threshold (dense NMS worst case);
     a negative shift gives the sparse detections of a trained network."""
     ws, bs = random_float_convs(seed)
+    if weight_gain != 1.0:
+        # nn.Conv2d's default init shrinks the signal layer after layer until the biases dominate and every cell of the
+        # prediction map holds nearly the same values; a He-like gain on every layer's weights keeps the input's structure
+        # alive through the ten layers (used by the detection-parity fixtures, which need distinct scores)
+        ws = [w * weight_gain for w in ws]
+    if head_gain != 1.0:
+        # a random-init `pred` answers with almost the same value everywhere (a few hundred distinct scores per frame):
+        # scaling its weights spreads the prediction map over the int8 range like a trained head does
+        ws[-1] = ws[-1] * head_gain
     if head_bias_shift:
         bs[-1] = bs[-1].clone()
         bs[-1][:5] += head_bias_shift
