@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include <math.h>
 #include <cstdio>
+#include <cstdlib>
 
 namespace yb {
 
@@ -712,6 +713,392 @@ __global__ void __launch_bounds__(NMS_THREADS, 2) head_nms_kernel(HeadArgs a)
     }
 }
 
+
+// ---- grid NMS: the python head without a sort ----------------------------------------------------------------
+//
+// Greedy NMS keeps a candidate iff no KEPT candidate of its class that precedes it (higher score; equal score: higher anchor
+// index) overlaps it beyond the threshold.  That fixed point depends only on the ORDER RELATION between overlapping pairs, so
+// no global sort is needed, and the python head returns its detections in anchor order anyway (slim_yolo_v2.py:205):
+//   1. every candidate (score >= conf) is filed by a counting sort under (area bucket, 16 x 16 centre cell): the same
+//      conservative pruning as the sorted kernel above (IoU > t => area ratio within [t, 1/t] => at most one bucket apart;
+//      centre distance per axis < (1-t)/(1+t) of the larger extent), but over ALL candidates at once and in CONTIGUOUS bins,
+//      so a window row is one range of the bin-ordered arrays;
+//   2. one thread per candidate, in bin order (the lanes of a warp are neighbours: similar ranges), walks those ranges as ONE
+//      flat loop (a per-lane state machine over bucket / row / entry, so lanes with different windows never wait for each
+//      other's inner loops) with the branch-free screen, and queues the pairs (candidate, possible predecessor) that pass;
+//   3. the queue is drained with all lanes busy: the reference's exact fp32 IoU decides each pair; a confirmed pair is an
+//      EDGE (predecessor -> candidate) and bumps the candidate's predecessor count;
+//   4. edge-parallel propagation rounds: candidates without predecessors are kept; an edge whose source is kept drops its
+//      target, an edge whose source is dropped releases it (count - 1; kept at zero); used edges are retired.  No pointer
+//      chasing, ~8 rounds on the dense random-init frames;
+//   5. kept anchors are flagged in a bitmap whose prefix counts give every kept candidate its slot in ascending anchor order.
+// One CTA of 1024 threads per frame.  If the pairs do not fit the queue (adversarial inputs: thousands of mutually overlapping
+// boxes) the frame falls back to pull rounds that re-walk the windows; degenerate (zero-area) candidates scan everything
+// (the reference's 0/0 = NaN quirk).  The decisions are exactly those of the sequential algorithm.
+constexpr int GN_THREADS = 1024;
+constexpr int GN_G = 16;
+constexpr int GN_CELLS = NMS_BUCKETS * GN_G * GN_G;
+constexpr int GN_PER = HEAD_MAX_CAND / GN_THREADS;
+enum { GN_UNKNOWN = 0, GN_KEPT = 1, GN_DEAD = 2 };
+constexpr unsigned GN_RETIRED = 0xffffffffu;
+
+struct GnSmem {                       // byte offsets into dynamic shared memory (host: gn_layout)
+    uint32_t box, score, npred, idx, cls, state, ofs, keepmap, misc, pool, pool_cap, total;
+};
+__host__ __device__ inline GnSmem gn_layout(int N, uint32_t budget)
+{
+    const uint32_t n = (uint32_t)((N + 3) & ~3);
+    GnSmem L;
+    L.box = 0; L.score = L.box + 16u * n; L.npred = L.score + 4u * n; L.idx = L.npred + 4u * n;
+    L.cls = L.idx + 2u * n; L.state = L.cls + n;
+    L.ofs = (L.state + n + 15u) & ~15u;
+    L.keepmap = (L.ofs + 2u * (GN_CELLS + 1) + 15u) & ~15u;
+    L.misc = (L.keepmap + 4u * ((n + 31u) / 32u + 1u) + 15u) & ~15u;
+    L.pool = L.misc + 512u;
+    const uint32_t min_pool = 4u * GN_CELLS;                    // the bin counters live in the pool area while the bins are built
+    uint32_t room = budget > L.pool ? budget - L.pool : 0u;
+    if (room < min_pool) room = min_pool;
+    L.pool_cap = room / 4u;
+    L.total = L.pool + 4u * L.pool_cap;
+    return L;
+}
+
+__device__ __forceinline__ int gn_cell(float c) { return min(max((int)(c * (float)GN_G), 0), GN_G - 1); }
+
+struct GnView {
+    float4 *box; unsigned *score; unsigned *npred; unsigned short *idx; unsigned char *cls; volatile unsigned char *state;
+    unsigned short *ofs; unsigned *pool; unsigned pool_cap; unsigned *pool_cnt; const float *gw, *gh;
+    float thresh, cfac, bscale, inv_t, grid_q;
+    int m;
+#ifdef YB_NMS_TIMELINE
+    unsigned *dbg;      // [4]: visits, queued pairs, -, ranges
+#endif
+};
+#ifdef YB_NMS_TIMELINE
+#define GN_COUNT(k) (dbgc[k]++)
+#else
+#define GN_COUNT(k) do { } while (0)
+#endif
+
+// Window of a candidate: which (bucket, row) ranges of the bin-ordered arrays can hold a box that overlaps it beyond the threshold
+struct GnWindow { float wj, hj, cxj, cyj, wcap, hcap; int b, b_hi, x0, x1, yc, y1; };
+__device__ __forceinline__ void gn_window_init(const GnView &v, float4 bj, float area_j, GnWindow &w)
+{
+    w.wj = bj.z - bj.x; w.hj = bj.w - bj.y;
+    w.cxj = 0.5f * (bj.x + bj.z); w.cyj = 0.5f * (bj.y + bj.w);
+    const int bk = nms_bucket(area_j, v.bscale);
+    w.wcap = w.wj * v.inv_t; w.hcap = w.hj * v.inv_t;
+    w.b = max(bk - 1, 0) - 1; w.b_hi = min(bk + 1, NMS_BUCKETS - 1);
+    w.yc = 0; w.y1 = -1; w.x0 = 0; w.x1 = 0;
+}
+// next non-empty-bucket row range [p, end); false when the window is exhausted
+__device__ __forceinline__ bool gn_window_next(const GnView &v, GnWindow &w, int &p, int &end)
+{
+    if (++w.yc > w.y1) {
+        float wm;
+        do { if (++w.b > w.b_hi) return false; wm = v.gw[w.b]; } while (wm < 0.f);          // skip buckets with nothing filed
+        const float rx = v.grid_q * fmaxf(w.wj, fminf(wm, w.wcap)) + 1e-6f, ry = v.grid_q * fmaxf(w.hj, fminf(v.gh[w.b], w.hcap)) + 1e-6f;
+        w.x0 = gn_cell(w.cxj - rx); w.x1 = gn_cell(w.cxj + rx); w.yc = gn_cell(w.cyj - ry); w.y1 = gn_cell(w.cyj + ry);
+    }
+    const int row = (w.b * GN_G + w.yc) * GN_G;
+    p = v.ofs[row + w.x0]; end = v.ofs[row + w.x1 + 1];
+    return true;
+}
+
+// Fallback only (queue overflow): the window of candidate j evaluated against the current states.
+// Returns bit 0 = a KEPT predecessor exists, bit 1 = an UNDECIDED one.
+__device__ __noinline__ unsigned gn_pull(const GnView &v, int j)
+{
+    const float4 bj = v.box[j];
+    const unsigned sj = v.score[j], ij = v.idx[j], cj = v.cls[j];
+    const float area_j = area_py(bj), caj = v.cfac * area_j;
+    unsigned res = 0u;
+    int p = 0, end = 0;
+    GnWindow w;
+    const bool degenerate = !(area_j >= 1e-20f);
+    if (degenerate) end = v.m; else gn_window_init(v, bj, area_j, w);
+    for (;;) {
+        if (p >= end) { if (degenerate || !gn_window_next(v, w, p, end)) break; continue; }
+        const float4 be = v.box[p];
+        const unsigned se = v.score[p];
+        if (p != j && v.cls[p] == cj && (se > sj || (se == sj && (unsigned)v.idx[p] > ij)) &&
+            screen_py(be, v.cfac * area_py(be), bj, caj) && suppress_py_exact(be, bj, v.thresh)) {
+            const unsigned st = v.state[p];
+            res |= st == GN_KEPT ? 1u : st == GN_UNKNOWN ? 2u : 0u;
+        }
+        ++p;
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a, GnSmem L)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x;
+    const int N = a.gh * a.gw * a.A;
+    const float *scores = a.scores + (size_t)f * N;
+    const int *cls = a.cls + (size_t)f * N;
+    const float4 *boxes = a.boxes + (size_t)f * N;
+    const int tid = threadIdx.x, lane = tid & 31;
+    float4 *sbox = reinterpret_cast<float4 *>(smem_raw + L.box);
+    unsigned *sscore = reinterpret_cast<unsigned *>(smem_raw + L.score);
+    unsigned *npred = reinterpret_cast<unsigned *>(smem_raw + L.npred);
+    unsigned short *sidx = reinterpret_cast<unsigned short *>(smem_raw + L.idx);
+    unsigned char *scls = smem_raw + L.cls;
+    volatile unsigned char *state = smem_raw + L.state;
+    unsigned short *ofs = reinterpret_cast<unsigned short *>(smem_raw + L.ofs);
+    unsigned *keepmap = reinterpret_cast<unsigned *>(smem_raw + L.keepmap);
+    int *warp_sums = reinterpret_cast<int *>(smem_raw + L.misc);                    // [33]
+    float *gw = reinterpret_cast<float *>(smem_raw + L.misc + 160), *gh = gw + NMS_BUCKETS;
+    unsigned *pool_cnt = reinterpret_cast<unsigned *>(smem_raw + L.misc + 160 + 8 * NMS_BUCKETS);
+    unsigned *pool = reinterpret_cast<unsigned *>(smem_raw + L.pool);
+    unsigned *cnt = pool;                                                           // bin counters while the bins are built
+
+    const float thresh = a.nms_thresh;
+    const float t_lo = fminf(thresh * 0.999f, 0.97f);
+    const float bscale = 1.f / log2f(1.f / t_lo);
+#ifdef YB_NMS_TIMELINE
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    int rounds = 0;
+    unsigned dbgc[4] = {0, 0, 0, 0};
+#endif
+
+    // 1. candidates -> (bucket, cell), counts, per-bucket extents
+    for (int i = tid; i < GN_CELLS; i += GN_THREADS) cnt[i] = 0u;
+    const int kwords = (N + 31) / 32;
+    for (int i = tid; i <= kwords; i += GN_THREADS) keepmap[i] = 0u;
+    if (tid < NMS_BUCKETS) { gw[tid] = -1.f; gh[tid] = -1.f; }
+    if (tid == 0) { pool_cnt[0] = 0u; pool_cnt[1] = 0u; }
+    __syncthreads();
+    float4 mybox[GN_PER]; float mysc[GN_PER]; int mybin[GN_PER]; unsigned myrank[GN_PER];
+#pragma unroll
+    for (int r = 0; r < GN_PER; ++r) {
+        const int i = tid + r * GN_THREADS;
+        mybin[r] = -1; myrank[r] = 0u; mysc[r] = 0.f; mybox[r] = make_float4(0, 0, 0, 0);
+        if (i < N) {
+            const float sc = scores[i];
+            if (sc >= a.conf_thresh) {
+                const float4 b = boxes[i];
+                const int bk = nms_bucket(area_py(b), bscale);
+                const int cell = (bk * GN_G + gn_cell(0.5f * (b.y + b.w))) * GN_G + gn_cell(0.5f * (b.x + b.z));
+                mybox[r] = b; mysc[r] = sc; mybin[r] = cell;
+                myrank[r] = atomicAdd(&cnt[cell], 1u);
+                // extents are >= 0: integer order = float order; the plain read only skips atomics that cannot raise the maximum
+                const float bw = fmaxf(b.z - b.x, 0.f), bh = fmaxf(b.w - b.y, 0.f);
+                if (bw > *reinterpret_cast<volatile float *>(&gw[bk])) atomicMax(reinterpret_cast<int *>(&gw[bk]), __float_as_int(bw));
+                if (bh > *reinterpret_cast<volatile float *>(&gh[bk])) atomicMax(reinterpret_cast<int *>(&gh[bk]), __float_as_int(bh));
+            }
+        }
+    }
+    __syncthreads();
+    NMS_T(0);
+    // 2. exclusive scan of the bin counts (3 bins per thread) -> bin offsets
+    int m;
+    {
+        constexpr int BPT = GN_CELLS / GN_THREADS;
+        static_assert(GN_CELLS % GN_THREADS == 0, "bins per thread");
+        unsigned c[BPT], sum = 0;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) { c[k] = cnt[tid * BPT + k]; sum += c[k]; }
+        unsigned inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        if (lane == 31) warp_sums[tid >> 5] = (int)inc;
+        __syncthreads();
+        const int v = warp_sums[lane];
+        const unsigned wbase = (unsigned)__reduce_add_sync(0xffffffffu, lane < (tid >> 5) ? v : 0);
+        m = __reduce_add_sync(0xffffffffu, v);
+        unsigned run = wbase + inc - sum;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) { ofs[tid * BPT + k] = (unsigned short)run; run += c[k]; }
+        if (tid == GN_THREADS - 1) ofs[GN_CELLS] = (unsigned short)run;
+    }
+    __syncthreads();
+    NMS_T(1);
+    // 3. scatter into bin order
+#pragma unroll
+    for (int r = 0; r < GN_PER; ++r) {
+        if (mybin[r] >= 0) {
+            const int i = tid + r * GN_THREADS;
+            const int p = (int)ofs[mybin[r]] + (int)myrank[r];
+            sbox[p] = mybox[r]; sscore[p] = __float_as_uint(mysc[r]); sidx[p] = (unsigned short)i; scls[p] = (unsigned char)cls[i];
+            npred[p] = 0u;
+        }
+    }
+    __syncthreads();            // the counters (pool area) are dead from here on
+    NMS_T(2);
+
+    GnView v;
+    v.box = sbox; v.score = sscore; v.npred = npred; v.idx = sidx; v.cls = scls; v.state = state; v.ofs = ofs;
+    v.pool = pool; v.pool_cap = L.pool_cap; v.pool_cnt = pool_cnt; v.gw = gw; v.gh = gh;
+    v.thresh = thresh; v.cfac = thresh / (1.f + thresh) * 0.99999f; v.bscale = bscale;
+    v.inv_t = 1.f / t_lo * 1.0001f; v.grid_q = fmaxf(1.f - t_lo, 0.f) / (1.f + t_lo) * 1.0001f; v.m = m;
+    // 4. candidate pairs.  Warps take chunks of 32 bin-ordered candidates from a counter, heaviest buckets first (the large
+    //    boxes at the end of the bin order have the widest windows).  Converged prologue: every lane loads its candidate and
+    //    packs its three bucket windows (x0, x1, y0, y1 in 4 bits each); then ONE flat loop per lane over its row ranges: an
+    //    iteration either visits one entry or steps to the next range (two table reads), so lanes with different windows
+    //    never wait for each other's inner loops.
+    {
+        unsigned *chunk_next = pool_cnt + 1;
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = (int)atomicAdd(chunk_next, 1u);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (32 * c >= m) break;
+            const int j = m - 1 - (32 * c + lane);
+            const bool valid = j >= 0;
+            const float4 bj = valid ? sbox[j] : make_float4(0, 0, 0, 0);
+            const unsigned sj = valid ? sscore[j] : 0u, ij = valid ? sidx[j] : 0u, cj = valid ? scls[j] : 0u;
+            const float area_j = area_py(bj), caj = v.cfac * area_j;
+            const bool degenerate = !(area_j >= 1e-20f);
+            const int bk = nms_bucket(area_j, bscale);
+            unsigned win[3];
+            {
+                const float wj = bj.z - bj.x, hj = bj.w - bj.y;
+                const float cxj = 0.5f * (bj.x + bj.z), cyj = 0.5f * (bj.y + bj.w);
+                const float wcap = wj * v.inv_t, hcap = hj * v.inv_t;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int b = bk - 1 + k;
+                    win[k] = 0x0100u;                                               // y0 = 1 > y1 = 0: empty
+                    if (b >= 0 && b < NMS_BUCKETS) {
+                        const float wm = gw[b];
+                        if (wm >= 0.f) {                                            // something is filed in this bucket
+                            const float rx = v.grid_q * fmaxf(wj, fminf(wm, wcap)) + 1e-6f, ry = v.grid_q * fmaxf(hj, fminf(gh[b], hcap)) + 1e-6f;
+                            win[k] = (unsigned)gn_cell(cxj - rx) | ((unsigned)gn_cell(cxj + rx) << 4) |
+                                     ((unsigned)gn_cell(cyj - ry) << 8) | ((unsigned)gn_cell(cyj + ry) << 12);
+                        }
+                    }
+                }
+            }
+            int k = -1, yc = 1, y1 = 0, x0 = 0, x1 = 0, p = 0, end = 0;
+            if (degenerate) { k = 2; yc = 0; y1 = 0; end = m; }                     // degenerate: everything, once
+            if (!valid) { k = 2; yc = 0; y1 = 0; end = 0; }
+            for (;;) {
+                if (p >= end) {
+                    if (++yc > y1) {
+                        if (++k > 2) break;
+                        const unsigned wk = k == 0 ? win[0] : k == 1 ? win[1] : win[2];
+                        x0 = wk & 15; x1 = (wk >> 4) & 15; yc = (wk >> 8) & 15; y1 = (wk >> 12) & 15;
+                        if (yc > y1) { yc = 1; y1 = 0; continue; }
+                    }
+                    const int row = ((bk - 1 + k) * GN_G + yc) * GN_G;
+                    p = ofs[row + x0]; end = ofs[row + x1 + 1];
+                    GN_COUNT(3);
+                    continue;
+                }
+                const float4 be = sbox[p];
+                GN_COUNT(0);
+                if (screen_py(be, v.cfac * area_py(be), bj, caj)) {
+                    const unsigned se = sscore[p];
+                    if (p != j && scls[p] == cj && (se > sj || (se == sj && (unsigned)sidx[p] > ij))) {   // same class, p precedes j
+                        GN_COUNT(1);
+                        const unsigned slot = atomicAdd(pool_cnt, 1u);
+                        if (slot < L.pool_cap) pool[slot] = (unsigned)j | ((unsigned)p << 16);
+                    }
+                }
+                ++p;
+            }
+            __syncwarp();
+        }
+    }
+    NMS_T(3);
+    __syncthreads();
+    NMS_T(4);
+    const unsigned npairs = *pool_cnt;
+    if (npairs <= L.pool_cap) {
+        // 5. exact test of the queued pairs (all lanes busy); confirmed pairs stay as edges (target | source << 16)
+        for (unsigned e = tid; e < npairs; e += GN_THREADS) {
+            const unsigned wd = pool[e], j = wd & 0xffffu, p = wd >> 16;
+            if (suppress_py_exact(sbox[p], sbox[j], thresh)) atomicAdd(&npred[j], 1u);
+            else pool[e] = GN_RETIRED;
+        }
+        __syncthreads();
+        for (int j = tid; j < m; j += GN_THREADS) state[j] = npred[j] ? GN_UNKNOWN : GN_KEPT;
+        __syncthreads();
+        NMS_T(7);
+        // 6. edge-parallel propagation rounds.  States are read while other threads update them: a value is either
+        //    "undecided" or final, so acting on it is always right; each round decides at least the first undecided candidate.
+        int again;
+        do {
+            int progress = 0;
+            for (unsigned e = tid; e < npairs; e += GN_THREADS) {
+                const unsigned wd = pool[e];
+                if (wd == GN_RETIRED) continue;
+                const unsigned j = wd & 0xffffu, p = wd >> 16;
+                const unsigned sp = state[p];
+                if (state[j] != GN_UNKNOWN) { pool[e] = GN_RETIRED; continue; }
+                if (sp == GN_KEPT) { state[j] = GN_DEAD; pool[e] = GN_RETIRED; progress = 1; }
+                else if (sp == GN_DEAD) {
+                    if (atomicSub(&npred[j], 1u) == 1u) state[j] = GN_KEPT;
+                    pool[e] = GN_RETIRED; progress = 1;
+                }
+            }
+            again = __syncthreads_or(progress);
+#ifdef YB_NMS_TIMELINE
+            ++rounds;
+#endif
+        } while (again);
+    } else {
+        // the pairs did not fit: pull rounds, every undecided candidate re-walks its window
+        for (int j = tid; j < m; j += GN_THREADS) state[j] = GN_UNKNOWN;
+        __syncthreads();
+        int again;
+        do {
+            int unk = 0;
+            for (int j = tid; j < m; j += GN_THREADS) {
+                if (state[j] != GN_UNKNOWN) continue;
+                const unsigned res = gn_pull(v, j);
+                if (res & 1u) state[j] = GN_DEAD; else if (!(res & 2u)) state[j] = GN_KEPT; else unk = 1;
+            }
+            again = __syncthreads_or(unk);
+        } while (again);
+    }
+    NMS_T(5);
+    // 7. kept anchors in ascending anchor order (np.where(keep > 0), slim_yolo_v2.py:205): bitmap by anchor index, exclusive
+    //    prefix counts of its words (<= 128 words: four per lane of one warp), every kept candidate then knows its slot
+    for (int j = tid; j < m; j += GN_THREADS)
+        if (state[j] == GN_KEPT) { const unsigned i = sidx[j]; atomicOr(&keepmap[i >> 5], 1u << (i & 31)); }
+    __syncthreads();
+    unsigned *kprefix = reinterpret_cast<unsigned *>(smem_raw + L.ofs);             // the bin offsets are dead: [kwords + 1] prefix counts
+    if (tid < 32) {
+        constexpr int WPL = HEAD_MAX_CAND / 32 / 32;                                // 4 words per lane
+        unsigned c[WPL], sum = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) { const int wi = lane * WPL + k; c[k] = wi < kwords ? __popc(keepmap[wi]) : 0u; sum += c[k]; }
+        unsigned inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        unsigned run = inc - sum;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) { const int wi = lane * WPL + k; if (wi <= kwords) kprefix[wi] = run; run += c[k]; }
+        if (lane == 31) { a.counts[f] = (int)inc; if (kwords == HEAD_MAX_CAND / 32) kprefix[kwords] = inc; }
+    }
+    __syncthreads();
+    yolo_b200_det *dets = a.dets + (size_t)f * a.max_det;
+    for (int j = tid; j < m; j += GN_THREADS) {
+        if (state[j] != GN_KEPT) continue;
+        const unsigned i = sidx[j];
+        const unsigned slot = kprefix[i >> 5] + __popc(keepmap[i >> 5] & ((1u << (i & 31)) - 1u));
+        if (slot < (unsigned)a.max_det) {
+            const float4 b = sbox[j];
+            yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w; d.score = __uint_as_float(sscore[j]); d.cls = scls[j];
+            d.anchor_index = (int)i; d.pad_ = 0;
+            dets[slot] = d;
+        }
+    }
+    NMS_T(6);
+#ifdef YB_NMS_TIMELINE
+    for (int k = 0; k < 4; ++k) atomicAdd(&reinterpret_cast<unsigned *>(smem_raw + L.misc + 272)[k], dbgc[k]);
+    __syncthreads();
+    if (tid == 0 && f < 2) {
+        const unsigned *dg = reinterpret_cast<unsigned *>(smem_raw + L.misc + 272);
+        printf("gridNMS frame %d m=%d: visits %u ranges %u queued pairs %u rounds %d | cycles: bin %lld scan %lld scatter %lld | walk(thread0) %lld wait %lld | exact %lld rounds %lld | output %lld\n",
+               f, m, dg[0], dg[3], npairs, rounds, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[7], tacc[5], tacc[6]);
+    }
+#endif
+}
+
 template <bool PY, bool FAST>
 static cudaError_t nms_attrs()
 {
@@ -726,6 +1113,7 @@ cudaError_t head_init(void)
     cudaError_t e = nms_attrs<true, true>();
     if (e == cudaSuccess) e = nms_attrs<true, false>();
     if (e == cudaSuccess) e = nms_attrs<false, false>();
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(head_nms_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     return e;
 }
 
@@ -733,6 +1121,13 @@ cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     if (a.gh * a.gw * a.A > HEAD_MAX_CAND || a.C > NMS_MAX_CLASSES) return cudaErrorInvalidValue;
+    // python head: the sort-free grid kernel (YOLO_B200_NMS_SORTED=1 keeps the sorted, chunked kernel for comparison)
+    static const bool sorted_nms = [] { const char *e = getenv("YOLO_B200_NMS_SORTED"); return e && atoi(e) != 0; }();
+    if (a.head_mode == YOLO_B200_HEAD_PYTHON && a.nms_thresh > 1e-6f && !sorted_nms) {
+        const GnSmem L = gn_layout(a.gh * a.gw * a.A, 226u * 1024u);
+        head_nms_grid_kernel<<<a.n, GN_THREADS, L.total, st>>>(a, L);
+        return cudaGetLastError();
+    }
     if (a.head_mode != YOLO_B200_HEAD_PYTHON) head_nms_kernel<false, false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
     else if (a.nms_thresh > 1e-6f) head_nms_kernel<true, true><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
     else head_nms_kernel<true, false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
