@@ -739,11 +739,12 @@ constexpr int GN_THREADS = 1024;
 constexpr int GN_G = 16;
 constexpr int GN_CELLS = NMS_BUCKETS * GN_G * GN_G;
 constexpr int GN_PER = HEAD_MAX_CAND / GN_THREADS;
+constexpr int GN_RMAX = 2 * (GN_G >> 1);                    // ranges per candidate: two buckets x row groups (row pairs at least)
 enum { GN_UNKNOWN = 0, GN_KEPT = 1, GN_DEAD = 2 };
 constexpr unsigned GN_RETIRED = 0xffffffffu;
 
 struct GnSmem {                       // byte offsets into dynamic shared memory (host: gn_layout)
-    uint32_t box, score, npred, idx, cls, state, ofs, keepmap, misc, pool, pool_cap, total;
+    uint32_t box, score, npred, idx, cls, state, ofs, keepmap, misc, rng, pool, pool_cap, total;
 };
 __host__ __device__ inline GnSmem gn_layout(int N, uint32_t budget)
 {
@@ -754,7 +755,8 @@ __host__ __device__ inline GnSmem gn_layout(int N, uint32_t budget)
     L.ofs = (L.state + n + 15u) & ~15u;
     L.keepmap = (L.ofs + 2u * (GN_CELLS + 1) + 15u) & ~15u;
     L.misc = (L.keepmap + 4u * ((n + 31u) / 32u + 1u) + 15u) & ~15u;
-    L.pool = L.misc + 512u;
+    L.rng = L.misc + 512u;                                      // per-lane range lists of the walk: [warps][32][GN_RMAX + 1]
+    L.pool = L.rng + 4u * (GN_THREADS / 32) * 32u * (GN_RMAX + 1);
     const uint32_t min_pool = 4u * GN_CELLS;                    // the bin counters live in the pool area while the bins are built
     uint32_t room = budget > L.pool ? budget - L.pool : 0u;
     if (room < min_pool) room = min_pool;
@@ -764,6 +766,14 @@ __host__ __device__ inline GnSmem gn_layout(int N, uint32_t budget)
 }
 
 __device__ __forceinline__ int gn_cell(float c) { return min(max((int)(c * (float)GN_G), 0), GN_G - 1); }
+// Bin order: (bucket, row GROUP, column, row inside the group).  A window's rows y0..y1 and columns x0..x1 are then one
+// contiguous range of entries per row group instead of one per row: longer ranges, fewer range changes in the walk.
+#ifndef GN_YSH
+#define GN_YSH 1
+#endif
+constexpr int GN_YG = GN_G >> GN_YSH;                       // row groups
+__device__ __forceinline__ int gn_bin(int b, int y, int x) { return (((b * GN_YG + (y >> GN_YSH)) * GN_G + x) << GN_YSH) + (y & ((1 << GN_YSH) - 1)); }
+__device__ __forceinline__ int gn_group_first(int b, int yg, int x) { return ((b * GN_YG + yg) * GN_G + x) << GN_YSH; }
 
 struct GnView {
     float4 *box; unsigned *score; unsigned *npred; unsigned short *idx; unsigned char *cls; volatile unsigned char *state;
@@ -798,10 +808,9 @@ __device__ __forceinline__ bool gn_window_next(const GnView &v, GnWindow &w, int
         float wm;
         do { if (++w.b > w.b_hi) return false; wm = v.gw[w.b]; } while (wm < 0.f);          // skip buckets with nothing filed
         const float rx = v.grid_q * fmaxf(w.wj, fminf(wm, w.wcap)) + 1e-6f, ry = v.grid_q * fmaxf(w.hj, fminf(v.gh[w.b], w.hcap)) + 1e-6f;
-        w.x0 = gn_cell(w.cxj - rx); w.x1 = gn_cell(w.cxj + rx); w.yc = gn_cell(w.cyj - ry); w.y1 = gn_cell(w.cyj + ry);
+        w.x0 = gn_cell(w.cxj - rx); w.x1 = gn_cell(w.cxj + rx); w.yc = gn_cell(w.cyj - ry) >> GN_YSH; w.y1 = gn_cell(w.cyj + ry) >> GN_YSH;
     }
-    const int row = (w.b * GN_G + w.yc) * GN_G;
-    p = v.ofs[row + w.x0]; end = v.ofs[row + w.x1 + 1];
+    p = v.ofs[gn_group_first(w.b, w.yc, w.x0)]; end = v.ofs[gn_group_first(w.b, w.yc, w.x1 + 1)];     // (x1 + 1 = 16 is the next group's first bin)
     return true;
 }
 
@@ -880,7 +889,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
             if (sc >= a.conf_thresh) {
                 const float4 b = boxes[i];
                 const int bk = nms_bucket(area_py(b), bscale);
-                const int cell = (bk * GN_G + gn_cell(0.5f * (b.y + b.w))) * GN_G + gn_cell(0.5f * (b.x + b.z));
+                const int cell = gn_bin(bk, gn_cell(0.5f * (b.y + b.w)), gn_cell(0.5f * (b.x + b.z)));
                 mybox[r] = b; mysc[r] = sc; mybin[r] = cell;
                 myrank[r] = atomicAdd(&cnt[cell], 1u);
                 // extents are >= 0: integer order = float order; the plain read only skips atomics that cannot raise the maximum
@@ -933,71 +942,78 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
     v.pool = pool; v.pool_cap = L.pool_cap; v.pool_cnt = pool_cnt; v.gw = gw; v.gh = gh;
     v.thresh = thresh; v.cfac = thresh / (1.f + thresh) * 0.99999f; v.bscale = bscale;
     v.inv_t = 1.f / t_lo * 1.0001f; v.grid_q = fmaxf(1.f - t_lo, 0.f) / (1.f + t_lo) * 1.0001f; v.m = m;
-    // 4. candidate pairs.  Warps take chunks of 32 bin-ordered candidates from a counter, heaviest buckets first (the large
-    //    boxes at the end of the bin order have the widest windows).  Converged prologue: every lane loads its candidate and
-    //    packs its three bucket windows (x0, x1, y0, y1 in 4 bits each); then ONE flat loop per lane over its row ranges: an
-    //    iteration either visits one entry or steps to the next range (two table reads), so lanes with different windows
-    //    never wait for each other's inner loops.
+    // 4. candidate pairs.  Every unordered pair is looked at ONCE, from its member with the lower bin-ordered position: a
+    //    candidate scans only entries BEHIND it (the rest of its own row group, the later row groups of its window in its own
+    //    bucket, and its window in the next bucket) and the queued pair is oriented by the order relation.  (A window always
+    //    contains every box that overlaps its owner beyond the threshold, so the lower member finds the higher one.)
+    //    Degenerate candidates scan everything; pairs with exactly one degenerate member are recorded by that member.
+    //    Warps take chunks of 32 bin-ordered candidates from a counter.  Converged prologue: every lane loads its candidate
+    //    and writes the list of its non-empty entry ranges (begin | end << 16) to its own strip of shared memory; the walk is
+    //    then ONE flat loop per lane (visit an entry; when the range is used up, fetch the next one: a handful of predicated
+    //    instructions), so lanes with different windows never wait for each other's inner loops.
     {
         unsigned *chunk_next = pool_cnt + 1;
+        unsigned *myrng = reinterpret_cast<unsigned *>(smem_raw + L.rng) + ((tid >> 5) * 32 + lane) * (GN_RMAX + 1);
         for (;;) {
             int c = 0;
             if (lane == 0) c = (int)atomicAdd(chunk_next, 1u);
             c = __shfl_sync(0xffffffffu, c, 0);
             if (32 * c >= m) break;
-            const int j = m - 1 - (32 * c + lane);
-            const bool valid = j >= 0;
+            const int j = 32 * c + lane;
+            const bool valid = j < m;
             const float4 bj = valid ? sbox[j] : make_float4(0, 0, 0, 0);
             const unsigned sj = valid ? sscore[j] : 0u, ij = valid ? sidx[j] : 0u, cj = valid ? scls[j] : 0u;
             const float area_j = area_py(bj), caj = v.cfac * area_j;
             const bool degenerate = !(area_j >= 1e-20f);
-            const int bk = nms_bucket(area_j, bscale);
-            unsigned win[3];
-            {
+            int nr = 0;
+            if (valid && degenerate) myrng[nr++] = (unsigned)m << 16;               // degenerate: everything, once
+            else if (valid) {
+                const int bk = nms_bucket(area_j, bscale);
                 const float wj = bj.z - bj.x, hj = bj.w - bj.y;
                 const float cxj = 0.5f * (bj.x + bj.z), cyj = 0.5f * (bj.y + bj.w);
                 const float wcap = wj * v.inv_t, hcap = hj * v.inv_t;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int b = bk - 1 + k;
-                    win[k] = 0x0100u;                                               // y0 = 1 > y1 = 0: empty
-                    if (b >= 0 && b < NMS_BUCKETS) {
-                        const float wm = gw[b];
-                        if (wm >= 0.f) {                                            // something is filed in this bucket
-                            const float rx = v.grid_q * fmaxf(wj, fminf(wm, wcap)) + 1e-6f, ry = v.grid_q * fmaxf(hj, fminf(gh[b], hcap)) + 1e-6f;
-                            win[k] = (unsigned)gn_cell(cxj - rx) | ((unsigned)gn_cell(cxj + rx) << 4) |
-                                     ((unsigned)gn_cell(cyj - ry) << 8) | ((unsigned)gn_cell(cyj + ry) << 12);
-                        }
+                for (int k = 0; k < 2; ++k) {
+                    const int b = bk + k;
+                    if (b >= NMS_BUCKETS) continue;
+                    const float wm = gw[b];
+                    if (wm < 0.f) continue;                                         // nothing filed in this bucket
+                    const float rx = v.grid_q * fmaxf(wj, fminf(wm, wcap)) + 1e-6f, ry = v.grid_q * fmaxf(hj, fminf(gh[b], hcap)) + 1e-6f;
+                    const int x0 = gn_cell(cxj - rx), x1 = gn_cell(cxj + rx);
+                    const int g0 = (k == 0 ? gn_cell(cyj) : gn_cell(cyj - ry)) >> GN_YSH;   // own bucket: from the candidate's own row group on
+                    const int g1 = gn_cell(cyj + ry) >> GN_YSH;
+                    for (int g = g0; g <= g1; ++g) {
+                        int beg = ofs[gn_group_first(b, g, x0)];
+                        const int end = ofs[gn_group_first(b, g, x1 + 1)];
+                        if (k == 0 && g == g0) beg = j + 1;                         // behind the candidate itself
+                        if (beg < end) myrng[nr++] = (unsigned)beg | ((unsigned)end << 16);
+                        GN_COUNT(3);
                     }
                 }
             }
-            int k = -1, yc = 1, y1 = 0, x0 = 0, x1 = 0, p = 0, end = 0;
-            if (degenerate) { k = 2; yc = 0; y1 = 0; end = m; }                     // degenerate: everything, once
-            if (!valid) { k = 2; yc = 0; y1 = 0; end = 0; }
-            for (;;) {
-                if (p >= end) {
-                    if (++yc > y1) {
-                        if (++k > 2) break;
-                        const unsigned wk = k == 0 ? win[0] : k == 1 ? win[1] : win[2];
-                        x0 = wk & 15; x1 = (wk >> 4) & 15; yc = (wk >> 8) & 15; y1 = (wk >> 12) & 15;
-                        if (yc > y1) { yc = 1; y1 = 0; continue; }
-                    }
-                    const int row = ((bk - 1 + k) * GN_G + yc) * GN_G;
-                    p = ofs[row + x0]; end = ofs[row + x1 + 1];
-                    GN_COUNT(3);
-                    continue;
-                }
+            __syncwarp();
+            int r = 0, p = 0, end = 0;
+            if (nr > 0) { const unsigned w0 = myrng[0]; p = w0 & 0xffffu; end = w0 >> 16; }
+            while (r < nr) {
                 const float4 be = sbox[p];
+                const float area_e = area_py(be);
                 GN_COUNT(0);
-                if (screen_py(be, v.cfac * area_py(be), bj, caj)) {
-                    const unsigned se = sscore[p];
-                    if (p != j && scls[p] == cj && (se > sj || (se == sj && (unsigned)sidx[p] > ij))) {   // same class, p precedes j
+                if (screen_py(be, v.cfac * area_e, bj, caj)) {
+                    // not itself; same class; a pair with ONE degenerate member belongs to that member's scan
+                    const bool mine = degenerate ? (p > j || area_e >= 1e-20f) : area_e >= 1e-20f;
+                    if (p != j && mine && scls[p] == cj) {
                         GN_COUNT(1);
+                        const unsigned se = sscore[p];
+                        const bool p_first = se > sj || (se == sj && (unsigned)sidx[p] > ij);      // p precedes j?
                         const unsigned slot = atomicAdd(pool_cnt, 1u);
-                        if (slot < L.pool_cap) pool[slot] = (unsigned)j | ((unsigned)p << 16);
+                        if (slot < L.pool_cap) pool[slot] = p_first ? ((unsigned)j | ((unsigned)p << 16)) : ((unsigned)p | ((unsigned)j << 16));
                     }
                 }
-                ++p;
+                if (++p >= end) {
+                    ++r;
+                    const unsigned wn = myrng[r];                                   // (one slot past the last range exists)
+                    p = wn & 0xffffu; end = wn >> 16;
+                }
             }
             __syncwarp();
         }
@@ -1007,11 +1023,30 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
     NMS_T(4);
     const unsigned npairs = *pool_cnt;
     if (npairs <= L.pool_cap) {
-        // 5. exact test of the queued pairs (all lanes busy); confirmed pairs stay as edges (target | source << 16)
-        for (unsigned e = tid; e < npairs; e += GN_THREADS) {
-            const unsigned wd = pool[e], j = wd & 0xffffu, p = wd >> 16;
-            if (suppress_py_exact(sbox[p], sbox[j], thresh)) atomicAdd(&npred[j], 1u);
-            else pool[e] = GN_RETIRED;
+        // 5. exact test of the queued pairs (all lanes busy).  Every warp owns one contiguous segment of the queue and
+        //    squeezes it in place (ballot offsets) to the pairs that are still needed: first to the confirmed pairs = EDGES
+        //    (target | source << 16), then, pass by pass below, to the edges that are still undecided, so a pass costs what
+        //    is left, not what was queued.
+        const int wid = tid >> 5;
+        const unsigned seg_beg = (unsigned)(((unsigned long long)npairs * (unsigned)wid) / (GN_THREADS / 32));
+        unsigned live_end = (unsigned)(((unsigned long long)npairs * (unsigned)(wid + 1)) / (GN_THREADS / 32));
+        {
+            unsigned wr = seg_beg;
+            for (unsigned e0 = seg_beg; e0 < live_end; e0 += 32) {
+                const unsigned e = e0 + lane;
+                bool keep = false;
+                unsigned wd = 0u;
+                if (e < live_end) {
+                    wd = pool[e];
+                    const unsigned j = wd & 0xffffu, p = wd >> 16;
+                    keep = suppress_py_exact(sbox[p], sbox[j], thresh);
+                    if (keep) atomicAdd(&npred[j], 1u);
+                }
+                const unsigned kb = __ballot_sync(0xffffffffu, keep);
+                if (keep) pool[wr + __popc(kb & ((1u << lane) - 1u))] = wd;
+                wr += __popc(kb);
+            }
+            live_end = wr;
         }
         __syncthreads();
         for (int j = tid; j < m; j += GN_THREADS) state[j] = npred[j] ? GN_UNKNOWN : GN_KEPT;
@@ -1019,20 +1054,33 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
         NMS_T(7);
         // 6. edge-parallel propagation rounds.  States are read while other threads update them: a value is either
         //    "undecided" or final, so acting on it is always right; each round decides at least the first undecided candidate.
+        //    An edge whose source is kept drops its target; one whose source is dropped releases it (count - 1, kept at zero);
+        //    used edges leave the segment.  Several passes per barrier: other warps' decisions are visible without one.
         int again;
         do {
             int progress = 0;
-            for (unsigned e = tid; e < npairs; e += GN_THREADS) {
-                const unsigned wd = pool[e];
-                if (wd == GN_RETIRED) continue;
-                const unsigned j = wd & 0xffffu, p = wd >> 16;
-                const unsigned sp = state[p];
-                if (state[j] != GN_UNKNOWN) { pool[e] = GN_RETIRED; continue; }
-                if (sp == GN_KEPT) { state[j] = GN_DEAD; pool[e] = GN_RETIRED; progress = 1; }
-                else if (sp == GN_DEAD) {
-                    if (atomicSub(&npred[j], 1u) == 1u) state[j] = GN_KEPT;
-                    pool[e] = GN_RETIRED; progress = 1;
+#pragma unroll 1
+            for (int pass = 0; pass < 3 && live_end > seg_beg; ++pass) {
+                unsigned wr = seg_beg;
+                for (unsigned e0 = seg_beg; e0 < live_end; e0 += 32) {
+                    const unsigned e = e0 + lane;
+                    bool keep = false;
+                    unsigned wd = 0u;
+                    if (e < live_end) {
+                        wd = pool[e];
+                        const unsigned j = wd & 0xffffu;
+                        const unsigned sp = state[wd >> 16], st = state[j];
+                        if (st == GN_UNKNOWN) {
+                            if (sp == GN_KEPT) { state[j] = GN_DEAD; progress = 1; }
+                            else if (sp == GN_DEAD) { if (atomicSub(&npred[j], 1u) == 1u) state[j] = GN_KEPT; progress = 1; }
+                            else keep = true;
+                        }
+                    }
+                    const unsigned kb = __ballot_sync(0xffffffffu, keep);
+                    if (keep) pool[wr + __popc(kb & ((1u << lane) - 1u))] = wd;
+                    wr += __popc(kb);
                 }
+                live_end = wr;
             }
             again = __syncthreads_or(progress);
 #ifdef YB_NMS_TIMELINE
@@ -1081,10 +1129,10 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
         const unsigned i = sidx[j];
         const unsigned slot = kprefix[i >> 5] + __popc(keepmap[i >> 5] & ((1u << (i & 31)) - 1u));
         if (slot < (unsigned)a.max_det) {
+            uint4 *dst = reinterpret_cast<uint4 *>(dets + slot);                   // 32-byte records, 16-byte aligned: two vector stores
             const float4 b = sbox[j];
-            yolo_b200_det d; d.x1 = b.x; d.y1 = b.y; d.x2 = b.z; d.y2 = b.w; d.score = __uint_as_float(sscore[j]); d.cls = scls[j];
-            d.anchor_index = (int)i; d.pad_ = 0;
-            dets[slot] = d;
+            dst[0] = make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+            dst[1] = make_uint4(sscore[j], (unsigned)scls[j], i, 0u);
         }
     }
     NMS_T(6);
