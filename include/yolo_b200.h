@@ -245,6 +245,21 @@ int yolo_b200_backbone(yolo_b200_ctx *ctx, const int8_t *d_nhwc4, int n, int h, 
 int yolo_b200_calibrate_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w,
                             int32_t *scale_a_out, int32_t *retune_out);
 
+/* Several calibration batches (trainable / un-frozen trackers, slim_yolo_v2.py:28-31): every tracker that has been called
+ * before (tracker_scale[t] != 0) moves by the exponential average scale <- scale * (1 - momentum) + (127 / max|a|) * momentum
+ * in float32 as the reference's tensor ops do, the others take the first-call rule; the exponent in force becomes
+ * floor(log2(scale)) (:33).  tracker_scale: num_layers + 1 floats = the `scale` buffers of a_tracker_in .. a_tracker_pred, in
+ * and out (all zero = fresh trackers = yolo_b200_calibrate_f32, which also fixes retune[]).  On any error the context keeps
+ * the tables it had. */
+int yolo_b200_update_trackers_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w, float momentum,
+                                  float *tracker_scale, int32_t *scale_a_out, int32_t *retune_out);
+
+/* The `find=True` overflow probe (slim_yolo_v2.py:222-226, repeated for every layer up to :327;
+ * retune_bias_quantize_findbest.py:364): one forward pass with the tables in force, nothing changes; max_abs[0] = max|x| of
+ * the input, max_abs[l + 1] = max|y_l| of layer l's output after the leaky-ReLU and before its tracker (exact: the
+ * activations are dyadic rationals).  num_layers + 1 doubles. */
+int yolo_b200_measure_f32(yolo_b200_ctx *ctx, const float *d_nchw, int n, int h, int w, double *max_abs);
+
 /* Copy layer l's output of the most recent backbone call to the host (debug / parity). */
 int yolo_b200_get_layer_output(yolo_b200_ctx *ctx, int layer, int8_t *host_out, size_t bytes);
 

@@ -86,7 +86,7 @@ def basetransform_frame(img_seed, H, W, image_kind="noise"):
 
 
 def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, head_bias_shift=0.0,
-             max_seed_tries=40, frame_kind="synthetic", head_gain=1.0, image_kind="noise", weight_gain=1.0):
+             max_seed_tries=40, frame_kind="synthetic", head_gain=1.0, image_kind="noise", weight_gain=1.0, find=False, ema_batches=0):
     refmod, quantize_tensor, quantize_tensor_b = import_reference()
     yb = load_pkg()
     ex = yb.export
@@ -130,6 +130,7 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
 
     calib = ex.synthetic_frames_f32(2, H, W, seed=1000 + seed)
     qnet = ex.build_quantnet(ws, bs, calib, anchors=anchors)
+    FIND_SHIFTS = [11, 10, 10, 11, 11, 10, 11, 11, 11, 10]       # slim_yolo_v2.py:227 ... :327
     sd = qnet.dequantized_state_dict()
     for c, key in zip(convs, ex.SLIM_CONV_KEYS):
         assert torch.equal(c.weight.detach(), sd[key + ".weight"]), key
@@ -152,9 +153,32 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
 
     with torch.no_grad():
         # calibration call: the reference handles batch element 0 only in its head, but trackers see the batch
-        net(calib, quantization=True)
+        net(calib, quantization=True, find=find)
+    first_scales = [float(t.scale) for t in trackers]
+    ema_scales = []
+    if ema_batches:
+        # un-frozen trackers (freeze = not trainable, slim_yolo_v2.py:215): every further call moves the scales by the
+        # exponential average of :31.  The training head needs targets; the trackers have all been updated by the time
+        # it raises, which is all this fixture records.
+        net.trainable = True
+        for bi in range(ema_batches):
+            try:
+                with torch.no_grad():
+                    net(ex.synthetic_frames_f32(2, H, W, seed=3000 + seed + bi) * (1.0 + 0.5 * bi), quantization=True, find=find)
+            except Exception as e:                      # noqa: the loss branch, after the conv stack
+                pass
+            ema_scales.append([float(t.scale) for t in trackers])
+        net.trainable = False
     sa_ref = [int(math.floor(math.log2(float(t.scale)))) for t in trackers]
+    if find or ema_batches:
+        # the exponents come from the reference's trackers themselves (the exporter's float restatement covers the plain
+        # first-call rule only); the weight / bias exponents absorb the find branch's divisions
+        qnet.sa = list(sa_ref)
+        if find:
+            qnet.sw = [e + k for e, k in zip(qnet.sw, FIND_SHIFTS)]
+            qnet.sb = [e + k for e, k in zip(qnet.sb, FIND_SHIFTS)]
     assert sa_ref == qnet.sa, (sa_ref, qnet.sa)
+    captured.clear()
 
     # the head's inputs to postprocess() are captured by wrapping the bound method (nothing is edited)
     head_in = []
@@ -199,7 +223,8 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
 
     out = {
         "H": H, "W": W, "seed": seed, "n_frames": n_frames, "conf_thresh": conf_thresh, "nms_thresh": nms_thresh,
-        "head_bias_shift": float(head_bias_shift), "frame_kind": frame_kind, "head_gain": float(head_gain), "image_kind": image_kind, "weight_gain": float(weight_gain),
+        "head_bias_shift": float(head_bias_shift), "frame_kind": frame_kind, "head_gain": float(head_gain), "image_kind": image_kind, "weight_gain": float(weight_gain), "find": int(find),
+        "tracker_scales_first": np.asarray(first_scales, np.float32), "tracker_scales_ema": np.asarray(ema_scales, np.float32).reshape(-1, 11),
         "anchors": np.asarray(anchors, dtype=np.float32),
         "sa": np.asarray(qnet.sa, np.int32), "sw": np.asarray(qnet.sw, np.int32),
         "sb": np.asarray(qnet.sb, np.int32), "retune": np.asarray(qnet.retune, np.int32),
@@ -214,7 +239,7 @@ def generate(name, H, W, seed, conf_thresh, nms_thresh, n_frames, store_maps, he
         frame = ex.synthetic_frames_f32(1, H, W, seed=fseed) if frame_kind == "synthetic" else basetransform_frame(fseed, H, W, image_kind)
         captured.clear(); head_in.clear()
         with torch.no_grad():
-            bboxes, scores, cls_inds = net(frame, quantization=True)
+            bboxes, scores, cls_inds = net(frame, quantization=True, find=find)
         assert len(captured) == 11
         robust = tie_robust(head_in[0][0], head_in[0][1], np.asarray(scores, np.float32))
         if not robust and fseed - fseed0 < max_seed_tries:
@@ -257,6 +282,10 @@ if __name__ == "__main__":
     # small, non-square, every map stored: layer-by-layer parity
     generate("ref_p_64x96", 64, 96, seed=0, conf_thresh=0.1, nms_thresh=0.5, n_frames=2, store_maps=True)
     # sparse head variant (few detections, exercises thresholding), odd grid (80/16 = 5)
+    # the find branch (every layer's output divided by 2**k before its tracker, slim_yolo_v2.py:222-227 ... :327), with the
+    # trackers first calibrated in that mode and then moved by two un-frozen calls (exponential average, :31)
+    generate("ref_p_64x96_find", 64, 96, seed=2, conf_thresh=0.1, nms_thresh=0.5, n_frames=1, store_maps=True, find=True,
+             ema_batches=2)
     generate("ref_p_80x64_sparse", 80, 64, seed=1, conf_thresh=0.1, nms_thresh=0.45, n_frames=1, store_maps=True,
              head_bias_shift=-1.4)
     # BASELINE.json configs[1]: batch 1 at 416x416; digests of the maps + input/pred maps + detections

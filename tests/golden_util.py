@@ -8,7 +8,7 @@ import yolo_b200  # noqa: F401
 from yolo_b200 import export as ex
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FIXTURES = ["ref_p_64x96", "ref_p_80x64_sparse", "ref_p_416x416", "ref_p_416x416_sparse"]
+FIXTURES = ["ref_p_64x96", "ref_p_80x64_sparse", "ref_p_416x416", "ref_p_416x416_sparse", "ref_p_64x96_find"]
 _cache = {}
 
 
@@ -43,6 +43,10 @@ def load(name):
     H, W, seed = int(g["H"]), int(g["W"]), int(g["seed"])
     qnet = ex.random_quantnet(seed=seed, calib_hw=(H, W), calib_frames=2, head_bias_shift=float(g["head_bias_shift"]),
                               anchors=g["anchors"].tolist(), head_gain=float(g.get("head_gain", 1.0)), weight_gain=float(g.get("weight_gain", 1.0)))
+    if int(g.get("find", 0)) or len(g.get("tracker_scales_ema", [])):
+        # the reference's trackers were calibrated in the find branch / moved by un-frozen calls: their exponents are part of
+        # the fixture, and the find branch's divisions by 2**k live in the weight / bias exponents (see model.py: _load)
+        qnet.sa = g["sa"].tolist(); qnet.sw = g["sw"].tolist(); qnet.sb = g["sb"].tolist()
     assert qnet.sha256() == str(g["net_sha256"]), "rebuilt network differs from the one the reference ran"
     assert qnet.sa == g["sa"].tolist()
     import torch

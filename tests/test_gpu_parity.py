@@ -143,6 +143,64 @@ def test_dropin_module_matches_golden():
         assert b.dtype == np.float32 and c.dtype == np.int64
 
 
+def test_dropin_find_branch_and_tracker_averaging_match_the_reference():
+    """forward(x, quantization=True, find=True) — what retune_bias_quantize_findbest.py:364 and the evaluator issue — on the
+    GPU: fresh trackers are calibrated in the find branch on the first batch (first-call rule), two more un-frozen batches move
+    them by the exponential average (slim_yolo_v2.py:31), and the detections of an unseen frame equal the reference's.
+    The tracker `scale` buffers must hold the reference's float32 values."""
+    from yolo_b200 import model
+    g, qnet, frames = gu.load("ref_p_64x96_find")
+    H, W, seed = int(g["H"]), int(g["W"]), int(g["seed"])
+    net = model.SlimYOLOv2_quantize_bnfuse(torch.device("cuda"), input_size=[H, W], num_classes=2, trainable=False,
+                                           conf_thresh=float(g["conf_thresh"]), nms_thresh=float(g["nms_thresh"]),
+                                           anchor_size=qnet.anchors)
+    sd = qnet.dequantized_state_dict()
+    for l, key in enumerate(ex.SLIM_CONV_KEYS):            # the checkpoint holds the plain exponents: undo the find shift
+        sd[key + ".weight"] = sd[key + ".weight"] * 2.0 ** net.FIND_SHIFTS[l]
+        sd[key + ".bias"] = sd[key + ".bias"] * 2.0 ** net.FIND_SHIFTS[l]
+    for k in ex.SLIM_TRACKER_KEYS:                          # fresh trackers
+        sd[k + ".scale"] = torch.zeros(1); sd[k + ".first_a"] = torch.zeros(1)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    calib = ex.synthetic_frames_f32(2, H, W, seed=1000 + seed).cuda()
+    net(calib, quantization=True, find=True)                # first call: calibrates (and decodes frame 0, discarded)
+    # (in the find branch an activation is acc * 2^-46 + b * 2^-23: more than 24 significant bits, so the reference's own
+    # float32 convolution output - and with it 127 / max|a| - carries a rounding that depends on MKL-DNN's summation order;
+    # the integer pass here is exact.  Hence a few-ulp tolerance on the float buffers; the exponents floor(log2(scale)) and
+    # every quantised map are compared exactly elsewhere.)
+    got = np.array([float(t.scale) for t in net._trackers()], np.float32)
+    np.testing.assert_allclose(got, g["tracker_scales_first"], rtol=1e-6, atol=0)
+    for bi in range(g["tracker_scales_ema"].shape[0]):
+        batch = (ex.synthetic_frames_f32(2, H, W, seed=3000 + seed + bi) * (1.0 + 0.5 * bi)).cuda()
+        net.update_trackers(batch, find=True)
+        got = np.array([float(t.scale) for t in net._trackers()], np.float32)
+        np.testing.assert_allclose(got, g["tracker_scales_ema"][bi], rtol=1e-6, atol=0)
+    assert [int(np.floor(np.log2(float(t.scale)))) for t in net._trackers()] == qnet.sa
+    b, s, c = net(frames[:1].cuda(), quantization=True, find=True)
+    assert net.last_overflow == 0
+    rk, rb_, rs_, rc_ = gu.reference_kept_indices(g, 0)
+    if int(g["f0_tie_robust"]):
+        np.testing.assert_array_equal(c, g["f0_cls"])
+        np.testing.assert_allclose(s, g["f0_scores"], atol=1e-5, rtol=0)
+        np.testing.assert_allclose(b, g["f0_bboxes"], atol=1e-5, rtol=0)
+    else:
+        assert abs(len(s) - len(g["f0_scores"])) <= max(2, len(g["f0_scores"]) // 10)
+    # the overflow probe (slim_yolo_v2.py:222-226): max|y| per tracker, exact; un-pooled layers can be checked against the
+    # reference's own integer maps: max|q| = RNE(max|y| * 2^sa) because rounding is monotone and odd
+    x = frames[:1].cuda().contiguous()
+    mx = net._ctx.measure_f32(x, 1, H, W)
+    assert mx[0] == float(frames[:1].abs().max())
+    for l, (cin, cout, activ, pool) in enumerate(qnet.layers):
+        assert mx[l + 1] * 2.0 ** net.FIND_SHIFTS[l] < 2 ** 15
+        if not pool:
+            assert int(np.abs(g["f0_map%d" % (l + 1)].astype(np.int32)).max()) == int(np.rint(mx[l + 1] * 2.0 ** qnet.sa[l + 1]))
+    # ... and it fires when a layer leaves the 16-bit accumulator range
+    net.FIND_SHIFTS = (30,) + tuple(net.FIND_SHIFTS[1:])
+    net._ctx_key = None
+    with pytest.raises((AssertionError, lib.YoloB200Error)):
+        net(frames[:1].cuda(), quantization=True, find=True)
+
+
 # ---- (2) oracle on seeded inputs: contract F, all rounding modes, random tables -----------------------
 
 def random_tables(rng, qnet):

@@ -213,3 +213,53 @@ def test_bn_fold_matches_the_reference_function():
     np.testing.assert_array_equal(f2["backbone.layer1.convs.0.weight"].numpy(), g["out/conv1.convs.0.weight"])
     with pytest.raises(ValueError):
         ex.fold_bn_state_dict({"bn.0.running_var": torch.ones(2)})
+
+
+def test_quantnet_from_state_dict_takes_the_head_width_from_the_checkpoint():
+    """The reference's default is num_classes=20 (VOC, test.py:165-172): 5 anchors x 25 = 125 prediction channels."""
+    from yolo_b200 import model
+    net = model.SlimYOLOv2_quantize_bnfuse("cpu", input_size=[64, 64], num_classes=20, anchor_size=ex.ANCHOR_SIZE)
+    q = net.quantnet(calib_frames=ex.synthetic_frames_f32(1, 64, 64))
+    assert q.layers[-1] == (256, 125, 0, 0) and q.w[-1].shape == (125, 3, 3, 256) and q.num_classes == 20
+    assert q.retune is not None and len(q.retune) == 10
+    with pytest.raises(ValueError):          # head width and (anchors, classes) must agree
+        ex.quantnet_from_state_dict(net.state_dict(), calib_frames=ex.synthetic_frames_f32(1, 64, 64), anchors=ex.ANCHOR_SIZE, num_classes=2)
+
+
+def test_retune_is_never_invented():
+    """A checkpoint with calibrated trackers and no calibration frames carries no accumulator scale: contract F and the
+    weight.h export refuse it instead of using a table tuned on noise; an explicit table or calibration frames fix it."""
+    q0 = ex.random_quantnet(seed=0, calib_hw=(64, 64), calib_frames=1)
+    sd = q0.dequantized_state_dict()
+    q = ex.quantnet_from_state_dict(sd, anchors=q0.anchors, num_classes=2)
+    assert q.retune is None and q.sa == q0.sa
+    with pytest.raises(ValueError):
+        lib.make_params(q, contract=lib.CONTRACT_F)
+    with pytest.raises(ValueError):
+        ex.write_weight_h(q, os.devnull)
+    lib.make_params(q, contract=lib.CONTRACT_P)                      # the fake-quant contract never reads retune
+    q2 = ex.quantnet_from_state_dict(sd, anchors=q0.anchors, num_classes=2, retune=ex.SHIPPED_RETUNE)
+    assert q2.retune == ex.SHIPPED_RETUNE
+    lib.make_params(q2, contract=lib.CONTRACT_F)
+    q3 = ex.quantnet_from_state_dict(sd, anchors=q0.anchors, num_classes=2, calib_frames=ex.synthetic_frames_f32(1, 64, 64, seed=1000))
+    assert q3.retune == q0.retune and q3.sa == q0.sa
+
+
+def test_bn_fold_with_two_batchnorms_in_one_sequential():
+    """Sequential(conv, bn, relu, conv, bn, relu): both convolutions are fused and the survivors are renumbered the way
+    nn.Sequential(fused, *rest) would (conv+bn2conv.py:317-326 generalised).  (Convolutions in front of a BatchNorm have no
+    bias, as in the reference's blocks, utils/modules.py:6-18: fuse_conv_and_bn adds a conv bias UNSCALED, :148.)"""
+    torch.manual_seed(3)
+    blk = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1, bias=False), torch.nn.BatchNorm2d(4), torch.nn.ReLU(),
+                              torch.nn.Conv2d(4, 5, 3, padding=1, bias=False), torch.nn.BatchNorm2d(5), torch.nn.ReLU()).eval()
+    for m in blk:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.uniform_(-1, 1); m.running_var.uniform_(0.5, 2); m.weight.data.uniform_(0.5, 1.5); m.bias.data.uniform_(-1, 1)
+    sd = {"blk." + k: v for k, v in blk.state_dict().items()}
+    out = ex.fold_bn_state_dict(sd)
+    assert sorted(out) == ["blk.0.bias", "blk.0.weight", "blk.2.bias", "blk.2.weight"]
+    fused = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 5, 3, padding=1), torch.nn.ReLU())
+    fused.load_state_dict({k[4:]: v for k, v in out.items()})
+    x = torch.randn(2, 3, 8, 8)
+    with torch.no_grad():
+        assert torch.allclose(fused(x), blk(x), atol=1e-5)

@@ -13,7 +13,9 @@ import bench  # noqa: E402
 import yolo_b200  # noqa
 from yolo_b200 import export as ex, lib
 
-if os.environ.get("YOLO_B200_DBG"):
+if os.environ.get("YOLO_B200_LIB"):
+    lib._lib = lib.load_library(os.environ["YOLO_B200_LIB"])
+elif os.environ.get("YOLO_B200_DBG"):
     lib._lib = lib.load_library(os.path.join(ROOT, "yolo-compression-and-deployment-in-fpga_b200", "build_dbg", "libyolo_b200_dbg.so"))
 H = W = 416
 sparse = float(os.environ.get("HEAD_BIAS", "0"))

@@ -261,7 +261,8 @@ static int derive_layer(yolo_b200_ctx *c, int l)
     } else if (p->contract == YOLO_B200_CONTRACT_P) {
         int ea = sa_i + sw, E = ea > sb ? ea : sb;
         q.la = E - ea; q.sh = E - sa_o;
-        if (q.la > 4 || E - sb > 22 || q.sh > 24 || q.sh < -8) return fail(E_UNSUPPORTED, "layer %d: exponents out of range (la %d lb %d sh %d)", l, q.la, E - sb, q.sh);
+        // |b << lb| <= 2^7 * 2^23 = 2^30 and |acc << la| < 2^27: the int32 numerator and the rounding add cannot wrap
+        if (q.la > 4 || E - sb > 23 || q.sh > 24 || q.sh < -8) return fail(E_UNSUPPORTED, "layer %d: exponents out of range (la %d lb %d sh %d)", l, q.la, E - sb, q.sh);
         for (int o = 0; o < L.cout; ++o) bsh[o] = (int)b[o] * (1 << (E - sb));
     } else return fail(E_ARG, "contract %d", p->contract);
     d.bias_abs_max = 0;
@@ -617,20 +618,40 @@ int yolo_b200_backbone(yolo_b200_ctx *c, const int8_t *d_nhwc4, int n, int h, in
     return backbone_from(c, 0, d_nhwc4, n, h, w, d_pred, gh, gw);
 }
 
-// Calibration on the GPU.  One forward pass over a calibration batch with FRESH trackers: every
-// AveragedRangeTracker takes scale = 127 / max|a| on its first call and the power of two below it
-// (slim_yolo_v2.py:22-27,33); retune[l] is the largest r that keeps max|y_l| * 2^r below 2^15, the overflow guard of
-// find=True (slim_yolo_v2.py:222-227; retune_bias_quantize_findbest.py:115-148).  The activations are exact dyadic
-// rationals y = num * 2^-E, so their maxima come from integer max/min reductions of the layer numerators: each layer is run
-// twice, once to reduce (conv_direct.cu statistics mode) and once, with the exponents just derived, to produce the
-// quantised map the next layer calibrates on.  Updates the context's tables and epilogue programmes in place.
-int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, int32_t *scale_a_out, int32_t *retune_out)
+// Tracker pass on the GPU: one forward pass over a float NCHW batch that visits every
+// AveragedRangeTracker (slim_yolo_v2.py:9-38) in order.  The activations are exact dyadic rationals y = num * 2^-E, so
+// max|a| of each tracker's input comes from integer max/min reductions of the layer numerators: each layer is run twice,
+// once to reduce (conv_direct.cu statistics mode) and once, with the exponents then in force, to produce the quantised map the
+// next layer sees.
+//   TRK_FIRST   fresh trackers: scale = 127 / max|a| (first-call rule, :22-27); retune[l] = largest r with max|y_l| * 2^r < 2^15
+//               (the overflow guard of find=True, :222-227; retune_bias_quantize_findbest.py:115-148)
+//   TRK_EMA     scale <- scale * (1 - momentum) + (127 / max|a|) * momentum for trackers that have been called before
+//               (scale != 0), first-call rule for the others (:25-31): a calibration set larger than one batch
+//   TRK_MEASURE nothing changes: reports max|a| per tracker under the tables in force (the `find` assertion, :222-226)
+// The exponent a tracker quantises with is floor(log2(scale)) (:33).  All arithmetic on the maxima follows the reference's
+// float32 tensor operations.  The context's tables are changed only if the whole pass succeeds.
+enum { TRK_FIRST = 0, TRK_EMA = 1, TRK_MEASURE = 2 };
+
+static int reprogram_all(yolo_b200_ctx *c)
 {
-    int rc = check_ready(c, n, h, w); if (rc) return rc;
-    if (!d_nchw || n < 1) return fail(E_ARG, "calibration needs at least one frame");
-    if (((size_t)h * w) % 4) return fail(E_UNSUPPORTED, "h*w must be a multiple of 4");
+    build_rgb444_lut(c->prm.scale_a[0], c->lut_host);
+    CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
+    c->lut8_saturates = build_u8_lut(c->prm.scale_a[0], c->lut8_host);
+    CU(cudaMemcpy(c->lut8_dev, c->lut8_host, sizeof c->lut8_host, cudaMemcpyHostToDevice));
+    for (size_t l = 0; l < c->layers.size(); ++l) { int rc = derive_layer(c, (int)l); if (rc) return rc; }
+    return 0;
+}
+
+static int tracker_pass_inner(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, int mode, float momentum,
+                              float *scales /*[L+1], in/out, may be NULL*/, double *max_abs /*[L+1], may be NULL*/)
+{
     yolo_b200_params &p = c->prm;
-    int hs[2];
+    int hs[2], rc;
+    auto new_scale = [&](int t, float m32) -> float {                 // tracker t sees max|a| = m32 (float32, as the tensor op yields)
+        const float fresh = 127.0f / m32;
+        if (mode == TRK_FIRST || !scales || scales[t] == 0.f) return fresh;
+        return scales[t] * (1.0f - momentum) + fresh * momentum;      // self.scale.mul_(1 - m).add_(scale * m), float32
+    };
     // input tracker
     CU(cudaMemsetAsync(c->stats_dev, 0, 2 * sizeof(int), c->stream));
     CU(absmax_f32(d_nchw, (size_t)n * 3 * h * w, reinterpret_cast<unsigned *>(c->stats_dev), c->stream));
@@ -638,12 +659,17 @@ int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h,
     CU(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     float m32; memcpy(&m32, &hs[0], 4);
-    if (!(m32 > 0.f) || !isfinite(m32)) return fail(E_ARG, "calibration input is all zero or not finite");
-    p.scale_a[0] = (int)floorf(log2f(127.0f / m32));
-    build_rgb444_lut(p.scale_a[0], c->lut_host);
-    CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
-    c->lut8_saturates = build_u8_lut(p.scale_a[0], c->lut8_host);
-    CU(cudaMemcpy(c->lut8_dev, c->lut8_host, sizeof c->lut8_host, cudaMemcpyHostToDevice));
+    if (!(m32 > 0.f) || !isfinite(m32)) return fail(E_ARG, "tracker pass: input is all zero or not finite");
+    if (max_abs) max_abs[0] = (double)m32;
+    if (mode != TRK_MEASURE) {
+        const float sc = new_scale(0, m32);
+        if (scales) scales[0] = sc;
+        p.scale_a[0] = (int)floorf(log2f(sc));
+        build_rgb444_lut(p.scale_a[0], c->lut_host);
+        CU(cudaMemcpy(c->lut_dev, c->lut_host, sizeof c->lut_host, cudaMemcpyHostToDevice));
+        c->lut8_saturates = build_u8_lut(p.scale_a[0], c->lut8_host);
+        CU(cudaMemcpy(c->lut8_dev, c->lut8_host, sizeof c->lut8_host, cudaMemcpyHostToDevice));
+    }
     rc = ensure((void **)&c->in_q, &c->in_q_cap, (size_t)n * h * w * 4); if (rc) return rc;
     rc = yolo_b200_quantize_f32(c, d_nchw, n, h, w, c->in_q); if (rc) return rc;
     const int8_t *cur = c->in_q;
@@ -651,10 +677,11 @@ int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h,
         LayerDev &L = c->layers[l];
         const yolo_b200_layer &Lp = p.layers[l];
         if (Lp.pool && (h < 2 || w < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, h, w);
-        // statistics pass: numerator at scale E = max(sa_i + sw, sb), biases shifted accordingly
+        // statistics pass: numerator at scale E = max(sa_i + sw, sb), biases shifted accordingly (|acc << la| < 2^28 and
+        // |b << lb| <= 2^30 by the limits below: the int32 numerator cannot wrap)
         const int ea = p.scale_a[l] + p.scale_w[l], E = ea > p.scale_b[l] ? ea : p.scale_b[l];
         const int la = E - ea, lb = E - p.scale_b[l];
-        if (la > 6 || lb > 22 || la < 0) return fail(E_UNSUPPORTED, "layer %zu: exponents out of range during calibration (la %d lb %d)", l, la, lb);
+        if (la > 6 || lb > 23 || la < 0) return fail(E_UNSUPPORTED, "layer %zu: exponents out of range in the tracker pass (la %d lb %d)", l, la, lb);
         std::vector<int> bp(L.cout_pad, 0);
         for (int o = 0; o < L.cout; ++o) bp[o] = (int)L.bias_host[o] * (1 << lb);
         CU(cudaMemcpy(L.bias_sh, bp.data(), bp.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -667,18 +694,24 @@ int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h,
         c->launches++;
         CU(cudaMemcpyAsync(hs, c->stats_dev, sizeof hs, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        const float pos = hs[0] > 0 ? (float)hs[0] : 0.f;
-        float neg = hs[1] < 0 ? -(float)hs[1] : 0.f;
-        if (Lp.activ) neg *= 0.125f;                                   // leaky-ReLU before the tracker (slim_yolo_v2.py:220-229)
-        const float my = ldexpf(pos > neg ? pos : neg, -E);            // max |y|, exact
-        if (!(my > 0.f)) return fail(E_ARG, "layer %zu produces only zeros on the calibration batch", l);
-        const double md = (double)my;
-        int r = (int)floor(log2(32768.0 / md));
-        while (md * ldexp(1.0, r) >= 32768.0) --r;
-        p.retune[l] = r;
-        p.scale_a[l + 1] = (int)floorf(log2f(127.0f / my));
-        rc = derive_layer(c, (int)l); if (rc) return rc;
-        // the layer itself, with the exponents just derived
+        const double pos = hs[0] > 0 ? (double)hs[0] : 0.0;
+        double neg = hs[1] < 0 ? -(double)hs[1] : 0.0;
+        if (Lp.activ) neg *= 0.125;                                    // leaky-ReLU before the tracker (slim_yolo_v2.py:220-229)
+        const double md = ldexp(pos > neg ? pos : neg, -E);            // max |y|, exact (|numerator| < 2^31, a power-of-two scale)
+        if (!(md > 0.0)) return fail(E_ARG, "layer %zu produces only zeros on this batch", l);
+        if (max_abs) max_abs[l + 1] = md;
+        if (mode != TRK_MEASURE) {
+            if (mode == TRK_FIRST || !scales || scales[l + 1] == 0.f) {   // the accumulator scale is tuned with the trackers' first call
+                int r = (int)floor(log2(32768.0 / md));
+                while (md * ldexp(1.0, r) >= 32768.0) --r;
+                p.retune[l] = r;
+            }
+            const float sc = new_scale((int)l + 1, (float)md);
+            if (scales) scales[l + 1] = sc;
+            p.scale_a[l + 1] = (int)floorf(log2f(sc));
+        }
+        rc = derive_layer(c, (int)l); if (rc) return rc;              // (also restores the epilogue's biases after the statistics pass)
+        // the layer itself, with the exponents in force
         const int oh = Lp.pool ? h / 2 : h, ow = Lp.pool ? w / 2 : w;
         rc = ensure((void **)&L.out, &L.out_cap, (size_t)n * oh * ow * L.cs_out); if (rc) return rc;
         L.oh = oh; L.ow = ow; L.view = L.out;
@@ -687,9 +720,55 @@ int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h,
     }
     c->last_n = n;
     CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int tracker_pass(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, int mode, float momentum, float *scales, double *max_abs)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (!d_nchw || n < 1) return fail(E_ARG, "the tracker pass needs at least one frame");
+    if (((size_t)h * w) % 4) return fail(E_UNSUPPORTED, "h*w must be a multiple of 4");
+    if (mode == TRK_EMA && !(momentum >= 0.f && momentum <= 1.f)) return fail(E_ARG, "momentum %g", (double)momentum);
+    const yolo_b200_params saved = c->prm;
+    std::vector<float> sc_saved;
+    if (scales) sc_saved.assign(scales, scales + c->prm.num_layers + 1);
+    rc = tracker_pass_inner(c, d_nchw, n, h, w, mode, momentum, scales, max_abs);
+    if (rc) {
+        // leave the context exactly as it was: tables, look-up tables and every layer's epilogue programme
+        char msg[sizeof g_err];
+        memcpy(msg, g_err, sizeof msg);
+        c->prm = saved;
+        if (scales) memcpy(scales, sc_saved.data(), sc_saved.size() * sizeof(float));
+        if (reprogram_all(c)) c->loaded = false;
+        memcpy(g_err, msg, sizeof msg);
+    }
+    return rc;
+}
+
+int yolo_b200_calibrate_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, int32_t *scale_a_out, int32_t *retune_out)
+{
+    int rc = tracker_pass(c, d_nchw, n, h, w, TRK_FIRST, 0.f, nullptr, nullptr); if (rc) return rc;
+    const yolo_b200_params &p = c->prm;
     if (scale_a_out) for (int l = 0; l <= p.num_layers; ++l) scale_a_out[l] = p.scale_a[l];
     if (retune_out) for (int l = 0; l < p.num_layers; ++l) retune_out[l] = p.retune[l];
     return 0;
+}
+
+int yolo_b200_update_trackers_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, float momentum,
+                                  float *tracker_scale, int32_t *scale_a_out, int32_t *retune_out)
+{
+    if (!tracker_scale) return fail(E_ARG, "null tracker_scale");
+    int rc = tracker_pass(c, d_nchw, n, h, w, TRK_EMA, momentum, tracker_scale, nullptr); if (rc) return rc;
+    const yolo_b200_params &p = c->prm;
+    if (scale_a_out) for (int l = 0; l <= p.num_layers; ++l) scale_a_out[l] = p.scale_a[l];
+    if (retune_out) for (int l = 0; l < p.num_layers; ++l) retune_out[l] = p.retune[l];
+    return 0;
+}
+
+int yolo_b200_measure_f32(yolo_b200_ctx *c, const float *d_nchw, int n, int h, int w, double *max_abs)
+{
+    if (!max_abs) return fail(E_ARG, "null max_abs");
+    return tracker_pass(c, d_nchw, n, h, w, TRK_MEASURE, 0.f, nullptr, max_abs);
 }
 
 int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, size_t bytes)

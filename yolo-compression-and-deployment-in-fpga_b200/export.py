@@ -74,7 +74,7 @@ class QuantNet:
     sw: List[int]
     sb: List[int]
     sa: List[int]                  # len(layers)+1, sa[0] = input
-    retune: List[int]
+    retune: Optional[List[int]]   # None = never derived from real activations: contract F / weight.h export refused
     anchors: List[List[float]] = field(default_factory=lambda: [list(a) for a in ANCHOR_SIZE_MASK])
     num_classes: int = 2
     stride: int = 16
@@ -84,8 +84,14 @@ class QuantNet:
         for w, b in zip(self.w, self.b):
             h.update(np.ascontiguousarray(w).tobytes())
             h.update(np.ascontiguousarray(b).tobytes())
-        h.update(np.asarray(self.sw + self.sb + self.sa + self.retune, dtype=np.int32).tobytes())
+        h.update(np.asarray(self.sw + self.sb + self.sa + (self.retune or []), dtype=np.int32).tobytes())
         return h.hexdigest()
+
+    def require_retune(self, what: str) -> List[int]:
+        if self.retune is None:
+            raise ValueError("%s needs retune[] (yolo_forward.c:35), which this network never derived from real activations: "
+                             "pass calib_frames= or retune= to quantnet_from_state_dict" % what)
+        return self.retune
 
     def dequantized_state_dict(self) -> Dict[str, torch.Tensor]:
         """The 42-key state_dict SlimYOLOv2_quantize_bnfuse.load_state_dict expects (weights as q/2**e,
@@ -123,18 +129,21 @@ def fold_bn_state_dict(sd: Dict[str, torch.Tensor], eps: float = 1e-5) -> Dict[s
     BatchNorm in the dict (any nesting depth, recognised by its `running_var`) is folded into the module one index before
     it in the same Sequential, its keys are dropped, and later indices of that Sequential move down by one — the layout
     the reference's `nn.Sequential(fused, *rest)` produces.  Keys of modules without a BatchNorm pass through."""
-    bn_prefixes = sorted(k[:-len(".running_var")] for k in sd if k.endswith(".running_var"))
+    def order(bp):      # BatchNorms of one Sequential from the LAST to the first: a fold only renumbers members behind it,
+        parent, _, idx = bp.rpartition(".")        # so the indices of the folds still to come stay valid
+        return (parent, -int(idx) if idx.isdigit() else 0)
+    bn_prefixes = sorted((k[:-len(".running_var")] for k in sd if k.endswith(".running_var")), key=order)
     out = dict(sd)
     for bp in bn_prefixes:
         parent, _, idx = bp.rpartition(".")
         if not idx.isdigit() or int(idx) == 0:
             raise ValueError("BatchNorm %s does not follow a convolution inside a Sequential" % bp)
         cp = "%s.%d" % (parent, int(idx) - 1)
-        if cp + ".weight" not in sd or sd[cp + ".weight"].dim() != 4:
+        if cp + ".weight" not in out or out[cp + ".weight"].dim() != 4:
             raise ValueError("no convolution at %s for BatchNorm %s" % (cp, bp))
-        w, b = fold_bn(sd[cp + ".weight"].float(), sd[cp + ".bias"].float() if cp + ".bias" in sd else None,
-                       sd[bp + ".weight"].float(), sd[bp + ".bias"].float(), sd[bp + ".running_mean"].float(),
-                       sd[bp + ".running_var"].float(), eps)
+        w, b = fold_bn(out[cp + ".weight"].float(), out[cp + ".bias"].float() if cp + ".bias" in out else None,
+                       out[bp + ".weight"].float(), out[bp + ".bias"].float(), out[bp + ".running_mean"].float(),
+                       out[bp + ".running_var"].float(), eps)
         out[cp + ".weight"], out[cp + ".bias"] = w, b
         for k in [k for k in out if k.startswith(bp + ".")]:
             del out[k]
@@ -314,25 +323,41 @@ def random_quantnet(seed: int = 0, calib_hw=(416, 416), calib_frames: int = 2, h
 
 
 def quantnet_from_state_dict(sd: Dict[str, torch.Tensor], calib_frames: Optional[torch.Tensor] = None,
-                             anchors=None, num_classes: int = 2) -> QuantNet:
+                             anchors=None, num_classes: int = 2, retune: Optional[Sequence[int]] = None) -> QuantNet:
     """q_bf state_dict (float or already-quantised `*_retune_quantize*.pth`, retune_bias_quantize.py:411-415)
-    -> QuantNet.  Activation exponents come from the checkpoint's trackers when they were calibrated
-    (first_a != 0), else from `calib_frames`."""
+    -> QuantNet.  The layer list comes from the state_dict itself (the head's width is `pred.weight.shape[0]`, which must
+    equal len(anchors) * (5 + num_classes), slim_yolo_v2.py:87).  Activation exponents come from the checkpoint's trackers
+    when they were calibrated (first_a != 0), else from `calib_frames`.
+
+    `retune[]` (the 16-bit accumulator scale of contract F / weight.h, yolo_forward.c:35) only means something when it was
+    derived from real activations: it is taken from `calib_frames` (the 2^15 rule of slim_yolo_v2.py:222-227) or from an
+    explicit table (`retune=`, e.g. SHIPPED_RETUNE); with neither it is None and the QuantNet refuses contract F and the
+    weight.h export (contract P, the PyTorch fake-quant arithmetic, never reads it)."""
     ws, bs = _float_convs_from_state_dict(sd)
+    anchors = [list(a) for a in (anchors or ANCHOR_SIZE_MASK)]
+    layers = [(int(w.shape[1]), int(w.shape[0]), a, p) for w, (_, _, a, p) in zip(ws, SLIM_YOLO_V2_LAYERS)]
+    for l in range(1, len(layers)):
+        if layers[l][0] != layers[l - 1][1]:
+            raise ValueError("state_dict: layer %d takes %d channels but layer %d produces %d" % (l, layers[l][0], l - 1, layers[l - 1][1]))
+    want = len(anchors) * (5 + num_classes)
+    if layers[-1][1] != want:
+        raise ValueError("pred.weight has %d output channels; %d anchors x (5 + %d classes) needs %d"
+                         % (layers[-1][1], len(anchors), num_classes, want))
     qw, qb, sw, sb, dw, db = quantize_convs(ws, bs)
     have_trackers = all((k + ".scale") in sd and float(sd[k + ".first_a"]) != 0 for k in SLIM_TRACKER_KEYS)
     if calib_frames is None and not have_trackers:
         raise ValueError("state_dict has uncalibrated activation trackers: pass calib_frames")
-    if calib_frames is None:
-        calib_frames = synthetic_frames_f32(1, 64, 64)
-    sa_c, retune = calibrate(dw, db, calib_frames)
-    if have_trackers:
-        sa = [int(math.floor(math.log2(float(sd[k + ".scale"])))) for k in SLIM_TRACKER_KEYS]
-        # retune must respect the 16-bit bound for the activations actually seen; keep the calibrated one
+    sa_c = rt_c = None
+    if calib_frames is not None:
+        sa_c, rt_c = calibrate(dw, db, calib_frames, layers)
+    sa = [int(math.floor(math.log2(float(sd[k + ".scale"])))) for k in SLIM_TRACKER_KEYS] if have_trackers else sa_c
+    if retune is not None:
+        if len(retune) != len(layers):
+            raise ValueError("retune table needs %d entries" % len(layers))
+        rt = [int(r) for r in retune]
     else:
-        sa = sa_c
-    return QuantNet(list(SLIM_YOLO_V2_LAYERS), qw, qb, sw, sb, sa, retune,
-                    [list(a) for a in (anchors or ANCHOR_SIZE_MASK)], num_classes)
+        rt = rt_c          # None when the checkpoint brought its own trackers and no calibration frames were given
+    return QuantNet(layers, qw, qb, sw, sb, sa, rt, anchors, num_classes)
 
 
 # ---- weight.h ---------------------------------------------------------------------------------------
@@ -370,6 +395,7 @@ def unpack_weight_h_order(flat: np.ndarray, cout: int, cin: int) -> np.ndarray:
 def write_weight_h(net: QuantNet, path: str) -> None:
     """Emit a weight.h with the symbols yolo_forward.c uses (w_conv0..9 / b_conv0..9, :1204-1260) plus the
     exponent tables of :32-35 as comments."""
+    net.require_retune("weight.h (the C driver's tables)")
     with open(path, "w") as f:
         f.write("/* generated by yolo_b200 export.write_weight_h — layout: see pack_weight_h_order */\n")
         f.write("/* scale_w = %s\n   scale_b = %s\n   scale_a = %s\n   retune  = %s */\n"

@@ -29,7 +29,7 @@ EXPORTS = [
     "yolo_b200_forward_u8bgr_dev", "yolo_b200_quantize_u8bgr", "yolo_b200_u8bgr_lut",
     "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev", "yolo_b200_sync",
     "yolo_b200_quantize_rgb444", "yolo_b200_quantize_f32", "yolo_b200_rgb444_lut", "yolo_b200_conv_layer",
-    "yolo_b200_backbone", "yolo_b200_calibrate_f32", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
+    "yolo_b200_backbone", "yolo_b200_calibrate_f32", "yolo_b200_update_trackers_f32", "yolo_b200_measure_f32", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
     "yolo_b200_launch_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
     "yolo_forward", "yolo_b200_set_default_context",
     "yolo_b200_resize_taps", "yolo_b200_resize_u8bgr", "yolo_b200_forward_u8bgr_resize", "yolo_b200_forward_u8bgr_resize_dev",
@@ -103,6 +103,8 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_rgb444_lut.argtypes = [vp, vp]
     L.yolo_b200_quantize_u8bgr.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_calibrate_f32.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.yolo_b200_update_trackers_f32.argtypes = [vp, vp, i32, i32, i32, C.c_float, vp, vp, vp]
+    L.yolo_b200_measure_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.yolo_b200_u8bgr_lut.argtypes = [vp, vp]
     L.yolo_b200_conv_layer.argtypes = [vp, i32, i8p, i32, i32, i32, i8p]
     L.yolo_b200_backbone.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]
@@ -127,9 +129,11 @@ def make_params(qnet, contract=CONTRACT_P, round_mode=ROUND_RNE, head_mode=HEAD_
     """Params from an export.QuantNet (tables are data, not compile-time constants)."""
     p = Params()
     p.num_layers = len(qnet.layers)
+    # contract F is the 16-bit accumulator programme: it needs a retune[] that was derived from real activations
+    retune = qnet.require_retune("contract F") if contract == CONTRACT_F else (qnet.retune or [0] * len(qnet.layers))
     for l, (cin, cout, activ, pool) in enumerate(qnet.layers):
         p.layers[l] = Layer(cin, cout, activ, pool)
-        p.scale_w[l] = qnet.sw[l]; p.scale_b[l] = qnet.sb[l]; p.retune[l] = qnet.retune[l]
+        p.scale_w[l] = qnet.sw[l]; p.scale_b[l] = qnet.sb[l]; p.retune[l] = retune[l]
     for l, v in enumerate(qnet.sa):
         p.scale_a[l] = v
     p.contract = contract; p.round_mode = round_mode; p.head_mode = head_mode
@@ -296,6 +300,30 @@ class Context:
             self.params.scale_a[l] = int(sa[l]); self.params.retune[l] = int(rt[l])
         self.params.scale_a[nl] = int(sa[nl])
         return sa.tolist(), rt.tolist()
+
+    def update_trackers_f32(self, d_nchw, n, h, w, momentum, tracker_scale):
+        """One more calibration batch (slim_yolo_v2.py:25-31): tracker_scale = float32 [num_layers + 1], the `scale`
+        buffers of a_tracker_in .. a_tracker_pred, updated in place (zeros = fresh trackers = first-call rule, otherwise the
+        exponential average); the context is re-programmed with floor(log2(scale)).  Returns (scale_a, retune)."""
+        nl = self.params.num_layers
+        ts = np.ascontiguousarray(tracker_scale, dtype=np.float32)
+        assert ts.shape == (nl + 1,)
+        sa = np.zeros(nl + 1, dtype=np.int32)
+        rt = np.zeros(nl, dtype=np.int32)
+        self._check(self.L.yolo_b200_update_trackers_f32(self._h, _ptr(d_nchw), n, h, w, C.c_float(momentum), ts.ctypes.data,
+                                                         sa.ctypes.data, rt.ctypes.data))
+        tracker_scale[...] = ts
+        for l in range(nl):
+            self.params.scale_a[l] = int(sa[l]); self.params.retune[l] = int(rt[l])
+        self.params.scale_a[nl] = int(sa[nl])
+        return sa.tolist(), rt.tolist()
+
+    def measure_f32(self, d_nchw, n, h, w):
+        """max|a| at every tracker (input, then each layer after its leaky-ReLU) under the tables in force: the quantity the
+        reference's find=True branch asserts on (slim_yolo_v2.py:222-226).  Nothing in the context changes."""
+        mx = np.zeros(self.params.num_layers + 1, dtype=np.float64)
+        self._check(self.L.yolo_b200_measure_f32(self._h, _ptr(d_nchw), n, h, w, mx.ctypes.data))
+        return mx
 
     def quantize_u8bgr(self, d_bgr, n, h, w, d_out):
         self._check(self.L.yolo_b200_quantize_u8bgr(self._h, _ptr(d_bgr), n, h, w, _ptr(d_out)))

@@ -8,8 +8,10 @@ same attributes (`input_size`, `stride`, `trainable`, `set_grid`) and the same 4
 `net.load_state_dict(torch.load(...))` works on reference checkpoints.
 
 Which path runs:
-  * `quantization=True`, inference  -> the fixed-point hot path (contract P) on the GPU through the C-ABI.
-    This is what `utils/vocapi_evaluator_mask.py:69` calls.  Requires CUDA; there is no CPU fallback.
+  * `quantization=True`, inference  -> the fixed-point hot path (contract P) on the GPU through the C-ABI, with or without
+    `find=True` (the overflow probe + the /2**k rescaling of retune_bias_quantize_findbest.py:364 run on the GPU too).
+    This is what `utils/vocapi_evaluator_mask.py:69` calls.  Requires CUDA; there is no CPU fallback.  Fresh trackers
+    (first_a == 0) are calibrated on the first batch by the GPU tracker pass, as the reference's first call does.
   * `quantization=False`, inference -> activations are NOT quantised in the reference (slim_yolo_v2.py:18-19), i.e.
     a plain float network: stock PyTorch ops + the same head, outside the fixed-point path.
   * `trainable=True` -> training is out of scope; raises.
@@ -114,7 +116,49 @@ class SlimYOLOv2_quantize_bnfuse(nn.Module):
         return ex.quantnet_from_state_dict(sd, calib_frames=calib_frames, anchors=self.anchor_size.tolist(),
                                            num_classes=self.num_classes)
 
-    def _context(self, x):
+    # the /2**k constants the reference hard-codes in its find branch, slim_yolo_v2.py:227,240,...,327
+    FIND_SHIFTS = (11, 10, 10, 11, 11, 10, 11, 11, 11, 10)
+
+    def _load(self, ctx, find):
+        """(Re)program the context from the module's parameters.  find=True: the reference divides every layer's output by
+        2**k before its tracker (slim_yolo_v2.py:222-227 ... :327); y / 2**k with y = acc * 2^-(sa_i + sw) + b * 2^-sb is the
+        same layer with BOTH exponents raised by k (the leaky-ReLU is positively homogeneous), so the find branch is the
+        fake-quant contract with shifted weight / bias exponent tables: no separate kernel path."""
+        from . import lib
+        sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+        fresh = any(float(t.first_a) == 0 for t in self._trackers())
+        if fresh:                                    # exponents are about to be calibrated on the GPU: placeholders
+            for k in ex.SLIM_TRACKER_KEYS:
+                sd[k + ".scale"] = torch.ones(1); sd[k + ".first_a"] = torch.ones(1)
+        qnet = ex.quantnet_from_state_dict(sd, anchors=self.anchor_size.tolist(), num_classes=self.num_classes)
+        if find:
+            qnet.sw = [e + k for e, k in zip(qnet.sw, self.FIND_SHIFTS)]
+            qnet.sb = [e + k for e, k in zip(qnet.sb, self.FIND_SHIFTS)]
+        ctx.load_quantnet(qnet, contract=lib.CONTRACT_P, head_mode=lib.HEAD_PYTHON,
+                          conf_thresh=float(self.conf_thresh), nms_thresh=float(self.nms_thresh), max_det=4096)
+
+    def update_trackers(self, x, find=False, momentum=None):
+        """One calibration batch on the GPU (yolo_b200_update_trackers_f32): fresh trackers take scale = 127 / max|a| (the
+        reference's first call, slim_yolo_v2.py:25-27); trackers that have been called before move by the exponential
+        average of :31 (what the reference does while `trainable`).  The `scale` / `first_a` buffers end up with the values
+        the reference's buffers would hold."""
+        from . import lib
+        if not (torch.cuda.is_available() and x.is_cuda):
+            raise lib.YoloB200Error("the trackers are calibrated by CUDA kernels; input is on %s and there is no CPU fallback" % x.device)
+        if self._ctx is None:
+            self._ctx = lib.Context(x.device.index or 0)
+        self._load(self._ctx, find)
+        trackers = self._trackers()
+        scales = np.array([float(t.scale) if float(t.first_a) != 0 else 0.0 for t in trackers], dtype=np.float32)
+        n, c, h, w = x.shape
+        self._ctx.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+        self._ctx.update_trackers_f32(x.contiguous().float(), n, h, w, self.a_tracker_in.momentum if momentum is None else momentum, scales)
+        for t, sc in zip(trackers, scales):
+            t.scale.fill_(float(sc))
+            t.first_a.fill_(1)
+        self._ctx_key = None
+
+    def _context(self, x, find=False):
         from . import lib
         if not (torch.cuda.is_available() and x.is_cuda):
             raise lib.YoloB200Error("quantization=True runs the fixed-point path on CUDA kernels; input is on %s and "
@@ -122,31 +166,37 @@ class SlimYOLOv2_quantize_bnfuse(nn.Module):
         trackers = self._trackers()
         if any(float(t.first_a) == 0 for t in trackers):
             # first call with fresh trackers: the reference calibrates on this batch (slim_yolo_v2.py:25-27)
-            ws, bs = ex._float_convs_from_state_dict({k: v.detach().cpu() for k, v in self.state_dict().items()})
-            _, _, _, _, dw, db = ex.quantize_convs(ws, bs)
-            sa, _ = ex.calibrate(dw, db, x.detach().float().cpu())
-            for t, e in zip(trackers, sa):
-                t.scale.fill_(2.0 ** e)
-                t.first_a.fill_(1)
+            self.update_trackers(x, find)
         key = (tuple(int(p._version) for p in self.parameters()), tuple(float(t.scale) for t in trackers),
-               float(self.conf_thresh), float(self.nms_thresh), x.device.index or 0)
+               float(self.conf_thresh), float(self.nms_thresh), x.device.index or 0, bool(find))
         if self._ctx is None or self._ctx_key != key:
-            qnet = self.quantnet()
             if self._ctx is None:
                 self._ctx = lib.Context(x.device.index or 0)
-            self._ctx.load_quantnet(qnet, contract=lib.CONTRACT_P, head_mode=lib.HEAD_PYTHON,
-                                    conf_thresh=float(self.conf_thresh), nms_thresh=float(self.nms_thresh), max_det=4096)
+            self._load(self._ctx, find)
             self._ctx_key = key
         return self._ctx
 
-    def forward_batch(self, x):
+    def forward_batch(self, x, find=False, frames=None):
         """Fixed-point inference for a whole batch: list of (bboxes, scores, cls_inds) per frame.
         (The reference's head only looks at batch element 0, slim_yolo_v2.py:348-350.)"""
         from . import lib
-        ctx = self._context(x)
+        ctx = self._context(x, find)
         n, c, h, w = x.shape
         x = x.contiguous().float()
         ctx.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+        if find:
+            # the overflow probe of the find branch (slim_yolo_v2.py:222-226 ... :322-326): every layer's output, BEFORE the
+            # division by 2**k, must stay below the 16-bit accumulator range
+            mx = ctx.measure_f32(x, n, h, w)
+            for l, k in enumerate(self.FIND_SHIFTS):
+                if mx[l + 1] * 2.0 ** k >= 2 ** (16 - 1):
+                    print("too high!!!")
+                    print(mx[l + 1] * 2.0 ** k)
+                    raise AssertionError("layer %d: max |output| %g exceeds the 16-bit accumulator (slim_yolo_v2.py:222-226)"
+                                         % (l, mx[l + 1] * 2.0 ** k))
+        if frames is not None:                       # trackers and the probe saw the whole batch; decode only these frames
+            x = x[:frames].contiguous()
+            n = x.shape[0]
         dets = torch.empty((n, ctx.params.max_det, 8), dtype=torch.int32, device=x.device)
         counts = torch.empty((n,), dtype=torch.int32, device=x.device)
         ctx.forward_f32_dev(x, n, h, w, dets, counts)
@@ -162,8 +212,9 @@ class SlimYOLOv2_quantize_bnfuse(nn.Module):
     def forward(self, x, target=None, quantization=False, find=False):
         if self.trainable:
             raise NotImplementedError("training (slim_yolo_v2.py:360-382) is outside this library's scope")
-        if quantization and not find:
-            return self.forward_batch(x[:1])[0]
+        if quantization:
+            # (the reference's head only decodes batch element 0, slim_yolo_v2.py:348-350, but its trackers see the whole batch)
+            return self.forward_batch(x, find, frames=1)[0]
         return self._forward_float(x, find)
 
     # -- float path (quantization=False): stock PyTorch, outside the fixed-point hot path -------------------
