@@ -19,6 +19,10 @@ oracle timed on this box's host cores on a bounded sample (rank 0, N=1 only).
 
 --impl reference times the reference's own CPU implementation of the path: the C restatement under oracle/
 (the C driver itself cannot run without the FPGA RTL) with all host threads.
+
+--scaling strong shards a FIXED global batch (--global-batch, default 2048 frames per step) over the GPUs instead of 256
+frames per GPU.  At N = 1 the line also carries `other_configs`: the same step at the C path's
+native geometry (240x320 RGB444), from fp32 NCHW input, and under contract P (the contract pinned on the reference module).
 """
 import argparse
 import json
@@ -52,12 +56,24 @@ def layer_work(qnet, h, w):
 
 
 def peaks():
+    """HBM GB/s and bf16 TFLOP/s from the driver-written MEASURED_PEAKS.json (else B200_PROFILING.md's fallback), and the
+    INT8 tensor peak MEASURED on this pool's B200 with tools/micro/umma_peak.cu (148 persistent CTAs issuing
+    tcgen05.mma.kind::i8 N=256 back to back; profiles/int8_peak_r2.json holds TOPS for a 4 ms burst and for 2 s sustained
+    with the clock / power record).  The per-kernel fractions and the ~25 ms timed region use the BURST figure."""
     p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             m = json.load(f)
         p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
         p["source"] = "measured"
+    except Exception:
+        pass
+    p["int8_tops"], p["int8_source"] = 2.0 * p["bf16_tflops"], "2 x bf16 burst of MEASURED_PEAKS.json (%s)" % p["source"]
+    try:
+        with open(os.path.join(ROOT, "profiles", "int8_peak_r2.json")) as f:
+            m = json.load(f)
+        p["int8_tops"], p["int8_tops_sustained"] = float(m["int8_tops_burst"]), float(m["int8_tops_sustained"])
+        p["int8_source"] = "measured_int8"
     except Exception:
         pass
     return p
@@ -124,9 +140,11 @@ def oracle_frames(qnet, frames_u16):
 
 def cpu_oracle_fps(qnet, seconds_budget):
     """Oracle on a bounded sample of the workload, all host threads (OpenMP over rows)."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import yolo_b200  # noqa: F401
     from yolo_b200 import export as ex
-    cores = os.cpu_count() or 1
+    import oracle_lib as ol
+    cores = ol.set_threads()
     done, t0 = 0, time.perf_counter()
     while True:
         oracle_frames(qnet, ex.synthetic_frames_rgb444(1, H, W, seed=9000 + done))
@@ -142,11 +160,15 @@ def run_reference(args, rank, world):
     cannot run (FPGA RTL and weight.h are not in the reference), so this is the oracle port."""
     if rank != 0:
         return
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm must use every host thread whether it is
+    # launched directly or under torchrun (set before the OpenMP runtime of liboracle.so starts)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import yolo_b200  # noqa: F401
     from yolo_b200 import export as ex
     import oracle_lib as ol
     qnet = make_qnet()
     ol.build()
+    cores = ol.set_threads()
     frames_per_step = 4
     xs = ex.synthetic_frames_rgb444(frames_per_step, H, W, seed=123)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -156,7 +178,6 @@ def run_reference(args, rank, world):
         oracle_frames(qnet, xs)
     dt = time.perf_counter() - t0
     fps = args.steps * frames_per_step / dt
-    cores = os.cpu_count() or 1
     sample = "%d frames/step of the 416x416 RGB444 workload (front-end LUT + backbone + head), OpenMP over rows, %d host threads" % (frames_per_step, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -169,15 +190,31 @@ def run_reference(args, rank, world):
     }))
 
 
+def time_steps(stream, fn, warm, steps):
+    import torch
+    for i in range(warm):
+        fn(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        fn(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--global-batch", type=int, default=2048, help="frames per step over all GPUs (strong scaling)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip other_configs / sparse head / image front end")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +236,12 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # keeps NCCL's banner out of stdout (one JSON line)
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.batch
+    strong = args.scaling == "strong"
+    if strong:
+        lo, hi = runner.shard_range(args.global_batch, rank, world)
+        B = hi - lo
+    else:
+        B = args.batch
     qnet = make_qnet()
     MAXDET = 4096
     ctx = lib.Context(local)
@@ -208,23 +250,28 @@ def main():
     ctx.set_stream(stream.cuda_stream)
 
     # synthetic camera frames, RGB444 (the C path's input format), 3 alternating batches of 88.6 MB each; a step also
-    # writes and reads 177 MB of quantised input and ~0.8 GB of feature maps, far more than the 126 MB L2
+    # streams ~1.3 GB of feature maps, far more than the 126 MB L2
     n_sets = 3
     host_sets = [torch.from_numpy(ex.synthetic_frames_rgb444(B, H, W, seed=100 * rank + s).view(np.int16)).pin_memory() for s in range(n_sets)]
     dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
     n_anchors = (H // 16) * (W // 16) * 5                       # bounds any per-frame detection count
-    gath = runner.DetectionGatherer(B, MAXDET, n_anchors, torch.device("cuda", local))
-    d_dets, d_counts = gath.bufs[0].dets, gath.bufs[0].counts
+    # N > 1: every rank's lists are collected on rank 0 by copy-engine peer writes of their filled part (runner.PeerCollector)
+    coll = runner.PeerCollector(ctx, B, MAXDET, n_anchors, torch.device("cuda", local)) if world > 1 else None
+    d_dets = torch.zeros((B, MAXDET, 8), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
 
     def step(i):
-        # detections of every rank are all-gathered asynchronously (double-buffered): the gather of step i overlaps step i+1
-        buf = gath.buffers(i)
-        ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, buf.dets, buf.counts)
-        gath.launch(i)
+        if coll is None:
+            ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, d_dets, d_counts)
+        else:
+            buf = coll.buffers(i)
+            ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, buf.dets, buf.counts)
+            coll.launch(i)          # packs step i; ships step i - 1 while step i computes
 
     def barrier():
-        gath.finish()
+        if coll is not None:
+            coll.finish()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -240,8 +287,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
-        step(i)
-    gath.finish()                      # the stream waits for the outstanding gathers: they are inside the timed region
+        step(args.warmup + i)
+    if coll is not None:
+        coll.finish()                  # the last lists have landed on rank 0: the collection is inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -250,8 +298,20 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    fps = world * B * args.steps / (ms / 1e3)
-    mean_dets = float(d_counts.float().mean().item())
+    total_frames = (args.global_batch if strong else world * B) * args.steps
+    fps = total_frames / (ms / 1e3)
+    collected = None
+    if coll is not None:
+        mean_dets = float(coll.bufs[(args.warmup + args.steps - 1) % coll.depth].counts.float().mean().item())
+        if rank == 0:   # what arrived on rank 0 for the last step: records per rank
+            collected = [int(off[-1].item()) for off, rec in coll.collected(args.warmup + args.steps - 1)]
+            assert all(c >= 0 for c in collected)
+        sent = torch.tensor([coll.sent_bytes / max(1, args.warmup + args.steps)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sent, op=dist.ReduceOp.SUM)
+        collect_bytes = float(sent.item())
+    else:
+        mean_dets = float(d_counts.float().mean().item())
+        collect_bytes = 0.0
 
     # ---- per-kernel device times (CUDA events on the launching stream) -> dominant kernel and its roofline
     # (the RGB444 -> int8 quantiser is fused into conv1's tile load: conv1 reads the 2-byte camera pixels)
@@ -270,7 +330,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     pk = peaks()
     work = layer_work(qnet, H, W)
-    int8_peak_tops = 2.0 * pk["bf16_tflops_sustained"]            # no measured INT8 figure: 2 x measured bf16
+    int8_peak_tops = pk["int8_tops"]                              # measured tcgen05 kind::i8 burst peak (profiles/int8_peak_r2.json)
     # algorithmic (MACs, bytes) per frame for every kernel of the step
     work[0]["bytes"] -= 2 * H * W      # conv1 reads RGB444 (2 B/pixel), not NHWC4
     rows = work + [{"macs": 0, "bytes": (H // 16) * (W // 16) * 48 + int(mean_dets) * 32}]
@@ -281,7 +341,7 @@ def main():
     tensor_bound = ops / (int8_peak_tops * 1e12) > byts / (pk["hbm_gbs"] * 1e9)
     if tensor_bound:
         roof = {"bound": "tensor", "achieved": ops / t_top / 1e12, "peak": int8_peak_tops, "unit": "TFLOP/s",
-                "note": "int8 ops (2*MAC) counted as FLOPs; peak = 2 x sustained bf16 of MEASURED_PEAKS.json (%s)" % pk["source"]}
+                "note": "int8 ops (2*MAC) counted as FLOPs; peak = %s" % pk["int8_source"]}
     else:
         roof = {"bound": "hbm", "achieved": byts / t_top / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "note": "algorithmic bytes (input map + output map, or prediction map + detection records for the head) / "
@@ -289,24 +349,36 @@ def main():
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["kernel"] = names[top]
     roof["kernel_ms"] = float(per[top])
+    roof["peak_source"] = pk["int8_source"]
+    roof["int8_peak_tops"] = {"burst_measured": pk.get("int8_tops"), "sustained_measured": pk.get("int8_tops_sustained"),
+                              "two_x_bf16_burst": 2.0 * pk["bf16_tflops"], "two_x_bf16_sustained": 2.0 * pk["bf16_tflops_sustained"]}
     roof["traffic"] = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-            tr = json.load(f)
-        if names[top] in tr and tr.get("batch") == B:
-            roof["traffic"] = tr[names[top]]
-    except Exception:
-        pass
+    for tf in ("traffic_r2.json", "traffic_r1.json"):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as f:
+                tr = json.load(f)
+            if names[top] in tr and tr.get("batch") == B:
+                roof["traffic"] = tr[names[top]]
+                roof["traffic_source"] = "profiles/" + tf
+                break
+        except Exception:
+            pass
+    bf2 = 2.0 * pk["bf16_tflops"]
     per_kernel = {}
     for n_, t_, r_ in zip(names, per, rows):
         tb = 2.0 * r_["macs"] * B / (int8_peak_tops * 1e12)
         hb = r_["bytes"] * B / (pk["hbm_gbs"] * 1e9)
+        tb2 = 2.0 * r_["macs"] * B / (bf2 * 1e12)
         per_kernel[n_] = {"ms": round(float(t_), 4), "bound": "tensor" if tb > hb else "hbm",
-                          "frac": round(max(tb, hb) / (float(t_) / 1e3), 4) if t_ > 0 else None}
+                          "frac": round(max(tb, hb) / (float(t_) / 1e3), 4) if t_ > 0 else None,
+                          "frac_vs_2x_bf16": round(max(tb2, hb) / (float(t_) / 1e3), 4) if t_ > 0 else None}
     roof["per_kernel"] = per_kernel
     t_roof = sum(max(2.0 * r["macs"] / (int8_peak_tops * 1e12), r["bytes"] / (pk["hbm_gbs"] * 1e9)) for r in rows)
+    t_roof2 = sum(max(2.0 * r["macs"] / (bf2 * 1e12), r["bytes"] / (pk["hbm_gbs"] * 1e9)) for r in rows)
+    per_frame_s = ms / 1e3 / (B * args.steps)
     roof["network_t_roof_us_per_frame"] = t_roof * 1e6
-    roof["network_frac_of_roofline"] = t_roof / (ms / 1e3 / (B * args.steps))
+    roof["network_frac_of_roofline"] = t_roof / per_frame_s
+    roof["network_frac_vs_2x_bf16"] = t_roof2 / per_frame_s
 
     # ---- e2e: the C-ABI host entry point, pinned host frames in, detections out (copies inside the timed region;
     #      the library pipelines them against the kernels chunk by chunk)
@@ -333,15 +405,46 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_fps = world * B * e2e_steps / e2e_s
+    e2e_fps = (args.global_batch if strong else world * B) * e2e_steps / e2e_s
     # bytes the library copies back per step: counts + one strided copy as wide as the batch's largest count
     hc = h_counts.numpy()
     d2h_bytes = int(4 * B + B * min(int(hc.max()), MAXDET) * 32)
     assert int(h_counts.sum()) > 0 or mean_dets == 0
 
     # ---- secondary: the same network with a trained-like sparse head (objectness bias - 5)
+    secondary = rank == 0 and world == 1 and not args.no_secondary and not strong
+    # ---- other configurations of SURVEY 8d config 3 (N = 1): the C path's native geometry, fp32 input, contract P
+    other = None
+    if secondary:
+        other = {}
+
+        def run_cfg(name, fn, frames, note):
+            ms_ = time_steps(stream, fn, 3, 10)
+            other[name] = {"value": frames / (ms_ / 1e3), "unit": "frames/s", "ms_per_step": ms_, "frames_per_step": frames, "note": note}
+        # 240 x 320 RGB444: what the camera delivers to yolo_forward (yolo_forward.c:1194-1197), shipped-style network calibrated at that size
+        q240 = ex.random_quantnet(seed=0, calib_hw=(240, 320), calib_frames=2, calib_input="rgb444")
+        ctx.load_quantnet(q240, contract=lib.CONTRACT_F, round_mode=lib.ROUND_RNE, conf_thresh=CONF, nms_thresh=NMS, max_det=MAXDET)
+        d240 = torch.from_numpy(ex.synthetic_frames_rgb444(B, 240, 320, seed=7).view(np.int16)).cuda()
+        run_cfg("rgb444_240x320_contract_F", lambda i: ctx.forward_rgb444_dev(d240, B, 240, 320, d_dets, d_counts), B,
+                "%d RGB444 frames of 240x320 (the C path's camera geometry), contract F/RNE, dense random-init head" % B)
+        del d240
+        # fp32 NCHW input at 416 x 416 (the Python path's input, test.py:79-80), contract P = the arithmetic pinned on the reference module
+        qp = ex.random_quantnet(seed=0, calib_hw=(H, W), calib_frames=2)
+        ctx.load_quantnet(qp, contract=lib.CONTRACT_P, conf_thresh=CONF, nms_thresh=NMS, max_det=MAXDET)
+        xf = ex.synthetic_frames_f32(B, H, W, seed=11).cuda()
+        run_cfg("f32_416x416_contract_P", lambda i: ctx.forward_f32_dev(xf, B, H, W, d_dets, d_counts), B,
+                "%d float32 NCHW frames of 416x416 (531 MB read per step by the quantiser), contract P (PyTorch fake-quant, pinned on the reference module)" % B)
+        ovf = ctx.overflow_count()
+        other["f32_416x416_contract_P"]["int8_saturations"] = int(ovf)
+        del xf
+        # RGB444 416 x 416 under contract P (same workload as the headline, the pinned contract)
+        qpr = make_qnet()
+        ctx.load_quantnet(qpr, contract=lib.CONTRACT_P, conf_thresh=CONF, nms_thresh=NMS, max_det=MAXDET)
+        run_cfg("rgb444_416x416_contract_P", lambda i: ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, d_dets, d_counts), B,
+                "the headline workload under contract P")
+
     sparse = None
-    if rank == 0 and world == 1:
+    if secondary:
         qs = ex.random_quantnet(seed=0, calib_hw=(H, W), calib_frames=2, calib_input="rgb444", head_bias_shift=-5.0)
         ctx.load_quantnet(qs, contract=lib.CONTRACT_F, round_mode=lib.ROUND_RNE, conf_thresh=CONF, nms_thresh=NMS, max_det=MAXDET)
         for i in range(3):
@@ -368,7 +471,7 @@ def main():
     #      480x640 BGR frames -> 416x416, then the fused normalise/quantise first layer): the resize kernel alone against
     #      HBM, and the host entry point with the camera-size images in pinned memory
     front = None
-    if rank == 0 and world == 1:
+    if secondary:
         SH, SW = 480, 640
         g = torch.Generator().manual_seed(5)
         h_imgs = torch.randint(0, 256, (B, SH, SW, 3), dtype=torch.uint8, generator=g).pin_memory()
@@ -410,6 +513,17 @@ def main():
                  "e2e": B * e2e_steps / (time.perf_counter() - t0), "h2d_bytes_per_step": int(h_imgs.numel())}
         del d_imgs, d_small, h_imgs
 
+    cpu_torch = None
+    try:    # the reference's PyTorch CPU path cannot travel to the GPU box: timed in the build container (oracle/time_reference_pytorch.py)
+        with open(os.path.join(ROOT, "profiles", "ref_pytorch_cpu_r2.json")) as f:
+            rp = json.load(f)
+        best = max((r for r in rp["runs"] if r["h"] == H and r["w"] == W), key=lambda r: r["frames_per_s"])
+        cpu_torch = {"value": best["frames_per_s"], "unit": "frames/s", "cores": best["threads"], "kind": "reference",
+                     "sample": "reference SlimYOLOv2_quantize_bnfuse.forward(quantization=True), batch 1 at %dx%d, 10 timed calls, measured in the "
+                               "BUILD CONTAINER (%s, torch %s; /root/reference does not exist on the GPU box)" % (H, W, rp["cpu"], rp["torch"]),
+                     "all_runs": rp["runs"]}
+    except Exception:
+        pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -422,20 +536,25 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int8", "data": "synthetic",
             "config": {"workload": WORKLOAD % B,
-                       "frames_per_gpu_per_step": B, "global_frames_per_step": B * world, "contract": "F/RNE",
+                       "frames_per_gpu_per_step": B, "global_frames_per_step": args.global_batch if strong else B * world, "contract": "F/RNE",
                        "weights": "random-init, reference quantisation + calibration rules (export.random_quantnet seed 0, calibrated on RGB444 input)",
                        "head": "conf %.2f nms %.2f, mean %.0f detections/frame (random-init dense worst case)" % (CONF, NMS, mean_dets),
-                       "l2": "3 alternating input batches of 88.6 MB; each step also streams ~0.6 GB of feature maps (> 126 MB L2)",
-                       "parallelism": "frames sharded over %d GPU(s), detections all-gathered" % world},
+                       "l2": "3 alternating input batches of 88.6 MB; each step also streams ~1.3 GB of feature maps (> 126 MB L2)",
+                       "parallelism": "frames sharded over %d GPU(s); filled detection lists collected on rank 0 by copy-engine peer writes (no collective kernel)" % world,
+                       "collection": None if coll is None else {"bytes_per_step_all_ranks": collect_bytes, "records_on_rank0_last_step": collected}},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(host_sets[0].numel() * 2),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "yolo_b200_forward_rgb444 (pinned host buffers; H2D of 64-frame chunks overlapped with the convolution layers; decode + NMS on a second stream: all chunks but the last while the last is copied in, then the last; filled part of the lists copied back)",
                     "gpu_launches": int(e2e_launches)},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "sparse_head": sparse, "image_front_end": front,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_pytorch": cpu_torch,
+            "other_configs": other, "sparse_head": sparse, "image_front_end": front,
         }))
+    if coll is not None:
+        dist.barrier()
+        coll.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -269,6 +269,24 @@ int yolo_b200_get_layer_output(yolo_b200_ctx *ctx, int layer, int8_t *host_out, 
 int yolo_b200_detect(yolo_b200_ctx *ctx, const int8_t *d_pred, int n, int gh, int gw,
                      int in_h, int in_w, yolo_b200_det *d_dets, int32_t *d_counts);
 
+/* ---- multi-GPU collection of the detection lists (frames are sharded, only the lists are gathered) -------------
+ * The reference has no counterpart (one camera, one accelerator).  The lists travel to ONE collecting GPU over NVLink by
+ * copy-engine peer writes: no collective kernel competes with the persistent convolution CTAs for SMs. */
+
+/* Squeeze the fixed-capacity lists to their filled part: d_offsets[f] = records of the frames before f (d_offsets[n] = total,
+ * n + 1 entries), d_packed[d_offsets[f] + i] = d_dets[f][i] for i < min(d_counts[f], max_det).  Asynchronous on the context stream. */
+int yolo_b200_pack_detections(yolo_b200_ctx *ctx, const yolo_b200_det *d_dets, const int32_t *d_counts, int n,
+                              yolo_b200_det *d_packed, int32_t *d_offsets);
+/* A device buffer other processes of this node can write: cudaMalloc + cudaIpcGetMemHandle (64-byte handle to hand to the peers). */
+int yolo_b200_ipc_alloc(yolo_b200_ctx *ctx, size_t bytes, void **d_ptr, unsigned char handle[64]);
+/* Map a peer's buffer into this process (cudaIpcOpenMemHandle with lazy peer access). */
+int yolo_b200_ipc_open(yolo_b200_ctx *ctx, const unsigned char handle[64], void **d_ptr);
+/* Release: opened != 0 unmaps a peer's buffer, opened == 0 frees a buffer made by yolo_b200_ipc_alloc. */
+int yolo_b200_ipc_close(yolo_b200_ctx *ctx, void *d_ptr, int opened);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `cuda_stream` (NULL = the context stream): device, peer-device or
+ * pinned-host memory on either side; between GPUs it runs on a copy engine. */
+int yolo_b200_copy_async(yolo_b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *cuda_stream);
+
 /* Sticky count of int8 saturations in contract P (the reference never clamps,
  * slim_yolo_v2.py:35; non-zero means the result may differ from it). Resets on read. */
 int yolo_b200_overflow_count(yolo_b200_ctx *ctx, int64_t *count);

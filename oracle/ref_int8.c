@@ -466,6 +466,22 @@ ORACLE_API int oracle_head_c(const int8_t *pred, int gh, int gw, int cs, int A,
     return cnt;
 }
 
+/* Number of OpenMP threads the oracle's loops use (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, and the
+ * OpenMP runtime may have read it before this library was loaded: bench.py sets the count explicitly).  Returns the maximum. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+ORACLE_API int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* ---- whole network ------------------------------------------------------------------------ */
 
 typedef struct {

@@ -43,7 +43,13 @@ def lib():
         _lib.oracle_nms_python.restype = C.c_int
         _lib.oracle_head_c.restype = C.c_int
         _lib.oracle_backbone.restype = C.c_int
+        _lib.oracle_set_threads.restype = C.c_int
     return _lib
+
+
+def set_threads(n=None):
+    """OpenMP threads of the oracle (default: every logical CPU); returns the count in force."""
+    return lib().oracle_set_threads(int(n or (os.cpu_count() or 1)))
 
 
 def tierA():

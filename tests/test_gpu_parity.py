@@ -931,3 +931,37 @@ def test_detect_cli_video_mode(tmp_path):
         assert frame.shape == (72, 96, 3)
         n += 1
     assert n == 7
+
+
+@pytest.mark.gpu
+def test_peer_collector_packs_and_collects_the_filled_lists(ctx):
+    """Multi-GPU collection path on one GPU (world 1: rank 0 writes its own slot through the same IPC buffer and copy
+    stream): the packed records and offsets that arrive equal the filled parts of the fixed-capacity lists, for several
+    pipelined steps including empty frames."""
+    from yolo_b200 import runner
+    g, qnet, frames = gu.load("ref_p_64x96")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_P, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    n, N = 5, 4 * 6 * 5
+    pc = runner.PeerCollector(ctx, n, 512, N, torch.device("cuda", 0), depth=3)
+    rng = np.random.default_rng(11)
+    want = {}
+    for step in range(5):
+        buf = pc.buffers(step)
+        x8 = rng.integers(-100, 100, (n, 64, 96, 4), dtype=np.int8)
+        x8[..., 3] = 0
+        if step == 2:
+            x8[1] = 0
+        ctx.forward_int8_dev(dev(x8), n, 64, 96, buf.dets, buf.counts)
+        pc.launch(step)
+        ctx.sync()
+        want[step] = (buf.counts.cpu().numpy().copy(), buf.dets.cpu().numpy().copy())
+    pc.finish()
+    for step in (2, 3, 4):                       # the ring holds the last three steps
+        (off, rec), = pc.collected(step)
+        counts, dets = want[step]
+        off = off.cpu().numpy(); rec = rec.cpu().numpy()
+        assert off[0] == 0 and np.array_equal(np.diff(off), np.minimum(counts, 512))
+        for f in range(n):
+            np.testing.assert_array_equal(rec[off[f]:off[f + 1]], dets[f, :counts[f]])
+    assert pc.sent_bytes > 0
+    pc.close()

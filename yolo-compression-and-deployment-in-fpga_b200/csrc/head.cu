@@ -1165,6 +1165,48 @@ cudaError_t head_init(void)
     return e;
 }
 
+// ---- detection packing (multi-GPU collection: only the filled part of the fixed-capacity lists travels) ----
+// offsets[f] = sum of min(counts[.], max_det) over the frames before f (offsets[n] = total); packed[offsets[f] + i] = dets[f][i].
+// One CTA: the prefix over <= a few thousand frames is one block scan per 1024 frames; the copy is 32 bytes per record.
+__global__ void __launch_bounds__(1024) pack_offsets_kernel(const int32_t *counts, int n, int max_det, int32_t *offsets)
+{
+    __shared__ int warp_sums[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int f = base + tid;
+        const int c = f < n ? min(max(counts[f], 0), max_det) : 0;
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        const int v = warp_sums[lane];
+        const int wbase = __reduce_add_sync(0xffffffffu, lane < wid ? v : 0);
+        const int tot = __reduce_add_sync(0xffffffffu, v);
+        if (f < n) offsets[f] = carry + wbase + inc - c;
+        carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = carry;
+}
+__global__ void __launch_bounds__(256) pack_copy_kernel(const yolo_b200_det *dets, const int32_t *offsets, int n, int max_det, yolo_b200_det *packed)
+{
+    // one CTA per frame slice: 16-byte halves of the 32-byte records, coalesced both ways
+    const int f = blockIdx.x;
+    const int beg = offsets[f], cnt = offsets[f + 1] - beg;
+    const uint4 *src = reinterpret_cast<const uint4 *>(dets + (size_t)f * max_det);
+    uint4 *dst = reinterpret_cast<uint4 *>(packed + beg);
+    for (int i = threadIdx.x; i < 2 * cnt; i += blockDim.x) dst[i] = src[i];
+}
+cudaError_t pack_detections(const yolo_b200_det *dets, const int32_t *counts, int n, int max_det, yolo_b200_det *packed, int32_t *offsets, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(counts, n, max_det, offsets);
+    pack_copy_kernel<<<n, 256, 0, st>>>(dets, offsets, n, max_det, packed);
+    return cudaGetLastError();
+}
+
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;

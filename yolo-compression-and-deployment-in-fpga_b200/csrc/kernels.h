@@ -77,5 +77,6 @@ constexpr int HEAD_MAX_CAND = 4096;   // candidates per frame the NMS kernel can
 cudaError_t head_decode(const HeadArgs &a, cudaStream_t st);
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st);
 cudaError_t head_init(void);          // one-time function attributes (dynamic shared memory)
+cudaError_t pack_detections(const yolo_b200_det *dets, const int32_t *counts, int n, int max_det, yolo_b200_det *packed, int32_t *offsets, cudaStream_t st);
 
 }  // namespace yb

@@ -1088,6 +1088,66 @@ int yolo_b200_forward_u8bgr_resize(yolo_b200_ctx *c, const uint8_t *bgr, int n, 
     return forward_host(c, bgr, (size_t)n * sh * sw * 3, 3, n, h, w, dets, counts, sh, sw);
 }
 
+// ---- multi-GPU collection of the detection lists -----------------------------------------------------------------
+int yolo_b200_pack_detections(yolo_b200_ctx *c, const yolo_b200_det *d_dets, const int32_t *d_counts, int n,
+                              yolo_b200_det *d_packed, int32_t *d_offsets)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (n < 0) return fail(E_ARG, "n %d", n);
+    if (n == 0) return 0;
+    if (!d_dets || !d_counts || !d_packed || !d_offsets) return fail(E_ARG, "null buffer");
+    if (((uintptr_t)d_dets | (uintptr_t)d_packed) & 15) return fail(E_ARG, "detection buffers must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    CU(pack_detections(d_dets, d_counts, n, c->prm.max_det, d_packed, d_offsets, c->stream));
+    c->launches += 2;
+    return 0;
+}
+
+int yolo_b200_ipc_alloc(yolo_b200_ctx *c, size_t bytes, void **d_ptr, unsigned char handle[64])
+{
+    if (!c || !d_ptr || !handle || bytes == 0) return fail(E_ARG, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(c->device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return 0;
+}
+
+int yolo_b200_ipc_open(yolo_b200_ctx *c, const unsigned char handle[64], void **d_ptr)
+{
+    if (!c || !d_ptr || !handle) return fail(E_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int yolo_b200_ipc_close(yolo_b200_ctx *c, void *d_ptr, int opened)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (!d_ptr) return 0;
+    CU(cudaSetDevice(c->device));
+    if (opened) CU(cudaIpcCloseMemHandle(d_ptr)); else CU(cudaFree(d_ptr));
+    return 0;
+}
+
+int yolo_b200_copy_async(yolo_b200_ctx *c, void *dst, const void *src, size_t bytes, void *cuda_stream)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (bytes == 0) return 0;
+    if (!dst || !src) return fail(E_ARG, "null buffer");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cuda_stream ? (cudaStream_t)cuda_stream : c->stream));
+    return 0;
+}
+
 int yolo_b200_overflow_count(yolo_b200_ctx *c, int64_t *count)
 {
     if (!c || !count) return fail(E_ARG, "null argument");

@@ -32,6 +32,7 @@ EXPORTS = [
     "yolo_b200_backbone", "yolo_b200_calibrate_f32", "yolo_b200_update_trackers_f32", "yolo_b200_measure_f32", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
     "yolo_b200_launch_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
     "yolo_forward", "yolo_b200_set_default_context",
+    "yolo_b200_pack_detections", "yolo_b200_ipc_alloc", "yolo_b200_ipc_open", "yolo_b200_ipc_close", "yolo_b200_copy_async",
     "yolo_b200_resize_taps", "yolo_b200_resize_u8bgr", "yolo_b200_forward_u8bgr_resize", "yolo_b200_forward_u8bgr_resize_dev",
 ]
 
@@ -105,6 +106,11 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_calibrate_f32.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.yolo_b200_update_trackers_f32.argtypes = [vp, vp, i32, i32, i32, C.c_float, vp, vp, vp]
     L.yolo_b200_measure_f32.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.yolo_b200_pack_detections.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.yolo_b200_ipc_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.yolo_b200_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.yolo_b200_ipc_close.argtypes = [vp, vp, i32]
+    L.yolo_b200_copy_async.argtypes = [vp, vp, vp, C.c_size_t, vp]
     L.yolo_b200_u8bgr_lut.argtypes = [vp, vp]
     L.yolo_b200_conv_layer.argtypes = [vp, i32, i8p, i32, i32, i32, i8p]
     L.yolo_b200_backbone.argtypes = [vp, vp, i32, i32, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]

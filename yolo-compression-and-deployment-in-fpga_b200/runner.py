@@ -3,7 +3,12 @@
 Frames are independent at inference (trackers frozen, slim_yolo_v2.py:215,28-29), so the batch is split contiguously
 by frame index, weights are replicated at load, and there is NO collective on the hot path.  Only the final
 per-frame detection lists are gathered (fixed-capacity [frames][max_det] records + counts), in frame order.
-One process per GPU; torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests)."""
+One process per GPU; torch.distributed is plumbing only (NCCL on GPUs, gloo in the CPU tests).
+
+On GPUs the lists are COLLECTED ON ONE RANK by copy-engine peer writes (PeerCollector): every rank squeezes its lists to their
+filled part on the device and copies exactly those bytes into its slot of a buffer that lives on the collecting GPU
+(CUDA IPC, NVLink).  No collective kernel runs, so nothing competes with the persistent convolution CTAs for SMs, and
+nobody receives lists it did not ask for.  gather_detections (a padded all-gather) remains for CPU / gloo."""
 from __future__ import annotations
 
 from typing import List, Tuple
@@ -95,3 +100,120 @@ class DetectionGatherer:
             for w in b.work:
                 w.wait()
             b.work = []
+
+
+class _DevView:
+    """A raw device pointer as something torch.as_tensor understands (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class PeerCollector:
+    """Collects every rank's detection lists on rank 0 by copy-engine peer writes; see the module docstring.
+
+    Per step:  buf = pc.buffers(i);  <forward writes buf.dets / buf.counts>;  pc.launch(i).   At the end: pc.finish().
+    launch(i) packs step i on the compute stream and, WITHOUT stalling the host on step i, ships step i - 1 (whose record
+    count has reached the host by then): the copy of step i - 1 overlaps the kernels of step i.  Rank 0 reads
+    pc.collected(step) after finish() + a barrier: a list of (offsets int32 [frames + 1], records int32 [total, 8]) per rank."""
+
+    class _Buf:
+        def __init__(self, frames, max_det, cap, device):
+            self.dets = torch.zeros((frames, max_det, 8), dtype=torch.int32, device=device)
+            self.counts = torch.zeros((frames,), dtype=torch.int32, device=device)
+            self.packed = torch.zeros((frames * cap, 8), dtype=torch.int32, device=device)
+            self.offsets = torch.zeros((frames + 1,), dtype=torch.int32, device=device)
+            self.total = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            self.ev_packed = torch.cuda.Event()
+            self.ev_total = torch.cuda.Event()
+            self.ev_sent = torch.cuda.Event()
+            self.step = -1
+            self.pending = False
+
+    def __init__(self, ctx, frames: int, max_det: int, cap: int, device, group=None, depth: int = 3):
+        self.ctx, self.frames, self.group, self.depth = ctx, frames, group, depth
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.cap = min(cap, max_det)
+        rec_bytes = frames * self.cap * 32
+        self.off_bytes = (frames + 1) * 4
+        self.slot_bytes = (rec_bytes + self.off_bytes + 255) // 256 * 256
+        self.rec_bytes = rec_bytes
+        import ctypes as C
+        self._C = C
+        total_bytes = depth * self.world * self.slot_bytes
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        if self.rank == 0:
+            ctx._check(ctx.L.yolo_b200_ipc_alloc(ctx._h, total_bytes, C.byref(ptr), handle))
+        box = [bytes(handle.raw)]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if self.rank != 0:
+            ctx._check(ctx.L.yolo_b200_ipc_open(ctx._h, box[0], C.byref(ptr)))
+        self.base = int(ptr.value)
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [self._Buf(frames, max_det, self.cap, device) for _ in range(depth)]
+        self.sent_bytes = 0
+
+    def _slot(self, step, rank):
+        return self.base + ((step % self.depth) * self.world + rank) * self.slot_bytes
+
+    def buffers(self, step: int):
+        b = self.bufs[step % self.depth]
+        if b.pending:
+            self._ship(b)
+        b.ev_sent.synchronize()                # its previous contents have left
+        return b
+
+    def launch(self, step: int):
+        b = self.bufs[step % self.depth]
+        cur = torch.cuda.current_stream()
+        self.ctx.set_stream(cur.cuda_stream)
+        self.ctx._check(self.ctx.L.yolo_b200_pack_detections(self.ctx._h, b.dets.data_ptr(), b.counts.data_ptr(), self.frames,
+                                                             b.packed.data_ptr(), b.offsets.data_ptr()))
+        b.ev_packed.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(b.ev_packed)
+            b.total.copy_(b.offsets[self.frames:], non_blocking=True)
+            b.ev_total.record(self.stream)
+        b.step, b.pending = step, True
+        prev = self.bufs[(step - 1) % self.depth]
+        if step > 0 and prev.pending and prev.step == step - 1:
+            self._ship(prev)
+        return b
+
+    def _ship(self, b):
+        b.ev_total.synchronize()
+        total = int(b.total[0])
+        L, h, st = self.ctx.L, self.ctx._h, self.stream.cuda_stream
+        slot = self._slot(b.step, self.rank)
+        self.ctx._check(L.yolo_b200_copy_async(h, slot, b.packed.data_ptr(), total * 32, st))
+        self.ctx._check(L.yolo_b200_copy_async(h, slot + self.rec_bytes, b.offsets.data_ptr(), self.off_bytes, st))
+        b.ev_sent.record(self.stream)
+        b.pending = False
+        self.sent_bytes += total * 32 + self.off_bytes
+
+    def finish(self):
+        for b in sorted(self.bufs, key=lambda x: x.step):
+            if b.pending:
+                self._ship(b)
+        self.stream.synchronize()
+
+    def collected(self, step: int):
+        """Rank 0, after finish() and a barrier: [(offsets, records)] per rank for `step` (views of the collection buffer)."""
+        assert self.rank == 0
+        out = []
+        for r in range(self.world):
+            slot = self._slot(step, r)
+            off = torch.as_tensor(_DevView(slot + self.rec_bytes, self.off_bytes), device="cuda").view(torch.int32)
+            total = int(off[self.frames])
+            rec = torch.as_tensor(_DevView(slot, max(total, 1) * 32), device="cuda").view(torch.int32).reshape(-1, 8)[:total]
+            out.append((off, rec))
+        return out
+
+    def close(self):
+        if self.base:
+            self.stream.synchronize()
+            self.ctx.L.yolo_b200_ipc_close(self.ctx._h, self.base, 0 if self.rank == 0 else 1)
+            self.base = 0
