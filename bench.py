@@ -230,6 +230,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, whatever NCCL_DEBUG says)
+    # is sent to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -534,7 +539,8 @@ def main():
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": "oracle unavailable: %s" % e}
 
     if rank == 0:
-        print(json.dumps({
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps({
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int8", "data": "synthetic",
@@ -551,7 +557,7 @@ def main():
                     "gpu_launches": int(e2e_launches)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_pytorch": cpu_torch,
             "other_configs": other, "sparse_head": sparse, "image_front_end": front,
-        }))
+        }) + "\n").encode())
     if coll is not None:
         dist.barrier()
         coll.close()
