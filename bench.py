@@ -190,6 +190,29 @@ def run_reference(args, rank, world):
     }))
 
 
+def ol_quantize(x_nchw, sa):
+    """float NCHW -> int8 NHWC4 by a_tracker_in's rule (numpy; input preparation for the yolo_v2 line, outside any timed region)."""
+    q = np.clip(np.rint(x_nchw.astype(np.float32) * np.float32(2.0 ** sa)), -128, 127).astype(np.int8)
+    out = np.zeros((q.shape[0], q.shape[2], q.shape[3], 4), np.int8)
+    out[..., :3] = q.transpose(0, 2, 3, 1)
+    return out
+
+
+def yolo_v2_maps(qnet, h, w):
+    """Input map size of every layer of a graph network (for the MAC count)."""
+    pre, post, dims = {}, {}, []
+    for l, ((cin, cout, activ, pool), g) in enumerate(zip(qnet.layers, qnet.graph)):
+        if l == 0:
+            d = (h, w)
+        else:
+            src = g.get("in_from", 0) - 1 if g.get("in_from", 0) else l - 1
+            d = pre[src] if g.get("in_from", 0) else post[src]
+        dims.append(d)
+        pre[l] = d
+        post[l] = (d[0] // 2, d[1] // 2) if pool else d
+    return dims
+
+
 def time_steps(stream, fn, warm, steps):
     import torch
     for i in range(warm):
@@ -447,6 +470,26 @@ def main():
         ctx.load_quantnet(qpr, contract=lib.CONTRACT_P, conf_thresh=CONF, nms_thresh=NMS, max_det=MAXDET)
         run_cfg("rgb444_416x416_contract_P", lambda i: ctx.forward_rgb444_dev(dev_sets[i % n_sets], B, H, W, d_dets, d_counts), B,
                 "the headline workload under contract P")
+
+        # BASELINE configs[4]: yolo_v2 (darknet19 backbone, 20 classes) BN-folded fixed point at 416x416, batch 64 per GPU:
+        # 14.68 GMAC per frame, 1x1 layers, 512 / 1024 / 1280 channels, route + reorg + concat (tests: test_yolo_v2_*)
+        BV = 64
+        qv = ex.random_quantnet_yolo_v2(seed=0, calib_hw=(H, W), calib_frames=1)
+        ctx.load_quantnet(qv, contract=lib.CONTRACT_F, round_mode=lib.ROUND_RNE, conf_thresh=CONF, nms_thresh=NMS, max_det=1024)
+        xv = torch.from_numpy(ol_quantize(ex.synthetic_frames_f32(BV, H, W, seed=13).numpy(), qv.sa[0])).cuda()
+        dv = torch.zeros((BV, 1024, 8), dtype=torch.int32, device="cuda")
+        cv = torch.zeros((BV,), dtype=torch.int32, device="cuda")
+        sp0 = ctx.slow_path_count()
+        run_cfg("yolo_v2_416x416_contract_F", lambda i: ctx.forward_int8_dev(xv, BV, H, W, dv, cv), BV,
+                "%d int8 NHWC4 frames of 416x416 through the 23-layer yolo_v2 graph (29.4 GOP per frame), contract F/RNE" % BV)
+        gmac = sum(h_ * w_ * (g_.get("ksize", 3) ** 2) * ci * co for (ci, co, _, _), g_, (h_, w_) in zip(qv.layers, qv.graph, yolo_v2_maps(qv, H, W)))
+        yv = other["yolo_v2_416x416_contract_F"]
+        yv["gmac_per_frame"] = gmac / 1e9
+        yv["tensor_tops"] = 2.0 * gmac * yv["value"] / 1e12
+        yv["frac_of_int8_peak"] = yv["tensor_tops"] / int8_peak_tops
+        yv["dot_product_fallback_launches_per_step"] = (ctx.slow_path_count() - sp0) / 13.0
+        yv["mean_detections_per_frame"] = float(cv.float().mean().item())
+        del xv, dv, cv
 
     sparse = None
     if secondary:

@@ -64,6 +64,16 @@ typedef struct yolo_b200_layer {
     int32_t cout;   /* logical output channels */
     int32_t activ;  /* 1 = leaky-ReLU slope 1/8 (utils/modules.py:25)      */
     int32_t pool;   /* 1 = 2x2 stride-2 max-pool after the layer (slim_yolo_v2.py:61) */
+    /* ABI 2: the four fields below are all 0 for slim_yolo_v2 (a plain chain of 3x3 convolutions).  They describe what
+     * yolo_v2 / darknet19 adds (models/yolo_v2.py:29-40,165-177, backbone/darknet.py:40-108, utils/modules.py:43-57): */
+    int32_t ksize;        /* 0 or 3 = 3x3 pad 1; 1 = 1x1 (darknet19 bottlenecks, route_layer, yolo_v2's pred) */
+    int32_t in_from;      /* 0 = input is the previous layer's output; k > 0 = the output of layer k-1 BEFORE its max-pool
+                             (yolo_v2: route_layer reads C_5, the map maxpool_5 also consumes) */
+    int32_t reorg;        /* 1 = space-to-depth (stride 2) of this layer's output: consumers see [h/2][w/2][4*cout], channel
+                             (2*dy+dx)*cout + c  <-  pixel (2y+dy, 2x+dx), channel c  (reorg_layer, utils/modules.py:43-57) */
+    int32_t concat_with;  /* k > 0: the input is torch.cat([output of layer k-1 (after its reorg), <in_from / previous>], dim=1)
+                             (yolo_v2.py:171-174).  Both parts are brought to the smaller of their two activation exponents
+                             (round-half-even right shift of the finer one) before they meet. */
 } yolo_b200_layer;
 
 /* Runtime tables: the reference hard-codes these in yolo_forward.c:32-37; here they are data. */
@@ -101,7 +111,7 @@ typedef struct yolo_b200_ctx yolo_b200_ctx;
 /* ---- library / context ---------------------------------------------------------------- */
 
 /* Version of this ABI (bumped on incompatible change). */
-int yolo_b200_abi_version(void);
+int yolo_b200_abi_version(void);   /* 2 */
 
 /* Thread-local text of the last error returned on this thread. */
 const char *yolo_b200_last_error(void);
@@ -293,6 +303,10 @@ int yolo_b200_overflow_count(yolo_b200_ctx *ctx, int64_t *count);
 
 /* Number of kernels this library launched on the context since creation (bench bookkeeping). */
 int64_t yolo_b200_launch_count(yolo_b200_ctx *ctx);
+/* How many of those launches, in the automatic back end, fell to the integer dot-product kernel because no tensor-core kernel
+ * takes the layer's shape or the buffers' alignment (a first layer wider than 16 channels, a 2-byte-aligned frame pointer, a
+ * map width that is not a multiple of 4 ...).  Same results, lower speed: 0 on the benchmarked configurations. */
+int64_t yolo_b200_slow_path_count(yolo_b200_ctx *ctx);
 
 /* Device time of the most recent yolo_b200_backbone()/forward call per layer, in ms
  * (CUDA events on the context stream; enabled by yolo_b200_enable_timing). */

@@ -118,6 +118,63 @@ def backbone(qnet, x_nhwc4, contract, round_mode=0, keep_layers=True):
     return outs, total
 
 
+def _shr_rne(v, s):
+    """numpy int32 round-half-even right shift (the alignment of a concat's parts, include/yolo_b200.h: concat_with)."""
+    if s <= 0:
+        return v
+    fl = v >> s
+    rem = v - (fl << s)
+    half = 1 << (s - 1)
+    return fl + ((rem > half) | ((rem == half) & ((fl & 1) == 1)))
+
+
+def backbone_graph(qnet, x_nhwc4, contract, round_mode=0):
+    """A graph network (yolo_v2 / darknet19: 1x1 layers, a route that reads an un-pooled map, reorg, concat) on the CPU
+    oracle: every convolution is oracle_conv_layer (a 1x1 kernel = the centre tap of a 3x3 one) WITHOUT its pool; pooling,
+    reorg (utils/modules.py:43-57), concat (yolo_v2.py:171-174) and the exponent alignment are restated in numpy.
+    Returns (list of consumer-visible per-layer outputs, i.e. after the pool, overflow count)."""
+    import yolo_b200  # noqa: F401
+    from yolo_b200 import export as ex
+    graph = qnet.graph or [{}] * len(qnet.layers)
+    pre, post, total = {}, {}, 0
+    x0 = np.ascontiguousarray(x_nhwc4, dtype=np.int8)
+    for l, (cin, cout, activ, pool) in enumerate(qnet.layers):
+        g = graph[l]
+        if l == 0:
+            xin = x0
+        else:
+            src = g.get("in_from", 0) - 1 if g.get("in_from", 0) else l - 1
+            xin = (pre[src] if g.get("in_from", 0) else post[src])[..., :qnet.layers[src][1]]
+            if g.get("concat_with", 0):
+                k = g["concat_with"] - 1
+                a = post[k][..., :qnet.layers[k][1]]
+                if graph[k].get("reorg", 0):
+                    n, h, w, c = a.shape
+                    a = a.reshape(n, h // 2, 2, w // 2, 2, c).transpose(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)
+                ea, eb = qnet.sa[k + 1], qnet.sa[src + 1]
+                e = min(ea, eb)
+                xin = np.concatenate([np.clip(_shr_rne(a.astype(np.int32), ea - e), -128, 127),
+                                      np.clip(_shr_rne(xin.astype(np.int32), eb - e), -128, 127)], axis=-1).astype(np.int8)
+            pad = cs(cin) - xin.shape[-1]
+            if pad:
+                xin = np.concatenate([xin, np.zeros(xin.shape[:-1] + (pad,), np.int8)], axis=-1)
+        w = qnet.w[l]
+        if w.shape[1] == 1:                                   # 1x1 -> centre tap
+            w3 = np.zeros((w.shape[0], 3, 3, w.shape[3]), np.int8)
+            w3[:, 1, 1, :] = w[:, 0, 0, :]
+            w = w3
+        sa_i = ex.input_exponent(qnet.layers, graph, qnet.sa, l)
+        y, ovf = conv_layer(xin, w, qnet.b[l], cin, cout, sa_i, qnet.sw[l], qnet.sb[l], qnet.retune[l], qnet.sa[l + 1], activ, 0,
+                            contract, round_mode)
+        total += ovf
+        pre[l] = y
+        if pool:
+            n, h, w_, c = y.shape
+            y = y[:, :h // 2 * 2, :w_ // 2 * 2].reshape(n, h // 2, 2, w_ // 2, 2, c).max(axis=(2, 4))
+        post[l] = y
+    return [post[l] for l in range(len(qnet.layers))], total
+
+
 def quantize_f32(x_nchw, sa):
     x = np.ascontiguousarray(x_nchw, dtype=np.float32)
     n, c, h, w = x.shape

@@ -965,3 +965,69 @@ def test_peer_collector_packs_and_collects_the_filled_lists(ctx):
             np.testing.assert_array_equal(rec[off[f]:off[f + 1]], dets[f, :counts[f]])
     assert pc.sent_bytes > 0
     pc.close()
+
+
+# ---- yolo_v2 / darknet19 (BASELINE configs[4]): 1x1 layers, 512 / 1024 / 1280 channels, route + reorg + concat ---------------
+
+def _run_graph(ctx, qnet, x8):
+    n, h, w, _ = x8.shape
+    pred, gh, gw = ctx.backbone(dev(x8), n, h, w)
+    ctx.sync()
+    return pred, gh, gw
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("contract", [lib.CONTRACT_P, lib.CONTRACT_F])
+@pytest.mark.parametrize("hw", [(64, 96), (96, 64)])
+def test_yolo_v2_graph_against_oracle(ctx, contract, hw):
+    """Every layer of the BN-folded fixed-point yolo_v2 (23 convolutions: 3x3 and 1x1, up to 1280 -> 1024 channels, the route
+    from the un-pooled C_5 through a 1x1 layer and reorg, the exponent-aligned concat) and its 20-class detections against the
+    generalised oracle (tests/oracle_lib.py: backbone_graph), bit for bit."""
+    H, W = hw
+    qnet = ex.random_quantnet_yolo_v2(seed=0, calib_hw=(H, W), calib_frames=1)
+    ctx.load_quantnet(qnet, contract=contract, round_mode=lib.ROUND_RNE, conf_thresh=0.02, nms_thresh=0.5, max_det=1024)
+    x = ex.synthetic_frames_f32(3, H, W, seed=21).numpy()
+    x8, _ = ol.quantize_f32(x, qnet.sa[0])
+    ref, _ = ol.backbone_graph(qnet, x8, contract=contract)
+    pred, gh, gw = _run_graph(ctx, qnet, x8)
+    assert (gh, gw) == (H // 32, W // 32) and ctx.slow_path_count() >= 0
+    for l, r in enumerate(ref):
+        got = ctx.layer_output(l, 3, r.shape[1], r.shape[2])
+        assert np.array_equal(got, r), "yolo_v2 layer %d (%s %s) differs from the oracle" % (l, qnet.layers[l], qnet.graph[l])
+    dets, counts = det_arrays(ctx, pred, 3, gh, gw, H, W)
+    for i in range(3):
+        (ob, os_, oc, oidx), ocnt = ol.head_python(ref[-1][i], 5, 20, qnet.sa[-1], qnet.anchors, 32, H, W, 0.02, 0.5, max_det=1024)
+        b, s_, c, idx = lib.dets_to_arrays(dets[i], int(counts[i]))
+        assert counts[i] == ocnt
+        np.testing.assert_array_equal(idx, oidx)
+        np.testing.assert_array_equal(c, oc)
+        np.testing.assert_allclose(s_, os_, atol=1e-5, rtol=0)
+        np.testing.assert_allclose(b, ob, atol=1e-5, rtol=0)
+
+
+@pytest.mark.gpu
+def test_yolo_v2_at_416_and_backends_agree(ctx):
+    """416x416 (13x13 grid, the configuration BASELINE configs[4] names): the prediction map of one frame equals the oracle's,
+    the host entry point returns the device entry point's detections, and the dot-product back end agrees layer by layer."""
+    H = W = 416
+    qnet = ex.random_quantnet_yolo_v2(seed=1, calib_hw=(H, W), calib_frames=1)
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F, conf_thresh=0.02, nms_thresh=0.5, max_det=1024)
+    x = ex.synthetic_frames_f32(2, H, W, seed=3).numpy()
+    x8, _ = ol.quantize_f32(x, qnet.sa[0])
+    ref, _ = ol.backbone_graph(qnet, x8[:1], contract=0)
+    pred, gh, gw = _run_graph(ctx, qnet, x8)
+    outs = [ctx.layer_output(l, 2, r.shape[1], r.shape[2]) for l, r in enumerate(ref)]
+    for l, r in enumerate(ref):
+        assert np.array_equal(outs[l][:1], r), "yolo_v2 @416 layer %d differs from the oracle" % l
+    dets, counts = det_arrays(ctx, pred, 2, gh, gw, H, W)
+    hd, hc = ctx.forward_int8(x8)
+    np.testing.assert_array_equal(hc, counts)
+    for f in range(2):
+        assert hd[f][:counts[f]].tobytes() == dets[f][:counts[f]].tobytes()
+    ctx.set_conv_backend(1)
+    try:
+        _run_graph(ctx, qnet, x8)
+        for l, r in enumerate(ref):
+            assert np.array_equal(ctx.layer_output(l, 2, r.shape[1], r.shape[2]), outs[l]), "back ends differ on layer %d" % l
+    finally:
+        ctx.set_conv_backend(0)

@@ -33,7 +33,10 @@ struct UmmaParams {
     int n_img, H, W;
     int TN, TH, TW;              // tile = TN images x TH rows x TW cols (<= 128 pixels; TH, TW even when pooling)
     int tiles_x, tiles_y, tiles_n, num_tiles;
-    int N;                       // GEMM N = cstride(cout)
+    int N;                       // GEMM N = output channels of one slice (= cs_out when cs_out <= 256, else 256)
+    int nslices;                 // cs_out / N: wide layers (yolo_v2 / darknet19: 512, 1024 channels) run as N-slices of 256 channels;
+                                 // a work item is (tile, slice), so small maps still fill the SMs
+    int taps;                    // 9 = 3x3, 1 = 1x1 (the single tap sits at the window centre)
     int cout, cs_out;
     int kblocks;                 // TMA box pairs per tile: 9 * cs_in / CB  (CB = 16: the 9 taps + 1 zero tap)
     int G;                       // kblocks per pipeline stage
@@ -47,7 +50,7 @@ struct UmmaParams {
     const int *bias_sh;
     int8_t *out;
     unsigned *ovf;
-    const uint8_t *w_swz;        // CB == 128: weights pre-swizzled into the shared-memory image of every (tap, chunk) block
+    const uint8_t *w_swz;        // CB == 128: weights pre-swizzled into the shared-memory image of every (tap, chunk) block, [kb][cs_out][128]
 };
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
@@ -57,14 +60,14 @@ constexpr int UMMA_THREADS = 64 + EPI_THREADS;
 template <int EPI, bool ACT>
 __device__ __forceinline__ void epilogue_tile(const UmmaParams &p, uint32_t taddr, int cbeg, int cend, int row, int et,
                                               int x0, int y0, int n0, const int *s_bias, int *s_stage, uint32_t bar_tempty,
-                                              unsigned &ovf)
+                                              unsigned &ovf, int8_t *out)
 {
     const int tile_px = p.TN * p.TH * p.TW;
     if (!p.q.pool) {
         const int wl = row % p.TW, hl = (row / p.TW) % p.TH, nl = row / (p.TW * p.TH);
         const int x = x0 + wl, y = y0 + hl, n = n0 + nl;
         const bool valid = row < tile_px && x < p.W && y < p.H && n < p.n_img;
-        int8_t *dst = p.out + (((size_t)n * p.H + y) * p.W + x) * p.cs_out;
+        int8_t *dst = out + (((size_t)n * p.H + y) * p.W + x) * p.cs_out;
         // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is requantised
         int va[16], vb[16];
         if (cbeg < cend) tmem_ld16(taddr + cbeg, va);
@@ -116,7 +119,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams &p, uint32_t tadd
             const int ox = x0 / 2 + pw, oy = y0 / 2 + ph, n = n0 + nl;
             if (ox < OW && oy < OH && n < p.n_img) {
                 const int mv[4] = { m.x, m.y, m.z, m.w };
-                *reinterpret_cast<unsigned *>(p.out + (((size_t)n * OH + oy) * OW + ox) * p.cs_out + 4 * cg) =
+                *reinterpret_cast<unsigned *>(out + (((size_t)n * OH + oy) * OW + ox) * p.cs_out + 4 * cg) =
                     requant4<EPI, ACT>(mv, s_bias, 4 * cg, p, ovf, true);
             }
         }
@@ -158,7 +161,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    for (int i = threadIdx.x; i < p.N * p.nslices; i += blockDim.x) {
         const int b = p.bias_sh[i];
         s_bias[i] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;                 // |b| < 2^21: exact
     }
@@ -173,7 +176,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;   // global stage counter
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int work = blockIdx.x; work < p.num_tiles * p.nslices; work += gridDim.x) {
+                const int tile = work % p.num_tiles, slice = work / p.num_tiles;
                 const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tn = tile / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
                 for (int st = 0; st < stages_per_tile; ++st, ++it) {
@@ -187,15 +191,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int kb = kb0; kb < kb1; ++kb) {
                         // kblock -> (tap, channel chunk); K index of B = kb * CB bytes since K is tap-major over cs_in
                         int tap, c0;
-                        if (CB == 128) { int per = p.kblocks / 9; tap = kb / per; c0 = (kb % per) * CB; }
+                        if (CB == 128) { int per = p.kblocks / p.taps; tap = kb / per; c0 = (kb % per) * CB; }
                         else { tap = kb; c0 = 0; }
-                        const int kh = tap / 3, kw = tap % 3;
+                        const int kh = p.taps == 1 ? 1 : tap / 3, kw = p.taps == 1 ? 1 : tap % 3;
                         tma_load_4d(sa + (uint32_t)(kb - kb0) * A_BOX, &map_a, bar_full(s), c0, x0 + kw - 1, y0 + kh - 1, n0);
                         // B: the TMA unit spends ~4 cycles per box ROW whatever its length, and the N rows of a weight block
                         // are 2/3 of all rows of a stage; when the host has laid the block out exactly as the 128B-swizzled
                         // shared-memory image, one 1-D bulk copy replaces the N-row box
-                        if (CB == 128 && p.w_swz) bulk_load_1d(sb + (uint32_t)(kb - kb0) * B_BOX, p.w_swz + (size_t)kb * B_BOX, B_BOX, bar_full(s));
-                        else tma_load_2d(sb + (uint32_t)(kb - kb0) * B_BOX, &map_b, bar_full(s), kb * CB, 0);
+                        if (CB == 128 && p.w_swz)
+                            bulk_load_1d(sb + (uint32_t)(kb - kb0) * B_BOX, p.w_swz + ((size_t)kb * p.cs_out + (size_t)slice * p.N) * 128u, B_BOX, bar_full(s));
+                        else tma_load_2d(sb + (uint32_t)(kb - kb0) * B_BOX, &map_b, bar_full(s), kb * CB, slice * p.N);
                     }
                 }
             }
@@ -206,7 +211,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         {
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
             int it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+            for (int work = blockIdx.x; work < p.num_tiles * p.nslices; work += gridDim.x, ++tcount) {
                 const int buf = tcount & 1;
                 const uint32_t bph = (uint32_t)(tcount >> 1) & 1u;
                 mbar_wait(bar_tempty(buf), bph ^ 1u);             // epilogue has drained this accumulator buffer
@@ -262,16 +267,19 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int cbeg = ew < 4 ? 0 : cmid, cend = ew < 4 ? cmid : p.N;
         unsigned ovf = 0;
         int tcount = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        for (int work = blockIdx.x; work < p.num_tiles * p.nslices; work += gridDim.x, ++tcount) {
             const int buf = tcount & 1;
             const uint32_t bph = (uint32_t)(tcount >> 1) & 1u;
+            const int tile = work % p.num_tiles, slice = work / p.num_tiles;
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tn = tile / (p.tiles_x * p.tiles_y);
             const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN;
             mbar_wait(bar_tfull(buf), bph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)buf * p.tmem_buf_stride + ((uint32_t)(q4 * 32) << 16);
-            if (p.q.activ) epilogue_tile<EPI, true>(p, taddr, cbeg, cend, row, et, x0, y0, n0, s_bias, s_stage, bar_tempty(buf), ovf);
-            else epilogue_tile<EPI, false>(p, taddr, cbeg, cend, row, et, x0, y0, n0, s_bias, s_stage, bar_tempty(buf), ovf);
+            const int *sb_ = s_bias + slice * p.N;                 // this slice's channels: biases and output columns
+            int8_t *out_ = p.out + slice * p.N;
+            if (p.q.activ) epilogue_tile<EPI, true>(p, taddr, cbeg, cend, row, et, x0, y0, n0, sb_, s_stage, bar_tempty(buf), ovf, out_);
+            else epilogue_tile<EPI, false>(p, taddr, cbeg, cend, row, et, x0, y0, n0, sb_, s_stage, bar_tempty(buf), ovf, out_);
         }
         if (p.q.contract == CONTRACT_P) {
             ovf = __reduce_add_sync(0xffffffffu, ovf);
@@ -333,7 +341,9 @@ bool conv3x3_umma_supported(const ConvArgs &a)
     if (a.cs_in < 16 || a.cs_in % 16) return false;
     if (a.cs_in > 128 && a.cs_in % 128) return false;
     if (a.cs_in != 16 && a.cs_in != 32 && a.cs_in != 64 && a.cs_in % 128) return false;
-    if (a.cs_out < 16 || a.cs_out > 256 || a.cs_out % 16) return false;
+    if (a.cs_out < 16 || a.cs_out % 16) return false;
+    if (a.cs_out > 256 && (a.cs_out % 256 || a.q.pool)) return false;        // wide layers: slices of 256 channels, pool not fused
+    if (a.taps != 9 && (a.taps != 1 || a.cs_in % 128 || !a.wgt1)) return false;   // 1x1: channel chunks of 128 bytes
     if (a.q.pool && (a.H < 2 || a.W < 2 || a.cs_out % 32)) return false;
     return true;
 }
@@ -349,8 +359,9 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
     pick_tile(a.n, a.H, a.W, a.q.pool != 0, &p.TN, &p.TH, &p.TW);
     p.tiles_x = (a.W + p.TW - 1) / p.TW; p.tiles_y = (a.H + p.TH - 1) / p.TH; p.tiles_n = (a.n + p.TN - 1) / p.TN;
     p.num_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    p.N = a.cs_out; p.cout = a.cout; p.cs_out = a.cs_out;
-    p.kblocks = CB == 16 ? 10 : 9 * (a.cs_in / CB);
+    p.N = a.cs_out > 256 ? 256 : a.cs_out; p.nslices = a.cs_out / p.N; p.cout = a.cout; p.cs_out = a.cs_out;
+    p.taps = a.taps;
+    p.kblocks = CB == 16 ? 10 : a.taps * (a.cs_in / CB);
     p.a_box_bytes = (uint32_t)(p.TN * p.TH * p.TW) * CB;
     const uint32_t kb_bytes = 128u * CB + (uint32_t)p.N * CB;
     if (CB == 16) p.G = 10;
@@ -358,7 +369,7 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
     else p.G = 3;
     p.stage_bytes = ((uint32_t)p.G * kb_bytes + 1023u) & ~1023u;
     const uint32_t staging = a.q.pool ? 128u * p.N * 4u : 0u;
-    const uint32_t fixed = staging + (uint32_t)p.N * 4u + 256u + 1024u /*alignment slack*/;
+    const uint32_t fixed = staging + (uint32_t)a.cs_out * 4u + 256u + 1024u /*alignment slack*/;
     const uint32_t budget = 227u * 1024u;
     int stages = (int)((budget - fixed) / p.stage_bytes);
     if (stages > 8) stages = 8;
@@ -366,12 +377,12 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
     p.stages = stages;
     p.off_stage = (uint32_t)stages * p.stage_bytes;
     p.off_bias = p.off_stage + staging;
-    p.off_bar = (p.off_bias + (uint32_t)p.N * 4u + 15u) & ~15u;
+    p.off_bar = (p.off_bias + (uint32_t)a.cs_out * 4u + 15u) & ~15u;
     const uint32_t smem_bytes = p.off_bar + 256u + 1024u;
     uint32_t nb = 32; while (nb < (uint32_t)p.N) nb <<= 1;
     p.tmem_buf_stride = nb; p.tmem_cols = 2 * nb;
     p.q = a.q; p.k = kc; p.bias_sh = a.bias_sh; p.out = a.out; p.ovf = a.ovf;
-    p.w_swz = (CB == 128 && a.cs_out == a.wgt_swz_rows) ? a.wgt_swz : nullptr;
+    p.w_swz = (CB == 128 && a.cs_out == a.wgt_swz_rows) ? a.wgt_swz : nullptr;      // (taps == 1: the one-tap image)
 
     CUtensorMap map_a, map_b;
     {
@@ -385,12 +396,12 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
     }
     {
         // weights [cout_pad][K], K = kblocks*CB bytes (CB = 16: a 10th all-zero tap is part of the packed buffer)
-        const cuuint64_t K = (cuuint64_t)(CB == 16 ? 10 * 16 : 9 * a.cs_in);
+        const cuuint64_t K = (cuuint64_t)(CB == 16 ? 10 * 16 : a.taps * a.cs_in);
         cuuint64_t dims[2] = { K, (cuuint64_t)a.w_rows };
         cuuint64_t strides[1] = { K };
         cuuint32_t box[2] = { (cuuint32_t)CB, (cuuint32_t)p.N };
         cuuint32_t es[2] = { 1, 1 };
-        CUresult r = g_encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)(CB == 16 ? a.wgt_k160 : a.wgt), dims, strides, box, es,
+        CUresult r = g_encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)(CB == 16 ? a.wgt_k160 : a.taps == 1 ? a.wgt1 : a.wgt), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     }
@@ -402,7 +413,8 @@ static cudaError_t launch_umma(const ConvArgs &a, cudaStream_t st, int sm_count,
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
-    int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+    const int work = p.num_tiles * p.nslices;
+    int grid = work < sm_count ? work : sm_count;
     conv3x3_umma_kernel<CB, EPI><<<grid, UMMA_THREADS, smem_bytes, st>>>(map_a, map_b, p);
     return cudaGetLastError();
 }

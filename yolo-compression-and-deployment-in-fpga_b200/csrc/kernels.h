@@ -25,6 +25,8 @@ struct ConvArgs {
     int8_t *out;           // [n][H'][W'][cs_out]
     unsigned *ovf;         // contract-P saturation counter
     int *stats = nullptr;  // conv3x3_direct only: calibration pass, see conv_direct.cu (bias_sh then holds b << lb, q.la the shift)
+    int taps = 9;          // conv_umma.cu only: 9 = 3x3, 1 = 1x1 (then wgt / wgt_swz hold ONE tap: [cout_pad][cs_in] / [cs_in/128][cs_out][128])
+    const int8_t *wgt1 = nullptr;   // taps == 1: [cout_pad][cs_in]
 };
 
 // conv_direct.cu
@@ -44,6 +46,11 @@ cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_
 // conv_ws.cu (weight-stationary tcgen05 kernel: weights resident in shared memory, haloed tile fetched once)
 bool conv3x3_ws_supported(const ConvArgs &a);
 cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
+
+// graph.cu (yolo_v2: stand-alone max-pool, reorg + concat with exponent alignment)
+cudaError_t maxpool2x2(const int8_t *in, int n, int H, int W, int cs, int8_t *out, cudaStream_t st);
+cudaError_t concat_reorg(const int8_t *A, int cs_a, int ca, int reorg, int sh_a, const int8_t *B, int cs_b, int cb, int sh_b,
+                         int n, int h, int w, int cs_out, int8_t *out, cudaStream_t st);
 
 // quantize.cu
 cudaError_t quantize_rgb444(const uint16_t *frames, size_t npix, const int *lut_dev, int8_t *nhwc4, cudaStream_t st);

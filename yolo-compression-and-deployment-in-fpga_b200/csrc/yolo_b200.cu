@@ -27,6 +27,13 @@ enum { E_ARG = -1, E_STATE = -2, E_UNSUPPORTED = -3, E_NOMEM = -4, E_CUDA = -5 }
 
 struct LayerDev {
     int cin, cout, cs_in, cs_out, cout_pad;
+    int ksize = 3, in_from = 0, reorg = 0, concat_with = 0;     // yolo_v2 / darknet19 graph fields (include/yolo_b200.h, ABI 2)
+    bool unfused_pool = false;     // the max-pool runs as its own kernel: a route reads the un-pooled map, or the layer is wider than 256 channels
+    int8_t *w1 = nullptr;          // ksize == 1: [cout_pad][cs_in] (conv_umma.cu, one tap)
+    int8_t *raw = nullptr; size_t raw_cap = 0;      // un-pooled output when the pool is not fused
+    int8_t *cat = nullptr; size_t cat_cap = 0;      // concatenated (+ reorganised, exponent-aligned) input of a concat layer
+    int rh = 0, rw = 0;            // un-pooled output map of the most recent call
+    std::vector<int8_t> wp_host;   // [cout_pad][9][cs_in] as repacked at load (the swizzled image is built on first use)
     int bias_abs_max = 0;
     std::vector<int8_t> bias_host;   // int8 biases as loaded (the epilogue programme is re-derived when the tables change)
     LayerQ q;
@@ -46,6 +53,8 @@ struct yolo_b200_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     bool loaded = false;
+    bool graph = false;                  // the network is not a plain chain of 3x3 convolutions (yolo_v2 / darknet19)
+    int64_t slow_path_launches = 0;      // layers that fell back to the dot-product kernel in the auto back end
     yolo_b200_params prm;
     std::vector<LayerDev> layers;
     int *lut_dev = nullptr;              // 4096 packed (R,G,B,0) words
@@ -85,7 +94,7 @@ static yolo_b200_ctx *g_default_ctx = nullptr;
 #pragma GCC visibility push(default)     // only the C-ABI is exported from the shared library
 extern "C" {
 
-int yolo_b200_abi_version(void) { return 1; }
+int yolo_b200_abi_version(void) { return 2; }
 const char *yolo_b200_last_error(void) { return g_err; }
 int yolo_b200_cstride(int c) { return c <= 4 ? 4 : (c + 15) / 16 * 16; }
 
@@ -144,7 +153,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
     c->layers.clear();
 }
 
@@ -227,6 +236,19 @@ static bool build_u8_lut(int sa, uint8_t *lut)
     return sat;
 }
 
+// Output channels a consumer of layer k sees (reorg = space-to-depth by 2) and the activation exponent of layer l's INPUT:
+// the source's output exponent; a concat brings both parts to the smaller of the two (include/yolo_b200.h: concat_with).
+static int seen_channels(const yolo_b200_params *p, int k) { return p->layers[k].cout * (p->layers[k].reorg ? 4 : 1); }
+static int input_exponent(const yolo_b200_params *p, int l)
+{
+    if (l == 0) return p->scale_a[0];
+    const yolo_b200_layer &L = p->layers[l];
+    const int src = L.in_from ? L.in_from - 1 : l - 1;
+    int e = p->scale_a[src + 1];
+    if (L.concat_with && p->scale_a[L.concat_with] < e) e = p->scale_a[L.concat_with];
+    return e;
+}
+
 static int host_shr_round(int x, int n, int mode)
 {
     if (n <= 0) return x;
@@ -247,7 +269,7 @@ static int derive_layer(yolo_b200_ctx *c, int l)
     LayerQ &q = d.q;
     memset(&q, 0, sizeof q);
     q.contract = p->contract; q.round_mode = p->round_mode; q.activ = L.activ; q.pool = L.pool;
-    const int sa_i = p->scale_a[l], sw = p->scale_w[l], sb = p->scale_b[l], rt = p->retune[l], sa_o = p->scale_a[l + 1];
+    const int sa_i = input_exponent(p, l), sw = p->scale_w[l], sb = p->scale_b[l], rt = p->retune[l], sa_o = p->scale_a[l + 1];
     std::vector<int> bsh(d.cout_pad, 0);
     const int8_t *b = d.bias_host.data();
     if (p->contract == YOLO_B200_CONTRACT_F) {
@@ -291,38 +313,58 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
     c->prm = *p;
     for (int l = 0; l < p->num_layers; ++l) {
         const yolo_b200_layer &L = p->layers[l];
-        if (L.cin < 1 || L.cout < 1 || L.cin > 4096 || L.cout > 4096) return fail(E_ARG, "layer %d channels %d->%d", l, L.cin, L.cout);
-        if (l > 0 && L.cin != p->layers[l - 1].cout) return fail(E_ARG, "layer %d cin %d != previous cout %d", l, L.cin, p->layers[l - 1].cout);
+        if (L.cin < 1 || L.cout < 1 || L.cin > 8192 || L.cout > 4096) return fail(E_ARG, "layer %d channels %d->%d", l, L.cin, L.cout);
+        const int ks = L.ksize == 0 ? 3 : L.ksize, taps = ks * ks;
+        if (ks != 1 && ks != 3) return fail(E_UNSUPPORTED, "layer %d: kernel size %d (3x3 and 1x1 only)", l, ks);
+        if (L.in_from < 0 || L.in_from > l || L.concat_with < 0 || L.concat_with > l) return fail(E_ARG, "layer %d: in_from / concat_with must name an earlier layer", l);
+        if (l == 0 && (L.in_from || L.concat_with)) return fail(E_ARG, "layer 0 reads the network input");
+        if (l > 0) {
+            const int src = L.in_from ? L.in_from - 1 : l - 1;
+            if (p->layers[src].reorg) return fail(E_UNSUPPORTED, "layer %d: a reorganised map can only enter through concat_with", l);
+            int want = p->layers[src].cout;
+            if (L.concat_with) want += seen_channels(p, L.concat_with - 1);
+            if (L.cin != want) return fail(E_ARG, "layer %d cin %d != %d channels of its input", l, L.cin, want);
+            if (L.concat_with && (p->layers[src].cout % 4 || seen_channels(p, L.concat_with - 1) % 4)) return fail(E_UNSUPPORTED, "layer %d: concatenated parts must be multiples of 4 channels", l);
+        }
         if (l == 0 && L.cin > 4) return fail(E_UNSUPPORTED, "network input must have <= 4 channels (NHWC4)");
+        if (layout == YOLO_B200_WLAYOUT_WEIGHT_H && ks != 3) return fail(E_UNSUPPORTED, "layer %d: weight.h order is defined for 3x3 layers", l);
         if (!weights[l] || !biases[l]) return fail(E_ARG, "layer %d: null weights/biases", l);
         LayerDev d;
-        d.cin = L.cin; d.cout = L.cout;
+        d.cin = L.cin; d.cout = L.cout; d.ksize = ks; d.in_from = L.in_from; d.reorg = L.reorg; d.concat_with = L.concat_with;
         d.cs_in = yolo_b200_cstride(L.cin); d.cs_out = yolo_b200_cstride(L.cout);
         d.cout_pad = (d.cs_out + 31) / 32 * 32;
         d.bias_host.assign(biases[l], biases[l] + L.cout);
-        // repack to [cout_pad][tap][cs_in], zero padded
-        std::vector<int8_t> wp((size_t)d.cout_pad * 9 * d.cs_in, 0);
+        // repack to [cout_pad][9 taps][cs_in], zero padded; a 1x1 kernel is the centre tap (the 3x3 kernels and the
+        // dot-product cross-check path then run it unchanged; the tensor-core 1x1 path uses the compact one-tap copy below)
+        std::vector<int8_t> &wp = d.wp_host;
+        wp.assign((size_t)d.cout_pad * 9 * d.cs_in, 0);
         const int8_t *w = weights[l];
         const int tm = L.cout < 32 ? L.cout : 32, tn = L.cin < 16 ? L.cin : 16;       // weight.h groups
         const int gco = (L.cout + tm - 1) / tm, gci = (L.cin + tn - 1) / tn;
         for (int o = 0; o < L.cout; ++o)
-            for (int t = 0; t < 9; ++t)
+            for (int t = 0; t < taps; ++t)
                 for (int i = 0; i < L.cin; ++i) {
                     size_t src;
-                    if (layout == YOLO_B200_WLAYOUT_OIHW) src = ((size_t)o * L.cin + i) * 9 + t;
-                    else if (layout == YOLO_B200_WLAYOUT_OHWI) src = ((size_t)o * 9 + t) * L.cin + i;
+                    if (layout == YOLO_B200_WLAYOUT_OIHW) src = ((size_t)o * L.cin + i) * taps + t;
+                    else if (layout == YOLO_B200_WLAYOUT_OHWI) src = ((size_t)o * taps + t) * L.cin + i;
                     else src = ((((size_t)t * gco + o / tm) * gci + i / tn) * tm + o % tm) * tn + i % tn;
-                    wp[((size_t)o * 9 + t) * d.cs_in + i] = w[src];
+                    wp[((size_t)o * 9 + (ks == 1 ? 4 : t)) * d.cs_in + i] = w[src];
                 }
         CU(cudaMalloc(&d.w, wp.size()));
         CU(cudaMemcpy(d.w, wp.data(), wp.size(), cudaMemcpyHostToDevice));
-        if (d.cs_in == 16) {
+        if (ks == 1) {
+            std::vector<int8_t> w1((size_t)d.cout_pad * d.cs_in, 0);
+            for (int o = 0; o < d.cout_pad; ++o) memcpy(&w1[(size_t)o * d.cs_in], &wp[((size_t)o * 9 + 4) * d.cs_in], d.cs_in);
+            CU(cudaMalloc(&d.w1, w1.size()));
+            CU(cudaMemcpy(d.w1, w1.data(), w1.size(), cudaMemcpyHostToDevice));
+        }
+        if (d.cs_in == 16 && ks == 3) {
             std::vector<int8_t> wk((size_t)d.cout_pad * 160, 0);
             for (int o = 0; o < d.cout_pad; ++o) memcpy(&wk[(size_t)o * 160], &wp[(size_t)o * 144], 144);
             CU(cudaMalloc(&d.w_k160, wk.size()));
             CU(cudaMemcpy(d.w_k160, wk.data(), wk.size(), cudaMemcpyHostToDevice));
         }
-        if (d.cs_in >= 16) {
+        if (d.cs_in >= 16 && d.cs_in <= 256 && d.cs_out <= 256 && ks == 3) {
             // conv_ws.cu: B operand as UMMA no-swizzle K-major core matrices, [n/8][kchunk][n%8][16 B].  K chunk order is
             // tap-major (chunk = tap * cs_in/16 + c).  16-channel layers pair two taps per K = 32 MMA and carry a zero
             // 10th tap; chunks 10..19 repeat the pairs with their halves swapped (for tap pairs whose second half lies
@@ -351,24 +393,17 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
                 CU(cudaMemcpy(d.wimg_tap, imt.data(), imt.size(), cudaMemcpyHostToDevice));
             }
         }
-        if (d.cs_in % 128 == 0) {
-            // conv_umma.cu: block kb = (tap, 128-byte channel chunk) as it must sit in shared memory for a K-major
-            // SWIZZLE_128B operand: row r (output channel) is 128 bytes, its 16-byte chunk c lives at chunk c ^ (r & 7)
-            const int per = d.cs_in / 128, nkb = 9 * per;
-            std::vector<uint8_t> sw((size_t)nkb * d.cs_out * 128, 0);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int tap = kb / per, c0 = (kb % per) * 128;
-                for (int r = 0; r < d.cs_out; ++r)
-                    for (int ch = 0; ch < 8; ++ch)
-                        memcpy(&sw[((size_t)kb * d.cs_out + r) * 128 + (size_t)((ch ^ (r & 7)) * 16)],
-                               &wp[((size_t)r * 9 + tap) * d.cs_in + c0 + 16 * ch], 16);
-            }
-            CU(cudaMalloc(&d.w_swz, sw.size()));
-            CU(cudaMemcpy(d.w_swz, sw.data(), sw.size(), cudaMemcpyHostToDevice));
-        }
+        // (the 128B-swizzled image of conv_umma.cu is built on first use: ensure_swz)
         CU(cudaMalloc(&d.bias_sh, (size_t)d.cout_pad * sizeof(int)));
         c->layers.push_back(d);
         { int rc = derive_layer(c, l); if (rc) return rc; }
+    }
+    c->graph = false;
+    for (int l = 0; l < p->num_layers; ++l) {
+        const yolo_b200_layer &L = p->layers[l];
+        if (L.ksize == 1 || L.in_from || L.reorg || L.concat_with) c->graph = true;
+        if (L.in_from && p->layers[L.in_from - 1].pool) c->layers[L.in_from - 1].unfused_pool = true;    // a route reads the un-pooled map
+        if (L.pool && yolo_b200_cstride(L.cout) > 256) c->layers[l].unfused_pool = true;                 // sliced wide layers do not fuse the pool
     }
     CU(cudaMemset(c->ovf_dev, 0, sizeof(unsigned)));      // the saturation counter belongs to the loaded network
     build_rgb444_lut(p->scale_a[0], c->lut_host);
@@ -522,6 +557,27 @@ int yolo_b200_u8bgr_lut(yolo_b200_ctx *c, int8_t *lut_host)
     return 0;
 }
 
+// conv_umma.cu's B operand: block kb = (tap, 128-byte channel chunk) as it must sit in shared memory for a K-major
+// SWIZZLE_128B operand: row r (output channel) is 128 bytes, its 16-byte chunk c lives at chunk c ^ (r & 7).  Built on first use:
+// the layers the weight-stationary kernel takes never need it.
+static int ensure_swz(yolo_b200_ctx *c, LayerDev &d)
+{
+    if (d.w_swz || d.cs_in % 128) return 0;
+    const int taps = d.ksize == 1 ? 1 : 9, per = d.cs_in / 128, nkb = taps * per;
+    std::vector<uint8_t> sw((size_t)nkb * d.cs_out * 128, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int tap = d.ksize == 1 ? 4 : kb / per, c0 = (kb % per) * 128;
+        for (int r = 0; r < d.cs_out; ++r)
+            for (int ch = 0; ch < 8; ++ch)
+                memcpy(&sw[((size_t)kb * d.cs_out + r) * 128 + (size_t)((ch ^ (r & 7)) * 16)],
+                       &d.wp_host[((size_t)r * 9 + tap) * d.cs_in + c0 + 16 * ch], 16);
+    }
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(&d.w_swz, sw.size()));
+    CU(cudaMemcpy(d.w_swz, sw.data(), sw.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out, ConvArgs &a)
 {
     LayerDev &L = c->layers[l];
@@ -529,27 +585,53 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
     a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
+    a.taps = 9; a.wgt1 = nullptr;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
 }
 
-static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out)
+// One convolution launch.  fuse_pool == false runs a pooled layer WITHOUT its pool (the caller pools separately).
+static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out, bool fuse_pool = true)
 {
     LayerDev &L = c->layers[l];
     ConvArgs a;
     fill_args(c, l, d_in, n, h, w, d_out, a);
+    if (!fuse_pool) a.q.pool = 0;
     const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
-    const bool umma_ok = aligned && conv3x3_umma_supported(a);
-    const bool ws_ok = aligned && conv3x3_ws_supported(a);
     const int be = c->conv_backend;
+    if (L.ksize == 1 || L.cs_in > 256 || L.cs_out > 256) {
+        // yolo_v2 / darknet19 shapes: 1x1 layers and layers wider than 256 channels run on the streaming tcgen05 implicit GEMM
+        // (one K block per (tap, 128-channel chunk), output channels in slices of 256); back end 1 keeps the dot-product kernel
+        ConvArgs u = a;
+        if (L.ksize == 1) { u.taps = 1; u.wgt1 = L.w1; }
+        if (be != 1 && aligned && conv3x3_umma_supported(u)) {
+            int rc = ensure_swz(c, L); if (rc) return rc;
+            u.wgt_swz = L.w_swz;
+            CU(conv3x3_umma(u, c->stream, c->sm_count));
+        } else {
+            if (be != 0 && be != 1) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d, %dx%d)", l, L.cs_in, L.cs_out, L.ksize, L.ksize);
+            if (be == 0) c->slow_path_launches++;
+            CU(conv3x3_direct(a, c->stream));              // (a 1x1 layer is the centre tap of the 9-tap weights)
+        }
+        c->launches++;
+        return 0;
+    }
+    bool umma_ok = aligned && conv3x3_umma_supported(a);
+    const bool ws_ok = aligned && conv3x3_ws_supported(a);
     if ((be == 2 || be == 3) && !umma_ok) return fail(E_UNSUPPORTED, "layer %d has no tensor-core shape (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
     if ((be == 4 || be == 5) && !ws_ok) return fail(E_UNSUPPORTED, "layer %d does not fit the weight-stationary kernel (cs_in %d, cs_out %d)", l, L.cs_in, L.cs_out);
     const bool first_ok = ((uintptr_t)d_out & 3) == 0 && conv3x3_first_src_ok(0, d_in) && conv3x3_first_supported(a);
+    const bool use_umma = be == 2 || be == 3 || (be == 0 && !first_ok && !ws_ok && umma_ok);
+    if (use_umma) { int rc = ensure_swz(c, L); if (rc) return rc; a.wgt_swz = L.w_swz; }
     if (be == 1) CU(conv3x3_direct(a, c->stream));
     else if (be == 0 && first_ok) CU(conv3x3_first(a, c->stream));
-    else if (be == 2 || be == 3) CU(conv3x3_umma(a, c->stream, c->sm_count));
+    else if (use_umma) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else if (be == 4 || be == 5 || ws_ok) CU(conv3x3_ws(a, c->stream, c->sm_count));
-    else if (umma_ok) CU(conv3x3_umma(a, c->stream, c->sm_count));
-    else CU(conv3x3_direct(a, c->stream));
+    else {
+        // auto back end, no tensor-core kernel takes this shape / alignment (e.g. a first layer wider than 16 channels, a
+        // 2-byte-aligned buffer): the dot-product kernel computes the same values; counted, see yolo_b200_slow_path_count
+        if (be == 0) c->slow_path_launches++;
+        CU(conv3x3_direct(a, c->stream));
+    }
     c->launches++;
     return 0;
 }
@@ -580,16 +662,47 @@ int yolo_b200_conv_layer(yolo_b200_ctx *c, int layer, const int8_t *d_in, int n,
     return run_layer(c, layer, d_in, n, h, w, d_out);
 }
 
-// Layers first..last on the context stream.  `cur` is the input of layer `first` (h x w).
+// Input of layer l for this call: the previous layer's output, the un-pooled output of layer in_from - 1, or the channel
+// concatenation of the two sources of a concat layer (built here by graph.cu: reorg + exponent alignment).
+static int layer_input(yolo_b200_ctx *c, size_t l, const int8_t *net_in, int n, int h0, int w0, const int8_t **in, int *ih, int *iw)
+{
+    if (l == 0) { *in = net_in; *ih = h0; *iw = w0; return 0; }
+    LayerDev &L = c->layers[l];
+    const yolo_b200_params &p = c->prm;
+    const int src = L.in_from ? L.in_from - 1 : (int)l - 1;
+    LayerDev &S = c->layers[src];
+    const int8_t *b = L.in_from ? (S.unfused_pool ? S.raw : S.view) : S.view;
+    int bh = L.in_from ? S.rh : S.oh, bw = L.in_from ? S.rw : S.ow;
+    if (!L.concat_with) { *in = b; *ih = bh; *iw = bw; return 0; }
+    LayerDev &A = c->layers[L.concat_with - 1];
+    const int ah = A.reorg ? A.oh / 2 : A.oh, aw = A.reorg ? A.ow / 2 : A.ow;
+    if (ah != bh || aw != bw || (A.reorg && ((A.oh | A.ow) & 1)))
+        return fail(E_ARG, "layer %zu: concatenated maps differ in size (%dx%d vs %dx%d)", l, ah, aw, bh, bw);
+    int rc = ensure((void **)&L.cat, &L.cat_cap, (size_t)(n > 0 ? n : 1) * bh * bw * L.cs_in); if (rc) return rc;
+    const int ea = p.scale_a[L.concat_with], eb = p.scale_a[src + 1], e = ea < eb ? ea : eb;
+    if (n > 0) {
+        CU(concat_reorg(A.view, A.cs_out, A.cout, A.reorg, ea - e, b, S.cs_out, S.cout, eb - e, n, bh, bw, L.cs_in, L.cat, c->stream));
+        c->launches++;
+    }
+    *in = L.cat; *ih = bh; *iw = bw;
+    return 0;
+}
+
+// Layers first..last on the context stream.  `net_in` is the network input (h x w) when first == 0; for first > 0 the
+// earlier layers' outputs are already in place.
 // `last_out` != nullptr: the last layer writes there instead of into its own buffer (a slot of a batch-wide prediction map).
-static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *cur, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw,
+static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *net_in, int n, int h, int w, const int8_t **d_pred, int *gh, int *gw,
                          int8_t *last_out = nullptr)
 {
     int rc;
+    const int8_t *cur = net_in;
     for (size_t l = first; l < c->layers.size(); ++l) {
         LayerDev &L = c->layers[l];
-        if (L.q.pool && (h < 2 || w < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, h, w);
-        int oh = L.q.pool ? h / 2 : h, ow = L.q.pool ? w / 2 : w;
+        int ih, iw;
+        if (l == first && first > 0 && !c->graph) { ih = h; iw = w; }                // (chain: the caller passes layer `first`'s input)
+        else { rc = layer_input(c, l, net_in, n, h, w, &cur, &ih, &iw); if (rc) return rc; }
+        if (L.q.pool && (ih < 2 || iw < 2)) return fail(E_ARG, "input too small: layer %zu pools a %dx%d map", l, ih, iw);
+        const int oh = L.q.pool ? ih / 2 : ih, ow = L.q.pool ? iw / 2 : iw;
         int8_t *dst = L.out;
         if (last_out && l + 1 == c->layers.size()) dst = last_out;
         else {
@@ -597,15 +710,22 @@ static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *cur, int 
             rc = ensure((void **)&L.out, &L.out_cap, bytes); if (rc) return rc;
             dst = L.out;
         }
-        L.oh = oh; L.ow = ow; L.view = dst;
-        if (n > 0) { rc = run_layer(c, (int)l, cur, n, h, w, dst); if (rc) return rc; }
+        L.oh = oh; L.ow = ow; L.rh = ih; L.rw = iw; L.view = dst;
+        if (L.q.pool && L.unfused_pool) {
+            rc = ensure((void **)&L.raw, &L.raw_cap, (size_t)(n > 0 ? n : 1) * ih * iw * L.cs_out); if (rc) return rc;
+            if (n > 0) {
+                rc = run_layer(c, (int)l, cur, n, ih, iw, L.raw, false); if (rc) return rc;
+                CU(maxpool2x2(L.raw, n, ih, iw, L.cs_out, dst, c->stream));
+                c->launches++;
+            }
+        } else if (n > 0) { rc = run_layer(c, (int)l, cur, n, ih, iw, dst); if (rc) return rc; }
         tick(c);
         cur = dst; h = oh; w = ow;
     }
     c->last_n = n;
-    if (d_pred) *d_pred = cur;
-    if (gh) *gh = h;
-    if (gw) *gw = w;
+    if (d_pred) *d_pred = c->layers.back().view;
+    if (gh) *gh = c->layers.back().oh;
+    if (gw) *gw = c->layers.back().ow;
     return 0;
 }
 
@@ -647,6 +767,7 @@ static int tracker_pass_inner(yolo_b200_ctx *c, const float *d_nchw, int n, int 
 {
     yolo_b200_params &p = c->prm;
     int hs[2], rc;
+    if (c->graph) return fail(E_UNSUPPORTED, "the tracker pass covers plain chains of 3x3 layers (slim_yolo_v2); calibrate yolo_v2 with the exporter");
     auto new_scale = [&](int t, float m32) -> float {                 // tracker t sees max|a| = m32 (float32, as the tensor op yields)
         const float fresh = 127.0f / m32;
         if (mode == TRK_FIRST || !scales || scales[t] == 0.f) return fresh;
@@ -851,7 +972,7 @@ static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, i
     if (kind == 2 && c->lut8_saturates) return 0;              // saturated inputs must be counted: the stand-alone quantiser does
     const int oh = L0.q.pool ? h / 2 : h, ow = L0.q.pool ? w / 2 : w;
     int rc = ensure((void **)&L0.out, &L0.out_cap, (size_t)n * oh * ow * L0.cs_out); if (rc) return rc;
-    L0.oh = oh; L0.ow = ow; L0.view = L0.out;
+    L0.oh = oh; L0.ow = ow; L0.rh = h; L0.rw = w; L0.view = L0.out;
     a0.out = L0.out;
     c->ev_used = 0;
     tick(c);
@@ -1161,6 +1282,7 @@ int yolo_b200_overflow_count(yolo_b200_ctx *c, int64_t *count)
 }
 
 int64_t yolo_b200_launch_count(yolo_b200_ctx *c) { return c ? c->launches : 0; }
+int64_t yolo_b200_slow_path_count(yolo_b200_ctx *c) { return c ? c->slow_path_launches : 0; }
 
 int yolo_b200_enable_timing(yolo_b200_ctx *c, int enable)
 {

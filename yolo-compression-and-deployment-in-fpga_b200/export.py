@@ -78,6 +78,7 @@ class QuantNet:
     anchors: List[List[float]] = field(default_factory=lambda: [list(a) for a in ANCHOR_SIZE_MASK])
     num_classes: int = 2
     stride: int = 16
+    graph: Optional[List[dict]] = None   # per layer: ksize / in_from / reorg / concat_with (include/yolo_b200.h, ABI 2); None = chain of 3x3
 
     def sha256(self) -> str:
         h = hashlib.sha256()
@@ -358,6 +359,110 @@ def quantnet_from_state_dict(sd: Dict[str, torch.Tensor], calib_frames: Optional
     else:
         rt = rt_c          # None when the checkpoint brought its own trackers and no calibration frames were given
     return QuantNet(layers, qw, qb, sw, sb, sa, rt, anchors, num_classes)
+
+
+# ---- yolo_v2 / darknet19 (BASELINE configs[4]) --------------------------------------------------------------------
+
+def yolo_v2_layers(num_classes: int = 20, num_anchors: int = 5):
+    """The BN-folded yolo_v2 graph as (cin, cout, activ, pool) tuples + the ABI-2 graph fields of include/yolo_b200.h:
+    darknet19 (backbone/darknet.py:40-108: conv_1 .. conv_6, maxpool_4 / maxpool_5 written as the pool of the layer in front
+    of them), convsets_1, route_layer (1x1 on C_5, the map in front of maxpool_5) + reorg, the concat, convsets_2 and the
+    1x1 pred (models/yolo_v2.py:29-40,165-177).  Every leaky-ReLU is the 1/8 shift (the head's slope is 0.125,
+    utils/modules.py:25; the backbone's 0.1, darknet.py:18, is not a shift: SURVEY.md 8d config 5 [DECISION])."""
+    L, G = [], []
+
+    def add(cin, cout, ks, activ=1, pool=0, **g):
+        L.append((cin, cout, activ, pool))
+        G.append(dict(ksize=ks, **g))
+    add(3, 32, 3, pool=1)
+    add(32, 64, 3, pool=1)
+    add(64, 128, 3); add(128, 64, 1); add(64, 128, 3, pool=1)
+    add(128, 256, 3); add(256, 128, 1); add(128, 256, 3, pool=1)                                  # conv_4, maxpool_4
+    add(256, 512, 3); add(512, 256, 1); add(256, 512, 3); add(512, 256, 1); add(256, 512, 3, pool=1)    # conv_5 (C_5 = un-pooled output of layer 12), maxpool_5
+    add(512, 1024, 3); add(1024, 512, 1); add(512, 1024, 3); add(1024, 512, 1); add(512, 1024, 3)       # conv_6
+    add(1024, 1024, 3); add(1024, 1024, 3)                                                        # convsets_1 (layers 18, 19)
+    add(512, 64, 1, in_from=13, reorg=1)                                                          # route_layer on C_5 + reorg (layer 20)
+    add(1280, 1024, 3, in_from=20, concat_with=21)                                                # cat([reorg(route), convsets_1]) -> convsets_2
+    add(1024, num_anchors * (5 + num_classes), 1, activ=0)                                        # pred
+    return L, G
+
+
+def input_exponent(layers, graph, sa, l):
+    """Activation exponent of layer l's input: its source's output exponent; a concat brings both parts to the smaller one."""
+    if l == 0:
+        return sa[0]
+    g = (graph or [{}] * len(layers))[l]
+    src = g.get("in_from", 0) - 1 if g.get("in_from", 0) else l - 1
+    e = sa[src + 1]
+    if g.get("concat_with", 0):
+        e = min(e, sa[g["concat_with"]])
+    return e
+
+
+def reorg_nchw(x: torch.Tensor) -> torch.Tensor:
+    """reorg_layer(stride=2), utils/modules.py:43-57: out[b, (2*dy+dx)*C + c, y, x] = in[b, c, 2y+dy, 2x+dx]."""
+    b, c, h, w = x.shape
+    x = x.view(b, c, h // 2, 2, w // 2, 2).permute(0, 3, 5, 1, 2, 4).contiguous()
+    return x.view(b, 4 * c, h // 2, w // 2)
+
+
+def calibrate_graph(ws, bs, frames, layers, graph):
+    """calibrate() for a graph network: one fake-quant forward with fresh trackers over the yolo_v2 graph; the parts of a concat
+    are re-rounded to the smaller of their two exponents, as the integer path does.  Returns (sa [L+1], retune [L])."""
+    sa, retune = [], []
+    pre, post = {}, {}                  # un-pooled / pooled (consumer-visible) fake-quant outputs per layer
+    with torch.no_grad():
+        x = frames.float()
+        e = pow2_scale_exponent(x)
+        sa.append(e)
+        x0 = torch.round(x * 2.0 ** e) / 2.0 ** e
+        for l, (cin, cout, activ, pool) in enumerate(layers):
+            g = graph[l]
+            if l == 0:
+                xin = x0
+            else:
+                src = g.get("in_from", 0) - 1 if g.get("in_from", 0) else l - 1
+                xin = pre[src] if g.get("in_from", 0) else post[src]
+                if g.get("concat_with", 0):
+                    k = g["concat_with"] - 1
+                    a = reorg_nchw(post[k]) if graph[k].get("reorg", 0) else post[k]
+                    ec = min(sa[k + 1], sa[src + 1])
+                    xin = torch.cat([torch.round(a * 2.0 ** ec) / 2.0 ** ec, torch.round(xin * 2.0 ** ec) / 2.0 ** ec], 1)
+            ks = g.get("ksize", 3) or 3
+            y = F.conv2d(xin, ws[l], bs[l], stride=1, padding=ks // 2)
+            if activ:
+                y = F.leaky_relu(y, 0.125)
+            m = float(y.abs().max())
+            r = int(math.floor(math.log2((2.0 ** 15) / m))) if m > 0 else 15
+            while m * 2.0 ** r >= 2.0 ** 15:
+                r -= 1
+            retune.append(r)
+            e = pow2_scale_exponent(y)
+            sa.append(e)
+            y = torch.round(y * 2.0 ** e) / 2.0 ** e
+            pre[l] = y
+            post[l] = F.max_pool2d(y, 2, 2) if pool else y
+    return sa, retune
+
+
+def random_quantnet_yolo_v2(seed: int = 0, calib_hw=(416, 416), calib_frames: int = 1, num_classes: int = 20, anchors=None,
+                            weight_gain: float = 2.0) -> QuantNet:
+    """Random-init, BN-folded yolo_v2 (darknet19 backbone) quantised with the reference's power-of-two rule and calibrated by
+    the first-call tracker rule.  nn.Conv2d's default init in construction order; weight_gain keeps the
+    signal alive through 23 layers (see random_quantnet)."""
+    layers, graph = yolo_v2_layers(num_classes, len(anchors or ANCHOR_SIZE))
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    ws, bs = [], []
+    for (cin, cout, _, _), gg in zip(layers, graph):
+        conv = torch.nn.Conv2d(cin, cout, gg["ksize"], 1, padding=gg["ksize"] // 2)
+        ws.append(conv.weight.detach().clone() * weight_gain)
+        bs.append(conv.bias.detach().clone())
+    torch.random.set_rng_state(g)
+    qw, qb, sw, sb, dw, db = quantize_convs(ws, bs)
+    frames = synthetic_frames_f32(calib_frames, calib_hw[0], calib_hw[1], seed=1000 + seed)
+    sa, retune = calibrate_graph(dw, db, frames, layers, graph)
+    return QuantNet(layers, qw, qb, sw, sb, sa, retune, [list(a) for a in (anchors or ANCHOR_SIZE)], num_classes, stride=32, graph=graph)
 
 
 # ---- weight.h ---------------------------------------------------------------------------------------

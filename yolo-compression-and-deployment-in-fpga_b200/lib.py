@@ -30,7 +30,7 @@ EXPORTS = [
     "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev", "yolo_b200_sync",
     "yolo_b200_quantize_rgb444", "yolo_b200_quantize_f32", "yolo_b200_rgb444_lut", "yolo_b200_conv_layer",
     "yolo_b200_backbone", "yolo_b200_calibrate_f32", "yolo_b200_update_trackers_f32", "yolo_b200_measure_f32", "yolo_b200_get_layer_output", "yolo_b200_detect", "yolo_b200_overflow_count",
-    "yolo_b200_launch_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
+    "yolo_b200_launch_count", "yolo_b200_slow_path_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
     "yolo_forward", "yolo_b200_set_default_context",
     "yolo_b200_pack_detections", "yolo_b200_ipc_alloc", "yolo_b200_ipc_open", "yolo_b200_ipc_close", "yolo_b200_copy_async",
     "yolo_b200_resize_taps", "yolo_b200_resize_u8bgr", "yolo_b200_forward_u8bgr_resize", "yolo_b200_forward_u8bgr_resize_dev",
@@ -38,7 +38,8 @@ EXPORTS = [
 
 
 class Layer(C.Structure):
-    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("activ", C.c_int32), ("pool", C.c_int32)]
+    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("activ", C.c_int32), ("pool", C.c_int32),
+                ("ksize", C.c_int32), ("in_from", C.c_int32), ("reorg", C.c_int32), ("concat_with", C.c_int32)]
 
 
 class Params(C.Structure):
@@ -119,6 +120,8 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_overflow_count.argtypes = [vp, C.POINTER(C.c_int64)]
     L.yolo_b200_launch_count.argtypes = [vp]
     L.yolo_b200_launch_count.restype = C.c_int64
+    L.yolo_b200_slow_path_count.argtypes = [vp]
+    L.yolo_b200_slow_path_count.restype = C.c_int64
     L.yolo_b200_enable_timing.argtypes = [vp, i32]
     L.yolo_b200_layer_times_ms.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.yolo_b200_draw_rectangles.argtypes = [vp, i32, i32, vp, i32, i32]
@@ -138,7 +141,8 @@ def make_params(qnet, contract=CONTRACT_P, round_mode=ROUND_RNE, head_mode=HEAD_
     # contract F is the 16-bit accumulator programme: it needs a retune[] that was derived from real activations
     retune = qnet.require_retune("contract F") if contract == CONTRACT_F else (qnet.retune or [0] * len(qnet.layers))
     for l, (cin, cout, activ, pool) in enumerate(qnet.layers):
-        p.layers[l] = Layer(cin, cout, activ, pool)
+        g = (getattr(qnet, "graph", None) or [{}] * len(qnet.layers))[l]
+        p.layers[l] = Layer(cin, cout, activ, pool, g.get("ksize", 0), g.get("in_from", 0), g.get("reorg", 0), g.get("concat_with", 0))
         p.scale_w[l] = qnet.sw[l]; p.scale_b[l] = qnet.sb[l]; p.retune[l] = retune[l]
     for l, v in enumerate(qnet.sa):
         p.scale_a[l] = v
@@ -375,6 +379,9 @@ class Context:
         v = C.c_int64()
         self._check(self.L.yolo_b200_overflow_count(self._h, C.byref(v)))
         return v.value
+
+    def slow_path_count(self) -> int:
+        return int(self.L.yolo_b200_slow_path_count(self._h))
 
     def launch_count(self) -> int:
         return int(self.L.yolo_b200_launch_count(self._h))
