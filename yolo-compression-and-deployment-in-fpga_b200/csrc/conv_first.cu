@@ -27,7 +27,8 @@ struct FirstParams {
     int n_img, H, W;
     int OH, OW;
     size_t out_img_bytes;      // OH * OW * cs_out
-    int cs_out;                // 16
+    int cs_out;                // 16; WIDE: any multiple of 16 (the kernel then writes the 16 channels co0 .. co0 + 15 of every pixel)
+    int co0;                   // first output channel of this pass
     const int8_t *wgt;         // [cout_pad][9][4]
     const int *bias_sh;
     LayerQ q;
@@ -72,9 +73,12 @@ static_assert(F_NQUAD <= F_THREADS && 4 * F_QUADS_ROW <= F_PITCH, "one quad per 
 
 __device__ __forceinline__ int keep(int v) { asm volatile("" : "+r"(v)); return v; }   // stops the compiler re-deriving v from tid per tile
 
-template <bool POOL, int EPI, bool ACT, int SRC>
+template <bool POOL, int EPI, bool ACT, int SRC, bool WIDE = false>
 __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const FirstParams p)
 {
+    // pixel stride of the output map in bytes: 16 for slim_yolo_v2's first layer (compile-time constant); WIDE = a first layer
+    // with more than 16 output channels (darknet19: 32), written in passes of 16 channels
+    const int PX = WIDE ? p.cs_out : 16;
     constexpr bool RGB444 = SRC == 1, U8 = SRC == 2;
     constexpr int RAWN = RGB444 ? 2 : U8 ? 3 : 4;                     // 32-bit words per pixel quad
     // fp32 epilogues: the accumulators start at the bit pattern of 1.5 * 2^23, so that read as fp32 they are MAGIC + sum
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
 
     // B fragments.  N-tile n, column c <-> output channel 4*(c>>1) + 2*n + (c&1), so that the C fragment of thread t
     // (columns 2t, 2t+1 of both tiles) is channels 4t .. 4t+3.
-    const unsigned *gw = reinterpret_cast<const unsigned *>(p.wgt);       // word (o*9 + tap) = the 4 channel bytes of one tap
+    const unsigned *gw = reinterpret_cast<const unsigned *>(p.wgt) + (WIDE ? p.co0 * 9 : 0);       // word (o*9 + tap) = the 4 channel bytes of one tap
     unsigned b0[2], b1[2], b2[2];
 #pragma unroll
     for (int n = 0; n < 2; ++n) {
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
         b1[n] = __ldg(gw + o * 9 + 4 + t);         //           k = 16+4t..     : tap 4+t
         b2[n] = t == 0 ? __ldg(gw + o * 9 + 8) : 0u;   // k16 step: tap 8, then three zero taps
     }
-    const int4 bias = *reinterpret_cast<const int4 *>(p.bias_sh + 4 * t);
+    const int4 bias = *reinterpret_cast<const int4 *>(p.bias_sh + (WIDE ? p.co0 : 0) + 4 * t);
     int4 bw = bias;
     if (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI)
         bw = make_int4(__float_as_int((float)bias.x), __float_as_int((float)bias.y), __float_as_int((float)bias.z), __float_as_int((float)bias.w));
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
     const int o_c = keep(a_org + 2 * F_PITCH + 2);
     // this thread's output pixel inside a tile (rows oy_t, oy_t + 1; column ox_t [+ 8 cg]) and its byte offset
     const int oy_t = keep(POOL ? 2 * (warp >> 1) : 2 * warp), ox_t = keep(POOL ? 8 * (warp & 1) + g : g);
-    const int o_thr = keep((oy_t * (POOL ? p.OW : p.W) + ox_t) * 16 + 4 * t);     // cs_out == 16 (conv3x3_first_supported)
+    const int o_thr = keep((oy_t * (POOL ? p.OW : p.W) + ox_t) * PX + 4 * t + (WIDE ? p.co0 : 0));
     unsigned ovf = 0;
 
     const int tiles_x = (p.W + F_TW - 1) / F_TW, tiles_y = (p.H + F_TH - 1) / F_TH;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
                 }
             }
             // this thread's 4 channels of pooled pixel (oy, ox)
-            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + ((((y0 >> 1) * p.OW + (x0 >> 1)) * 16) + o_thr);
+            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + ((((y0 >> 1) * p.OW + (x0 >> 1)) * PX) + o_thr);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 int m[4];
@@ -224,10 +228,10 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
                 const int oy = (y0 >> 1) + oy_t + h, ox = (x0 >> 1) + ox_t;
                 const bool valid = oy < p.OH && ox < p.OW;
                 const unsigned w = requant4v<EPI, ACT, FirstParams, PRE>(m, bw, p, ovf, valid);
-                if (valid) *reinterpret_cast<unsigned *>(out_px + h * p.OW * 16) = w;
+                if (valid) *reinterpret_cast<unsigned *>(out_px + h * p.OW * PX) = w;
             }
         } else {
-            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + (((y0 * p.W + x0) * 16) + o_thr);
+            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + (((y0 * p.W + x0) * PX) + o_thr);
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
                 int acc[2][4];
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
                     const int y = y0 + oy_t + h, x = x0 + 8 * cg + ox_t;
                     const bool valid = y < p.H && x < p.W;
                     const unsigned w = requant4v<EPI, ACT, FirstParams, PRE>(m, bw, p, ovf, valid);
-                    if (valid) *reinterpret_cast<unsigned *>(out_px + (h * p.W + 8 * cg) * 16) = w;
+                    if (valid) *reinterpret_cast<unsigned *>(out_px + (h * p.W + 8 * cg) * PX) = w;
                 }
             }
         }
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
 
 bool conv3x3_first_supported(const ConvArgs &a)
 {
-    if (a.cs_in != 4 || a.cs_out != 16 || a.w_rows < 16) return false;
+    if (a.cs_in != 4 || a.cs_out % 16 || a.cs_out > 64 || a.w_rows < a.cs_out) return false;   // 16 channels per pass
     if (a.q.pool && (a.H < 2 || a.W < 2)) return false;
     if (a.W % 4) return false;                                                     // the halo is fetched as aligned pixel quads
     if ((long long)a.n * a.H * a.W >= (1ll << 31) - (1ll << 20)) return false;     // 32-bit pixel offsets in the halo fetch
@@ -279,7 +283,7 @@ bool conv3x3_first_src_ok(int src_kind, const void *src)
     return ((uintptr_t)src % (src_kind == 1 ? 8 : src_kind == 2 ? 4 : 16)) == 0;
 }
 
-template <bool POOL, int EPI, int SRC>
+template <bool POOL, int EPI, int SRC, bool WIDE = false>
 static cudaError_t launch_first3(const FirstParams &p, cudaStream_t st)
 {
     const long long total = (long long)((p.W + F_TW - 1) / F_TW) * ((p.H + F_TH - 1) / F_TH) * p.n_img;
@@ -288,20 +292,29 @@ static cudaError_t launch_first3(const FirstParams &p, cudaStream_t st)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // persistent grid = exactly the CTAs that are resident at once
     int per_sm = 0;
-    cudaError_t e = p.q.activ ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv3x3_first_kernel<POOL, EPI, true, SRC>, F_THREADS, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv3x3_first_kernel<POOL, EPI, false, SRC>, F_THREADS, 0);
+    cudaError_t e = p.q.activ ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv3x3_first_kernel<POOL, EPI, true, SRC, WIDE>, F_THREADS, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv3x3_first_kernel<POOL, EPI, false, SRC, WIDE>, F_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const long long cap = (long long)sms * per_sm;
     const int grid = (int)(total < cap ? total : cap);
-    if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, SRC><<<grid, F_THREADS, 0, st>>>(p);
-    else conv3x3_first_kernel<POOL, EPI, false, SRC><<<grid, F_THREADS, 0, st>>>(p);
+    if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, SRC, WIDE><<<grid, F_THREADS, 0, st>>>(p);
+    else conv3x3_first_kernel<POOL, EPI, false, SRC, WIDE><<<grid, F_THREADS, 0, st>>>(p);
     return cudaGetLastError();
 }
 
 template <bool POOL, int EPI>
 static cudaError_t launch_first2(const FirstParams &p, cudaStream_t st)
 {
+    if (p.cs_out != 16) {
+        // wider first layers (darknet19's 3 -> 32): one pass per 16 output channels over the same input
+        FirstParams q = p;
+        for (q.co0 = 0; q.co0 < p.cs_out; q.co0 += 16) {
+            cudaError_t e = p.in16 ? launch_first3<POOL, EPI, 1, true>(q, st) : p.in8 ? launch_first3<POOL, EPI, 2, true>(q, st) : launch_first3<POOL, EPI, 0, true>(q, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     if (p.in16) return launch_first3<POOL, EPI, 1>(p, st);
     if (p.in8) return launch_first3<POOL, EPI, 2>(p, st);
     return launch_first3<POOL, EPI, 0>(p, st);
