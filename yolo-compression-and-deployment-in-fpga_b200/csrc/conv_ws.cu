@@ -82,6 +82,7 @@ struct WsParams {
     const uint8_t *wtap;         // [tap][128-channel plane][N/8][8][8][16 B]: one chunk = b_chunk_bytes = N * 128
     uint32_t b_chunk_bytes;
     int b_slots;
+    int b_resident;              // all 9 * planes chunks fit in shared memory (pred: 18 x 6 KB): loaded once, no ring traffic per tile
     // flattened-raster tiles (BSTREAM, un-pooled, narrow maps): the canvas rows are W + 1 pixels wide (the extra one is out of
     // bounds for the TMA box = zero = the horizontal padding of both neighbours), an M tile is 128 consecutive pixels of
     // that stream, its halo is raster_rows whole rows (+ one zero pixel in front), every tap is a start offset
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         const uint32_t plane16 = p.plane_stride >> 4;             // LBO of A: the next 16-byte channel plane
         const uint32_t half16 = p.plane_stride >> 5;              // PHASE: x-parity half-plane, in 16-byte units
         const uint32_t cstep16 = p.plane_stride >> 3;             // two channel planes = one K = 32 step
-        if (!BSTREAM) mbar_wait(bar_w, 0);
+        if (!BSTREAM || p.b_resident) mbar_wait(bar_w, 0);
         int it = 0, s = 0, bslot = 0;
         uint32_t ph = 0, rph = 0;                                 // stage phase, weight-ring phase
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -391,18 +392,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
                     row_px = p.rP; sbo_px = 8u;
                 }
                 constexpr int NPL = KHALF / 4;                     // 128-channel planes = weight chunks per tap
+                if (p.b_resident) {
+                    // every chunk is in shared memory: one fully unrolled issue sequence with compile-time tap offsets (the
+                    // chunk loop below costs ~100 cycles per MMA at N = 48, twice what the tensor pipe needs)
+                    if (elect_one()) {
+                        const uint32_t w16 = wsm >> 4, ch16 = p.b_chunk_bytes >> 4;
+#pragma unroll
+                        for (int ck = 0; ck < 9 * NPL; ++ck)
+                            ws_issue_tap<KHALF>(d0, a16 + (uint32_t)(ck % NPL) * plane16, plane16, ck / NPL, row_px, sbo_px,
+                                                w16 + (uint32_t)ck * ch16, ck == 0, idesc);
+                        umma_commit(bar_empty(s));
+                        umma_commit(bar_tfull(buf));
+                    }
+                    __syncwarp();
+                } else
                 for (int ck = 0; ck < 9 * NPL; ++ck) {
                     const int tap = ck / NPL, pl = ck - tap * NPL;
-                    mbar_wait(bar_bfull(bslot), rph);
-                    tc_fence_after();
+                    if (!p.b_resident) { mbar_wait(bar_bfull(bslot), rph); tc_fence_after(); }
                     if (elect_one()) {
                         ws_issue_tap<KHALF>(d0, a16 + (uint32_t)pl * plane16, plane16, tap, row_px, sbo_px,
-                                            (wsm + (uint32_t)bslot * p.b_chunk_bytes) >> 4, ck == 0, idesc);
-                        umma_commit(bar_bempty(bslot));
+                                            (wsm + (uint32_t)(p.b_resident ? ck : bslot) * p.b_chunk_bytes) >> 4, ck == 0, idesc);
+                        if (!p.b_resident) umma_commit(bar_bempty(bslot));
                         if (ck == 9 * NPL - 1) { umma_commit(bar_empty(s)); umma_commit(bar_tfull(buf)); }
                     }
                     __syncwarp();
-                    if (++bslot == p.b_slots) { bslot = 0; rph ^= 1u; }
+                    if (!p.b_resident && ++bslot == p.b_slots) { bslot = 0; rph ^= 1u; }
                 }
             } else {
                 if (elect_one()) {
@@ -419,7 +433,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
         }
     } else if (TMAIN && warp <= WS_PROD_WARPS) {
         // ===================== TMA producer: one thread =====================
-        if (BSTREAM && warp == 2 && lane == 0) {
+        if (BSTREAM && warp == 2 && lane == 0 && p.b_resident) {
+            // every weight chunk once: they all fit
+            const uint32_t total = (uint32_t)(9 * (KHALF / 4)) * p.b_chunk_bytes;
+            mbar_expect_tx(bar_w, total);
+            for (uint32_t o = 0; o < total; o += 32768u) {
+                const uint32_t nb = total - o < 32768u ? total - o : 32768u;
+                bulk_load_1d(wsm + o, p.wtap + o, nb, bar_w);
+            }
+        } else if (BSTREAM && warp == 2 && lane == 0) {
             // weight chunks: tile after tile, tap after tap
             int slot = 0;
             uint32_t bph = 0;
@@ -717,6 +739,8 @@ static bool ws_plan_stream(const ConvArgs &a, WsParams *p)
     p->stages = 2;
     int slots = (int)((budget - tail - 2 * p->stage_bytes) / p->b_chunk_bytes);
     p->b_slots = slots > 4 ? 4 : slots;
+    static const bool resident_on = [] { const char *e = getenv("YOLO_B200_WS_RESIDENT"); return e ? atoi(e) != 0 : true; }();
+    if (resident_on && slots >= 9 * npl) { p->b_resident = 1; p->b_slots = 9 * npl; }   // the whole layer fits beside two stages (pred)
     int stages = (int)((budget - tail - (uint32_t)p->b_slots * p->b_chunk_bytes) / p->stage_bytes);
     p->stages = stages > WS_MAX_STAGES ? WS_MAX_STAGES : stages;
     p->off_stage = ((uint32_t)p->b_slots * p->b_chunk_bytes + 1023u) & ~1023u;
