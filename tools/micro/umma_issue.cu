@@ -83,6 +83,10 @@ template <int V> void run(const char *name, long long *d, uint32_t a_lbo = 2960,
 int main()
 {
     long long *d; cudaMalloc(&d, 8);
+    run<2>("noswz sbo128 lbo16         ", d, 16, 128, 0, 0, 0);
+    run<2>("noswz sbo128 lbo1664       ", d, 1664, 128, 0, 32, 0);
+    run<2>("noswz sbo128 lbo16 +1696+16", d, 16, 128, 0, 1696 + 16, 0);
+    run<2>("noswz sbo160 lbo16         ", d, 16, 160, 0, 0, 0);
     run<2>("noswz sbo160 lbo2960 step1 ", d, 2960, 160, 0, 0, 1);
     run<2>("noswz sbo160 lbo2960 step0 ", d, 2960, 160, 0, 0, 0);
     run<2>("noswz sbo128 lbo2048 step0 ", d, 2048, 128, 0, 0, 0);

@@ -16,6 +16,7 @@ struct ConvArgs {
     int wgt_swz_rows = 0;              // rows per block of wgt_swz (= cs_out)
     const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
     const uint8_t *wimg_tap;   // cs_in 128 / 256: the same image tap-major, [tap][128-channel plane][cs_out/8][8][8][16 B] (conv_ws.cu, weight streaming)
+    const uint8_t *wimg_rp = nullptr;  // cs_in == 16, cs_out == 32, pooled: row-pair image [2*cs_out/8][12][8][16 B] (conv_rp.cu)
     int w_rows;            // cout_pad
     int bias_abs_max;      // max |bias_sh[c]| (decides whether the exact fp32 epilogue applies)
     int force_generic_epilogue;   // tests: run the integer epilogue even where the fp32 one applies
@@ -46,6 +47,10 @@ cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_
 // conv_ws.cu (weight-stationary tcgen05 kernel: weights resident in shared memory, haloed tile fetched once)
 bool conv3x3_ws_supported(const ConvArgs &a);
 cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
+
+// conv_rp.cu (row-pair tcgen05 kernel for the thin pooled layers: two output rows in the GEMM N dimension, dense TMA-fed halo)
+bool conv3x3_rp_supported(const ConvArgs &a);
+cudaError_t conv3x3_rp(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // graph.cu (yolo_v2: stand-alone max-pool, reorg + concat with exponent alignment)
 cudaError_t maxpool2x2(const int8_t *in, int n, int H, int W, int cs, int8_t *out, cudaStream_t st);

@@ -41,6 +41,7 @@ struct LayerDev {
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
     uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: chunk-major image [tap][plane][cs_out/8][8][8][16] (conv_ws.cu, streamed weights)
+    uint8_t *wimg_rp = nullptr;    // cs_in == 16, cs_out == 32, pooled: row-pair image (conv_rp.cu)
     uint8_t *w_swz = nullptr;  // cs_in % 128 == 0: 128B-swizzled blocks [9*cs_in/128][cs_out][128] (conv_umma.cu B operand)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
@@ -153,7 +154,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_rp); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
     c->layers.clear();
 }
 
@@ -393,6 +394,21 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
                 CU(cudaMemcpy(d.wimg_tap, imt.data(), imt.size(), cudaMemcpyHostToDevice));
             }
         }
+        if (d.cs_in == 16 && d.cs_out == 32 && ks == 3 && L.pool) {
+            // conv_rp.cu: GEMM column n = dy * 32 + co (output row 2Y + dy), K chunk = (input row khh = 0..3 of 2Y-1 .. 2Y+2, tap kw):
+            // the weights of tap (kh = khh - dy, kw), zero where kh falls outside 0..2.  [n/8][chunk][n%8][16 B]
+            std::vector<uint8_t> img((size_t)64 * 12 * 16, 0);
+            for (int dy = 0; dy < 2; ++dy)
+                for (int o = 0; o < 32; ++o)
+                    for (int khh = 0; khh < 4; ++khh)
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const int kh = khh - dy, n = dy * 32 + o;
+                            if (kh < 0 || kh > 2) continue;
+                            memcpy(&img[(((size_t)(n / 8) * 12 + khh * 3 + kw) * 8 + (n % 8)) * 16], &wp[((size_t)o * 9 + kh * 3 + kw) * 16], 16);
+                        }
+            CU(cudaMalloc(&d.wimg_rp, img.size()));
+            CU(cudaMemcpy(d.wimg_rp, img.data(), img.size(), cudaMemcpyHostToDevice));
+        }
         // (the 128B-swizzled image of conv_umma.cu is built on first use: ensure_swz)
         CU(cudaMalloc(&d.bias_sh, (size_t)d.cout_pad * sizeof(int)));
         c->layers.push_back(d);
@@ -583,7 +599,7 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     LayerDev &L = c->layers[l];
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_rp = L.wimg_rp; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
     a.taps = 9; a.wgt1 = nullptr;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
@@ -625,6 +641,7 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     if (be == 1) CU(conv3x3_direct(a, c->stream));
     else if (be == 0 && first_ok) { CU(conv3x3_first(a, c->stream)); c->launches += L.cs_out / 16 - 1; }   // one pass per 16 output channels
     else if (use_umma) CU(conv3x3_umma(a, c->stream, c->sm_count));
+    else if (be == 0 && conv3x3_rp_supported(a)) CU(conv3x3_rp(a, c->stream, c->sm_count));
     else if (be == 4 || be == 5 || ws_ok) CU(conv3x3_ws(a, c->stream, c->sm_count));
     else {
         // auto back end, no tensor-core kernel takes this shape / alignment (e.g. a first layer wider than 16 channels, a
