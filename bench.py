@@ -43,6 +43,7 @@ BATCH = 256
 METRIC = "frames/sec slim_yolo_v2 fixed-point"
 WORKLOAD = "slim_yolo_v2 fixed-point batched inference, batch %d x 416x416 RGB444 camera frames per GPU (front-end quantiser + 10 conv layers + decode + NMS)"
 CONF, NMS = 0.1, 0.5     # test.py:22-24 defaults
+E2E_CHUNK = 64           # frames per copy / compute chunk of the host path (tools/t_e2e.py: 64 is best blocking and streamed)
 
 
 def layer_work(qnet, h, w):
@@ -427,13 +428,39 @@ def main():
     for i in range(e2e_steps):
         e2e_step(i)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_blocking_s = time.perf_counter() - t0
     e2e_launches = ctx.launch_count() - l1
+    # the same K steps as a stream of batches: yolo_b200_submit_rgb444 / yolo_b200_wait with two calls in flight, each with its
+    # own pinned output buffers (the tail of step i overlaps the host-to-device copy of step i + 1; every step's frames go
+    # host -> device and every step's detections device -> host inside the timed region, the last wait included)
+    out_bufs = [(h_dets, h_counts), (torch.zeros((B, MAXDET, 8), dtype=torch.int32).pin_memory(), torch.zeros((B,), dtype=torch.int32).pin_memory())]
+    ctx.set_host_chunk(E2E_CHUNK)
+
+    def e2e_stream(k0, k):
+        tickets = []
+        for i in range(k0, k0 + k):
+            if len(tickets) == 2:
+                ctx.wait(tickets.pop(0))
+            d_, c_ = out_bufs[i % 2]
+            t = L.yolo_b200_submit_rgb444(ctx._h, host_sets[i % n_sets].data_ptr(), B, H, W, d_.data_ptr(), c_.data_ptr())
+            if t < 0:
+                raise RuntimeError(L.yolo_b200_last_error())
+            tickets.append(t)
+        while tickets:
+            ctx.wait(tickets.pop(0))
+    e2e_stream(0, 3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stream(3, e2e_steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    ctx.set_host_chunk(64)
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([e2e_s, e2e_blocking_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s, e2e_blocking_s = float(t[0].item()), float(t[1].item())
     e2e_fps = (args.global_batch if strong else world * B) * e2e_steps / e2e_s
+    e2e_blocking_fps = (args.global_batch if strong else world * B) * e2e_steps / e2e_blocking_s
     # bytes the library copies back per step: counts + one strided copy as wide as the batch's largest count
     hc = h_counts.numpy()
     d2h_bytes = int(4 * B + B * min(int(hc.max()), MAXDET) * 32)
@@ -596,7 +623,8 @@ def main():
                        "collection": None if coll is None else {"bytes_per_step_all_ranks": collect_bytes, "records_on_rank0_last_step": collected}},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(host_sets[0].numel() * 2),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "api": "yolo_b200_forward_rgb444 (pinned host buffers; H2D of 64-frame chunks overlapped with the convolution layers; decode + NMS on a second stream: all chunks but the last while the last is copied in, then the last; filled part of the lists copied back)",
+                    "api": "yolo_b200_submit_rgb444 + yolo_b200_wait, two calls in flight (pinned host buffers; every step copies its 256 frames host -> device in %d-frame chunks overlapped with the convolution layers, runs decode + NMS on a second stream and copies the filled part of its lists back; the tail of step i overlaps the copy of step i + 1; timed to the last wait)" % E2E_CHUNK,
+                    "blocking_call": {"value": e2e_blocking_fps, "unit": "frames/s", "api": "yolo_b200_forward_rgb444, one call at a time (64-frame chunks)"},
                     "gpu_launches": int(e2e_launches)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_pytorch": cpu_torch,
             "other_configs": other, "sparse_head": sparse, "image_front_end": front,

@@ -163,6 +163,19 @@ int yolo_b200_set_thresholds(yolo_b200_ctx *ctx, float conf_thresh, float nms_th
 int yolo_b200_forward_rgb444(yolo_b200_ctx *ctx, const uint16_t *frames, int n, int h, int w,
                              yolo_b200_det *dets, int32_t *counts);
 
+/* Asynchronous pair for a stream of batches (the camera loop of main.c:44-49 calls yolo_forward once per frame buffer while
+ * the other buffer fills; here the unit is a batch).  yolo_b200_submit_* queues the whole call (copies, layers, decode + NMS)
+ * and returns a ticket >= 0 without waiting; yolo_b200_wait(ticket) returns once dets / counts of that call are filled.
+ * Up to two calls may be in flight: the tail of call i (the last chunk's layers, decode + NMS, the copy of the detections)
+ * then overlaps the host-to-device copy of call i + 1, which keeps the PCIe link busy across calls.  `frames`, `dets` and
+ * `counts` belong to the library between submit and wait (pinned host memory is needed for the copies to be asynchronous).
+ * Results are those of the blocking call.  Errors: negative status; E_STATE (-2) when two calls are already in flight. */
+int yolo_b200_submit_rgb444(yolo_b200_ctx *ctx, const uint16_t *frames, int n, int h, int w,
+                            yolo_b200_det *dets, int32_t *counts);
+int yolo_b200_submit_u8bgr(yolo_b200_ctx *ctx, const uint8_t *bgr, int n, int h, int w,
+                           yolo_b200_det *dets, int32_t *counts);
+int yolo_b200_wait(yolo_b200_ctx *ctx, int ticket);
+
 /* Same from already-quantised int8 NHWC4 input (what camera_to_inpBuf writes, yolo_forward.c:87-123). */
 int yolo_b200_forward_int8(yolo_b200_ctx *ctx, const int8_t *nhwc4, int n, int h, int w,
                            yolo_b200_det *dets, int32_t *counts);

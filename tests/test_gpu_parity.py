@@ -505,6 +505,39 @@ def test_pipelined_host_entry_points_do_not_depend_on_the_chunk_size(ctx):
         ctx.set_host_chunk(64)
 
 
+def test_submit_wait_pairs_in_flight_match_the_blocking_call(ctx):
+    """yolo_b200_submit_rgb444 / yolo_b200_wait with two calls in flight (the tail of one call overlaps the copy of the next)
+    return exactly what the blocking entry point returns for each batch; a third submission is refused."""
+    qnet = ex.random_quantnet(seed=3, calib_hw=(64, 96), calib_frames=2, calib_input="rgb444")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    n, h, w = 9, 64, 96
+    batches = [torch.from_numpy(ex.synthetic_frames_rgb444(n, h, w, seed=20 + b).view(np.int16)).pin_memory() for b in range(5)]
+    want = [ctx.forward_rgb444(b.numpy().view(np.uint16)) for b in batches]
+    assert sum(int(c.sum()) for _, c in want) > 0
+    ctx.set_host_chunk(4)
+    try:
+        outs = [(torch.zeros((n, 512, 8), dtype=torch.int32).pin_memory(), torch.zeros((n,), dtype=torch.int32).pin_memory()) for _ in batches]
+        tickets = []
+        for b, (dets, counts) in zip(batches, outs):
+            if len(tickets) == 2:
+                ctx.wait(tickets.pop(0))
+            tickets.append(ctx.submit_rgb444(b.numpy().view(np.uint16), dets.numpy().view(lib.DET_DTYPE).reshape(n, 512), counts.numpy()))
+            if len(tickets) == 2:        # both slots busy: a third call (blocking or not) is refused, nothing is disturbed
+                with pytest.raises(RuntimeError):
+                    ctx.forward_rgb444(batches[0].numpy().view(np.uint16))
+        while tickets:
+            ctx.wait(tickets.pop(0))
+        with pytest.raises(RuntimeError):
+            ctx.wait(0)                  # nothing in flight
+        for (dets, counts), (wd, wc) in zip(outs, want):
+            np.testing.assert_array_equal(counts.numpy(), wc)
+            for i in range(n):
+                k = int(wc[i])
+                np.testing.assert_array_equal(dets.numpy()[i, :k], wd[i][:k].view(np.int32).reshape(k, 8))
+    finally:
+        ctx.set_host_chunk(64)
+
+
 def test_fused_rgb444_front_end_edge_cases(ctx):
     """The first layer with the camera quantiser fused in: upper nibble of the pixels ignored (camera_to_inpBuf masks
     it, yolo_forward.c:87-123), frame widths that are / are not a multiple of 4 and a frame pointer that is only 2-byte

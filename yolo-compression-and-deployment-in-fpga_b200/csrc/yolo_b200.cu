@@ -50,6 +50,43 @@ struct LayerDev {
     int oh = 0, ow = 0;
 };
 
+// YOLO_B200_TRACE_HOST=1: timeline of one host-buffer call (ms since its start), printed to stderr
+struct HostTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> ev;
+    void mark(const char *what, int k, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        ev.push_back({std::string(what) + " " + std::to_string(k), e});
+    }
+    void dump() {
+        if (!on) return;
+        for (auto &p : ev) { float ms = 0; cudaEventSynchronize(p.second); cudaEventElapsedTime(&ms, t0, p.second); fprintf(stderr, "  %-22s %7.3f ms\n", p.first.c_str(), ms); cudaEventDestroy(p.second); }
+        cudaEventDestroy(t0);
+    }
+};
+
+// One host-buffer call in flight: its device staging, batch-wide prediction map, detection lists, the pinned landing
+// area of the counts and its events.  Two slots let the tail of call i (last chunk's layers, decode + NMS, copy of the
+// detections) overlap the host-to-device copy of call i + 1 (yolo_b200_submit_* / yolo_b200_wait).
+constexpr int YB_HOST_SLOTS = 2;
+struct HostSlot {
+    void *stage_in = nullptr; size_t stage_in_cap = 0;      // device staging of the host frames (network-size frames)
+    void *rs_src = nullptr; size_t rs_src_cap = 0;          // resize front end: staged source images
+    int8_t *pred_all = nullptr; size_t pred_all_cap = 0;    // batch-wide prediction map
+    yolo_b200_det *d_dets = nullptr; size_t dets_cap = 0;
+    int32_t *d_counts = nullptr; size_t counts_cap = 0;
+    int32_t *counts_pinned = nullptr; size_t counts_pinned_cap = 0;   // counts land here first: the caller's array may be pageable
+    std::vector<cudaEvent_t> ev_in, ev_done, ev_cnt;
+    cudaEvent_t ev_out = nullptr;
+    bool busy = false;
+    // the call in flight
+    int ngroups = 0, grp_f0[2] = {0, 0}, grp_n[2] = {0, 0};
+    yolo_b200_det *dets = nullptr; int32_t *counts = nullptr;
+    HostTrace tr;
+};
+
 struct yolo_b200_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -66,14 +103,11 @@ struct yolo_b200_ctx {
     unsigned *ovf_dev = nullptr;
     int *stats_dev = nullptr;            // calibration: {max, min} of a layer's numerator / abs-max bits of the input
     int8_t *in_q = nullptr; size_t in_q_cap = 0;        // quantised NHWC4 input
-    void *stage_in = nullptr; size_t stage_in_cap = 0;  // device staging of host inputs
-    void *rs_src = nullptr; size_t rs_src_cap = 0;      // resize front end: staged source images (host entry point)
     uint8_t *rs_out = nullptr; size_t rs_out_cap = 0;   // resize front end: resized images (device entry point)
     void *rs_tab = nullptr; size_t rs_tab_cap = 0;      // [dh] int4 row taps/weights, then [dw] int2 column offsets/weights
     const int4 *rs_ytab = nullptr; const int2 *rs_xtab = nullptr;
     int rs_key[4] = {0, 0, 0, 0};                       // (sh, sw, dh, dw) the tables were built for
     float *h_scores = nullptr; int *h_cls = nullptr; float4 *h_boxes = nullptr; size_t head_cap = 0;
-    yolo_b200_det *d_dets = nullptr; int32_t *d_counts = nullptr; size_t dets_cap = 0, counts_cap = 0;
     int last_n = 0;
     int64_t launches = 0;
     int sm_count = 148;
@@ -83,10 +117,8 @@ struct yolo_b200_ctx {
     int ev_used = 0;
     // host-buffer entry points: copies of chunk k+1 / k-1 overlap the kernels of chunk k
     cudaStream_t s_in = nullptr, s_out = nullptr, s_head = nullptr;
-    int32_t *counts_pinned = nullptr; size_t counts_pinned_cap = 0;   // counts land here first: the caller's array may be pageable
-    std::vector<cudaEvent_t> ev_in, ev_done, ev_cnt;
     int host_chunk = 64;                 // frames per chunk (measured best at 416x416: tools/t_e2e.py)
-    int8_t *pred_all = nullptr; size_t pred_all_cap = 0;   // batch-wide prediction map of the host-buffer entry points
+    HostSlot slots[YB_HOST_SLOTS];       // buffers of the host-buffer calls in flight (yolo_b200_submit_* / yolo_b200_wait)
 };
 
 static std::mutex g_default_mu;
@@ -168,18 +200,21 @@ void yolo_b200_destroy(yolo_b200_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_layers(c);
-    cudaFree(c->pred_all);
-    cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->stats_dev); cudaFree(c->in_q); cudaFree(c->stage_in);
-    cudaFree(c->rs_src); cudaFree(c->rs_out); cudaFree(c->rs_tab);
-    cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes); cudaFree(c->d_dets); cudaFree(c->d_counts);
+    cudaFree(c->lut_dev); cudaFree(c->lut8_dev); cudaFree(c->ovf_dev); cudaFree(c->stats_dev); cudaFree(c->in_q);
+    cudaFree(c->rs_out); cudaFree(c->rs_tab);
+    cudaFree(c->h_scores); cudaFree(c->h_cls); cudaFree(c->h_boxes);
     for (auto e : c->ev) cudaEventDestroy(e);
-    for (auto e : c->ev_in) cudaEventDestroy(e);
-    for (auto e : c->ev_done) cudaEventDestroy(e);
-    for (auto e : c->ev_cnt) cudaEventDestroy(e);
+    for (auto &S : c->slots) {
+        cudaFree(S.stage_in); cudaFree(S.rs_src); cudaFree(S.pred_all); cudaFree(S.d_dets); cudaFree(S.d_counts);
+        if (S.counts_pinned) cudaFreeHost(S.counts_pinned);
+        for (auto e : S.ev_in) cudaEventDestroy(e);
+        for (auto e : S.ev_done) cudaEventDestroy(e);
+        for (auto e : S.ev_cnt) cudaEventDestroy(e);
+        if (S.ev_out) cudaEventDestroy(S.ev_out);
+    }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->s_head) cudaStreamDestroy(c->s_head);
-    if (c->counts_pinned) cudaFreeHost(c->counts_pinned);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1065,42 +1100,26 @@ int yolo_b200_sync(yolo_b200_ctx *c)
 // chunking changes no result); every chunk's prediction map lands in one batch-wide buffer and decode + NMS then run once
 // over the whole batch (a per-chunk NMS launch cannot fill the GPU: it is one CTA per frame).  Only the filled part of the
 // detection lists is copied back.
-// YOLO_B200_TRACE_HOST=1: timeline of one host-buffer call (ms since its start), printed to stderr
-struct HostTrace {
-    bool on = false;
-    cudaEvent_t t0 = nullptr;
-    std::vector<std::pair<std::string, cudaEvent_t>> ev;
-    void mark(const char *what, int k, cudaStream_t st) {
-        if (!on) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
-        ev.push_back({std::string(what) + " " + std::to_string(k), e});
-    }
-    void dump() {
-        if (!on) return;
-        for (auto &p : ev) { float ms = 0; cudaEventSynchronize(p.second); cudaEventElapsedTime(&ms, t0, p.second); fprintf(stderr, "  %-22s %7.3f ms\n", p.first.c_str(), ms); cudaEventDestroy(p.second); }
-        cudaEventDestroy(t0);
-    }
-};
-
 // sh, sw > 0 (kind 3 only): the host images are sh x sw and are resized to h x w on the GPU chunk by chunk, between the
 // copy and the first layer (in_bytes = bytes of the source images).
-static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
+// host_enqueue queues the whole call (copies in, layers, decode + NMS, copy of the counts) on the context's streams and
+// returns; host_complete waits for the counts, copies the filled part of the lists back and waits for that copy.
+static int host_enqueue(yolo_b200_ctx *c, int si, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
                         yolo_b200_det *dets, int32_t *counts, int sh = 0, int sw = 0)
 {
-    int rc = check_ready(c, n, h, w); if (rc) return rc;
-    if (n == 0) return 0;
-    if (!host_in || !dets || !counts) return fail(E_ARG, "null buffer");
+    HostSlot &S = c->slots[si];
+    S.ngroups = 0; S.dets = dets; S.counts = counts;
     const bool resize = sh > 0 && sw > 0 && !(sh == h && sw == w);
     const size_t net_frame_bytes = resize ? (size_t)h * w * 3 : in_bytes / (size_t)n;
-    rc = ensure(&c->stage_in, &c->stage_in_cap, (size_t)n * net_frame_bytes); if (rc) return rc;
+    int rc = ensure(&S.stage_in, &S.stage_in_cap, (size_t)n * net_frame_bytes); if (rc) return rc;
     if (resize) {
         if ((size_t)sh * sw * 3 > (size_t)INT32_MAX) return fail(E_UNSUPPORTED, "source image larger than 2 GiB");
-        rc = ensure(&c->rs_src, &c->rs_src_cap, in_bytes); if (rc) return rc;
+        rc = ensure(&S.rs_src, &S.rs_src_cap, in_bytes); if (rc) return rc;
         rc = ensure_resize_tables(c, sh, sw, h, w); if (rc) return rc;
     }
     const size_t md = (size_t)c->prm.max_det;
-    rc = ensure((void **)&c->d_dets, &c->dets_cap, (size_t)n * md * sizeof(yolo_b200_det)); if (rc) return rc;
-    rc = ensure((void **)&c->d_counts, &c->counts_cap, (size_t)n * sizeof(int32_t)); if (rc) return rc;
+    rc = ensure((void **)&S.d_dets, &S.dets_cap, (size_t)n * md * sizeof(yolo_b200_det)); if (rc) return rc;
+    rc = ensure((void **)&S.d_counts, &S.counts_cap, (size_t)n * sizeof(int32_t)); if (rc) return rc;
     // prediction map of the whole batch
     int gh = h, gw = w;
     for (auto &L : c->layers) {
@@ -1108,7 +1127,7 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         if (L.q.pool) { gh /= 2; gw /= 2; }
     }
     const size_t pred_frame = (size_t)gh * gw * c->layers.back().cs_out;
-    rc = ensure((void **)&c->pred_all, &c->pred_all_cap, (size_t)n * pred_frame); if (rc) return rc;
+    rc = ensure((void **)&S.pred_all, &S.pred_all_cap, (size_t)n * pred_frame); if (rc) return rc;
     const int chunk = c->host_chunk > 0 ? c->host_chunk : n;
     std::vector<int> cf0, cnk;                                   // first frame / frames of each chunk
     if (const char *sched = getenv("YOLO_B200_CHUNKS")) {        // experiment hook: explicit chunk sizes, the last one repeats
@@ -1127,17 +1146,18 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
     const size_t N = (size_t)gh * gw * c->prm.num_anchors;
     if (N > (size_t)HEAD_MAX_CAND) return fail(E_UNSUPPORTED, "grid %dx%d x %d anchors exceeds %d candidates per frame", gh, gw, c->prm.num_anchors, HEAD_MAX_CAND);
     rc = ensure_head(c, (size_t)n, N); if (rc) return rc;
-    if (c->counts_pinned_cap < (size_t)n) {
-        if (c->counts_pinned) cudaFreeHost(c->counts_pinned);
-        c->counts_pinned = nullptr; c->counts_pinned_cap = 0;
-        CU(cudaHostAlloc((void **)&c->counts_pinned, (size_t)n * sizeof(int32_t), cudaHostAllocDefault));
-        c->counts_pinned_cap = (size_t)n;
+    if (S.counts_pinned_cap < (size_t)n) {
+        if (S.counts_pinned) cudaFreeHost(S.counts_pinned);
+        S.counts_pinned = nullptr; S.counts_pinned_cap = 0;
+        CU(cudaHostAlloc((void **)&S.counts_pinned, (size_t)n * sizeof(int32_t), cudaHostAllocDefault));
+        S.counts_pinned_cap = (size_t)n;
     }
     if (!c->s_in) {
         CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->s_head, cudaStreamNonBlocking));
     }
+    if (!S.ev_out) CU(cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming));
     auto grow = [](std::vector<cudaEvent_t> &v, int want) -> cudaError_t {
         while ((int)v.size() < want) {
             cudaEvent_t e1;
@@ -1147,69 +1167,126 @@ static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, 
         }
         return cudaSuccess;
     };
-    CU(grow(c->ev_in, nchunks + 1)); CU(grow(c->ev_done, nchunks)); CU(grow(c->ev_cnt, nchunks));
+    CU(grow(S.ev_in, nchunks)); CU(grow(S.ev_done, nchunks)); CU(grow(S.ev_cnt, nchunks));
     auto drain = [&]() { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_head); cudaStreamSynchronize(c->s_out); };
-    HostTrace tr;
+    HostTrace &tr = S.tr;
+    tr.ev.clear();
     tr.on = getenv("YOLO_B200_TRACE_HOST") != nullptr;
-    if (tr.on) { cudaEventCreate(&tr.t0); cudaEventRecord(tr.t0, c->stream); }
-    // the staging buffers may still be read by work queued earlier on the context stream
-    CU(cudaEventRecord(c->ev_in[nchunks], c->stream));
-    CU(cudaStreamWaitEvent(c->s_in, c->ev_in[nchunks], 0));
-    CU(cudaStreamWaitEvent(c->s_head, c->ev_in[nchunks], 0));
+    if (tr.on) { cudaEventCreate(&tr.t0); cudaEventRecord(tr.t0, c->s_in); }
+    // The slot's buffers are its own: nothing queued earlier reads or writes them once the slot's previous call has been
+    // completed, so the copies of this call do NOT wait for the context stream (the layers of the previous call may still
+    // be running there: that overlap is the point of the second slot).
     // Three stages, all queued up front: chunk k's frames are copied in on s_in, its convolution layers run on the
     // context stream, decode + NMS and the copy of the counts on s_head.  The head runs twice: once for all chunks but the
     // last, as soon as the second-to-last chunk's layers are done (it then overlaps the last chunk's copy, which the GPU
     // would otherwise wait for), and once for the last chunk.  (A head per chunk was measured slower: the NMS CTAs hold
     // shared memory the persistent convolution CTAs of the next chunk need, so the two serialise.)
-    int head_f0 = 0, ngroups = 0, grp_f0[2] = {0, 0}, grp_n[2] = {0, 0};
+    int head_f0 = 0;
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = cf0[k], nk = cnk[k];
-        char *stage = (char *)c->stage_in + (size_t)f0 * net_frame_bytes;
-        char *land = resize ? (char *)c->rs_src + (size_t)f0 * frame_bytes : stage;
+        char *stage = (char *)S.stage_in + (size_t)f0 * net_frame_bytes;
+        char *land = resize ? (char *)S.rs_src + (size_t)f0 * frame_bytes : stage;
         CU(cudaMemcpyAsync(land, (const char *)host_in + (size_t)f0 * frame_bytes, (size_t)nk * frame_bytes, cudaMemcpyHostToDevice, c->s_in));
-        CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        CU(cudaEventRecord(S.ev_in[k], c->s_in));
         tr.mark("h2d done", k, c->s_in);
-        CU(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        CU(cudaStreamWaitEvent(c->stream, S.ev_in[k], 0));
         if (resize) {
             cudaError_t e = resize_u8bgr((const uint8_t *)land, nk, sh, sw, (uint8_t *)stage, h, w, c->rs_xtab, c->rs_ytab, c->sm_count, c->stream);
             if (e != cudaSuccess) { drain(); return fail(E_CUDA, "resize: %s", cudaGetErrorString(e)); }
             c->launches++;
         }
         const int8_t *pred; int g1, g2;
-        rc = features_dev(c, kind, stage, nk, h, w, c->pred_all + (size_t)f0 * pred_frame, &pred, &g1, &g2);
+        rc = features_dev(c, kind, stage, nk, h, w, S.pred_all + (size_t)f0 * pred_frame, &pred, &g1, &g2);
         if (rc) { drain(); return rc; }
         tr.mark("layers done", k, c->stream);
         if (k == nchunks - 2 || k == nchunks - 1) {
             const int hn = f0 + nk - head_f0;                                  // frames [head_f0, f0 + nk)
-            CU(cudaEventRecord(c->ev_done[ngroups], c->stream));
-            CU(cudaStreamWaitEvent(c->s_head, c->ev_done[ngroups], 0));
-            rc = detect_on(c, c->s_head, (size_t)head_f0, c->pred_all + (size_t)head_f0 * pred_frame, hn, gh, gw, h, w,
-                           c->d_dets + (size_t)head_f0 * md, c->d_counts + head_f0);
+            CU(cudaEventRecord(S.ev_done[S.ngroups], c->stream));
+            CU(cudaStreamWaitEvent(c->s_head, S.ev_done[S.ngroups], 0));
+            rc = detect_on(c, c->s_head, (size_t)head_f0, S.pred_all + (size_t)head_f0 * pred_frame, hn, gh, gw, h, w,
+                           S.d_dets + (size_t)head_f0 * md, S.d_counts + head_f0);
             if (rc) { drain(); return rc; }
-            CU(cudaMemcpyAsync(c->counts_pinned + head_f0, c->d_counts + head_f0, (size_t)hn * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_head));
-            CU(cudaEventRecord(c->ev_cnt[ngroups], c->s_head));
-            tr.mark("head+counts done", ngroups, c->s_head);
-            grp_f0[ngroups] = head_f0; grp_n[ngroups] = hn; ++ngroups;
+            CU(cudaMemcpyAsync(S.counts_pinned + head_f0, S.d_counts + head_f0, (size_t)hn * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_head));
+            CU(cudaEventRecord(S.ev_cnt[S.ngroups], c->s_head));
+            tr.mark("head+counts done", S.ngroups, c->s_head);
+            S.grp_f0[S.ngroups] = head_f0; S.grp_n[S.ngroups] = hn; ++S.ngroups;
             head_f0 = f0 + nk;
         }
     }
+    S.busy = true;
+    return 0;
+}
+
+static int host_complete(yolo_b200_ctx *c, int si)
+{
+    HostSlot &S = c->slots[si];
+    if (!S.busy) return fail(E_STATE, "nothing in flight on ticket %d", si);
+    S.busy = false;
+    auto drain = [&]() { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_head); cudaStreamSynchronize(c->s_out); };
+    const size_t md = (size_t)c->prm.max_det;
     // detections: per head launch, one strided copy as wide as its largest count, as soon as its counts are here
-    for (int k = 0; k < ngroups; ++k) {
-        const int f0 = grp_f0[k], nk = grp_n[k];
-        cudaError_t e = cudaEventSynchronize(c->ev_cnt[k]);
+    for (int k = 0; k < S.ngroups; ++k) {
+        const int f0 = S.grp_f0[k], nk = S.grp_n[k];
+        cudaError_t e = cudaEventSynchronize(S.ev_cnt[k]);
         if (e != cudaSuccess) { drain(); return fail(E_CUDA, "%s", cudaGetErrorString(e)); }
         int maxc = 0;
-        for (int i = 0; i < nk; ++i) { counts[f0 + i] = c->counts_pinned[f0 + i]; maxc = counts[f0 + i] > maxc ? counts[f0 + i] : maxc; }
+        for (int i = 0; i < nk; ++i) { S.counts[f0 + i] = S.counts_pinned[f0 + i]; maxc = S.counts[f0 + i] > maxc ? S.counts[f0 + i] : maxc; }
         if (maxc > (int)md) maxc = (int)md;
         if (maxc > 0)
-            CU(cudaMemcpy2DAsync(dets + (size_t)f0 * md, md * sizeof(yolo_b200_det), c->d_dets + (size_t)f0 * md, md * sizeof(yolo_b200_det),
+            CU(cudaMemcpy2DAsync(S.dets + (size_t)f0 * md, md * sizeof(yolo_b200_det), S.d_dets + (size_t)f0 * md, md * sizeof(yolo_b200_det),
                                  (size_t)maxc * sizeof(yolo_b200_det), (size_t)nk, cudaMemcpyDeviceToHost, c->s_out));
-        tr.mark("dets d2h done", k, c->s_out);
+        S.tr.mark("dets d2h done", k, c->s_out);
     }
-    CU(cudaStreamSynchronize(c->s_out));
-    CU(cudaStreamSynchronize(c->stream));
-    tr.dump();
+    CU(cudaEventRecord(S.ev_out, c->s_out));
+    CU(cudaEventSynchronize(S.ev_out));       // the lists are in the caller's buffers (everything the call queued has finished before them)
+    S.tr.dump();
+    S.tr.on = false;
     return 0;
+}
+
+static int host_free_slot(yolo_b200_ctx *c)
+{
+    for (int i = 0; i < YB_HOST_SLOTS; ++i) if (!c->slots[i].busy) return i;
+    return -1;
+}
+
+// blocking call = submit + wait on any free slot
+static int forward_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
+                        yolo_b200_det *dets, int32_t *counts, int sh = 0, int sw = 0)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (n == 0) return 0;
+    if (!host_in || !dets || !counts) return fail(E_ARG, "null buffer");
+    const int si = host_free_slot(c);
+    if (si < 0) return fail(E_STATE, "%d submissions in flight: call yolo_b200_wait first", YB_HOST_SLOTS);
+    rc = host_enqueue(c, si, host_in, in_bytes, kind, n, h, w, dets, counts, sh, sw); if (rc) return rc;
+    return host_complete(c, si);
+}
+
+// asynchronous pair: returns a ticket (>= 0) once the call is queued; the caller's buffers belong to the library until
+// yolo_b200_wait(ticket) returns
+static int submit_host(yolo_b200_ctx *c, const void *host_in, size_t in_bytes, int kind, int n, int h, int w,
+                       yolo_b200_det *dets, int32_t *counts)
+{
+    int rc = check_ready(c, n, h, w); if (rc) return rc;
+    if (n < 1) return fail(E_ARG, "submit needs n >= 1");
+    if (!host_in || !dets || !counts) return fail(E_ARG, "null buffer");
+    const int si = host_free_slot(c);
+    if (si < 0) return fail(E_STATE, "%d submissions in flight: call yolo_b200_wait first", YB_HOST_SLOTS);
+    rc = host_enqueue(c, si, host_in, in_bytes, kind, n, h, w, dets, counts); if (rc) return rc;
+    return si;
+}
+
+int yolo_b200_submit_rgb444(yolo_b200_ctx *c, const uint16_t *frames, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{ return submit_host(c, frames, (size_t)n * h * w * 2, 0, n, h, w, dets, counts); }
+int yolo_b200_submit_u8bgr(yolo_b200_ctx *c, const uint8_t *bgr, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)
+{ return submit_host(c, bgr, (size_t)n * h * w * 3, 3, n, h, w, dets, counts); }
+int yolo_b200_wait(yolo_b200_ctx *c, int ticket)
+{
+    if (!c) return fail(E_ARG, "null ctx");
+    if (ticket < 0 || ticket >= YB_HOST_SLOTS) return fail(E_ARG, "ticket %d", ticket);
+    CU(cudaSetDevice(c->device));
+    return host_complete(c, ticket);
 }
 
 int yolo_b200_forward_rgb444(yolo_b200_ctx *c, const uint16_t *frames, int n, int h, int w, yolo_b200_det *dets, int32_t *counts)

@@ -33,6 +33,7 @@ EXPORTS = [
     "yolo_b200_launch_count", "yolo_b200_slow_path_count", "yolo_b200_enable_timing", "yolo_b200_layer_times_ms", "yolo_b200_draw_rectangles",
     "yolo_forward", "yolo_b200_set_default_context",
     "yolo_b200_pack_detections", "yolo_b200_ipc_alloc", "yolo_b200_ipc_open", "yolo_b200_ipc_close", "yolo_b200_copy_async",
+    "yolo_b200_submit_rgb444", "yolo_b200_submit_u8bgr", "yolo_b200_wait",
     "yolo_b200_resize_taps", "yolo_b200_resize_u8bgr", "yolo_b200_forward_u8bgr_resize", "yolo_b200_forward_u8bgr_resize_dev",
 ]
 
@@ -92,7 +93,9 @@ def load_library(path: Optional[str] = None):
     L.yolo_b200_set_conv_backend.argtypes = [vp, i32]
     L.yolo_b200_set_host_chunk.argtypes = [vp, i32]
     L.yolo_b200_debug_requant.argtypes = [vp, i32, vp, C.c_size_t, vp, i32]
+    L.yolo_b200_wait.argtypes = [vp, i32]
     for name in ("yolo_b200_forward_rgb444", "yolo_b200_forward_int8", "yolo_b200_forward_f32", "yolo_b200_forward_u8bgr",
+                 "yolo_b200_submit_rgb444", "yolo_b200_submit_u8bgr",
                  "yolo_b200_forward_u8bgr_dev", "yolo_b200_forward_rgb444_dev", "yolo_b200_forward_int8_dev", "yolo_b200_forward_f32_dev"):
         getattr(L, name).argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.yolo_b200_sync.argtypes = [vp]
@@ -245,6 +248,19 @@ class Context:
         f = np.ascontiguousarray(frames, dtype=np.uint16)
         n, h, w = f.shape
         return self._forward_host(self.L.yolo_b200_forward_rgb444, f, n, h, w)
+
+    def submit_rgb444(self, frames: np.ndarray, dets: np.ndarray, counts: np.ndarray) -> int:
+        """Queue one batch (uint16 [n][h][w], C-contiguous; dets [n][max_det] DET_DTYPE, counts int32 [n]: the arrays must
+        stay alive and untouched until wait(ticket)).  Returns the ticket."""
+        assert frames.dtype == np.uint16 and frames.flags.c_contiguous and dets.flags.c_contiguous and counts.flags.c_contiguous
+        n, h, w = frames.shape
+        t = self.L.yolo_b200_submit_rgb444(self._h, frames.ctypes.data, n, h, w, dets.ctypes.data, counts.ctypes.data)
+        if t < 0:
+            self._check(t)
+        return t
+
+    def wait(self, ticket: int):
+        self._check(self.L.yolo_b200_wait(self._h, ticket))
 
     def forward_u8bgr(self, images: np.ndarray):
         """uint8 BGR images [n][h][w][3] at network size (what cv2 delivers): BaseTransform arithmetic + tracker quantiser
