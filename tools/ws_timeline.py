@@ -13,7 +13,7 @@ import bench  # noqa: E402
 import yolo_b200  # noqa
 from yolo_b200 import export as ex, lib
 
-lib._lib = lib.load_library(os.path.join(ROOT, "yolo-compression-and-deployment-in-fpga_b200", "build_dbg", "libyolo_b200_dbg.so"))
+lib._lib = lib.load_library(os.path.join(ROOT, "yolo-compression-and-deployment-in-fpga_b200", "build_dbg", "libyolo_b200_dbg%s.so" % os.environ.get("YB_RP_EXP", "")))
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 H = W = 416
 qnet = bench.make_qnet()

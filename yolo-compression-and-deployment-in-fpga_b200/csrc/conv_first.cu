@@ -29,6 +29,7 @@ struct FirstParams {
     size_t out_img_bytes;      // OH * OW * cs_out
     int cs_out;                // 16; WIDE: any multiple of 16 (the kernel then writes the 16 channels co0 .. co0 + 15 of every pixel)
     int co0;                   // first output channel of this pass
+    int xsplit;                // POOL, cs_out == 16: output rows are stored split by x parity, [even pixels][odd pixels] (conv_rp.cu reads them)
     const int8_t *wgt;         // [cout_pad][9][4]
     const int *bias_sh;
     LayerQ q;
@@ -118,7 +119,10 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
     const int o_c = keep(a_org + 2 * F_PITCH + 2);
     // this thread's output pixel inside a tile (rows oy_t, oy_t + 1; column ox_t [+ 8 cg]) and its byte offset
     const int oy_t = keep(POOL ? 2 * (warp >> 1) : 2 * warp), ox_t = keep(POOL ? 8 * (warp & 1) + g : g);
-    const int o_thr = keep((oy_t * (POOL ? p.OW : p.W) + ox_t) * PX + 4 * t + (WIDE ? p.co0 : 0));
+    // x-split rows (POOL only): pooled pixel x lives at (x & 1) * OW/2 + (x >> 1) of its row; a tile's 16 pooled columns start at an
+    // even x, so the split is a per-thread constant
+    const int ox_s = (POOL && p.xsplit) ? (ox_t & 1) * (p.OW >> 1) + (ox_t >> 1) : ox_t;
+    const int o_thr = keep((oy_t * (POOL ? p.OW : p.W) + ox_s) * PX + 4 * t + (WIDE ? p.co0 : 0));
     unsigned ovf = 0;
 
     const int tiles_x = (p.W + F_TW - 1) / F_TW, tiles_y = (p.H + F_TH - 1) / F_TH;
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
                 }
             }
             // this thread's 4 channels of pooled pixel (oy, ox)
-            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + ((((y0 >> 1) * p.OW + (x0 >> 1)) * PX) + o_thr);
+            int8_t *out_px = p.out + (size_t)img * p.out_img_bytes + ((((y0 >> 1) * p.OW + (p.xsplit ? x0 >> 2 : x0 >> 1)) * PX) + o_thr);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 int m[4];
@@ -346,6 +350,10 @@ cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind, cons
     p.OH = a.q.pool ? a.H / 2 : a.H; p.OW = a.q.pool ? a.W / 2 : a.W;
     p.out_img_bytes = (size_t)p.OH * p.OW * a.cs_out;
     p.cs_out = a.cs_out; p.wgt = a.wgt; p.bias_sh = a.bias_sh; p.q = a.q; p.out = a.out; p.ovf = a.ovf;
+    if (a.out_xsplit) {
+        if (!a.q.pool || a.cs_out != 16 || (p.OW & 1)) return cudaErrorInvalidValue;
+        p.xsplit = 1;
+    }
     return a.q.pool ? launch_first<true>(a, p, st) : launch_first<false>(a, p, st);
 }
 

@@ -43,6 +43,13 @@ __device__ __forceinline__ unsigned pack_sat_u8(int a, int b, unsigned c)
     return d;
 }
 #define YB_MAGIC_BITS 0x4B400000
+// bits - MAGIC_BITS as a multiply-add with the run-time constant one = 1 (EpiConst::one): issues on the FMA pipe
+__device__ __forceinline__ int unbias_magic(int bits, int one)
+{
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(bits), "r"(one), "n"(-YB_MAGIC_BITS));
+    return r;
+}
 
 // Contract F, round-half-even, two channels at a time.  fb = (float)sh(bias).  Returns o as an integer that is
 // exact inside [-128,127] and on the correct side outside it (the pack saturates).  See requant_f_rne in common.cuh for
@@ -69,7 +76,7 @@ __device__ __forceinline__ int2 requant_f_rne_x2(int a0, int a1, float2 fb, cons
     }
     if (HI16) { v.x = fminf(v.x, YB_MAGIC + 32767.f); v.y = fminf(v.y, YB_MAGIC + 32767.f); }
     v = ffma2(v, make_float2(k.s_out, k.s_out), make_float2(k.out_add, k.out_add));
-    return make_int2(__float_as_int(v.x) - YB_MAGIC_BITS, __float_as_int(v.y) - YB_MAGIC_BITS);
+    return make_int2(unbias_magic(__float_as_int(v.x), k.one), unbias_magic(__float_as_int(v.y), k.one));
 }
 
 // Contract P, two channels.  bp = bias << (E - sb).  Returns o + 128 (exact inside [0,255], on the correct side outside).
@@ -120,21 +127,21 @@ __device__ __forceinline__ unsigned requant4v(const int *acc, int4 b, const P &p
 }
 
 // `bias` points at the per-channel words in shared memory; c is a multiple of 4.
-template <int EPI, bool ACT, class P>
+template <int EPI, bool ACT, class P, bool PRE = false>
 __device__ __forceinline__ unsigned requant4(const int *acc, const int *bias, int c, const P &p, unsigned &ovf, bool count)
 {
-    return requant4v<EPI, ACT, P>(acc, *reinterpret_cast<const int4 *>(bias + c), p, ovf, count);
+    return requant4v<EPI, ACT, P, PRE>(acc, *reinterpret_cast<const int4 *>(bias + c), p, ovf, count);
 }
 
 // 16 accumulators (channels c0..c0+15) -> 16 output bytes
-template <int EPI, bool ACT, class P>
+template <int EPI, bool ACT, class P, bool PRE = false>
 __device__ __forceinline__ uint4 requant16(const int (&v)[16], const int *bias, int c0, const P &p, unsigned &ovf, bool count)
 {
     uint4 w;
-    w.x = requant4<EPI, ACT, P>(&v[0], bias, c0, p, ovf, count);
-    w.y = requant4<EPI, ACT, P>(&v[4], bias, c0 + 4, p, ovf, count);
-    w.z = requant4<EPI, ACT, P>(&v[8], bias, c0 + 8, p, ovf, count);
-    w.w = requant4<EPI, ACT, P>(&v[12], bias, c0 + 12, p, ovf, count);
+    w.x = requant4<EPI, ACT, P, PRE>(&v[0], bias, c0, p, ovf, count);
+    w.y = requant4<EPI, ACT, P, PRE>(&v[4], bias, c0 + 4, p, ovf, count);
+    w.z = requant4<EPI, ACT, P, PRE>(&v[8], bias, c0 + 8, p, ovf, count);
+    w.w = requant4<EPI, ACT, P, PRE>(&v[12], bias, c0 + 12, p, ovf, count);
     return w;
 }
 
@@ -157,6 +164,7 @@ static inline long long host_f_tail(long long t, const LayerQ &q)
 static inline int epi_mode_for(const ConvArgs &a, EpiConst *k)
 {
     memset(k, 0, sizeof *k);
+    k->one = 1;
     const LayerQ &q = a.q;
     if (a.force_generic_epilogue) return EPI_GENERIC;
     if (q.contract == CONTRACT_F && q.round_mode == ROUND_RNE) {

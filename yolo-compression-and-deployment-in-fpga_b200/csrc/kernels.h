@@ -17,6 +17,7 @@ struct ConvArgs {
     const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
     const uint8_t *wimg_tap;   // cs_in 128 / 256: the same image tap-major, [tap][128-channel plane][cs_out/8][8][8][16 B] (conv_ws.cu, weight streaming)
     const uint8_t *wimg_rp = nullptr;  // cs_in == 16, cs_out == 32, pooled: row-pair image [2*cs_out/8][12][8][16 B] (conv_rp.cu)
+    const uint8_t *wimg_rps = nullptr; // the same for an x-split input map (chunk order (row, kw 0), (row, kw 2) x 4 rows, then (row, kw 1) x 4)
     int w_rows;            // cout_pad
     int bias_abs_max;      // max |bias_sh[c]| (decides whether the exact fp32 epilogue applies)
     int force_generic_epilogue;   // tests: run the integer epilogue even where the fp32 one applies
@@ -26,6 +27,8 @@ struct ConvArgs {
     int8_t *out;           // [n][H'][W'][cs_out]
     unsigned *ovf;         // contract-P saturation counter
     int *stats = nullptr;  // conv3x3_direct only: calibration pass, see conv_direct.cu (bias_sh then holds b << lb, q.la the shift)
+    int out_xsplit = 0;    // conv_first.cu (pooled, 16 output channels, even output width): rows stored split by x parity, [even pixels][odd pixels]
+    int in_xsplit = 0;     // conv_rp.cu: the input map is stored that way
     int taps = 9;          // conv_umma.cu only: 9 = 3x3, 1 = 1x1 (then wgt / wgt_swz hold ONE tap: [cout_pad][cs_in] / [cs_in/128][cs_out][128])
     const int8_t *wgt1 = nullptr;   // taps == 1: [cout_pad][cs_in]
 };
@@ -50,6 +53,7 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // conv_rp.cu (row-pair tcgen05 kernel for the thin pooled layers: two output rows in the GEMM N dimension, dense TMA-fed halo)
 bool conv3x3_rp_supported(const ConvArgs &a);
+bool conv3x3_rp_split_supported(const ConvArgs &a);      // the variant that reads an x-split input map (a.in_xsplit is ignored by the test)
 cudaError_t conv3x3_rp(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // graph.cu (yolo_v2: stand-alone max-pool, reorg + concat with exponent alignment)

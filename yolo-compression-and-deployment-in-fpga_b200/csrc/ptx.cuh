@@ -71,12 +71,18 @@ __device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t alo, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+// 16 columns of this warp's 32 lanes as TWO .x8 loads: 16 warps sustain ~270 B/clk/SM of TMEM reads with .x8, ~175 with .x16 and
+// ~127 with .x32 (tools/micro/ldtm_bench.cu, profiles/ldtm_bench_r2.txt), and the TMEM port is shared with the running MMAs
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
+    tmem_ld8(taddr, &v[0]);
+    tmem_ld8(taddr + 8, &v[8]);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int *v)
 {
@@ -88,6 +94,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int *v)
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
 }
+// 16 columns of this warp's 32 lanes <- one constant (re-arms a drained accumulator: see conv_rp.cu, pre-biased accumulators)
+__device__ __forceinline__ void tmem_st16_const(uint32_t taddr, int v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                 ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }

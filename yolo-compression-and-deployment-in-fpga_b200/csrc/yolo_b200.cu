@@ -42,6 +42,8 @@ struct LayerDev {
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
     uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: chunk-major image [tap][plane][cs_out/8][8][8][16] (conv_ws.cu, streamed weights)
     uint8_t *wimg_rp = nullptr;    // cs_in == 16, cs_out == 32, pooled: row-pair image (conv_rp.cu)
+    uint8_t *wimg_rps = nullptr;   // the same in the chunk order of the x-split variant
+    bool xsplit = false;           // the most recent output map is stored with its rows split by x parity ([even pixels][odd pixels])
     uint8_t *w_swz = nullptr;  // cs_in % 128 == 0: 128B-swizzled blocks [9*cs_in/128][cs_out][128] (conv_umma.cu B operand)
     int *bias_sh = nullptr;    // [cout_pad]
     int8_t *out = nullptr;     // [n][h'][w'][cs_out] of the most recent backbone call
@@ -186,7 +188,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_rp); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_rp); cudaFree(l.wimg_rps); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
     c->layers.clear();
 }
 
@@ -443,6 +445,19 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
                         }
             CU(cudaMalloc(&d.wimg_rp, img.size()));
             CU(cudaMemcpy(d.wimg_rp, img.data(), img.size(), cudaMemcpyHostToDevice));
+            // x-split variant: chunks 2r, 2r+1 = (input row r, kw 0), (r, kw 2); chunks 8 + r = (r, kw 1)
+            std::vector<uint8_t> ims((size_t)64 * 12 * 16, 0);
+            for (int dy = 0; dy < 2; ++dy)
+                for (int o = 0; o < 32; ++o)
+                    for (int khh = 0; khh < 4; ++khh)
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const int kh = khh - dy, n = dy * 32 + o;
+                            if (kh < 0 || kh > 2) continue;
+                            const int chunk = kw == 1 ? 8 + khh : 2 * khh + (kw >> 1);
+                            memcpy(&ims[(((size_t)(n / 8) * 12 + chunk) * 8 + (n % 8)) * 16], &wp[((size_t)o * 9 + kh * 3 + kw) * 16], 16);
+                        }
+            CU(cudaMalloc(&d.wimg_rps, ims.size()));
+            CU(cudaMemcpy(d.wimg_rps, ims.data(), ims.size(), cudaMemcpyHostToDevice));
         }
         // (the 128B-swizzled image of conv_umma.cu is built on first use: ensure_swz)
         CU(cudaMalloc(&d.bias_sh, (size_t)d.cout_pad * sizeof(int)));
@@ -634,19 +649,42 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     LayerDev &L = c->layers[l];
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_rp = L.wimg_rp; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_rp = L.wimg_rp; a.wimg_rps = L.wimg_rps; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
     a.taps = 9; a.wgt1 = nullptr;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
 }
 
+// Layer l's output map may be stored with its rows split by x parity when the kernel that produces it can write that layout
+// (the first-layer kernel, pooled, 16 channels) and its only reader, layer l + 1, runs on the row-pair kernel's x-split variant
+// (conv_rp.cu).  (oh, ow) = layer l's output size.  The layout is private to the chain: yolo_b200_get_layer_output undoes it.
+static bool want_xsplit(yolo_b200_ctx *c, size_t l, const void *d_in0, int n, int oh, int ow)
+{
+    if (c->conv_backend != 0 || c->graph || l != 0 || c->layers.size() < 2 || n < 1) return false;
+    LayerDev &L = c->layers[0];
+    if (!L.q.pool || L.cs_out != 16 || (ow & 1) || L.unfused_pool) return false;
+    (void)d_in0;
+    ConvArgs a1;
+    fill_args(c, 1, L.out, n, oh, ow, c->layers[1].out, a1);
+    a1.in = (const int8_t *)nullptr; a1.out = nullptr;             // alignment of the real buffers: cudaMalloc'ed, 256-byte aligned
+    return conv3x3_rp_split_supported(a1);
+}
+
 // One convolution launch.  fuse_pool == false runs a pooled layer WITHOUT its pool (the caller pools separately).
-static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out, bool fuse_pool = true)
+static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, int w, int8_t *d_out, bool fuse_pool = true,
+                     bool in_xsplit = false, bool out_xsplit = false)
 {
     LayerDev &L = c->layers[l];
     ConvArgs a;
     fill_args(c, l, d_in, n, h, w, d_out, a);
     if (!fuse_pool) a.q.pool = 0;
+    a.in_xsplit = in_xsplit; a.out_xsplit = out_xsplit;
+    if (in_xsplit) {                     // only the row-pair kernel reads that layout (want_xsplit checked that it takes this layer)
+        if (c->conv_backend != 0 || !conv3x3_rp_split_supported(a)) return fail(E_STATE, "layer %d cannot read an x-split map", l);
+        CU(conv3x3_rp(a, c->stream, c->sm_count));
+        c->launches++;
+        return 0;
+    }
     const bool aligned = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
     const int be = c->conv_backend;
     if (L.ksize == 1 || L.cs_in > 256 || L.cs_out > 256) {
@@ -763,6 +801,11 @@ static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *net_in, i
             dst = L.out;
         }
         L.oh = oh; L.ow = ow; L.rh = ih; L.rw = iw; L.view = dst;
+        const bool in_split = l > 0 && !c->graph && c->layers[l - 1].xsplit;
+        ConvArgs a0chk;
+        fill_args(c, (int)l, cur, n, ih, iw, dst, a0chk);
+        L.xsplit = l == 0 && dst == L.out && ((uintptr_t)dst & 3) == 0 && conv3x3_first_src_ok(0, cur) && conv3x3_first_supported(a0chk) &&
+                   want_xsplit(c, l, cur, n, oh, ow);
         if (L.q.pool && L.unfused_pool) {
             rc = ensure((void **)&L.raw, &L.raw_cap, (size_t)(n > 0 ? n : 1) * ih * iw * L.cs_out); if (rc) return rc;
             if (n > 0) {
@@ -770,7 +813,7 @@ static int backbone_from(yolo_b200_ctx *c, size_t first, const int8_t *net_in, i
                 CU(maxpool2x2(L.raw, n, ih, iw, L.cs_out, dst, c->stream));
                 c->launches++;
             }
-        } else if (n > 0) { rc = run_layer(c, (int)l, cur, n, ih, iw, dst); if (rc) return rc; }
+        } else if (n > 0) { rc = run_layer(c, (int)l, cur, n, ih, iw, dst, true, in_split, L.xsplit); if (rc) return rc; }
         tick(c);
         cur = dst; h = oh; w = ow;
     }
@@ -887,7 +930,7 @@ static int tracker_pass_inner(yolo_b200_ctx *c, const float *d_nchw, int n, int 
         // the layer itself, with the exponents in force
         const int oh = Lp.pool ? h / 2 : h, ow = Lp.pool ? w / 2 : w;
         rc = ensure((void **)&L.out, &L.out_cap, (size_t)n * oh * ow * L.cs_out); if (rc) return rc;
-        L.oh = oh; L.ow = ow; L.view = L.out;
+        L.oh = oh; L.ow = ow; L.view = L.out; L.xsplit = false;
         rc = run_layer(c, (int)l, cur, n, h, w, L.out); if (rc) return rc;
         cur = L.out; h = oh; w = ow;
     }
@@ -954,6 +997,16 @@ int yolo_b200_get_layer_output(yolo_b200_ctx *c, int layer, int8_t *host_out, si
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(host_out, L.view ? L.view : L.out, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (L.xsplit) {
+        // the chain kept this map with its rows split by x parity ([even pixels][odd pixels]): hand out plain NHWC
+        const size_t px = (size_t)L.cs_out, row = (size_t)L.ow * px, half = (size_t)(L.ow / 2);
+        std::vector<int8_t> tmp(row);
+        for (size_t r = 0; r < (size_t)c->last_n * L.oh; ++r) {
+            int8_t *p = host_out + r * row;
+            memcpy(tmp.data(), p, row);
+            for (size_t x = 0; x < (size_t)L.ow; ++x) memcpy(p + x * px, tmp.data() + ((x & 1) * half + (x >> 1)) * px, px);
+        }
+    }
     return 0;
 }
 
@@ -1026,6 +1079,8 @@ static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, i
     int rc = ensure((void **)&L0.out, &L0.out_cap, (size_t)n * oh * ow * L0.cs_out); if (rc) return rc;
     L0.oh = oh; L0.ow = ow; L0.rh = h; L0.rw = w; L0.view = L0.out;
     a0.out = L0.out;
+    L0.xsplit = want_xsplit(c, 0, d_src, n, oh, ow);
+    a0.out_xsplit = L0.xsplit;
     c->ev_used = 0;
     tick(c);
     CU(conv3x3_first(a0, c->stream, kind, d_src, kind == 1 ? (const void *)c->lut_dev : (const void *)c->lut8_dev));
