@@ -16,6 +16,7 @@ struct ConvArgs {
     int wgt_swz_rows = 0;              // rows per block of wgt_swz (= cs_out)
     const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
     const uint8_t *wimg_tap;   // cs_in 128 / 256: the same image tap-major, [tap][128-channel plane][cs_out/8][8][8][16 B] (conv_ws.cu, weight streaming)
+    const uint8_t *wimg_tap2 = nullptr; // cs_in 128 / 256, cs_out 256: [half of cs_out][plane][tap][128/8][8][8][16 B] chunks of 16 KB (conv_wsp.cu)
     const uint8_t *wimg_rp = nullptr;  // cs_in == 16, cs_out == 32, pooled: row-pair image [2*cs_out/8][12][8][16 B] (conv_rp.cu)
     const uint8_t *wimg_rps = nullptr; // the same for an x-split input map (chunk order (row, kw 0), (row, kw 2) x 4 rows, then (row, kw 1) x 4)
     int w_rows;            // cout_pad
@@ -50,6 +51,10 @@ cudaError_t requant_probe(const ConvArgs &a, const int *acc, size_t count, int8_
 // conv_ws.cu (weight-stationary tcgen05 kernel: weights resident in shared memory, haloed tile fetched once)
 bool conv3x3_ws_supported(const ConvArgs &a);
 cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
+
+// conv_wsp.cu (pair-streamed tcgen05 kernel for the deep narrow layers: each streamed weight chunk feeds two 128-pixel tiles)
+bool conv3x3_wsp_supported(const ConvArgs &a);
+cudaError_t conv3x3_wsp(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // conv_rp.cu (row-pair tcgen05 kernel for the thin pooled layers: two output rows in the GEMM N dimension, dense TMA-fed halo)
 bool conv3x3_rp_supported(const ConvArgs &a);

@@ -41,6 +41,7 @@ struct LayerDev {
     int8_t *w_k160 = nullptr;  // cs_in == 16: [cout_pad][10][16] with a zero 10th tap (conv_umma.cu)
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
     uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: chunk-major image [tap][plane][cs_out/8][8][8][16] (conv_ws.cu, streamed weights)
+    uint8_t *wimg_tap2 = nullptr;  // cs_in 128 / 256, cs_out 256: 16 KB chunks [half][plane][tap] (conv_wsp.cu)
     uint8_t *wimg_rp = nullptr;    // cs_in == 16, cs_out == 32, pooled: row-pair image (conv_rp.cu)
     uint8_t *wimg_rps = nullptr;   // the same in the chunk order of the x-split variant
     bool xsplit = false;           // the most recent output map is stored with its rows split by x parity ([even pixels][odd pixels])
@@ -188,7 +189,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_rp); cudaFree(l.wimg_rps); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_tap2); cudaFree(l.wimg_rp); cudaFree(l.wimg_rps); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
     c->layers.clear();
 }
 
@@ -429,6 +430,20 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
                                    &wp[((size_t)o * 9 + tap) * d.cs_in + 16 * cc], 16);
                 CU(cudaMalloc(&d.wimg_tap, imt.size()));
                 CU(cudaMemcpy(d.wimg_tap, imt.data(), imt.size(), cudaMemcpyHostToDevice));
+                if (d.cs_out == 256) {
+                    // conv_wsp.cu: chunk = (half of the output channels, 128-channel plane, tap): [half][plane][tap][128/8][8 K chunks][8][16 B]
+                    std::vector<uint8_t> im2(imt.size(), 0);
+                    const int npl = np / 8;
+                    for (int nh = 0; nh < 2; ++nh)
+                        for (int pl = 0; pl < npl; ++pl)
+                            for (int tap = 0; tap < 9; ++tap)
+                                for (int o = 0; o < 128; ++o)
+                                    for (int cc = 0; cc < 8; ++cc)
+                                        memcpy(&im2[((((size_t)(nh * npl + pl) * 9 + tap) * 16 + o / 8) * 8 + cc) * 128 + (size_t)(o % 8) * 16],
+                                               &wp[((size_t)(nh * 128 + o) * 9 + tap) * d.cs_in + pl * 128 + 16 * cc], 16);
+                    CU(cudaMalloc(&d.wimg_tap2, im2.size()));
+                    CU(cudaMemcpy(d.wimg_tap2, im2.data(), im2.size(), cudaMemcpyHostToDevice));
+                }
             }
         }
         if (d.cs_in == 16 && d.cs_out == 32 && ks == 3 && L.pool) {
@@ -649,7 +664,7 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     LayerDev &L = c->layers[l];
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_rp = L.wimg_rp; a.wimg_rps = L.wimg_rps; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_tap2 = L.wimg_tap2; a.wimg_rp = L.wimg_rp; a.wimg_rps = L.wimg_rps; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
     a.taps = 9; a.wgt1 = nullptr;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
@@ -715,6 +730,7 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     else if (be == 0 && first_ok) { CU(conv3x3_first(a, c->stream)); c->launches += L.cs_out / 16 - 1; }   // one pass per 16 output channels
     else if (use_umma) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else if (be == 0 && conv3x3_rp_supported(a)) CU(conv3x3_rp(a, c->stream, c->sm_count));
+    else if (be == 0 && aligned && conv3x3_wsp_supported(a)) CU(conv3x3_wsp(a, c->stream, c->sm_count));
     else if (be == 4 || be == 5 || ws_ok) CU(conv3x3_ws(a, c->stream, c->sm_count));
     else {
         // auto back end, no tensor-core kernel takes this shape / alignment (e.g. a first layer wider than 16 channels, a
