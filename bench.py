@@ -461,6 +461,24 @@ def main():
         e2e_s, e2e_blocking_s = float(t[0].item()), float(t[1].item())
     e2e_fps = (args.global_batch if strong else world * B) * e2e_steps / e2e_s
     e2e_blocking_fps = (args.global_batch if strong else world * B) * e2e_steps / e2e_blocking_s
+    # what the end-to-end number is bounded by: the host -> device link, measured here with every rank copying its pinned batch at the
+    # same time (GB/s per GPU; at N > 1 the ranks share the host's PCIe switches and memory controllers)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(stream)
+    for i in range(4):
+        dev_sets[i % n_sets].copy_(host_sets[i % n_sets], non_blocking=True)
+    h1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * host_sets[0].numel() * 2 / (h0.elapsed_time(h1) / 1e3) / 1e9
+    if world > 1:
+        t = torch.tensor([h2d_gbs], dtype=torch.float64, device="cuda")
+        allg = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allg, t)
+        h2d_all = [round(float(x.item()), 1) for x in allg]
+    else:
+        h2d_all = [round(h2d_gbs, 1)]
+    h2d_bound_fps = sum(g * 1e9 / (H * W * 2) for g in h2d_all)     # frames/s the measured links could carry (2 bytes per pixel)
     # bytes the library copies back per step: counts + one strided copy as wide as the batch's largest count
     hc = h_counts.numpy()
     d2h_bytes = int(4 * B + B * min(int(hc.max()), MAXDET) * 32)
@@ -624,6 +642,7 @@ def main():
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(host_sets[0].numel() * 2),
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "yolo_b200_submit_rgb444 + yolo_b200_wait, two calls in flight (pinned host buffers; every step copies its 256 frames host -> device in %d-frame chunks overlapped with the convolution layers, runs decode + NMS on a second stream and copies the filled part of its lists back; the tail of step i overlaps the copy of step i + 1; timed to the last wait)" % E2E_CHUNK,
+                    "h2d_gbs_per_gpu_concurrent": h2d_all, "h2d_bound_frames_per_s": h2d_bound_fps, "frac_of_h2d_bound": e2e_fps / h2d_bound_fps,
                     "blocking_call": {"value": e2e_blocking_fps, "unit": "frames/s", "api": "yolo_b200_forward_rgb444, one call at a time (64-frame chunks)"},
                     "gpu_launches": int(e2e_launches)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_pytorch": cpu_torch,

@@ -2,13 +2,16 @@
 // (slim_yolo_v2 conv5 / conv6 / conv7: 128 / 256 -> 256 channels on 26 x 26 maps; conv_normal, c_embedding/yolo_forward.c:575-770,
 // models/slim_yolo_v2.py:283-316).
 //
-// conv_ws.cu streams these layers' weights (295 / 590 KB) through a shared-memory ring once per 128-pixel tile and is bound
-// by that L2 -> SM traffic: ~52 B/clk/SM, the chip-wide L2 cap, 11.3 k cycles per tile where the 72 MMAs need 9.4 k
-// (clock64 timeline, profiles/README.md).  Here a CTA works on a PAIR of 128-pixel raster tiles at once and walks the output
-// channels in two halves of 128: every weight chunk (one tap x 128 input channels x 128 output channels = 16 KB) feeds
-// EIGHT MMAs (4 K-steps x 2 tiles) instead of four, so the weights are fetched once per 256 pixels and the layer becomes
-// MMA-bound.  Two tiles x 128 columns x two passes in flight = the 512 TMEM columns: while pass (pair, half) accumulates, the
-// two epilogue groups (one per tile) drain the previous pass.
+// conv_ws.cu streams these layers' weights (295 / 590 KB) through a shared-memory ring once per 128-pixel tile: 11.3 k cycles
+// per tile where the 72 MMAs need 9.4 k (clock64 timeline, profiles/README.md).  What bounds it is the SHARED-MEMORY port: an
+// M = 128, K = 32 MMA reads (128 + N) x 32 operand bytes (that is exactly the measured 43 / 51 / 67 cycles at N = 32 / 64 / 128:
+// 32 + N/4 at 128 B/clk), and the streamed weights are written through the same port: 72 x 12 KB + 590 KB + 55 KB per tile =
+// 11.8 k cycles.  Here a CTA works on a PAIR of 128-pixel raster tiles at once and walks the output channels in two halves of
+// 128: every weight chunk (one tap x 128 input channels x 128 output channels = 16 KB) feeds EIGHT MMAs (4 K-steps x 2
+// tiles) instead of four, so the weights cross the L2 and the shared-memory port once per 256 pixels (288 x 8 KB + 590 KB +
+// 110 KB per pair = 11.7 k cycles per tile of port time; measured 10.9-11.1 k).  Two tiles x 128 columns x two passes in
+// flight = the 512 TMEM columns: while pass (pair, half) accumulates, the two epilogue groups (one per tile) drain the previous
+// pass.  (Beyond this: cta_group::2, where each SM of a pair reads half of B.)
 //
 //   * A (activations): flattened-raster halo tiles as in conv_ws.cu (rows of W + 1 pixels written by swizzled TMA boxes,
 //     one 128-byte channel plane per buffer, every tap a descriptor start offset).  The plane buffers form ONE in-order
