@@ -56,6 +56,10 @@ cudaError_t conv3x3_ws(const ConvArgs &a, cudaStream_t st, int sm_count);
 bool conv3x3_wsp_supported(const ConvArgs &a);
 cudaError_t conv3x3_wsp(const ConvArgs &a, cudaStream_t st, int sm_count);
 
+// conv_ws2.cu (CTA-pair tcgen05 kernel, cta_group::2: each SM of a pair holds one 128-pixel tile and half of the weights)
+bool conv3x3_ws2_supported(const ConvArgs &a, int sm_count);
+cudaError_t conv3x3_ws2(const ConvArgs &a, cudaStream_t st, int sm_count);
+
 // conv_rp.cu (row-pair tcgen05 kernel for the thin pooled layers: two output rows in the GEMM N dimension, dense TMA-fed halo)
 bool conv3x3_rp_supported(const ConvArgs &a);
 bool conv3x3_rp_split_supported(const ConvArgs &a);      // the variant that reads an x-split input map (a.in_xsplit is ignored by the test)

@@ -730,6 +730,7 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     else if (be == 0 && first_ok) { CU(conv3x3_first(a, c->stream)); c->launches += L.cs_out / 16 - 1; }   // one pass per 16 output channels
     else if (use_umma) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else if (be == 0 && conv3x3_rp_supported(a)) CU(conv3x3_rp(a, c->stream, c->sm_count));
+    else if (be == 0 && aligned && conv3x3_ws2_supported(a, c->sm_count)) CU(conv3x3_ws2(a, c->stream, c->sm_count));
     else if (be == 0 && aligned && conv3x3_wsp_supported(a)) CU(conv3x3_wsp(a, c->stream, c->sm_count));
     else if (be == 4 || be == 5 || ws_ok) CU(conv3x3_ws(a, c->stream, c->sm_count));
     else {
