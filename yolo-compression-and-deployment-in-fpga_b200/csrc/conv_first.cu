@@ -15,6 +15,7 @@
 // pixel: one 32-bit store per pixel, 16 contiguous bytes per quad, 128 per warp row.
 #include "kernels.h"
 #include "epilogue.cuh"
+#include "ptx.cuh"
 
 namespace yb {
 
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
     // pixel stride of the output map in bytes: 16 for slim_yolo_v2's first layer (compile-time constant); WIDE = a first layer
     // with more than 16 output channels (darknet19: 32), written in passes of 16 channels
     const int PX = WIDE ? p.cs_out : 16;
+    pdl_launch_dependents();
     constexpr bool RGB444 = SRC == 1, U8 = SRC == 2;
     constexpr int RAWN = RGB444 ? 2 : U8 ? 3 : 4;                     // 32-bit words per pixel quad
     // fp32 epilogues: the accumulators start at the bit pattern of 1.5 * 2^23, so that read as fp32 they are MAGIC + sum
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(F_THREADS, 4) conv3x3_first_kernel(const First
     };
 
     __syncthreads();                                                   // tables loaded
+    pdl_wait();                                                        // the previous kernel is done: the input may be read, the output map written
     fetch(img, ty * F_TH, tx * F_TW);
     stage(s_in[0]);
     __syncthreads();
@@ -302,9 +305,8 @@ static cudaError_t launch_first3(const FirstParams &p, cudaStream_t st)
     if (per_sm < 1) per_sm = 1;
     const long long cap = (long long)sms * per_sm;
     const int grid = (int)(total < cap ? total : cap);
-    if (p.q.activ) conv3x3_first_kernel<POOL, EPI, true, SRC, WIDE><<<grid, F_THREADS, 0, st>>>(p);
-    else conv3x3_first_kernel<POOL, EPI, false, SRC, WIDE><<<grid, F_THREADS, 0, st>>>(p);
-    return cudaGetLastError();
+    if (p.q.activ) return launch_pdl(conv3x3_first_kernel<POOL, EPI, true, SRC, WIDE>, dim3(grid), dim3(F_THREADS), 0, st, p);
+    return launch_pdl(conv3x3_first_kernel<POOL, EPI, false, SRC, WIDE>, dim3(grid), dim3(F_THREADS), 0, st, p);
 }
 
 template <bool POOL, int EPI>

@@ -114,6 +114,7 @@ __device__ __forceinline__ void rp16_epilogue_tile(const RpParams &p, uint32_t t
 template <int EPI>
 __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_rp16_kernel(const RpParams p, const __grid_constant__ CUtensorMap map)
 {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_rp16_kernel(const RpPar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
 
     if (warp < 2) {
         // ===================== MMA issuers =====================
@@ -291,6 +293,7 @@ __device__ __forceinline__ void rs16_epilogue_tile(const RsParams &p, uint32_t t
 template <int EPI>
 __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_rs16_kernel(const RsParams p, const __grid_constant__ CUtensorMap map)
 {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -326,6 +329,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) conv3x3_rs16_kernel(const RsPar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
 
     if (warp < 2) {
         // ===================== MMA issuers: alternate tiles (see conv3x3_rp16_kernel) =====================
@@ -471,7 +475,7 @@ static cudaError_t launch_rp16(RpParams &p, const CUtensorMap &map, cudaStream_t
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-    conv3x3_rp16_kernel<EPI><<<grid, RP_THREADS, smem_bytes, st>>>(p, map);
+    { cudaError_t le = launch_pdl(conv3x3_rp16_kernel<EPI>, dim3(grid), dim3(RP_THREADS), smem_bytes, st, p, map); if (le != cudaSuccess) return le; }
 #ifdef YB_WS_TIMELINE
     {
         long long h[64 * 8];
@@ -519,7 +523,7 @@ static cudaError_t launch_rs16(RsParams &p, const CUtensorMap &map, cudaStream_t
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-    conv3x3_rs16_kernel<EPI><<<grid, RP_THREADS, smem_bytes, st>>>(p, map);
+    { cudaError_t le = launch_pdl(conv3x3_rs16_kernel<EPI>, dim3(grid), dim3(RP_THREADS), smem_bytes, st, p, map); if (le != cudaSuccess) return le; }
 #ifdef YB_WS_TIMELINE
     {
         long long h[64 * 8];

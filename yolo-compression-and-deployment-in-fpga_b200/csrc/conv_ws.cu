@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
 {
     static_assert(!BSTREAM || (TMAIN && !PHASE && (KHALF == 4 || KHALF == 8)), "weight streaming: TMA-fed un-phased tiles, 128 / 256 input channels");
     using G = WsGeom<PHASE>;
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = TMAIN ? (smem_u32(smem_raw) + 1023u) & ~1023u : (smem_u32(smem_raw) + 127u) & ~127u;   // swizzle atoms: 1024 B
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
@@ -839,7 +841,7 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
     }
     const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
     p.step_x = grid % p.tiles_x; p.step_y = grid / p.tiles_x;
-    conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN, BSTREAM><<<grid, WS_THREADS, smem_bytes, st>>>(p, maps);
+    { cudaError_t le = launch_pdl(conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN, BSTREAM>, dim3(grid), dim3(WS_THREADS), smem_bytes, st, p, maps); if (le != cudaSuccess) return le; }
 #ifdef YB_WS_TIMELINE
     {
         long long h[64 * 8];

@@ -103,6 +103,7 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar)
 template <int EPI>
 __global__ void __launch_bounds__(W2_THREADS, 1) conv3x3_ws2_kernel(const W2Params p, const __grid_constant__ W2Maps maps)
 {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv3x3_ws2_kernel(const W2Para
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
     const int nchunks = 9 * p.npl;
 
     if (warp == 0 && rank == 0) {
@@ -390,10 +392,13 @@ static cudaError_t launch_ws2(W2Params &p, const W2Maps &maps, cudaStream_t st, 
     cfg.blockDim = dim3(W2_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    static const bool pdl_on = [] { const char *e = getenv("YOLO_B200_PDL"); return e ? atoi(e) != 0 : true; }();
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_on ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ws2_kernel<EPI>, p, maps);
     if (e != cudaSuccess) return e;
 #ifdef YB_WS_TIMELINE

@@ -69,6 +69,7 @@ struct WpMaps { CUtensorMap m[5]; };          // box heights 1, 2, 4, 8, 16 rows
 template <int EPI>
 __global__ void __launch_bounds__(WP_THREADS, 1) conv3x3_wsp_kernel(const WpParams p, const __grid_constant__ WpMaps maps)
 {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(WP_THREADS, 1) conv3x3_wsp_kernel(const WpPara
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();
     const int per_pair = 2 * p.npl;                                       // plane buffers a pair occupies
 
     if (warp == 0) {
@@ -352,7 +354,7 @@ static cudaError_t launch_wsp(WpParams &p, const WpMaps &maps, cudaStream_t st, 
         attr_set[dev & 63] = true;
     }
     const int grid = p.num_pairs < sm_count ? p.num_pairs : sm_count;
-    conv3x3_wsp_kernel<EPI><<<grid, WP_THREADS, smem_bytes, st>>>(p, maps);
+    { cudaError_t le = launch_pdl(conv3x3_wsp_kernel<EPI>, dim3(grid), dim3(WP_THREADS), smem_bytes, st, p, maps); if (le != cudaSuccess) return le; }
 #ifdef YB_WS_TIMELINE
     {
         long long h[32 * 8];

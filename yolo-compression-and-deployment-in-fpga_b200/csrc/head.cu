@@ -7,6 +7,7 @@
 // them into FMAs: the reference evaluates each product/sum separately in fp32 (NumPy / torch CPU), and NMS decisions
 // compare against the threshold bit-for-bit.
 #include "kernels.h"
+#include "ptx.cuh"
 #include <math.h>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,8 @@ __device__ __forceinline__ float sigmoid_c(float x) { return (float)(1 / (exp((d
 // A conf | A*C class scores (anchor-major) | A*4 box terms (anchor-major).
 __global__ void __launch_bounds__(256) head_decode_kernel(HeadArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int N = a.gh * a.gw * a.A;
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= a.n * N) return;
@@ -81,7 +84,7 @@ cudaError_t head_decode(const HeadArgs &a, cudaStream_t st)
 {
     int total = a.n * a.gh * a.gw * a.A;
     if (total == 0) return cudaSuccess;
-    head_decode_kernel<<<(total + 255) / 256, 256, 0, st>>>(a);
+    { cudaError_t le = launch_pdl(head_decode_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, a); if (le != cudaSuccess) return le; }
     return cudaGetLastError();
 }
 
@@ -842,6 +845,8 @@ __device__ __noinline__ unsigned gn_pull(const GnView &v, int j)
 
 __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a, GnSmem L)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x;
     const int N = a.gh * a.gw * a.A;
@@ -1215,7 +1220,7 @@ cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
     static const bool sorted_nms = [] { const char *e = getenv("YOLO_B200_NMS_SORTED"); return e && atoi(e) != 0; }();
     if (a.head_mode == YOLO_B200_HEAD_PYTHON && a.nms_thresh > 1e-6f && !sorted_nms) {
         const GnSmem L = gn_layout(a.gh * a.gw * a.A, 226u * 1024u);
-        head_nms_grid_kernel<<<a.n, GN_THREADS, L.total, st>>>(a, L);
+        { cudaError_t le = launch_pdl(head_nms_grid_kernel, dim3((unsigned)a.n), dim3(GN_THREADS), L.total, st, a, L); if (le != cudaSuccess) return le; }
         return cudaGetLastError();
     }
     if (a.head_mode != YOLO_B200_HEAD_PYTHON) head_nms_kernel<false, false><<<a.n, NMS_THREADS, sizeof(NmsSmem), st>>>(a);
