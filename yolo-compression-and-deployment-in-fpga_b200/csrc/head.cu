@@ -18,6 +18,44 @@ __device__ __forceinline__ float sigmoid_py(float x) { return __fdiv_rn(1.0f, __
 // sigmoid() as written in the C driver: 1/(exp(x)+1) = sigma(-x) (yolo_forward.c:965-968), double math
 __device__ __forceinline__ float sigmoid_c(float x) { return (float)(1 / (exp((double)x) + 1)); }
 
+// Python head of one anchor (slim_yolo_v2.py:330-358), split so that the NMS kernel can decode in place: the score first, the
+// box only for anchors that pass the confidence threshold.  Same expressions as head_decode_kernel (explicit rn operations).
+__device__ __forceinline__ float decode_py_score(const HeadArgs &a, const int8_t *p, int an, int &best)
+{
+    const int8_t *pc = p + a.A + an * a.C;
+    const float inv = ldexpf(1.0f, -a.sa_pred);
+    const float obj = sigmoid_py(p[an] * inv);
+    float m = -INFINITY;
+    for (int c = 0; c < a.C; ++c) m = fmaxf(m, pc[c] * inv);
+    float sum = 0.f;
+    for (int c = 0; c < a.C; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(pc[c] * inv, m)));
+    best = 0;
+    float score = -1.f;
+    for (int c = 0; c < a.C; ++c) {
+        const float s = __fmul_rn(__fdiv_rn(expf(__fsub_rn(pc[c] * inv, m)), sum), obj);
+        if (s > score) { score = s; best = c; }
+    }
+    return score;
+}
+__device__ __forceinline__ float4 decode_py_box(const HeadArgs &a, const int8_t *p, int an, int row, int col)
+{
+    const int8_t *pb = p + a.A * (1 + a.C) + an * 4;
+    const float inv = ldexpf(1.0f, -a.sa_pred);
+    const float st = (float)a.stride;
+    const float cx = __fmul_rn(__fadd_rn(sigmoid_py(pb[0] * inv), (float)col), st);
+    const float cy = __fmul_rn(__fadd_rn(sigmoid_py(pb[1] * inv), (float)row), st);
+    const float bw = __fmul_rn(__fmul_rn(expf(pb[2] * inv), a.anchors[an][0]), st);
+    const float bh = __fmul_rn(__fmul_rn(expf(pb[3] * inv), a.anchors[an][1]), st);
+    const float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
+    const float iw = (float)a.in_w, ih = (float)a.in_h;
+    float4 box;
+    box.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(cx, hw), iw), 0.f), 1.f);
+    box.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(cy, hh), ih), 0.f), 1.f);
+    box.z = fminf(fmaxf(__fdiv_rn(__fadd_rn(cx, hw), iw), 0.f), 1.f);
+    box.w = fminf(fmaxf(__fdiv_rn(__fadd_rn(cy, hh), ih), 0.f), 1.f);
+    return box;
+}
+
 // One thread per (frame, cell, anchor).  Channel order of a cell (slim_yolo_v2.py:337-341, yolo_forward.c:1273):
 // A conf | A*C class scores (anchor-major) | A*4 box terms (anchor-major).
 __global__ void __launch_bounds__(256) head_decode_kernel(HeadArgs a)
@@ -35,28 +73,8 @@ __global__ void __launch_bounds__(256) head_decode_kernel(HeadArgs a)
     const int8_t *pb = p + a.A * (1 + a.C) + an * 4;
     float score; int best; float4 box;
     if (a.head_mode == YOLO_B200_HEAD_PYTHON) {
-        const float inv = ldexpf(1.0f, -a.sa_pred);
-        float obj = sigmoid_py(p[an] * inv);
-        float m = -INFINITY;
-        for (int c = 0; c < a.C; ++c) m = fmaxf(m, pc[c] * inv);
-        float sum = 0.f;
-        for (int c = 0; c < a.C; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(pc[c] * inv, m)));
-        best = 0; score = -1.f;
-        for (int c = 0; c < a.C; ++c) {
-            float s = __fmul_rn(__fdiv_rn(expf(__fsub_rn(pc[c] * inv, m)), sum), obj);
-            if (s > score) { score = s; best = c; }
-        }
-        float st = (float)a.stride;
-        float cx = __fmul_rn(__fadd_rn(sigmoid_py(pb[0] * inv), (float)col), st);
-        float cy = __fmul_rn(__fadd_rn(sigmoid_py(pb[1] * inv), (float)row), st);
-        float bw = __fmul_rn(__fmul_rn(expf(pb[2] * inv), a.anchors[an][0]), st);
-        float bh = __fmul_rn(__fmul_rn(expf(pb[3] * inv), a.anchors[an][1]), st);
-        float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
-        float iw = (float)a.in_w, ih = (float)a.in_h;
-        box.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(cx, hw), iw), 0.f), 1.f);
-        box.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(cy, hh), ih), 0.f), 1.f);
-        box.z = fminf(fmaxf(__fdiv_rn(__fadd_rn(cx, hw), iw), 0.f), 1.f);
-        box.w = fminf(fmaxf(__fdiv_rn(__fadd_rn(cy, hh), ih), 0.f), 1.f);
+        score = decode_py_score(a, p, an, best);
+        box = decode_py_box(a, p, an, row, col);
     } else {
         // C head on its well-defined subset (see include/yolo_b200.h, YOLO_B200_HEAD_C)
         const double sc = exp2((double)a.sa_pred);
@@ -885,14 +903,23 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
     if (tid == 0) { pool_cnt[0] = 0u; pool_cnt[1] = 0u; }
     __syncthreads();
     float4 mybox[GN_PER]; float mysc[GN_PER]; int mybin[GN_PER]; unsigned myrank[GN_PER];
+    unsigned mycls = 0u;                                                            // fused decode: class of candidate r in byte r
+    static_assert(GN_PER <= 4, "one class byte per candidate");
 #pragma unroll
     for (int r = 0; r < GN_PER; ++r) {
         const int i = tid + r * GN_THREADS;
         mybin[r] = -1; myrank[r] = 0u; mysc[r] = 0.f; mybox[r] = make_float4(0, 0, 0, 0);
         if (i < N) {
-            const float sc = scores[i];
+            // fused decode (a.fused_decode): the prediction map is decoded here, the score first and the box only for anchors
+            // that pass the threshold; otherwise head_decode_kernel's scratch is read
+            const int cell = i / a.A, an = i - cell * a.A;
+            const int8_t *pp = a.pred + ((size_t)f * a.gh * a.gw + cell) * a.cs;
+            int best = 0;
+            const float sc = a.fused_decode ? decode_py_score(a, pp, an, best) : scores[i];
             if (sc >= a.conf_thresh) {
-                const float4 b = boxes[i];
+                const int row = cell / a.gw;
+                const float4 b = a.fused_decode ? decode_py_box(a, pp, an, row, cell - row * a.gw) : boxes[i];
+                mycls |= (unsigned)best << (8 * r);
                 const int bk = nms_bucket(area_py(b), bscale);
                 const int cell = gn_bin(bk, gn_cell(0.5f * (b.y + b.w)), gn_cell(0.5f * (b.x + b.z)));
                 mybox[r] = b; mysc[r] = sc; mybin[r] = cell;
@@ -935,7 +962,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
         if (mybin[r] >= 0) {
             const int i = tid + r * GN_THREADS;
             const int p = (int)ofs[mybin[r]] + (int)myrank[r];
-            sbox[p] = mybox[r]; sscore[p] = __float_as_uint(mysc[r]); sidx[p] = (unsigned short)i; scls[p] = (unsigned char)cls[i];
+            sbox[p] = mybox[r]; sscore[p] = __float_as_uint(mysc[r]); sidx[p] = (unsigned short)i; scls[p] = a.fused_decode ? (unsigned char)(mycls >> (8 * r)) : (unsigned char)cls[i];
             npred[p] = 0u;
         }
     }
@@ -1212,13 +1239,24 @@ cudaError_t pack_detections(const yolo_b200_det *dets, const int32_t *counts, in
     return cudaGetLastError();
 }
 
+static bool nms_grid_selected(const HeadArgs &a)
+{
+    // python head: the sort-free grid kernel (YOLO_B200_NMS_SORTED=1 keeps the sorted, chunked kernel for comparison)
+    static const bool sorted_nms = [] { const char *e = getenv("YOLO_B200_NMS_SORTED"); return e && atoi(e) != 0; }();
+    return a.head_mode == YOLO_B200_HEAD_PYTHON && a.nms_thresh > 1e-6f && !sorted_nms;
+}
+
+bool head_nms_fuses_decode(const HeadArgs &a)
+{
+    static const bool fuse = [] { const char *e = getenv("YOLO_B200_FUSE_DECODE"); return e ? atoi(e) != 0 : true; }();
+    return fuse && nms_grid_selected(a) && a.C <= 255;
+}
+
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     if (a.gh * a.gw * a.A > HEAD_MAX_CAND || a.C > NMS_MAX_CLASSES) return cudaErrorInvalidValue;
-    // python head: the sort-free grid kernel (YOLO_B200_NMS_SORTED=1 keeps the sorted, chunked kernel for comparison)
-    static const bool sorted_nms = [] { const char *e = getenv("YOLO_B200_NMS_SORTED"); return e && atoi(e) != 0; }();
-    if (a.head_mode == YOLO_B200_HEAD_PYTHON && a.nms_thresh > 1e-6f && !sorted_nms) {
+    if (nms_grid_selected(a)) {
         const GnSmem L = gn_layout(a.gh * a.gw * a.A, 226u * 1024u);
         { cudaError_t le = launch_pdl(head_nms_grid_kernel, dim3((unsigned)a.n), dim3(GN_THREADS), L.total, st, a, L); if (le != cudaSuccess) return le; }
         return cudaGetLastError();

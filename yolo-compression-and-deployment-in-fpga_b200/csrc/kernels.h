@@ -93,6 +93,7 @@ struct HeadArgs {
     float conf_thresh, nms_thresh;
     int head_mode;
     int max_det;
+    int fused_decode = 0;  // head_nms decodes the prediction map itself (head_nms_fuses_decode): scores / cls / boxes are not read
     // scratch [n][N]: best-class score, class, box
     float *scores; int *cls; float4 *boxes;
     yolo_b200_det *dets;   // [n][max_det]
@@ -100,6 +101,7 @@ struct HeadArgs {
 };
 constexpr int HEAD_MAX_CAND = 4096;   // candidates per frame the NMS kernel can hold in shared memory
 cudaError_t head_decode(const HeadArgs &a, cudaStream_t st);
+bool head_nms_fuses_decode(const HeadArgs &a);   // the python head's grid NMS kernel decodes in place: no head_decode launch, no scratch traffic
 cudaError_t head_nms(const HeadArgs &a, cudaStream_t st);
 cudaError_t head_init(void);          // one-time function attributes (dynamic shared memory)
 cudaError_t pack_detections(const yolo_b200_det *dets, const int32_t *counts, int n, int max_det, yolo_b200_det *packed, int32_t *offsets, cudaStream_t st);

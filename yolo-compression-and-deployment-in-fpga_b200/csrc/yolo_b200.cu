@@ -1053,9 +1053,10 @@ static int detect_on(yolo_b200_ctx *c, cudaStream_t st, size_t slot0, const int8
     a.stride = p.stride; a.in_h = in_h; a.in_w = in_w; a.conf_thresh = p.conf_thresh; a.nms_thresh = p.nms_thresh;
     a.head_mode = p.head_mode; a.max_det = p.max_det;
     a.scores = c->h_scores + slot0 * N; a.cls = c->h_cls + slot0 * N; a.boxes = c->h_boxes + slot0 * N; a.dets = d_dets; a.counts = d_counts;
-    CU(head_decode(a, st));
+    a.fused_decode = head_nms_fuses_decode(a) ? 1 : 0;
+    if (!a.fused_decode) { CU(head_decode(a, st)); c->launches++; }
     CU(head_nms(a, st));
-    c->launches += 2;
+    c->launches++;
     return 0;
 }
 
