@@ -43,7 +43,7 @@ BATCH = 256
 METRIC = "frames/sec slim_yolo_v2 fixed-point"
 WORKLOAD = "slim_yolo_v2 fixed-point batched inference, batch %d x 416x416 RGB444 camera frames per GPU (front-end quantiser + 10 conv layers + decode + NMS)"
 CONF, NMS = 0.1, 0.5     # test.py:22-24 defaults
-E2E_CHUNK = 64           # frames per copy / compute chunk of the host path (tools/t_e2e.py: 64 is best blocking and streamed)
+E2E_CHUNK = 128          # frames per copy / compute chunk of the streamed host path (tools/t_e2e_host.py: as fast as 64 on one GPU, 9 % faster with 4 GPUs copying at once)
 
 
 def layer_work(qnet, h, w):

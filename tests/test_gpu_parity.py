@@ -258,6 +258,43 @@ def test_single_layer_ragged_shapes(ctx, hw, layer):
         np.testing.assert_array_equal(d_out.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("nhw", [(3, 32, 36), (2, 48, 100), (2, 34, 38), (5, 208, 208), (1, 416, 416)])
+def test_chain_kernels_on_odd_geometries(ctx, nhw):
+    """The whole chain (conv1 writing x-split rows for the row-pair kernel where its output width is even, plain rows where it is
+    odd: 34x38 -> 17x19; the CTA-pair kernel on 13x13 / 26x26 maps with odd and even tile counts) against the oracle on all maps."""
+    g, qnet, frames = gu.load("ref_p_64x96")
+    n, h, w = nhw
+    rng = np.random.default_rng(n * 1000 + h + w)
+    x8 = rng.integers(-128, 128, (n, h, w, 4), dtype=np.int8)
+    x8[..., 3] = 0
+    for contract in (lib.CONTRACT_F, lib.CONTRACT_P):
+        ctx.load_quantnet(qnet, contract=contract)
+        outs, _ = run_backbone(ctx, x8)
+        ref, _ = ol.backbone(qnet, x8, contract=contract)
+        for l, (a, b) in enumerate(zip(outs, ref)):
+            np.testing.assert_array_equal(a, b, err_msg="layer %d" % l)
+
+
+@pytest.mark.parametrize("n", [1, 4, 5, 7])
+@pytest.mark.parametrize("hw", [(26, 26), (13, 13), (15, 20)])
+@pytest.mark.parametrize("layer", [6, 7])
+def test_cta_pair_kernel_tile_counts(ctx, layer, hw, n):
+    """conv5 / conv6 shapes on the CTA-pair kernel (tcgen05.mma.cta_group::2) for batch sizes that give odd tile counts (the pair's
+    second tile is then a dummy) and fewer pairs than SMs."""
+    g, qnet, frames = gu.load("ref_p_64x96")
+    cin, cout, activ, pool = qnet.layers[layer]
+    h, w = hw
+    rng = np.random.default_rng(layer * 100 + h + n)
+    x = rng.integers(-128, 128, (n, h, w, cin), dtype=np.int8)
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F)
+    d_out = torch.full((n, h, w, ex.cstride(cout)), 77, dtype=torch.int8, device="cuda")
+    ctx.conv_layer(layer, dev(x), n, h, w, d_out)
+    ctx.sync()
+    ref, _ = ol.conv_layer(x, qnet.w[layer], qnet.b[layer], cin, cout, qnet.sa[layer], qnet.sw[layer], qnet.sb[layer],
+                           qnet.retune[layer], qnet.sa[layer + 1], activ, pool, lib.CONTRACT_F)
+    np.testing.assert_array_equal(d_out.cpu().numpy(), ref)
+
+
 def test_saturation_extremes(ctx):
     """All-max / all-min inputs drive the 16-bit and 8-bit saturation points of contract F."""
     g, qnet, frames = gu.load("ref_p_64x96")

@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     static_assert(!BSTREAM || (TMAIN && !PHASE && (KHALF == 4 || KHALF == 8)), "weight streaming: TMA-fed un-phased tiles, 128 / 256 input channels");
     using G = WsGeom<PHASE>;
     pdl_launch_dependents();
+#ifdef YB_WS_TIMELINE
+    if (p.dbg && threadIdx.x == 0 && blockIdx.x < 256) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[512 + blockIdx.x] = t; }
+#endif
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = TMAIN ? (smem_u32(smem_raw) + 1023u) & ~1023u : (smem_u32(smem_raw) + 127u) & ~127u;   // swizzle atoms: 1024 B
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -655,6 +658,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, p.tmem_cols);
+#ifdef YB_WS_TIMELINE
+    if (p.dbg && threadIdx.x == 0 && blockIdx.x < 256) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[768 + blockIdx.x] = t; }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -825,8 +831,8 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
 #ifdef YB_WS_TIMELINE
     {   // debug builds only: stamps of CTA 0's first 64 tiles, printed after the launch (synchronises)
         static long long *dbg = nullptr;
-        if (!dbg) cudaMalloc(&dbg, 64 * 8 * sizeof(long long));
-        cudaMemsetAsync(dbg, 0, 64 * 8 * sizeof(long long), st);
+        if (!dbg) cudaMalloc(&dbg, (64 * 8 + 512) * sizeof(long long));
+        cudaMemsetAsync(dbg, 0, (64 * 8 + 512) * sizeof(long long), st);
         p.dbg = dbg;
     }
 #endif
@@ -844,9 +850,14 @@ static cudaError_t launch_ws_k(const ConvArgs &a, WsParams &p, cudaStream_t st, 
     { cudaError_t le = launch_pdl(conv3x3_ws_kernel<PHASE, EPI, KHALF, TMAIN, BSTREAM>, dim3(grid), dim3(WS_THREADS), smem_bytes, st, p, maps); if (le != cudaSuccess) return le; }
 #ifdef YB_WS_TIMELINE
     {
-        long long h[64 * 8];
+        long long h[64 * 8 + 512];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, p.dbg, sizeof h, cudaMemcpyDeviceToHost);
+        {
+            long long s0 = h[512], s1 = h[512], e0 = h[768], e1 = h[768];
+            for (int i = 0; i < grid && i < 256; ++i) { s0 = s0 < h[512 + i] ? s0 : h[512 + i]; s1 = s1 > h[512 + i] ? s1 : h[512 + i]; e0 = e0 < h[768 + i] ? e0 : h[768 + i]; e1 = e1 > h[768 + i] ? e1 : h[768 + i]; }
+            printf("WS cta times (globaltimer ns): first start 0, last start %lld, first end %lld, last end %lld; cta0 %lld .. %lld\n", s1 - s0, e0 - s0, e1 - s0, h[512] - s0, h[768] - s0);
+        }
         const long long t0 = h[3] ? h[3] : h[0];
         printf("WS timeline PHASE=%d N=%d nplanes=%d stages=%d tiles=%d (cycles since first stamp): tile | mma: tempty_ok full_ok issued | prod: empty_ok loads_issued arrived | epi: tfull_ok done\n",
                (int)PHASE, p.N, p.nplanes, p.stages, p.num_tiles);
