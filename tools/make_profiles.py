@@ -5,7 +5,7 @@ import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rnd = sys.argv[1] if len(sys.argv) > 1 else "r1"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-names = ["conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2", "conv5", "conv6", "conv7", "pred", "head_decode", "head"]
+names = ["conv1", "conv2", "conv3_1", "conv3_2", "conv4_1", "conv4_2", "conv5", "conv6", "conv7", "pred", "head"]     # (the decode is fused into the NMS kernel: 11 launches per step)
 raw = subprocess.run(["ncu", "-i", os.path.join(G, "prof_%s_step.ncu-rep" % rnd), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines())); hdr = rows[0]; units = rows[1]
 t_unit = units[hdr.index('gpu__time_duration.sum')]
