@@ -12,5 +12,5 @@ nvcc $FLAGS -DYB_WS_TIMELINE -c "$PKG/csrc/conv_ws2.cu" -o "$PKG/build_dbg/conv_
 nvcc $FLAGS -DYB_NMS_TIMELINE -c "$PKG/csrc/head.cu" -o "$PKG/build_dbg/head.o" &
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$PKG/build_dbg/libyolo_b200_dbg${YB_RP_EXP}.so" "$PKG/build/yolo_b200.o" "$PKG/build/conv_direct.o" \
-  "$PKG/build/conv_first.o" "$PKG/build/resize.o" "$PKG/build/graph.o" "$PKG/build/conv_umma.o" "$PKG/build_dbg/conv_ws.o" "$PKG/build_dbg/conv_rp.o" "$PKG/build_dbg/conv_wsp.o" "$PKG/build_dbg/conv_ws2.o" "$PKG/build/quantize.o" "$PKG/build_dbg/head.o" -cudart static
+  "$PKG/build/conv_first.o" "$PKG/build/resize.o" "$PKG/build/graph.o" "$PKG/build/conv_umma.o" "$PKG/build_dbg/conv_ws.o" "$PKG/build_dbg/conv_rp.o" "$PKG/build_dbg/conv_wsp.o" "$PKG/build_dbg/conv_ws2.o" "$PKG/build/conv_ws3.o" "$PKG/build/quantize.o" "$PKG/build_dbg/head.o" -cudart static
 echo built "$PKG/build_dbg/libyolo_b200_dbg${YB_RP_EXP}.so"

@@ -65,41 +65,6 @@ struct W2Params {
 
 struct W2Maps { CUtensorMap m[5]; CUtensorMap px; };          // row boxes of 1, 2, 4, 8, 16 rows; one pixel
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank)
-{
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(rank));
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");      // (with .release.cluster every relayed arrival cost ~1300 cycles)
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols)
-{ asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory"); }
-__device__ __forceinline__ void tmem_relinquish2()
-{ asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
-{ asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory"); }
-template <bool ACCUM>
-__device__ __forceinline__ void umma2_i8_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc)
-{
-    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
-                 "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n}"
-                 ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "n"(ACCUM ? 1 : 0) : "memory");
-}
-// completion of this thread's cta_group::2 MMAs -> the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma2_commit_mc(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((unsigned short)3) : "memory");
-}
-
 template <int EPI>
 __global__ void __launch_bounds__(W2_THREADS, 1) conv3x3_ws2_kernel(const W2Params p, const __grid_constant__ W2Maps maps)
 {

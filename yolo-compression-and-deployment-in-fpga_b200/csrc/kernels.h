@@ -17,6 +17,7 @@ struct ConvArgs {
     const uint8_t *wimg;   // cs_in >= 16: UMMA no-swizzle core-matrix image of the weights for conv_ws.cu (see pack_wimg)
     const uint8_t *wimg_tap;   // cs_in 128 / 256: the same image tap-major, [tap][128-channel plane][cs_out/8][8][8][16 B] (conv_ws.cu, weight streaming)
     const uint8_t *wimg_tap2 = nullptr; // cs_in 128 / 256, cs_out 256: [half of cs_out][plane][tap][128/8][8][8][16 B] chunks of 16 KB (conv_wsp.cu)
+    const uint8_t *wimg_tap3 = nullptr; // 3x3, cs_in % 128 == 0, cs_out % 256 == 0, wider than 256: [slice of 256][half][plane][tap] chunks of 16 KB (conv_ws3.cu)
     const uint8_t *wimg_rp = nullptr;  // cs_in == 16, cs_out == 32, pooled: row-pair image [2*cs_out/8][12][8][16 B] (conv_rp.cu)
     const uint8_t *wimg_rps = nullptr; // the same for an x-split input map (chunk order (row, kw 0), (row, kw 2) x 4 rows, then (row, kw 1) x 4)
     int w_rows;            // cout_pad
@@ -59,6 +60,10 @@ cudaError_t conv3x3_wsp(const ConvArgs &a, cudaStream_t st, int sm_count);
 // conv_ws2.cu (CTA-pair tcgen05 kernel, cta_group::2: each SM of a pair holds one 128-pixel tile and half of the weights)
 bool conv3x3_ws2_supported(const ConvArgs &a, int sm_count);
 cudaError_t conv3x3_ws2(const ConvArgs &a, cudaStream_t st, int sm_count);
+
+// conv_ws3.cu (the CTA-pair kernel for the wide 3x3 layers of yolo_v2: units of (tile pair, 256-channel slice), halo planes streamed)
+bool conv3x3_ws3_supported(const ConvArgs &a, int sm_count);
+cudaError_t conv3x3_ws3(const ConvArgs &a, cudaStream_t st, int sm_count);
 
 // conv_rp.cu (row-pair tcgen05 kernel for the thin pooled layers: two output rows in the GEMM N dimension, dense TMA-fed halo)
 bool conv3x3_rp_supported(const ConvArgs &a);

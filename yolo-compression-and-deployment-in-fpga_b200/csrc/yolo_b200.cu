@@ -42,6 +42,7 @@ struct LayerDev {
     uint8_t *wimg = nullptr;   // cs_in >= 16: core-matrix image [cs_out/8][kc][8][16] (conv_ws.cu)
     uint8_t *wimg_tap = nullptr;   // cs_in 128 / 256: chunk-major image [tap][plane][cs_out/8][8][8][16] (conv_ws.cu, streamed weights)
     uint8_t *wimg_tap2 = nullptr;  // cs_in 128 / 256, cs_out 256: 16 KB chunks [half][plane][tap] (conv_wsp.cu)
+    uint8_t *wimg_tap3 = nullptr;  // wide 3x3 layers (yolo_v2): 16 KB chunks [slice][half][plane][tap] (conv_ws3.cu)
     uint8_t *wimg_rp = nullptr;    // cs_in == 16, cs_out == 32, pooled: row-pair image (conv_rp.cu)
     uint8_t *wimg_rps = nullptr;   // the same in the chunk order of the x-split variant
     bool xsplit = false;           // the most recent output map is stored with its rows split by x parity ([even pixels][odd pixels])
@@ -189,7 +190,7 @@ int yolo_b200_create(yolo_b200_ctx **out, int device)
 
 static void free_layers(yolo_b200_ctx *c)
 {
-    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_tap2); cudaFree(l.wimg_rp); cudaFree(l.wimg_rps); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
+    for (auto &l : c->layers) { l.view = nullptr; cudaFree(l.w); cudaFree(l.w_k160); cudaFree(l.wimg); cudaFree(l.wimg_tap); cudaFree(l.wimg_tap2); cudaFree(l.wimg_tap3); cudaFree(l.wimg_rp); cudaFree(l.wimg_rps); cudaFree(l.w_swz); cudaFree(l.bias_sh); cudaFree(l.out); cudaFree(l.w1); cudaFree(l.raw); cudaFree(l.cat); }
     c->layers.clear();
 }
 
@@ -474,6 +475,21 @@ int yolo_b200_load(yolo_b200_ctx *c, const int8_t *const *weights, const int8_t 
             CU(cudaMalloc(&d.wimg_rps, ims.size()));
             CU(cudaMemcpy(d.wimg_rps, ims.data(), ims.size(), cudaMemcpyHostToDevice));
         }
+        if (ks == 3 && d.cs_in % 128 == 0 && d.cs_out % 256 == 0 && (d.cs_in > 256 || d.cs_out > 256)) {
+            // conv_ws3.cu: chunk = (slice of 256 output channels, half of the slice, 128-channel plane, tap): [128/8][8 K chunks][8][16 B]
+            const int npl = d.cs_in / 128, nsl = d.cs_out / 256;
+            std::vector<uint8_t> im3((size_t)d.cs_out * 9 * d.cs_in, 0);
+            for (int sl = 0; sl < nsl; ++sl)
+                for (int hf = 0; hf < 2; ++hf)
+                    for (int pl = 0; pl < npl; ++pl)
+                        for (int tap = 0; tap < 9; ++tap)
+                            for (int o = 0; o < 128; ++o)
+                                for (int cc = 0; cc < 8; ++cc)
+                                    memcpy(&im3[((((((size_t)(sl * 2 + hf) * npl + pl) * 9 + tap) * 16 + o / 8) * 8 + cc) * 8 + (o % 8)) * 16],
+                                           &wp[((size_t)(sl * 256 + hf * 128 + o) * 9 + tap) * d.cs_in + pl * 128 + 16 * cc], 16);
+            CU(cudaMalloc(&d.wimg_tap3, im3.size()));
+            CU(cudaMemcpy(d.wimg_tap3, im3.data(), im3.size(), cudaMemcpyHostToDevice));
+        }
         // (the 128B-swizzled image of conv_umma.cu is built on first use: ensure_swz)
         CU(cudaMalloc(&d.bias_sh, (size_t)d.cout_pad * sizeof(int)));
         c->layers.push_back(d);
@@ -664,7 +680,7 @@ static void fill_args(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h,
     LayerDev &L = c->layers[l];
     a.in = d_in; a.n = n; a.H = h; a.W = w; a.cs_in = L.cs_in; a.wgt = L.w; a.bias_sh = L.bias_sh;
     a.cout = L.cout; a.cs_out = L.cs_out; a.q = L.q; a.out = d_out; a.ovf = c->ovf_dev;
-    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_tap2 = L.wimg_tap2; a.wimg_rp = L.wimg_rp; a.wimg_rps = L.wimg_rps; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
+    a.wgt_k160 = L.w_k160; a.wimg = L.wimg; a.wimg_tap = L.wimg_tap; a.wimg_tap2 = L.wimg_tap2; a.wimg_tap3 = L.wimg_tap3; a.wimg_rp = L.wimg_rp; a.wimg_rps = L.wimg_rps; a.w_rows = L.cout_pad; a.bias_abs_max = L.bias_abs_max;
     a.wgt_swz = L.w_swz; a.wgt_swz_rows = L.cs_out;
     a.taps = 9; a.wgt1 = nullptr;
     a.force_generic_epilogue = c->conv_backend == 3 || c->conv_backend == 5;
@@ -707,7 +723,9 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
         // (one K block per (tap, 128-channel chunk), output channels in slices of 256); back end 1 keeps the dot-product kernel
         ConvArgs u = a;
         if (L.ksize == 1) { u.taps = 1; u.wgt1 = L.w1; }
-        if (be != 1 && aligned && conv3x3_umma_supported(u)) {
+        if (be == 0 && L.ksize == 3 && aligned && conv3x3_ws3_supported(a, c->sm_count)) {
+            CU(conv3x3_ws3(a, c->stream, c->sm_count));        // wide 3x3 layer on a narrow map: the CTA-pair kernel
+        } else if (be != 1 && aligned && conv3x3_umma_supported(u)) {
             int rc = ensure_swz(c, L); if (rc) return rc;
             u.wgt_swz = L.w_swz;
             CU(conv3x3_umma(u, c->stream, c->sm_count));
