@@ -775,6 +775,44 @@ def test_first_layer_kernel_against_oracle(ctx, pool):
             np.testing.assert_array_equal(outs[1], ref, err_msg="dp4a kernel, shape %s contract %d" % ((n, h, w), contract))
 
 
+@pytest.mark.parametrize("pool_shape", [(1, 2, 256), (2, 6, 264), (3, 50, 272), (1, 33, 320), (2, 130, 416), (1, 20, 640), (1, 416, 416)])
+def test_first_layer_tcgen05_kernel_against_oracle(ctx, pool_shape):
+    """conv1 on the tcgen05 slot kernel (conv_fs.cu: pooled, 16 channels, pooled width >= 128): int8 NHWC4 input through the
+    single-layer entry point under both contracts, and RGB444 frames through the fused front end (x-split hand-off to conv2
+    where the chain takes it): layer-1 and layer-2 maps of the oracle.  Shapes: one tile, tiles that cross rows and frames,
+    odd heights, a ragged last tile, a ring of 8 rows (640 wide)."""
+    g, qnet0, frames = gu.load("ref_p_64x96")
+    n, h, w = pool_shape
+    rng = np.random.default_rng(100 + h + w)
+    cin, cout, activ, pool = qnet0.layers[0]
+    assert pool == 1 and cout == 16
+    x = np.zeros((n, h, w, 4), dtype=np.int8)
+    x[..., :3] = rng.integers(-128, 128, (n, h, w, 3), dtype=np.int8)
+    for contract in (lib.CONTRACT_F, lib.CONTRACT_P):
+        ctx.load_quantnet(qnet0, contract=contract)
+        d_out = torch.full((n, h // 2, w // 2, 16), 77, dtype=torch.int8, device="cuda")
+        ctx.conv_layer(0, dev(x), n, h, w, d_out)
+        ctx.sync()
+        ref, _ = ol.conv_layer(x, qnet0.w[0], qnet0.b[0], cin, cout, qnet0.sa[0], qnet0.sw[0], qnet0.sb[0],
+                               qnet0.retune[0], qnet0.sa[1], activ, pool, contract)
+        np.testing.assert_array_equal(d_out.cpu().numpy(), ref, err_msg="shape %s contract %d" % ((n, h, w), contract))
+    if h < 32:
+        return
+    qnet = ex.random_quantnet(seed=5, calib_hw=(64, 96), calib_frames=2, calib_input="rgb444")
+    ctx.load_quantnet(qnet, contract=lib.CONTRACT_F, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    u16 = rng.integers(0, 65536, (n, h, w), dtype=np.uint16)
+    x8 = ol.quantize_rgb444(u16 & 0x0fff, qnet.sa[0])
+    ref, _ = ol.backbone(qnet, x8, contract=0)
+    d = torch.from_numpy(u16.reshape(-1).view(np.int16)).cuda()
+    d_dets = torch.zeros((n, 512, 8), dtype=torch.int32, device="cuda")
+    d_counts = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    ctx.forward_rgb444_dev(d, n, h, w, d_dets, d_counts)
+    ctx.sync()
+    for l in (0, 1):
+        shp = ref[l].shape
+        np.testing.assert_array_equal(ctx.layer_output(l, shp[0], shp[1], shp[2]), ref[l], err_msg="rgb444 shape %s layer %d" % ((n, h, w), l))
+
+
 def test_weight_stationary_layers_with_cp_async_producers_in_a_subprocess():
     """YOLO_B200_WS_TMA=0 (read once per process) keeps the cp.async producers for conv3_1 / conv4_1 / conv4_2: same
     results as the oracle (the TMA-fed default is what every other test runs)."""

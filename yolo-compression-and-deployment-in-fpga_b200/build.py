@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyolo_b200.so")
-SOURCES = ["yolo_b200.cu", "conv_direct.cu", "conv_first.cu", "conv_umma.cu", "conv_ws.cu", "conv_rp.cu", "conv_wsp.cu", "conv_ws2.cu", "conv_ws3.cu", "quantize.cu", "resize.cu", "head.cu", "graph.cu"]
+SOURCES = ["yolo_b200.cu", "conv_direct.cu", "conv_first.cu", "conv_fs.cu", "conv_umma.cu", "conv_ws.cu", "conv_rp.cu", "conv_wsp.cu", "conv_ws2.cu", "conv_ws3.cu", "quantize.cu", "resize.cu", "head.cu", "graph.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function", "-Xptxas", "-v",
               "--expt-relaxed-constexpr"]

@@ -44,6 +44,10 @@ bool conv3x3_first_src_ok(int src_kind, const void *src);      // pointer alignm
 // src_kind: 0 = a.in (int8 NHWC4), 1 = RGB444 uint16 frames + 4096-word table, 2 = uint8 BGR images + 3x256-byte table
 cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind = 0, const void *src = nullptr, const void *lut = nullptr);
 
+// conv_fs.cu (first layer on tcgen05: 3 -> 16 channels + pool for pooled widths >= 128; src_kind 0 = int8 NHWC4, 1 = RGB444 + table)
+bool conv3x3_fs_supported(const ConvArgs &a, int src_kind, const void *src);
+cudaError_t conv3x3_fs(const ConvArgs &a, cudaStream_t st, int src_kind, const void *src, const void *lut);
+
 // conv_umma.cu (tcgen05 / TMEM / TMA implicit GEMM)
 bool conv3x3_umma_supported(const ConvArgs &a);
 cudaError_t conv3x3_umma(const ConvArgs &a, cudaStream_t st, int sm_count);
