@@ -4,33 +4,34 @@
 // Replaces first_conv (c_embedding/yolo_forward.c:269-418) and conv1 + tracker + pool (models/slim_yolo_v2.py:220-231), like
 // conv_first.cu, which stays the general kernel (un-pooled / wide / narrow / BGR-byte first layers).  conv_first.cu runs on
 // warp-level integer MMAs and is bound by instruction issue (61 % of the issue slots, 0.22 ms per 256 frames of 416x416 against
-// 0.04 ms of HBM time).  Here the convolution runs on tcgen05 without an im2col buffer per output pixel:
+// 0.04 ms of HBM time).  Here the convolution runs on tcgen05 without an im2col row per output pixel:
 //
-//   * K.  A pixel is one 32-bit word (R, G, B, 0).  A SLOT is 16 bytes = the words of pixels x-1, x, x+1, x+2 of one input row:
-//     the three horizontal taps of output pixel x (the fourth word meets zero weights).  The GEMM N dimension carries TWO
-//     output rows (column dy * 16 + co = channel co of row 2Y + dy), so K spans the four input rows 2Y-1 .. 2Y+2 = four slots =
-//     two K = 32 instructions; the weight images hold zeros where kh = row - dy falls outside 0..2.  The vertical half of the
-//     max-pool is then a maximum over two column ranges of one TMEM lane.
-//   * x parity.  Slots are kept in separate arrays for even and odd x, so that one instruction's 128 M rows are 128 output pixels
-//     of ONE x parity: pooled pixels j .. j+127.  Two accumulators (x = 2j and x = 2j + 1) put all four members of a pooled
-//     pixel into one TMEM lane: the pool is three integer maxima per channel, no shuffles.
-//   * rows.  Input rows 2i-1 ("odd") and 2i ("even") form PAIR-ROW i; odd and even rows live in separate arrays with the same
-//     pitch of OW slots.  Pooled row Y reads pair-rows Y and Y+1; within one instruction the second K chunk (the even row) is
-//     the first one's address + LBO = the distance between the two arrays.  Because the pitch is exactly OW slots, the M rows of
-//     an instruction may run over the end of a row into the next pair-row: a tile is ANY 128 consecutive pooled pixels of the
-//     frame in raster order (416x416: 43264 = 338 x 128, no ragged tiles), and the output of a tile is 2 KB of consecutive bytes.
+//   * K.  A pixel is one 32-bit word (R, G, B, 0).  A SLOT is 16 bytes = the words of pixels 2j-1, 2j, 2j+1, 2j+2 of one input row.
+//     Output pixel x = 2j reads its three horizontal taps from words 0-2 of slot j, output pixel x = 2j+1 from words 1-3: ONE slot
+//     array serves both x parities, the parity only selects which three of the four weight words are non-zero.  The GEMM N dimension
+//     carries two x parities x two output rows x 16 channels (column e * 32 + dy * 16 + co = channel co of pixel (2Y + dy, 2j + e)),
+//     so K spans the four input rows 2Y-1 .. 2Y+2 = four slots = two K = 32 instructions of N = 64; the weight images hold zeros
+//     where kh = row - dy or kw = word - e falls outside 0..2.  All four members of pooled pixel (Y, j) land in ONE TMEM lane: the
+//     2x2 max-pool is three integer maxima per channel, no shuffles (requantisation is monotone: slim_yolo_v2.py:229-231).
+//   * rows.  Input rows 2i-1 ("odd") and 2i ("even") form PAIR-ROW i; odd and even rows live in two arrays with the same pitch of
+//     OW slots.  Pooled row Y reads pair-rows Y and Y+1; within one instruction the second K chunk (the even row) is the first
+//     one's address + LBO = the distance between the two arrays.  Because the pitch is exactly OW slots, the 128 M rows of an
+//     instruction may run over the end of a row into the next pair-row: a tile is ANY 128 consecutive pooled pixels of the frame
+//     in raster order (416x416: 43264 = 338 x 128, no ragged tiles), and the output of a tile is 2 KB of consecutive bytes.
 //   * the arrays are rings of R pair-rows (+ a mirror of the first row behind the last one, so that a tile that starts in the
-//     last ring row continues into valid data).  Builder warps fill them: the raw frame rows arrive in a small ring by 1-D bulk
-//     copies (no register staging, no exposed global latency), a builder lane reads two pixels, quantises them through the
-//     4096-entry table (camera_to_inpBuf + pixel_norm_quantize, yolo_forward.c:57-123), takes its neighbours' words by
-//     shuffles and writes the two slots (one per parity) with two conflict-free 128-bit stores: 16 bytes of shared-memory
-//     writes per pixel, where an im2col row per pixel would need 32 and byte shuffling.
+//     last ring row continues into valid data).  Builder warps fill them: the raw frame rows arrive in a ring of 16 pair-rows by
+//     1-D bulk copies (no register staging, no exposed HBM latency), a builder lane reads two pixels, quantises them through the
+//     4096-entry table (camera_to_inpBuf + pixel_norm_quantize, yolo_forward.c:57-123), takes one word from each neighbour by
+//     shuffles and writes the slot with one conflict-free 128-bit store: 8 bytes of shared-memory writes per pixel, where an
+//     im2col row per pixel would need 32 and byte shuffling.
 //
-// Shared-memory port budget per 512 input pixels: 8 KB of slot writes + 4 x (4 KB of A + 1 KB of B) operand reads.
+// Shared-memory port budget per 512 input pixels (one tile): 4 KB of slot writes + 2 x (4 KB of A + 2 KB of B) operand reads.
+// What bounds the kernel is instruction issue (~1300 warp instructions per tile: 4 x 210 in the requantisation epilogue, ~310 in
+// the builders, ~130 in the issuer; ~3 issued per clock and SM), see profiles/README.md.
 //
-// Warp roles (896 threads): warps 0, 1, 3 MMA issuers (tile t -> issuer t % 3), warp 2 raw-row loader (one lane), warps 4-11 slot builders
-// (teams of two warps, one input row each; four pair-rows in flight), warps 12-27 four epilogue groups (tile t -> group t % 4; one warp per
-// TMEM lane quarter).  Tile t of a CTA uses TMEM buffer t % 8.
+// Warp roles (896 threads): warps 0, 1, 3 MMA issuers (tile t -> issuer t % 3), warp 2 raw-row loader (one lane), warps 4-11 slot
+// builders (teams of two warps, one input row each; four pair-rows in flight), warps 12-27 four epilogue groups (tile t -> group
+// t % 4; one warp per TMEM lane quarter).  Tile t of a CTA uses TMEM buffer t % 8 (64 columns).
 #include "kernels.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -39,8 +40,8 @@
 
 namespace yb {
 
-// YB_FS_TIMELINE builds (tools/dbg_build.sh): clock64 stamps of CTA 0: builder warp 0's first 64 rows (slots 0-2: start, barriers
-// passed, row published), issuer warp 0's first 64 tiles (3-5: rows there, accumulator free, issued), epilogue group 0 (6-7)
+// YB_FS_TIMELINE builds (tools/dbg_build.sh): clock64 stamps of CTA 0, 24 slots per entry: builder warps 0 and 7 (slots 0-5 / 6-11: start, raw row
+// there, ring slot free, stored, fenced, published), issuer 0 (12-15: loop top, rows there, accumulator free, issued), epilogue group 0 (16-17)
 #ifdef YB_FS_TIMELINE
 #define FS_STAMP(n, slot) do { if (p.dbg && blockIdx.x == 0 && (n) < 64 && lane == 0) p.dbg[(n) * 24 + (slot)] = clock64(); } while (0)
 #else
