@@ -6,12 +6,16 @@ import bench, yolo_b200
 from yolo_b200 import export as ex, lib
 H = W = 416
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+import faulthandler, time; faulthandler.dump_traceback_later(100, exit=True)
+t0 = time.time()
 q = ex.random_quantnet_yolo_v2(seed=0, calib_hw=(H, W), calib_frames=1)
+print("quantnet %.1f s" % (time.time() - t0), flush=True)
 ctx = lib.Context(0)
 ctx.load_quantnet(q, contract=lib.CONTRACT_F, conf_thresh=0.1, nms_thresh=0.5, max_det=1024)
 x = torch.from_numpy(bench.ol_quantize(ex.synthetic_frames_f32(B, H, W, seed=13).numpy(), q.sa[0])).cuda()
 dets = torch.zeros((B, 1024, 8), dtype=torch.int32, device="cuda"); counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
 for i in range(3): ctx.forward_int8_dev(x, B, H, W, dets, counts)
+ctx.sync(); print("warm-up done %.1f s" % (time.time() - t0), flush=True)
 ctx.enable_timing(True)
 acc = None
 for i in range(5):

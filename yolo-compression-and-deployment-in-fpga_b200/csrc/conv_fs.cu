@@ -29,14 +29,15 @@
 // What bounds the kernel is instruction issue (~1300 warp instructions per tile: 4 x 210 in the requantisation epilogue, ~310 in
 // the builders, ~130 in the issuer; ~3 issued per clock and SM), see profiles/README.md.
 //
-// Warp roles (896 threads): warps 0, 1, 3 MMA issuers (tile t -> issuer t % 3), warp 2 raw-row loader (one lane), warps 4-11 slot
-// builders (teams of two warps, one input row each; four pair-rows in flight), warps 12-27 four epilogue groups (tile t -> group
-// t % 4; one warp per TMEM lane quarter).  Tile t of a CTA uses TMEM buffer t % 8 (64 columns).
+// Warp roles (928 threads): warps 0-3 MMA issuers (tile t -> issuer t % 4), warp 4 raw-row loader (one lane), warps 5-12 slot
+// builders (teams of two warps, one input row each; four pair-rows in flight), warps 13-28 four epilogue groups (tile t -> group
+// t % 4; one warp per TMEM lane quarter).  Tile t uses TMEM buffer t % 8 (64 columns; t % 4 and 128 columns for 32 channels).
 #include "kernels.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <time.h>
 
 namespace yb {
 
@@ -47,17 +48,25 @@ namespace yb {
 #else
 #define FS_STAMP(n, slot) do { } while (0)
 #endif
+// YB_FS_WATCH builds: every role publishes its progress to host-mapped memory; the launcher prints the table if the kernel does not finish
+#ifdef YB_FS_WATCH
+#define FS_WATCH(slot, val) do { if (p.watch && lane == 0) ((volatile unsigned *)p.watch)[blockIdx.x * 32 + (slot)] = (unsigned)(val); } while (0)
+#else
+#define FS_WATCH(slot, val) do { } while (0)
+#endif
 #define FS_STAMP_B(slot) do { if (bw == 0) FS_STAMP(gl / FS_NTEAM, slot); else if (bw == 7) FS_STAMP(gl / FS_NTEAM, 6 + (slot)); } while (0)
 
-constexpr int FS_THREADS = 896;
-constexpr int FS_NI = 3;                 // MMA issuer warps: 0, 1 and 3 (tile t -> issuer t % 3); a lone warp needs ~1250 cycles per tile (barrier polls,
-                                         // descriptor arithmetic, four MMAs, commits: one dependent instruction every ~8 cycles next to 27 other warps)
-constexpr int FS_BW0 = 4, FS_NBW = 8;    // builder warps 4 .. 11: teams of two (odd input row / even input row); team m fills the pair-rows m, m + 4, ...
+constexpr int FS_THREADS = 928;
+constexpr int FS_NI = 4;                 // MMA issuer warps 0-3 (tile t -> issuer t % 4): a lone warp needs ~1250 cycles per tile (barrier polls, descriptor
+                                         // arithmetic, MMAs, commits: one dependent instruction every ~8 cycles next to the other warps)
+constexpr int FS_LW = 4;                 // raw-row loader warp
+constexpr int FS_BW0 = 5, FS_NBW = 8;    // builder warps 5 .. 12: teams of two (odd input row / even input row); team m fills the pair-rows m, m + 4, ...
 constexpr int FS_NTEAM = FS_NBW / 2;
-constexpr int FS_EW0 = 12, FS_EG = 4;    // epilogue warps 12 .. 27: four groups of four
+constexpr int FS_EW0 = 13, FS_EG = 4;    // epilogue warps 13 .. 28: four groups of four (any four consecutive warps cover the four TMEM lane quarters)
 constexpr int FS_RAWR = 16;              // raw pair-row ring: the loader runs up to 16 pair-rows ahead of the builders (HBM latency)
 constexpr int FS_RMAX = 16;              // slot ring rows (barrier space)
-constexpr int FS_TBUF = 8;               // 8 x 64 TMEM columns
+// CO output channels (16: slim_yolo_v2, 32: darknet19): a tile's accumulators are 4 CO TMEM columns (x parity, row, channel)
+constexpr int FS_TBUF_MAX = 8;
 constexpr int FS_SEGW = 30;              // pixel pairs a builder warp produces per pass (lanes 0 and 31 only feed their neighbours)
 
 struct FsParams {
@@ -74,6 +83,7 @@ struct FsParams {
     uint32_t arr_bytes;          // one slot array: (R + MR) * OW * 16, rounded up to 128
     uint32_t off_lut, off_raw, off_bias, off_bar, off_arr;
     int xsplit;
+    int co;                      // 16 or 32 output channels = bytes per output pixel
     const int8_t *wgt;           // [cout_pad][9][4]
     const int *bias_sh;
     LayerQ q;
@@ -81,6 +91,7 @@ struct FsParams {
     int8_t *out;
     unsigned *ovf;
     long long *dbg;
+    unsigned *watch;
 };
 
 // predicated 128-bit shared store (a predicate, not a branch: the shuffles of the next pass are not held behind a reconvergence point)
@@ -111,46 +122,52 @@ __device__ __forceinline__ bool fs_next_seg(const FsParams &p, int &U, int U1, F
 // (Accumulators pre-biased with the fp32 magic constant by tcgen05.st from the epilogue warps, which would save the 16 int -> float
 // conversions per thread and tile, were measured and rejected: re-arming 64 columns + tcgen05.wait::st costs ~1500 cycles per tile
 // and group, 0.186 -> 0.260 ms.)
-template <int EPI, bool ACT>
+template <int EPI, bool ACT, int CO>
 __device__ __forceinline__ void fs_epilogue_tile(const FsParams &p, uint32_t taddr, int q, int img, const int *s_bias, uint32_t bar_tempty, unsigned &ovf)
 {
     const bool valid = q < p.ohw;
-    uint4 w;
-    unsigned *wp = &w.x;
+    int pos = q;
+    if (CO == 16 && p.xsplit) {
+        const int pr = (int)__umulhi((unsigned)q, p.ow_magic), j = q - pr * p.OW;
+        pos = pr * p.OW + (j & 1) * (p.OW >> 1) + (j >> 1);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((size_t)img * p.ohw + pos) * CO);
+    unsigned w[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {                              // channels 8h .. 8h + 7
+    for (int h = 0; h < CO / 8; ++h) {                         // channels 8h .. 8h + 7
         int a[8], b[8], c[8], d[8];
         tmem_ld8(taddr + 8 * h, a);                            // x even, row 2Y
-        tmem_ld8(taddr + 16 + 8 * h, b);                       // x even, row 2Y + 1
-        tmem_ld8(taddr + 32 + 8 * h, c);                       // x odd,  row 2Y
-        tmem_ld8(taddr + 48 + 8 * h, d);                       // x odd,  row 2Y + 1
+        tmem_ld8(taddr + CO + 8 * h, b);                       // x even, row 2Y + 1
+        tmem_ld8(taddr + 2 * CO + 8 * h, c);                   // x odd,  row 2Y
+        tmem_ld8(taddr + 3 * CO + 8 * h, d);                   // x odd,  row 2Y + 1
         tmem_ld_wait();
-        if (h == 1) { tc_fence_before(); mbar_arrive(bar_tempty); }      // all of the tile's accumulators are in registers
+        if (h == CO / 8 - 1) { tc_fence_before(); mbar_arrive(bar_tempty); }      // all of the tile's accumulators are in registers
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = max(max(a[j], b[j]), max(c[j], d[j]));
-        wp[2 * h] = requant4<EPI, ACT>(&a[0], s_bias, 8 * h, p, ovf, valid);
-        wp[2 * h + 1] = requant4<EPI, ACT>(&a[4], s_bias, 8 * h + 4, p, ovf, valid);
-    }
-    if (valid) {
-        int pos = q;
-        if (p.xsplit) {
-            const int pr = (int)__umulhi((unsigned)q, p.ow_magic), j = q - pr * p.OW;
-            pos = pr * p.OW + (j & 1) * (p.OW >> 1) + (j >> 1);
-        }
-        *reinterpret_cast<uint4 *>(p.out + ((size_t)img * p.ohw + pos) * 16) = w;
+        w[2 * (h & 1)] = requant4<EPI, ACT>(&a[0], s_bias, 8 * h, p, ovf, valid);
+        w[2 * (h & 1) + 1] = requant4<EPI, ACT>(&a[4], s_bias, 8 * h + 4, p, ovf, valid);
+        if ((h & 1) && valid) dst[h >> 1] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
-template <int EPI, int SRC>
+template <int EPI, int SRC, int CO>
 __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParams p)
 {
+    // Accumulator columns per tile, TMEM buffers.  Tile t: issuer t % 4, epilogue group t % 4, buffer t % TBUF, use t / TBUF of that
+    // buffer.  TBUF is a multiple of 4, so every buffer belongs to ONE issuer warp and ONE epilogue group: whoever waits for a phase
+    // of `tfull` / `tempty` by parity took part in the previous phase itself, so an older phase can never satisfy the wait.  (With
+    // three issuers over 4 / 8 buffers a stalled issuer let another one run two uses ahead of the drain: a deadlock at >= 64 tiles
+    // per CTA with four buffers, found with the YB_FS_WATCH build.)
+    constexpr int NCOL = 4 * CO, TBUF = 512 / NCOL;
+    static_assert(TBUF % FS_NI == 0 && TBUF % FS_EG == 0, "buffers are owned");
+    static_assert(CO == 16 || CO == 32, "16 or 32 output channels");
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // broadcast: provably warp-uniform
 
-    const uint32_t bsm = base;                                 // two weight images of 2 KB
+    const uint32_t bsm = base;                                 // two weight images of NCOL x 32 bytes
     unsigned *s_lut = reinterpret_cast<unsigned *>(base_ptr + p.off_lut);
     const uint8_t *s_rawp = base_ptr + p.off_raw;
     const uint32_t raw0 = base + p.off_raw;
@@ -162,31 +179,31 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
     auto bar_full = [&](int s) { return bar0 + 8u * (2 * FS_RAWR + s); };
     auto bar_empty = [&](int s) { return bar0 + 8u * (2 * FS_RAWR + FS_RMAX + s); };
     auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * FS_RAWR + 2 * FS_RMAX + b); };
-    auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * FS_RAWR + 2 * FS_RMAX + FS_TBUF + b); };
-    const uint32_t tmem_slot = bar0 + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF);
-    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF));
+    auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * FS_RAWR + 2 * FS_RMAX + FS_TBUF_MAX + b); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF_MAX);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + p.off_bar + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF_MAX));
     const uint32_t raw_slot_bytes = 2u * p.row_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FS_RAWR; ++s) { mbar_init(bar_rawfull(s), 1); mbar_init(bar_rawempty(s), 64); }
         for (int s = 0; s < FS_RMAX; ++s) { mbar_init(bar_full(s), 64); mbar_init(bar_empty(s), FS_NI); }
-        for (int b = 0; b < FS_TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 128); }
+        for (int b = 0; b < TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 128); }
         fence_barrier_init();
     }
     if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-    // weight images: image bi = K chunks (2 bi, 2 bi + 1) = input rows (2Y - 1 + 2 bi, 2Y + 2 bi); GEMM column n = e * 32 + dy * 16 + co =
+    // weight images: image bi = K chunks (2 bi, 2 bi + 1) = input rows (2Y - 1 + 2 bi, 2Y + 2 bi); GEMM column n = e * 2 CO + dy * CO + co =
     // channel co of output pixel (row 2Y + dy, x = 2j + e); word (n / 8, chunk, n % 8, w) of the no-swizzle K-major layout = the 4 channel
     // bytes of tap (kh = chunk row - dy, kw = w - e): the slot of pooled pixel j holds pixels 2j-1 .. 2j+2, an even x reads words 0-2, an odd x words 1-3
-    for (int wd = threadIdx.x; wd < 1024; wd += FS_THREADS) {
-        const int bi = wd >> 9, rem = wd & 511;
+    for (int wd = threadIdx.x; wd < 16 * NCOL; wd += FS_THREADS) {
+        const int bi = wd / (8 * NCOL), rem = wd - bi * (8 * NCOL);
         const int n = ((rem >> 6) << 3) | ((rem >> 2) & 7), cc = (rem >> 5) & 1, w = rem & 3;
-        const int e = n >> 5, dy = (n >> 4) & 1, co = n & 15, kh = 2 * bi + cc - dy, kw = w - e;
+        const int e = n / (2 * CO), dy = (n / CO) & 1, co = n % CO, kh = 2 * bi + cc - dy, kw = w - e;
         unsigned v = 0;
         if (kh >= 0 && kh <= 2 && kw >= 0 && kw <= 2) v = __ldg(reinterpret_cast<const unsigned *>(p.wgt) + co * 9 + kh * 3 + kw);
         reinterpret_cast<unsigned *>(base_ptr)[wd] = v;
     }
     if (SRC == 1) for (int i = threadIdx.x; i <= 4096; i += FS_THREADS) s_lut[i] = i < 4096 ? (unsigned)__ldg(p.lut + i) : 0u;   // entry 4096: outside the frame
-    if (threadIdx.x < 16) {
+    if (threadIdx.x < CO) {
         const int b = p.bias_sh[threadIdx.x];
         s_bias[threadIdx.x] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;
     }
@@ -201,14 +218,14 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
     const int U0 = (int)(((long long)p.total_units * blockIdx.x) / G), U1 = (int)(((long long)p.total_units * (blockIdx.x + 1)) / G);
     const uint32_t row_pitch = (uint32_t)p.OW * 16u;           // one ring row of one array
 
-    if (warp < 2 || warp == 3) {
-        // ===================== MMA issuers: tile t -> issuer t % 3 =====================
-        const int rank = warp == 3 ? 2 : warp;
-        static_assert(FS_NI == 3, "issuer warps 0, 1, 3; the row advance of FS_NI tiles is found with three comparisons (pooled width >= 128)");
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);     // M = 128, N = 64
+    if (warp < FS_NI) {
+        // ===================== MMA issuers: tile t -> issuer t % 4 =====================
+        const int rank = warp;
+        static_assert(FS_NI == 4, "the row advance of FS_NI tiles is found with four comparisons (pooled width >= 128)");
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((128u >> 4) << 24);     // M = 128, N = 4 CO
         const uint32_t ahi = 8u | (1u << 14);                  // SBO = 128 B: 8 consecutive slots are one core matrix
         const uint32_t bhi = 16u | (1u << 14);                 // SBO = 256 B between 8-column groups
-        const uint32_t b1lo = (bsm >> 4) | (8u << 16), b2lo = ((bsm + 2048u) >> 4) | (8u << 16);     // LBO = 128 B between the two K chunks
+        const uint32_t b1lo = (bsm >> 4) | (8u << 16), b2lo = ((bsm + (uint32_t)NCOL * 32u) >> 4) | (8u << 16);     // LBO = 128 B between the two K chunks
         const uint32_t albo = (p.arr_bytes >> 4) << 16;        // odd-row array -> even-row array
         int U = U0, gbase = 0, tbase = 0;
         int waited = 0, wphys = 0; uint32_t wphase = 0;        // pair-rows [0, waited) of this CTA's sequence are known to be filled
@@ -228,22 +245,24 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
             int ph = (gbase + pr0 - sg.ia) % p.R;              // ring row of pair-row pr0
             int myrel = sg.ia - 1, relph = gbase % p.R;        // pair-rows <= myrel of this frame have been released by this warp; ring row of myrel + 1
             for (; k < ntiles; k += FS_NI) {
-                const int t = tbase + k, buf = t & (FS_TBUF - 1);
+                const int t = tbase + k, buf = t % TBUF, use = t / TBUF;
                 const int need = min(sg.ib, pr0 + 1 + (j0 + 127 >= p.OW ? 1 : 0));
                 const int wnext = j0 + 128 * FS_NI;
-                const int adv = (wnext >= p.OW ? 1 : 0) + (wnext >= 2 * p.OW ? 1 : 0) + (wnext >= 3 * p.OW ? 1 : 0);
+                const int adv = (wnext >= p.OW ? 1 : 0) + (wnext >= 2 * p.OW ? 1 : 0) + (wnext >= 3 * p.OW ? 1 : 0) + (wnext >= 4 * p.OW ? 1 : 0);
                 // rows no later tile of this warp reads (a row may only be released after it was seen filled: the arrivals on
                 // its `empty` barrier must stay behind those of the row that used the ring slot before)
                 const int relupto = k + FS_NI < ntiles ? pr0 + adv - 1 : myrel;
                 if (rank == 0) FS_STAMP(t / FS_NI, 12);
+                FS_WATCH(rank, (t << 8) | 0x10 | (gbase + (max(need, relupto) - sg.ia)) << 16);
                 wait_rows(gbase + (max(need, relupto) - sg.ia));
                 if (rank == 0) FS_STAMP(t / FS_NI, 13);
-                mbar_wait(bar_tempty(buf), (((uint32_t)t >> 3) & 1u) ^ 1u);
+                FS_WATCH(rank, (t << 8) | 0x20);
+                mbar_wait(bar_tempty(buf), ((uint32_t)use & 1u) ^ 1u);
                 if (rank == 0) FS_STAMP(t / FS_NI, 14);
                 tc_fence_after();
                 if (elect_one()) {
                     const int ph2 = ph + 1 == p.R ? 0 : ph + 1;
-                    const uint32_t d = tmem_base + (uint32_t)buf * 64u;
+                    const uint32_t d = tmem_base + (uint32_t)buf * (uint32_t)NCOL;
                     const uint32_t s1 = arr16 + (uint32_t)(ph * p.OW + j0), s2 = arr16 + (uint32_t)(ph2 * p.OW + j0);
                     umma_i8_lohi<false>(d, s1 | albo, ahi, b1lo, bhi, idesc);           // input rows 2Y - 1, 2Y
                     umma_i8_lohi<true>(d, s2 | albo, ahi, b2lo, bhi, idesc);            // input rows 2Y + 1, 2Y + 2
@@ -253,10 +272,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
                 }
                 __syncwarp();
                 if (rank == 0) FS_STAMP(t / FS_NI, 15);
+                FS_WATCH(rank, (t << 8) | 0x30);
                 if (relupto > myrel) { relph += relupto - myrel; if (relph >= p.R) relph -= p.R; myrel = relupto; }
                 j0 = wnext - adv * p.OW; pr0 += adv; ph += adv; if (ph >= p.R) ph -= p.R;
             }
             // the rest of the frame segment's rows (after this warp's last tile)
+            FS_WATCH(rank, 0x40 | (gbase + (sg.ib - sg.ia)) << 16);
             wait_rows(gbase + (sg.ib - sg.ia));
             if (elect_one()) {
                 int rp = relph;
@@ -266,7 +287,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
             gbase += sg.ib - sg.ia + 1;
             tbase += ntiles;
         }
-    } else if (warp == 2) {
+    } else if (warp == FS_LW) {
         // ===================== raw-row loader: one bulk copy per pair-row =====================
         if (lane == 0) {
             int U = U0, rs = 0; uint32_t rphase = 0;
@@ -274,6 +295,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
             const uint8_t *src = reinterpret_cast<const uint8_t *>(p.src);
             while (fs_next_seg(p, U, U1, sg)) {
                 for (int r = sg.ia; r <= sg.ib; ++r) {
+                    FS_WATCH(4, (r << 16) | rs);
                     mbar_wait(bar_rawempty(rs), rphase ^ 1u);
                     const int ya = 2 * r - 1, yb = 2 * r;
                     const bool va = ya >= 0, vb = yb < p.H;
@@ -309,10 +331,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
             for (int r = sg.ia; r <= sg.ib; ++r, ++gl) {
                 if (gl != mine) continue;
                 FS_STAMP_B(0);
+                FS_WATCH(5 + bw, (gl << 8) | 1);
                 mbar_wait(bar_rawfull(rs), rphase);
+                FS_WATCH(5 + bw, (gl << 8) | 2);
                 FS_STAMP_B(1);
                 mbar_wait(bar_empty(phys), phase ^ 1u);
                 FS_STAMP_B(2);
+                FS_WATCH(5 + bw, (gl << 8) | 3);
                 const uint8_t *rawp = s_rawp + (size_t)rs * raw_slot_bytes;
                 const bool mirror = phys < p.MR;
                 {
@@ -358,6 +383,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
                 mbar_arrive(bar_full(phys));
                 mbar_arrive(bar_rawempty(rs));
                 FS_STAMP_B(5);
+                FS_WATCH(5 + bw, (gl << 8) | 4);
                 rs += FS_NTEAM; if (rs >= FS_RAWR) { rs -= FS_RAWR; rphase ^= 1u; }
                 mine += FS_NTEAM;
                 phys += FS_NTEAM; while (phys >= p.R) { phys -= p.R; phase ^= 1u; }
@@ -372,15 +398,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
         while (fs_next_seg(p, U, U1, sg)) {
             const int ntiles = sg.ub - sg.ua;
             for (int k = (grp - tbase) & (FS_EG - 1); k < ntiles; k += FS_EG) {
-                const int t = tbase + k, buf = t & (FS_TBUF - 1);
-                mbar_wait(bar_tfull(buf), ((uint32_t)t >> 3) & 1u);
+                const int t = tbase + k, buf = t % TBUF, use = t / TBUF;
+                FS_WATCH(13 + (warp - FS_EW0), (t << 8) | 1);
+                mbar_wait(bar_tfull(buf), (uint32_t)use & 1u);
+                FS_WATCH(13 + (warp - FS_EW0), (t << 8) | 2);
                 if (grp == 0 && q4 == 0) FS_STAMP(t >> 2, 16);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (uint32_t)buf * 64u + ((uint32_t)(q4 * 32) << 16);
+                const uint32_t taddr = tmem_base + (uint32_t)buf * (uint32_t)NCOL + ((uint32_t)(q4 * 32) << 16);
                 const int q = 128 * (sg.ua + k) + q4 * 32 + lane;
-                if (p.q.activ) fs_epilogue_tile<EPI, true>(p, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
-                else fs_epilogue_tile<EPI, false>(p, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
+                if (p.q.activ) fs_epilogue_tile<EPI, true, CO>(p, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
+                else fs_epilogue_tile<EPI, false, CO>(p, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
                 if (grp == 0 && q4 == 0) FS_STAMP(t >> 2, 17);
+                FS_WATCH(13 + (warp - FS_EW0), (t << 8) | 3);
             }
             tbase += ntiles;
         }
@@ -411,10 +440,10 @@ static bool fs_plan(const ConvArgs &a, int src_kind, const void *src, FsParams &
 {
     memset(&p, 0, sizeof p);
     if (!fs_enabled() || (src_kind != 0 && src_kind != 1)) return false;
-    if (a.cs_in != 4 || a.cs_out != 16 || a.w_rows < 16 || !a.q.pool) return false;
+    if (a.cs_in != 4 || (a.cs_out != 16 && a.cs_out != 32) || a.w_rows < a.cs_out || !a.q.pool) return false;
     if (a.H < 2 || a.W < 256 || (a.W % 8)) return false;       // pooled width >= 128: a tile spans at most two pooled rows
     if (((uintptr_t)src & 15) || ((uintptr_t)a.out & 15)) return false;
-    p.n_img = a.n; p.H = a.H; p.W = a.W; p.OH = a.H / 2; p.OW = a.W / 2;
+    p.n_img = a.n; p.H = a.H; p.W = a.W; p.OH = a.H / 2; p.OW = a.W / 2; p.co = a.cs_out;
     const long long ohw = (long long)p.OH * p.OW;
     if ((ohw + 512) * p.OW >= (1ll << 32) || ohw + 512 >= (1ll << 24)) return false;   // multiply-high divisions stay exact
     p.ohw = (int)ohw;
@@ -426,11 +455,11 @@ static bool fs_plan(const ConvArgs &a, int src_kind, const void *src, FsParams &
     p.MR = (127 + p.OW - 1) / p.OW;                            // = 1
     p.segs = (p.OW + FS_SEGW - 1) / FS_SEGW;
     p.row_bytes = (uint32_t)a.W * (src_kind == 1 ? 2u : 4u);
-    p.off_lut = 4096;
+    p.off_lut = 2u * 4u * (uint32_t)a.cs_out * 32u;             // the two weight images
     p.off_raw = p.off_lut + (src_kind == 1 ? 4112u * 4u : 0u);       // 4097 table words
     p.off_bias = p.off_raw + (uint32_t)FS_RAWR * 2u * p.row_bytes;
-    p.off_bar = (p.off_bias + 64u + 15u) & ~15u;
-    p.off_arr = (p.off_bar + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF + 1) + 127u) & ~127u;
+    p.off_bar = (p.off_bias + 128u + 15u) & ~15u;
+    p.off_arr = (p.off_bar + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF_MAX + 1) + 127u) & ~127u;
     const uint32_t avail = FS_SMEM_MAX - 128u - p.off_arr;
     const uint32_t row2 = 2u * (uint32_t)p.OW * 16u;           // one ring row of the two arrays
     int rows = (int)(avail / row2) - 1;                        // -1: rounding of arr_bytes
@@ -449,7 +478,7 @@ bool conv3x3_fs_supported(const ConvArgs &a, int src_kind, const void *src)
     return fs_plan(a, src_kind, src, p);
 }
 
-template <int EPI, int SRC>
+template <int EPI, int SRC, int CO>
 static cudaError_t launch_fs2(const FsParams &p, cudaStream_t st, int sm_count)
 {
     const uint32_t smem_bytes = p.off_arr + 2u * p.arr_bytes + 128u;
@@ -457,7 +486,7 @@ static cudaError_t launch_fs2(const FsParams &p, cudaStream_t st, int sm_count)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_fs_kernel<EPI, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_fs_kernel<EPI, SRC, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_SMEM_MAX);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
@@ -470,14 +499,14 @@ static cudaError_t launch_fs2(const FsParams &p, cudaStream_t st, int sm_count)
         cudaMemsetAsync(dbg, 0, 64 * 24 * sizeof(long long), st);
         pd.dbg = dbg;
     }
-    cudaError_t le = launch_pdl(conv3x3_fs_kernel<EPI, SRC>, dim3(grid), dim3(FS_THREADS), smem_bytes, st, pd);
+    cudaError_t le = launch_pdl(conv3x3_fs_kernel<EPI, SRC, CO>, dim3(grid), dim3(FS_THREADS), smem_bytes, st, pd);
     if (le != cudaSuccess) return le;
     {
         static long long h[64 * 24];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, pd.dbg, sizeof h, cudaMemcpyDeviceToHost);
         const long long t0 = h[0];
-        printf("FS timeline OW=%d R=%d units=%d grid=%d (cycles since builder 0's first stamp): n | builder warp 0, row 4n: start raw_ok slot_ok stored fenced published | builder warp 7, row 4n+3: same | issuer0 tile 3n: top rows_ok tmem_ok issued | epi0 tile 4n: tfull_ok done\n", p.OW, p.R, p.total_units, grid);
+        printf("FS timeline OW=%d R=%d units=%d grid=%d (cycles since builder 0's first stamp): n | builder warp 0, row 4n: start raw_ok slot_ok stored fenced published | builder warp 7, row 4n+3: same | issuer0 tile 4n: top rows_ok tmem_ok issued | epi0 tile 4n: tfull_ok done\n", p.OW, p.R, p.total_units, grid);
         for (int i = 0; i < 40; ++i) {
             printf("  %2d |", i);
             for (int j = 0; j < 18; ++j) printf("%s%7lld", (j == 6 || j == 12 || j == 16) ? " |" : "", h[i * 24 + j] - t0);
@@ -485,15 +514,38 @@ static cudaError_t launch_fs2(const FsParams &p, cudaStream_t st, int sm_count)
         }
     }
     return cudaGetLastError();
+#elif defined(YB_FS_WATCH)
+    FsParams pw = p;
+    static unsigned *wh = nullptr, *wd = nullptr;
+    if (!wh) { cudaHostAlloc((void **)&wh, 148 * 32 * 4, cudaHostAllocMapped); cudaHostGetDevicePointer((void **)&wd, wh, 0); }
+    memset(wh, 0, 148 * 32 * 4);
+    pw.watch = wd;
+    cudaError_t le = launch_pdl(conv3x3_fs_kernel<EPI, SRC, CO>, dim3(grid), dim3(FS_THREADS), smem_bytes, st, pw);
+    if (le != cudaSuccess) return le;
+    for (int i = 0; i < 300; ++i) { if (cudaStreamQuery(st) == cudaSuccess) return cudaSuccess; struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); }
+    printf("FS WATCH: kernel not finished after 3 s.  CO=%d SRC=%d OW=%d R=%d units=%d upi=%d grid=%d\n", CO, SRC, p.OW, p.R, p.total_units, p.upi, grid);
+    for (int c = 0; c < grid; ++c) {
+        printf("cta %3d [%d,%d) iss", c, (int)(((long long)p.total_units * c) / grid), (int)(((long long)p.total_units * (c + 1)) / grid));
+        for (int j = 0; j < 4; ++j) printf(" t%u:%02x:r%u", (wh[c * 32 + j] >> 8) & 0xff, wh[c * 32 + j] & 0xff, wh[c * 32 + j] >> 16);
+        printf(" | ld r%u s%u | bld", wh[c * 32 + 4] >> 16, wh[c * 32 + 4] & 0xffff);
+        for (int j = 0; j < FS_NBW; ++j) printf(" %u:%u", wh[c * 32 + 5 + j] >> 8, wh[c * 32 + 5 + j] & 0xff);
+        printf(" | epi");
+        for (int j = 0; j < 16; j += 4) printf(" %u:%u", wh[c * 32 + 13 + j] >> 8, wh[c * 32 + 13 + j] & 0xff);
+        printf("\n");
+        if (c > 12) break;
+    }
+    fflush(stdout);
+    abort();
 #else
-    return launch_pdl(conv3x3_fs_kernel<EPI, SRC>, dim3(grid), dim3(FS_THREADS), smem_bytes, st, p);
+    return launch_pdl(conv3x3_fs_kernel<EPI, SRC, CO>, dim3(grid), dim3(FS_THREADS), smem_bytes, st, p);
 #endif
 }
 
 template <int EPI>
 static cudaError_t launch_fs(const FsParams &p, int src_kind, cudaStream_t st, int sm_count)
 {
-    return src_kind == 1 ? launch_fs2<EPI, 1>(p, st, sm_count) : launch_fs2<EPI, 0>(p, st, sm_count);
+    if (p.co == 32) return src_kind == 1 ? launch_fs2<EPI, 1, 32>(p, st, sm_count) : launch_fs2<EPI, 0, 32>(p, st, sm_count);
+    return src_kind == 1 ? launch_fs2<EPI, 1, 16>(p, st, sm_count) : launch_fs2<EPI, 0, 16>(p, st, sm_count);
 }
 
 cudaError_t conv3x3_fs(const ConvArgs &a, cudaStream_t st, int src_kind, const void *src, const void *lut)
@@ -505,7 +557,7 @@ cudaError_t conv3x3_fs(const ConvArgs &a, cudaStream_t st, int src_kind, const v
     p.src = src; p.lut = (const int *)lut;
     p.wgt = a.wgt; p.bias_sh = a.bias_sh; p.q = a.q; p.out = a.out; p.ovf = a.ovf;
     p.xsplit = a.out_xsplit ? 1 : 0;
-    if (p.xsplit && (p.OW & 1)) return cudaErrorInvalidValue;
+    if (p.xsplit && ((p.OW & 1) || p.co != 16)) return cudaErrorInvalidValue;
     static int sms[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -745,7 +745,7 @@ static int run_layer(yolo_b200_ctx *c, int l, const int8_t *d_in, int n, int h, 
     const bool use_umma = be == 2 || be == 3 || (be == 0 && !first_ok && !ws_ok && umma_ok);
     if (use_umma) { int rc = ensure_swz(c, L); if (rc) return rc; a.wgt_swz = L.w_swz; }
     if (be == 1) CU(conv3x3_direct(a, c->stream));
-    else if (be == 0 && first_ok) { CU(conv3x3_first(a, c->stream)); c->launches += L.cs_out / 16 - 1; }   // one pass per 16 output channels
+    else if (be == 0 && first_ok) { CU(conv3x3_first(a, c->stream)); c->launches += conv3x3_fs_supported(a, 0, a.in) ? 0 : L.cs_out / 16 - 1; }   // conv_first.cu: one pass per 16 output channels
     else if (use_umma) CU(conv3x3_umma(a, c->stream, c->sm_count));
     else if (be == 0 && conv3x3_rp_supported(a)) CU(conv3x3_rp(a, c->stream, c->sm_count));
     else if (be == 0 && aligned && conv3x3_ws2_supported(a, c->sm_count)) CU(conv3x3_ws2(a, c->stream, c->sm_count));
@@ -1120,7 +1120,7 @@ static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, i
     c->ev_used = 0;
     tick(c);
     CU(conv3x3_first(a0, c->stream, kind, d_src, kind == 1 ? (const void *)c->lut_dev : (const void *)c->lut8_dev));
-    c->launches += L0.cs_out / 16;
+    c->launches += (kind <= 1 && conv3x3_fs_supported(a0, kind, d_src)) ? 1 : L0.cs_out / 16;
     tick(c);
     rc = backbone_from(c, 1, L0.out, n, oh, ow, pred, gh, gw, last_out); if (rc) return rc;
     *done = true;
