@@ -813,6 +813,30 @@ def test_first_layer_tcgen05_kernel_against_oracle(ctx, pool_shape):
         np.testing.assert_array_equal(ctx.layer_output(l, shp[0], shp[1], shp[2]), ref[l], err_msg="rgb444 shape %s layer %d" % ((n, h, w), l))
 
 
+def test_first_layer_tcgen05_kernel_32_channels_many_tiles_per_cta(ctx):
+    """darknet19's first layer (3 -> 32 + pool) on the tcgen05 slot kernel with 40 frames of 416x416: ~90 tiles per CTA over four
+    TMEM buffers (the configuration in which issuer warps that shared buffers once ran two uses ahead of the drain and hung);
+    frames 0 / 17 / 39 against the oracle, both contracts."""
+    qnet = ex.random_quantnet_yolo_v2(seed=0, calib_hw=(64, 96), calib_frames=1)
+    cin, cout, activ, pool = qnet.layers[0]
+    assert (cout, pool) == (32, 1)
+    n, h, w = 40, 416, 416
+    rng = np.random.default_rng(5)
+    x = np.zeros((n, h, w, 4), dtype=np.int8)
+    x[..., :3] = rng.integers(-128, 128, (n, h, w, 3), dtype=np.int8)
+    for contract in (lib.CONTRACT_F, lib.CONTRACT_P):
+        ctx.load_quantnet(qnet, contract=contract)
+        d_out = torch.full((n, h // 2, w // 2, 32), 77, dtype=torch.int8, device="cuda")
+        for _ in range(3):
+            ctx.conv_layer(0, dev(x), n, h, w, d_out)
+        ctx.sync()
+        got = d_out.cpu().numpy()
+        for f in (0, 17, 39):
+            ref, _ = ol.conv_layer(x[f:f + 1], qnet.w[0], qnet.b[0], cin, cout, qnet.sa[0], qnet.sw[0], qnet.sb[0],
+                                   qnet.retune[0], qnet.sa[1], activ, pool, contract)
+            np.testing.assert_array_equal(got[f:f + 1], ref, err_msg="frame %d contract %d" % (f, contract))
+
+
 def test_weight_stationary_layers_with_cp_async_producers_in_a_subprocess():
     """YOLO_B200_WS_TMA=0 (read once per process) keeps the cp.async producers for conv3_1 / conv4_1 / conv4_2: same
     results as the oracle (the TMA-fed default is what every other test runs)."""
