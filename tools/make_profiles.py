@@ -46,4 +46,6 @@ for n in (2, 4, 8):
         lines = [l for l in open(f) if l.startswith("{")]
         if lines:
             open(os.path.join(P, "bench_%s_n%d.json" % (rnd, n)), "w").write(lines[-1])
+if os.path.exists(os.path.join(G, "clocks_after_profiles.csv")):
+    shutil.copy(os.path.join(G, "clocks_after_profiles.csv"), os.path.join(P, "clocks_%s.csv" % rnd))
 print("\n".join(md))
