@@ -54,7 +54,7 @@ namespace yb {
 #else
 #define FS_WATCH(slot, val) do { } while (0)
 #endif
-#define FS_STAMP_B(slot) do { if (bw == 0) FS_STAMP(gl / FS_NTEAM, slot); else if (bw == 7) FS_STAMP(gl / FS_NTEAM, 6 + (slot)); } while (0)
+#define FS_STAMP_B(slot) do { if (bw == 0) FS_STAMP(gl_row / FS_NTEAM, slot); else if (bw == 7) FS_STAMP(gl_row / FS_NTEAM, 6 + (slot)); } while (0)
 
 constexpr int FS_THREADS = 928;
 constexpr int FS_NI = 4;                 // MMA issuer warps 0-3 (tile t -> issuer t % 4): a lone warp needs ~1250 cycles per tile (barrier polls, descriptor
@@ -93,6 +93,17 @@ struct FsParams {
     long long *dbg;
     unsigned *watch;
 };
+
+// mbarrier wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// re-issuing the poll every few hundred cycles (the epilogue groups wait ~60 % of the time: ~35 polls per tile without it)
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    } while (!done);
+}
 
 // predicated 128-bit shared store (a predicate, not a branch: the shuffles of the next pass are not held behind a reconvergence point)
 __device__ __forceinline__ void st_shared_v4_if(bool pred, uint32_t addr, unsigned a, unsigned b, unsigned c, unsigned d)
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
             while (fs_next_seg(p, U, U1, sg)) {
                 for (int r = sg.ia; r <= sg.ib; ++r) {
                     FS_WATCH(4, (r << 16) | rs);
-                    mbar_wait(bar_rawempty(rs), rphase ^ 1u);
+                    mbar_wait_hint(bar_rawempty(rs), rphase ^ 1u);
                     const int ya = 2 * r - 1, yb = 2 * r;
                     const bool va = ya >= 0, vb = yb < p.H;
                     const uint32_t dst = raw0 + (uint32_t)rs * raw_slot_bytes;
@@ -328,16 +339,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
         const bool lane_st = lane >= 1 && lane <= FS_SEGW;
         const int jmax = p.OW - 1;
         while (fs_next_seg(p, U, U1, sg)) {
-            for (int r = sg.ia; r <= sg.ib; ++r, ++gl) {
-                if (gl != mine) continue;
+            const int gend = gl + (sg.ib - sg.ia + 1);             // the segment's pair-rows are gl .. gend - 1 of the CTA's sequence
+            for (; mine < gend; ) {
+                const int r = sg.ia + (mine - gl);
+                const int gl_row = mine;
                 FS_STAMP_B(0);
-                FS_WATCH(5 + bw, (gl << 8) | 1);
-                mbar_wait(bar_rawfull(rs), rphase);
-                FS_WATCH(5 + bw, (gl << 8) | 2);
+                FS_WATCH(5 + bw, (gl_row << 8) | 1);
+                mbar_wait_hint(bar_rawfull(rs), rphase);
+                FS_WATCH(5 + bw, (gl_row << 8) | 2);
                 FS_STAMP_B(1);
-                mbar_wait(bar_empty(phys), phase ^ 1u);
+                mbar_wait_hint(bar_empty(phys), phase ^ 1u);
                 FS_STAMP_B(2);
-                FS_WATCH(5 + bw, (gl << 8) | 3);
+                FS_WATCH(5 + bw, (gl_row << 8) | 3);
                 const uint8_t *rawp = s_rawp + (size_t)rs * raw_slot_bytes;
                 const bool mirror = phys < p.MR;
                 {
@@ -383,11 +396,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
                 mbar_arrive(bar_full(phys));
                 mbar_arrive(bar_rawempty(rs));
                 FS_STAMP_B(5);
-                FS_WATCH(5 + bw, (gl << 8) | 4);
+                FS_WATCH(5 + bw, (gl_row << 8) | 4);
                 rs += FS_NTEAM; if (rs >= FS_RAWR) { rs -= FS_RAWR; rphase ^= 1u; }
                 mine += FS_NTEAM;
                 phys += FS_NTEAM; while (phys >= p.R) { phys -= p.R; phase ^= 1u; }
             }
+            gl = gend;
         }
     } else if (warp >= FS_EW0) {
         // ===================== epilogue warps: tile t -> group t % 4 =====================
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
             for (int k = (grp - tbase) & (FS_EG - 1); k < ntiles; k += FS_EG) {
                 const int t = tbase + k, buf = t % TBUF, use = t / TBUF;
                 FS_WATCH(13 + (warp - FS_EW0), (t << 8) | 1);
-                mbar_wait(bar_tfull(buf), (uint32_t)use & 1u);
+                mbar_wait_hint(bar_tfull(buf), (uint32_t)use & 1u);
                 FS_WATCH(13 + (warp - FS_EW0), (t << 8) | 2);
                 if (grp == 0 && q4 == 0) FS_STAMP(t >> 2, 16);
                 tc_fence_after();
