@@ -134,7 +134,7 @@ __device__ __forceinline__ bool fs_next_seg(const FsParams &p, int &U, int U1, F
 // conversions per thread and tile, were measured and rejected: re-arming 64 columns + tcgen05.wait::st costs ~1500 cycles per tile
 // and group, 0.186 -> 0.260 ms.)
 template <int EPI, bool ACT, int CO>
-__device__ __forceinline__ void fs_epilogue_tile(const FsParams &p, uint32_t taddr, int q, int img, const int *s_bias, uint32_t bar_tempty, unsigned &ovf)
+__device__ __forceinline__ void fs_epilogue_tile(const FsParams &p, const EpiPk &kp, uint32_t taddr, int q, int img, const int *s_bias, uint32_t bar_tempty, unsigned &ovf)
 {
     const bool valid = q < p.ohw;
     int pos = q;
@@ -155,8 +155,8 @@ __device__ __forceinline__ void fs_epilogue_tile(const FsParams &p, uint32_t tad
         if (h == CO / 8 - 1) { tc_fence_before(); mbar_arrive(bar_tempty); }      // all of the tile's accumulators are in registers
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = max(max(a[j], b[j]), max(c[j], d[j]));
-        w[2 * (h & 1)] = requant4<EPI, ACT>(&a[0], s_bias, 8 * h, p, ovf, valid);
-        w[2 * (h & 1) + 1] = requant4<EPI, ACT>(&a[4], s_bias, 8 * h + 4, p, ovf, valid);
+        w[2 * (h & 1)] = requant4_pk<EPI, ACT>(&a[0], s_bias, 8 * h, p, kp, ovf, valid);
+        w[2 * (h & 1) + 1] = requant4_pk<EPI, ACT>(&a[4], s_bias, 8 * h + 4, p, kp, ovf, valid);
         if ((h & 1) && valid) dst[h >> 1] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
         unsigned ovf = 0;
         int U = U0, tbase = 0;
         FsSeg sg;
+        const EpiPk kp = epi_pack(p.k);                        // the epilogue constants as packed register pairs
         while (fs_next_seg(p, U, U1, sg)) {
             const int ntiles = sg.ub - sg.ua;
             for (int k = (grp - tbase) & (FS_EG - 1); k < ntiles; k += FS_EG) {
@@ -420,8 +421,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t)buf * (uint32_t)NCOL + ((uint32_t)(q4 * 32) << 16);
                 const int q = 128 * (sg.ua + k) + q4 * 32 + lane;
-                if (p.q.activ) fs_epilogue_tile<EPI, true, CO>(p, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
-                else fs_epilogue_tile<EPI, false, CO>(p, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
+                if (p.q.activ) fs_epilogue_tile<EPI, true, CO>(p, kp, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
+                else fs_epilogue_tile<EPI, false, CO>(p, kp, taddr, q, sg.img, s_bias, bar_tempty(buf), ovf);
                 if (grp == 0 && q4 == 0) FS_STAMP(t >> 2, 17);
                 FS_WATCH(13 + (warp - FS_EW0), (t << 8) | 3);
             }

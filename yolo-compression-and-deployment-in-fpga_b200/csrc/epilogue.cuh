@@ -79,6 +79,56 @@ __device__ __forceinline__ int2 requant_f_rne_x2(int a0, int a1, float2 fb, cons
     return make_int2(unbias_magic(__float_as_int(v.x), k.one), unbias_magic(__float_as_int(v.y), k.one));
 }
 
+// ---- the same with the constants held as packed register pairs ------------------------------------------------------
+// requant_f_rne_x2 builds every f32x2 operand ({s_in, s_in}, {MAGIC, MAGIC}, ...) from the constant bank at each use (conv3_1, ncu
+// source counters: 38 IMAD.MOV + 28 LDC / LDCU per 32 values).  EpiPk holds the pairs in registers for the lifetime of an epilogue
+// warp; `pin` keeps the compiler from re-materialising them.  Used by conv_fs.cu (no spills at 64 registers).  In conv_ws.cu the
+// same change removed ~18 % of the epilogue's instructions and did NOT make the layers faster (conv3_1 0.101 -> 0.107 ms, conv3_2
+// 0.113 -> 0.110): those epilogues are paced by TMEM-load and dependency latency with two groups, not by issue slots; not kept there.
+struct EpiPk { unsigned long long s_in, magic, in_add, eighth, leak_add, s_out, out_add; int one; };
+__device__ __forceinline__ unsigned long long epi_pair(float v)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+    asm volatile("" : "+l"(r));                                // pin
+    return r;
+}
+__device__ __forceinline__ EpiPk epi_pack(const EpiConst &k)
+{
+    EpiPk e;
+    e.s_in = epi_pair(k.s_in); e.magic = epi_pair(YB_MAGIC); e.in_add = epi_pair(k.in_add); e.eighth = epi_pair(0.125f);
+    e.leak_add = epi_pair(k.leak_add); e.s_out = epi_pair(k.s_out); e.out_add = epi_pair(k.out_add); e.one = k.one;
+    return e;
+}
+__device__ __forceinline__ unsigned long long ffma2_pk(unsigned long long a, unsigned long long b, unsigned long long c)
+{ unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ unsigned long long fadd2_pk(unsigned long long a, unsigned long long b)
+{ unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ unsigned long long pack_f2(float x, float y)
+{ unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ float2 unpack_f2(unsigned long long v)
+{ float2 d; asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v)); return d; }
+
+// Contract F / RNE, two channels, packed constants; fb = the two fp32 biases as one pair.  Same arithmetic as requant_f_rne_x2.
+template <bool ACT, bool HI16, bool PRE = false>
+__device__ __forceinline__ int2 requant_f_rne_x2_pk(int a0, int a1, unsigned long long fb, const EpiPk &k)
+{
+    unsigned long long v;
+    if (PRE) v = ffma2_pk(pack_f2(__int_as_float(a0), __int_as_float(a1)), k.s_in, k.in_add);
+    else v = ffma2_pk(pack_f2(__int2float_rn(a0), __int2float_rn(a1)), k.s_in, k.magic);
+    v = fadd2_pk(v, fb);
+    float2 t = unpack_f2(v);
+    if (ACT) {
+        const float2 l = unpack_f2(ffma2_pk(v, k.eighth, k.leak_add));
+        t.x = fmaxf(fmaxf(t.x, l.x), YB_MAGIC - 4096.f); t.y = fmaxf(fmaxf(t.y, l.y), YB_MAGIC - 4096.f);
+    } else {
+        t.x = fmaxf(t.x, YB_MAGIC - 32768.f); t.y = fmaxf(t.y, YB_MAGIC - 32768.f);
+    }
+    if (HI16) { t.x = fminf(t.x, YB_MAGIC + 32767.f); t.y = fminf(t.y, YB_MAGIC + 32767.f); }
+    const float2 o = unpack_f2(ffma2_pk(pack_f2(t.x, t.y), k.s_out, k.out_add));
+    return make_int2(unbias_magic(__float_as_int(o.x), k.one), unbias_magic(__float_as_int(o.y), k.one));
+}
+
 // Contract P, two channels.  bp = bias << (E - sb).  Returns o + 128 (exact inside [0,255], on the correct side outside).
 template <bool ACT>
 __device__ __forceinline__ int2 requant_p_x2(int a0, int a1, int bp0, int bp1, const EpiConst &k)
@@ -143,6 +193,21 @@ __device__ __forceinline__ uint4 requant16(const int (&v)[16], const int *bias, 
     w.z = requant4<EPI, ACT, P, PRE>(&v[8], bias, c0 + 8, p, ovf, count);
     w.w = requant4<EPI, ACT, P, PRE>(&v[12], bias, c0 + 12, p, ovf, count);
     return w;
+}
+
+// 4 accumulators -> one word; the F fast paths run on the packed constants, every other epilogue on requant4v.
+template <int EPI, bool ACT, class P, bool PRE = false>
+__device__ __forceinline__ unsigned requant4_pk(const int *acc, const int *bias, int c, const P &p, const EpiPk &k, unsigned &ovf, bool count)
+{
+    if (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) {
+        constexpr bool HI = EPI == EPI_F_RNE;
+        const ulonglong2 fb = *reinterpret_cast<const ulonglong2 *>(bias + c);         // four fp32 biases = two pairs
+        const int2 lo = requant_f_rne_x2_pk<ACT, HI, PRE>(acc[0], acc[1], fb.x, k);
+        const int2 hi = requant_f_rne_x2_pk<ACT, HI, PRE>(acc[2], acc[3], fb.y, k);
+        return pack_sat_s8(lo.x, lo.y, pack_sat_s8(hi.x, hi.y, 0u));
+    } else {
+        return requant4v<EPI, ACT, P, false>(acc, *reinterpret_cast<const int4 *>(bias + c), p, ovf, count);
+    }
 }
 
 // host: exact contract-F arithmetic on one value of t (after the 16-bit clamp), used to prove clamps redundant
