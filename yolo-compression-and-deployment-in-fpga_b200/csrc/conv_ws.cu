@@ -154,23 +154,24 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
         const bool inside = cy < p.canvas_rows && y < p.H && x < p.W;
         if (!p.q.pool) {
             int8_t *dst = p.out + (((size_t)n * p.H + y) * p.W + x) * p.cs_out;
-            // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is requantised
+            // both 16-column chunks of a 32-column block are loaded at once: one wait, the accumulator buffer is released as soon
+            // as the last block is in registers (the MMA warp does not wait for the requantisation), and the two requantisations
+            // are independent instruction streams
             int va[16], vb[16];
-            if (cbeg < cend) tmem_ld16(taddr + cbeg, va);
             for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                const bool two = c0 + 16 < cend;
+                tmem_ld16(taddr + c0, va);
+                if (two) tmem_ld16(taddr + c0 + 16, vb);
                 tmem_ld_wait();
-                if (c0 + 16 < cend) tmem_ld16(taddr + c0 + 16, vb);
-                uint4 w = requant16<EPI, ACT>(va, s_bias, c0, p, ovf, inside);
-                if (inside) *reinterpret_cast<uint4 *>(dst + c0) = w;
-                if (c0 + 16 < cend) {
-                    tmem_ld_wait();
-                    if (c0 + 32 < cend) tmem_ld16(taddr + c0 + 32, va);
-                    w = requant16<EPI, ACT>(vb, s_bias, c0 + 16, p, ovf, inside);
-                    if (inside) *reinterpret_cast<uint4 *>(dst + c0 + 16) = w;
+                if (c0 + 32 >= cend) { tc_fence_before(); mbar_arrive(bar_tempty); }
+                const uint4 w0 = requant16<EPI, ACT>(va, s_bias, c0, p, ovf, inside);
+                if (inside) *reinterpret_cast<uint4 *>(dst + c0) = w0;
+                if (two) {
+                    const uint4 w1 = requant16<EPI, ACT>(vb, s_bias, c0 + 16, p, ovf, inside);
+                    if (inside) *reinterpret_cast<uint4 *>(dst + c0 + 16) = w1;
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty);
+            if (cbeg >= cend) { tc_fence_before(); mbar_arrive(bar_tempty); }
         } else {
             // pooled layer on the un-phased tile (weights + phased tile do not fit): the 2x2 window of a pixel is lanes
             // {l, l^1, l^8, l^9} of this warp.  Max the raw accumulators with two shuffles, then every lane requantises
