@@ -135,13 +135,13 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
             tmem_ld16(taddr + 2 * accs + c0, v2);
             tmem_ld16(taddr + 3 * accs + c0, v3);
             tmem_ld_wait();
+            if (c0 + 16 >= cend) { tc_fence_before(); mbar_arrive(bar_tempty); }      // the last chunk is in registers: release the accumulators
 #pragma unroll
             for (int j = 0; j < 16; ++j) v0[j] = max(max(v0[j], v1[j]), max(v2[j], v3[j]));
             const uint4 w = requant16<EPI, ACT>(v0, s_bias, c0, p, ovf, valid);
             if (valid) *reinterpret_cast<uint4 *>(dst + c0) = w;
         }
-        tc_fence_before();
-        mbar_arrive(bar_tempty);
+        if (cbeg >= cend) { tc_fence_before(); mbar_arrive(bar_tempty); }
     } else {
         int cy = ty0 + g, x = tx0 + xl;
         if (p.raster) {                                        // row r = stream pixel 128 * tile + r (ty0 = 16 * tile)
@@ -184,6 +184,7 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
                 int v[16];
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
+                if (c0 + 16 >= cend) { tc_fence_before(); mbar_arrive(bar_tempty); }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     v[j] = max(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
@@ -196,8 +197,7 @@ __device__ __forceinline__ void ws_epilogue_tile(const WsParams &p, uint32_t tad
                 const unsigned w = requant4<EPI, ACT>(mine, s_bias, c0 + 4 * role, p, ovf, valid);
                 if (valid) *reinterpret_cast<unsigned *>(dst + c0) = w;
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty);
+            if (cbeg >= cend) { tc_fence_before(); mbar_arrive(bar_tempty); }
         }
     }
 }
