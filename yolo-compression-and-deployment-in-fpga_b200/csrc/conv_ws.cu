@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WS_MAX_STAGES; ++s) { mbar_init(bar_full(s), TMAIN ? 1 : WS_PROD_THREADS); mbar_init(bar_empty(s), 1); }
-        for (int b = 0; b < WS_MAX_TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), WS_EPI_THREADS); }
+        for (int b = 0; b < WS_MAX_TBUF; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), (!PHASE && p.tbufs == 4) ? WS_EPI_THREADS / 2 : WS_EPI_THREADS); }
         mbar_init(bar_w, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(bar_bfull(i), 1); mbar_init(bar_bempty(i), 1); }
         fence_barrier_init();
@@ -624,24 +624,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv3x3_ws_kernel(const WsParam
     } else {
         // ===================== epilogue warps =====================
         const int ew_all = warp - (1 + WS_PROD_WARPS);
-        const int grp = ew_all / WS_EPI_WARPS;                     // = accumulator buffer this group drains
-        const int ew = ew_all % WS_EPI_WARPS;
+        // Epilogue groups.  Two groups of eight warps (two warps per TMEM lane quarter, half of the columns each) when only two
+        // accumulator buffers fit; FOUR groups of four warps (one warp per quarter, all columns) over four buffers otherwise: the
+        // epilogue of a thin layer is paced by the dependency latency of ~400 instructions per warp and tile (two groups were
+        // 85-90 % busy at ~2300 cycles per tile on conv3_1), so four tiles in flight with the per-tile address arithmetic
+        // amortised over twice the columns beat two.  Tile it -> group it % ngrp, buffer it % tbufs: a buffer always has the
+        // same group (parity waits on `tfull` are only safe for a waiter that drained the previous use itself).
+        const int ngrp = (!PHASE && p.tbufs == 4) ? 4 : 2;
+        const int wpg = (WS_EPI_GROUPS * WS_EPI_WARPS) / ngrp;
+        const int grp = ew_all / wpg;
+        const int ew = ew_all % wpg;
         const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
         const int cmid = ((p.N / 16 + 1) / 2) * 16;                // column split between the two warps of a quarter
-        const int cbeg = ew < 4 ? 0 : cmid, cend = ew < 4 ? cmid : p.N;
+        const int cbeg = (wpg == 4 || ew < 4) ? 0 : cmid, cend = (wpg == 4 || ew >= 4) ? p.N : cmid;
         unsigned ovf = 0;
-        // tiles blockIdx.x + (grp + 2k) * gridDim.x: advance the tile coordinates two grid strides at a time
+        // tiles blockIdx.x + (grp + ngrp k) * gridDim.x: advance the tile coordinates ngrp grid strides at a time
         int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-        if (grp) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
-        // tile it of this CTA: accumulator buffer it % tbufs (2 or 4), drained by group it % 2.  With four buffers the MMA
-        // warp runs up to three tiles ahead of a group's epilogue instead of waiting for "its" buffer every other tile.
+        for (int g = 0; g < grp; ++g) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
         int it = grp;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += ngrp * gridDim.x, it += ngrp) {
             const int buf = it & (p.tbufs - 1);
             const uint32_t bph = (uint32_t)(it >> p.tbufs_log2) & 1u;
             const int tx0 = tx * G::TW, ty0 = ty * G::TH;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
+            for (int r = 0; r < ngrp; ++r) { tx += p.step_x; ty += p.step_y; if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; } }
             mbar_wait(bar_tfull(buf), bph);
             if (ew_all == 0) WS_STAMP(6);
             tc_fence_after();
