@@ -24,6 +24,7 @@
 // row per warp at a time), warps 4-19 = two epilogue groups of 8 warps (two warps per TMEM lane quarter, each half of the
 // columns); group g drains accumulator buffer g, so the epilogues of two consecutive tiles run concurrently (a single
 // group is latency-bound: ~0.2 instructions per cycle per warp, measured with clock64 stamps, tools/ws_timeline.py).
+// Un-phased layers with four accumulator buffers run FOUR groups of four warps instead (one warp per quarter, all columns).
 // The MMA warp stays converged and elects one lane per tile to issue (elect.sync): with `if (lane == 0)` the issue interval
 // is ~80-120 cycles per MMA, with an elected lane ~42 (tools/micro/umma_issue.cu), which is what the thin layers need.
 #include "kernels.h"
