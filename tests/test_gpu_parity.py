@@ -811,6 +811,20 @@ def test_first_layer_tcgen05_kernel_against_oracle(ctx, pool_shape):
     for l in (0, 1):
         shp = ref[l].shape
         np.testing.assert_array_equal(ctx.layer_output(l, shp[0], shp[1], shp[2]), ref[l], err_msg="rgb444 shape %s layer %d" % ((n, h, w), l))
+    if w % 16:
+        return
+    # uint8 BGR images (BaseTransform without resize + tracker quantiser as three byte tables, fused into the same kernel)
+    ctx.load_quantnet(qnet0, contract=lib.CONTRACT_P, conf_thresh=0.1, nms_thresh=0.5, max_det=512)
+    img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    lut = ctx.u8bgr_lut()                                                     # [R, G, B][256] int8
+    x8 = np.zeros((n, h, w, 4), dtype=np.int8)
+    for c in range(3):
+        x8[..., c] = lut[c][img[..., 2 - c]]
+    ref, _ = ol.backbone(qnet0, x8, contract=1)
+    ctx.forward_u8bgr(img)
+    for l in (0, 1):
+        shp = ref[l].shape
+        np.testing.assert_array_equal(ctx.layer_output(l, shp[0], shp[1], shp[2]), ref[l], err_msg="u8 bgr shape %s layer %d" % ((n, h, w), l))
 
 
 def test_first_layer_tcgen05_kernel_32_channels_many_tiles_per_cta(ctx):

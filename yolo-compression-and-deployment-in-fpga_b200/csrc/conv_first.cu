@@ -343,7 +343,7 @@ cudaError_t conv3x3_first(const ConvArgs &a, cudaStream_t st, int src_kind, cons
     if (a.n == 0) return cudaSuccess;
     if (!conv3x3_first_supported(a)) return cudaErrorInvalidValue;
     // the benchmark geometries (pooled, 16 channels, pooled width >= 128) run on the tcgen05 kernel of conv_fs.cu
-    if (src_kind <= 1 && conv3x3_fs_supported(a, src_kind, src_kind ? src : (const void *)a.in))
+    if (conv3x3_fs_supported(a, src_kind, src_kind ? src : (const void *)a.in))
         return conv3x3_fs(a, st, src_kind, src_kind ? src : (const void *)a.in, lut);
     FirstParams p;
     memset(&p, 0, sizeof p);

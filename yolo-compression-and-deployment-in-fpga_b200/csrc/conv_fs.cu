@@ -70,8 +70,8 @@ constexpr int FS_TBUF_MAX = 8;
 constexpr int FS_SEGW = 30;              // pixel pairs a builder warp produces per pass (lanes 0 and 31 only feed their neighbours)
 
 struct FsParams {
-    const void *src;             // SRC 1: uint16 RGB444 frames [n][H][W]; SRC 0: int8 NHWC4 [n][H][W][4]
-    const int *lut;              // SRC 1: 4096 packed (R,G,B,0) words
+    const void *src;             // SRC 1: uint16 RGB444 frames [n][H][W]; SRC 0: int8 NHWC4 [n][H][W][4]; SRC 2: uint8 BGR images [n][H][W][3]
+    const int *lut;              // SRC 1: 4096 packed (R,G,B,0) words; SRC 2: three 256-byte tables (R from byte 2, G, B: quantize.cu)
     int n_img, H, W, OH, OW;
     int ohw;                     // OH * OW pooled pixels per frame
     int upi;                     // units (tiles of 128 pooled pixels) per frame
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
         reinterpret_cast<unsigned *>(base_ptr)[wd] = v;
     }
     if (SRC == 1) for (int i = threadIdx.x; i <= 4096; i += FS_THREADS) s_lut[i] = i < 4096 ? (unsigned)__ldg(p.lut + i) : 0u;   // entry 4096: outside the frame
+    if (SRC == 2) for (int i = threadIdx.x; i < 192; i += FS_THREADS) s_lut[i] = (unsigned)__ldg(p.lut + i);
     if (threadIdx.x < CO) {
         const int b = p.bias_sh[threadIdx.x];
         s_bias[threadIdx.x] = (EPI == EPI_F_RNE || EPI == EPI_F_RNE_NOHI) ? __float_as_int((float)b) : b;
@@ -370,6 +371,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
                             if (SRC == 1) {
                                 const unsigned raw = reinterpret_cast<const unsigned *>(rr)[jc];
                                 wl[i] = ok ? (raw & 0x0fff0fffu) : 0x10001000u;
+                            } else if (SRC == 2) {
+                                // two BGR pixels = six bytes at a 2-byte aligned offset: B0 G0 | R0 B1 | G1 R1
+                                const unsigned short *h = reinterpret_cast<const unsigned short *>(rr) + 3 * jc;
+                                const unsigned h0 = h[0], h1 = h[1], h2 = h[2];
+                                wl[i] = h0 | (h1 << 16);                           // B0 G0 R0 B1
+                                wh[i] = ok ? (h2 | 0x10000u) : 0u;                 // G1 R1, bit 16 = inside the frame
                             } else {
                                 const uint2 v = reinterpret_cast<const uint2 *>(rr)[jc];
                                 wl[i] = ok ? v.x : 0u; wh[i] = ok ? v.y : 0u;
@@ -378,6 +385,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) conv3x3_fs_kernel(const FsParam
                         if (SRC == 1) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) { const unsigned c = wl[i]; wl[i] = s_lut[c & 0xffffu]; wh[i] = s_lut[c >> 16]; }
+                        }
+                        if (SRC == 2) {
+                            const unsigned char *t8 = reinterpret_cast<const unsigned char *>(s_lut);       // [R | G | B][256]
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const unsigned a = wl[i], b = wh[i];
+                                const unsigned p0 = (unsigned)t8[(a >> 16) & 255u] | ((unsigned)t8[256 + ((a >> 8) & 255u)] << 8) | ((unsigned)t8[512 + (a & 255u)] << 16);
+                                const unsigned p1 = (unsigned)t8[(b >> 8) & 255u] | ((unsigned)t8[256 + (b & 255u)] << 8) | ((unsigned)t8[512 + (a >> 24)] << 16);
+                                const bool in = (b >> 16) != 0u;
+                                wl[i] = in ? p0 : 0u; wh[i] = in ? p1 : 0u;
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -454,7 +472,8 @@ constexpr uint32_t FS_SMEM_MAX = 227u * 1024u;
 static bool fs_plan(const ConvArgs &a, int src_kind, const void *src, FsParams &p)
 {
     memset(&p, 0, sizeof p);
-    if (!fs_enabled() || (src_kind != 0 && src_kind != 1)) return false;
+    if (!fs_enabled() || src_kind < 0 || src_kind > 2) return false;
+    if (src_kind == 2 && (a.W % 16)) return false;                 // rows of 3 W bytes are bulk-copied: multiples of 16 bytes
     if (a.cs_in != 4 || (a.cs_out != 16 && a.cs_out != 32) || a.w_rows < a.cs_out || !a.q.pool) return false;
     if (a.H < 2 || a.W < 256 || (a.W % 8)) return false;       // pooled width >= 128: a tile spans at most two pooled rows
     if (((uintptr_t)src & 15) || ((uintptr_t)a.out & 15)) return false;
@@ -469,9 +488,9 @@ static bool fs_plan(const ConvArgs &a, int src_kind, const void *src, FsParams &
     p.ow_magic = fs_magic(p.OW); p.upi_magic = fs_magic(p.upi);
     p.MR = (127 + p.OW - 1) / p.OW;                            // = 1
     p.segs = (p.OW + FS_SEGW - 1) / FS_SEGW;
-    p.row_bytes = (uint32_t)a.W * (src_kind == 1 ? 2u : 4u);
+    p.row_bytes = (uint32_t)a.W * (src_kind == 1 ? 2u : src_kind == 2 ? 3u : 4u);
     p.off_lut = 2u * 4u * (uint32_t)a.cs_out * 32u;             // the two weight images
-    p.off_raw = p.off_lut + (src_kind == 1 ? 4112u * 4u : 0u);       // 4097 table words
+    p.off_raw = p.off_lut + (src_kind == 1 ? 4112u * 4u : src_kind == 2 ? 768u : 0u);       // 4097 table words / three byte tables
     p.off_bias = p.off_raw + (uint32_t)FS_RAWR * 2u * p.row_bytes;
     p.off_bar = (p.off_bias + 128u + 15u) & ~15u;
     p.off_arr = (p.off_bar + 8u * (2 * FS_RAWR + 2 * FS_RMAX + 2 * FS_TBUF_MAX + 1) + 127u) & ~127u;
@@ -559,8 +578,8 @@ static cudaError_t launch_fs2(const FsParams &p, cudaStream_t st, int sm_count)
 template <int EPI>
 static cudaError_t launch_fs(const FsParams &p, int src_kind, cudaStream_t st, int sm_count)
 {
-    if (p.co == 32) return src_kind == 1 ? launch_fs2<EPI, 1, 32>(p, st, sm_count) : launch_fs2<EPI, 0, 32>(p, st, sm_count);
-    return src_kind == 1 ? launch_fs2<EPI, 1, 16>(p, st, sm_count) : launch_fs2<EPI, 0, 16>(p, st, sm_count);
+    if (p.co == 32) return src_kind == 1 ? launch_fs2<EPI, 1, 32>(p, st, sm_count) : src_kind == 2 ? launch_fs2<EPI, 2, 32>(p, st, sm_count) : launch_fs2<EPI, 0, 32>(p, st, sm_count);
+    return src_kind == 1 ? launch_fs2<EPI, 1, 16>(p, st, sm_count) : src_kind == 2 ? launch_fs2<EPI, 2, 16>(p, st, sm_count) : launch_fs2<EPI, 0, 16>(p, st, sm_count);
 }
 
 cudaError_t conv3x3_fs(const ConvArgs &a, cudaStream_t st, int src_kind, const void *src, const void *lut)
@@ -568,7 +587,7 @@ cudaError_t conv3x3_fs(const ConvArgs &a, cudaStream_t st, int src_kind, const v
     if (a.n == 0) return cudaSuccess;
     FsParams p;
     if (!fs_plan(a, src_kind, src, p)) return cudaErrorInvalidValue;
-    if (src_kind == 1 && !lut) return cudaErrorInvalidValue;
+    if (src_kind >= 1 && !lut) return cudaErrorInvalidValue;
     p.src = src; p.lut = (const int *)lut;
     p.wgt = a.wgt; p.bias_sh = a.bias_sh; p.q = a.q; p.out = a.out; p.ovf = a.ovf;
     p.xsplit = a.out_xsplit ? 1 : 0;

@@ -1120,7 +1120,7 @@ static int fused_front_features(yolo_b200_ctx *c, int kind, const void *d_src, i
     c->ev_used = 0;
     tick(c);
     CU(conv3x3_first(a0, c->stream, kind, d_src, kind == 1 ? (const void *)c->lut_dev : (const void *)c->lut8_dev));
-    c->launches += (kind <= 1 && conv3x3_fs_supported(a0, kind, d_src)) ? 1 : L0.cs_out / 16;
+    c->launches += conv3x3_fs_supported(a0, kind, d_src) ? 1 : L0.cs_out / 16;
     tick(c);
     rc = backbone_from(c, 1, L0.out, n, oh, ow, pred, gh, gw, last_out); if (rc) return rc;
     *done = true;
