@@ -991,6 +991,8 @@ __global__ void __launch_bounds__(GN_THREADS, 1) head_nms_grid_kernel(HeadArgs a
             if (lane == 0) c = (int)atomicAdd(chunk_next, 1u);
             c = __shfl_sync(0xffffffffu, c, 0);
             if (32 * c >= m) break;
+            c = (m + 31) / 32 - 1 - c;                           // last chunks first: the large-box buckets at the end of the bin order walk the widest
+                                                                 // windows, so they should not be the ones left for the tail (0.150 -> 0.1475 ms per 256 dense frames)
             const int j = 32 * c + lane;
             const bool valid = j < m;
             const float4 bj = valid ? sbox[j] : make_float4(0, 0, 0, 0);
